@@ -1,0 +1,160 @@
+// ms_vcf_core.h — one VCF line per applied mutation (K7), host/device shared.
+//
+// Restates vcf_writer.py:44-52,118-126 and the per-type REF/ALT/POS/END/SVLEN
+// rules of mutator.py:334-421.  The same templated emitter is instantiated with
+// a counting sink (pass 1: sizes) and a writing sink (pass 2: bytes), so the two
+// passes cannot disagree.
+#pragma once
+#include "ms_records.h"
+
+namespace ms {
+
+struct VcfView {
+    const uint8_t* genome;
+    const uint8_t* lit;
+    const uint8_t* names;   // contig names blob
+    const uint8_t* conv;
+    const uint8_t* comp;
+};
+
+struct CountSink {
+    uint32_t n = 0;
+    MS_HD void put(uint8_t) { ++n; }
+    MS_HD void skip(uint32_t k) { n += k; }
+    static constexpr bool counting = true;
+};
+
+struct WriteSink {
+    uint8_t* p;
+    MS_HD void put(uint8_t c) { *p++ = c; }
+    MS_HD void skip(uint32_t) {}
+    static constexpr bool counting = false;
+};
+
+template <class S> MS_HD void put_uint(S& s, uint64_t v) {
+    char buf[20];
+    int n = 0;
+    do { buf[n++] = (char)('0' + (v % 10)); v /= 10; } while (v);
+    if (S::counting) { s.skip((uint32_t)n); return; }
+    while (n) s.put((uint8_t)buf[--n]);
+}
+
+template <class S> MS_HD void put_str(S& s, const char* t, int n) {
+    if (S::counting) { s.skip((uint32_t)n); return; }
+    for (int i = 0; i < n; ++i) s.put((uint8_t)t[i]);
+}
+
+// n bytes of genome from g, optionally IUPAC-converted
+template <class S> MS_HD void put_bases(S& s, const VcfView& v, int64_t g, uint32_t n, bool convert) {
+    if (S::counting) { s.skip(n); return; }
+    for (uint32_t i = 0; i < n; ++i) { uint8_t c = v.genome[g + i]; s.put(convert ? v.conv[c] : c); }
+}
+
+// reverse complement of the converted bases [g, g+n)
+template <class S> MS_HD void put_rc(S& s, const VcfView& v, int64_t g, uint32_t n) {
+    if (S::counting) { s.skip(n); return; }
+    for (uint32_t i = 0; i < n; ++i) s.put(v.comp[v.conv[v.genome[g + (int64_t)(n - 1 - i)]]]);
+}
+
+// payload bytes of a record as the FASTA shows them (insert of IN / TLI)
+template <class S> MS_HD void put_payload(S& s, const VcfView& v, const Rec& r) {
+    if (S::counting) { s.skip(r.prod); return; }
+    switch (r.kind) {
+        case K_LIT:  for (uint32_t i = 0; i < r.prod; ++i) s.put(v.lit[r.src + i]); break;
+        case K_RAW:  put_bases(s, v, r.src, r.prod, false); break;
+        case K_CONV: put_bases(s, v, r.src, r.prod, true); break;
+        case K_RC:   put_rc(s, v, r.src, r.prod); break;
+        default: break;
+    }
+}
+
+// vcf_writer.py:123 — records with REF == ALT are not written.
+MS_HD bool vcf_omitted(const VcfView& v, const Contig& c, const Rec& r) {
+    switch (r.type) {
+        case T_SN: return r.ref == r.alt;
+        case T_IV: {  // REF == reverse complement of itself
+            const int64_t g = c.goff + r.pos;
+            for (uint32_t i = 0; i < r.cons; ++i)
+                if (v.conv[v.genome[g + i]] != v.comp[v.conv[v.genome[g + (int64_t)(r.cons - 1 - i)]]]) return false;
+            return true;
+        }
+        case T_DE: case T_TL:  // only a deletion of a whole 1-base contig degenerates to REF == ALT
+            return r.pos == 0 && c.len == 1;
+        case T_IT: return true;
+        default: return false;
+    }
+}
+
+template <class S> MS_HD void put_info(S& s, const char* sv, int svn, uint64_t end, uint64_t len) {
+    put_str(s, "SVTYPE=", 7); put_str(s, sv, svn);
+    put_str(s, ";END=", 5); put_uint(s, end);
+    put_str(s, ";SVLEN=", 7); put_uint(s, len);
+}
+
+// Emits the whole line (caller has checked vcf_omitted).
+template <class S> MS_HD void vcf_emit(S& s, const VcfView& v, const Contig& c, const Rec& r) {
+    const int64_t g0 = c.goff;
+    const uint64_t p = r.pos;
+    if (S::counting) s.skip((uint32_t)c.name_len);
+    else for (int i = 0; i < c.name_len; ++i) s.put(v.names[c.name_src + i]);
+    s.put('\t');
+    const char* sv = ""; int svn = 0; uint64_t pos1 = 0, end = 0, svlen = 0;
+    // POS first, REF/ALT below
+    switch (r.type) {
+        case T_SN: pos1 = p + 1; break;
+        case T_IN: pos1 = p > 0 ? p : 1; end = pos1; svlen = r.prod; sv = "INS"; svn = 3; break;
+        case T_TLI: pos1 = p > 0 ? p : 1; end = pos1; svlen = r.prod; sv = "INS:ME"; svn = 6; break;
+        case T_DE: case T_TL:
+            pos1 = p > 0 ? p : 1; end = p > 0 ? p + r.cons : (uint64_t)r.cons + 1; svlen = r.cons;
+            if (r.type == T_DE) { sv = "DEL"; svn = 3; } else { sv = "DEL:ME"; svn = 6; }
+            break;
+        case T_IV: pos1 = p + 1; end = p + r.cons; svlen = 0; sv = "INV"; svn = 3; break;
+        case T_DU: pos1 = p + 1; end = p + r.prod; svlen = r.prod; sv = "DUP"; svn = 3; break;
+        default: break;
+    }
+    put_uint(s, pos1);
+    put_str(s, "\t.\t", 3);
+    switch (r.type) {
+        case T_SN:  // mutator.py:334-341
+            s.put(r.ref); s.put('\t'); s.put(r.alt);
+            break;
+        case T_IN: case T_TLI: {  // mutator.py:343-358, 401-421
+            const uint8_t anchor = v.conv[v.genome[g0 + (p > 0 ? (int64_t)p - 1 : 0)]];
+            s.put(anchor); s.put('\t');
+            if (p > 0) { s.put(anchor); put_payload(s, v, r); }
+            else       { put_payload(s, v, r); s.put(anchor); }
+        } break;
+        case T_DE: case T_TL: {  // mutator.py:360-377
+            if (p > 0) {
+                put_bases(s, v, g0 + (int64_t)p - 1, r.cons + 1, true); s.put('\t');
+                s.put(v.conv[v.genome[g0 + (int64_t)p - 1]]);
+            } else {
+                uint64_t rl = (uint64_t)r.cons + 1;  // sequence[0:stop+2], truncated at the contig end
+                if (rl > (uint64_t)c.len) rl = (uint64_t)c.len;
+                put_bases(s, v, g0, (uint32_t)rl, true); s.put('\t');
+                s.put(v.conv[v.genome[g0 + (int64_t)rl - 1]]);
+            }
+        } break;
+        case T_IV:  // mutator.py:379-387
+            put_bases(s, v, g0 + (int64_t)p, r.cons, true); s.put('\t');
+            put_rc(s, v, g0 + (int64_t)p, r.cons);
+            break;
+        case T_DU:  // mutator.py:389-399 (raw bases)
+            put_bases(s, v, g0 + (int64_t)p, r.prod, false); s.put('\t');
+            put_bases(s, v, g0 + (int64_t)p, r.prod, false); put_bases(s, v, g0 + (int64_t)p, r.prod, false);
+            break;
+        default: break;
+    }
+    put_str(s, "\t.\t.\t", 5);
+    if (r.type == T_SN) s.put('.'); else put_info(s, sv, svn, end, svlen);
+    put_str(s, "\tGT\t1\n", 6);
+}
+
+MS_HD uint32_t vcf_line_size(const VcfView& v, const Contig& c, const Rec& r) {
+    if (vcf_omitted(v, c, r)) return 0;
+    CountSink s;
+    vcf_emit(s, v, c, r);
+    return s.n;
+}
+
+}  // namespace ms

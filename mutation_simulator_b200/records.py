@@ -1,0 +1,112 @@
+"""Host-side construction of splice descriptors (``Rec``, csrc/ms_records.h) from
+a typed mutation table — the replay input of Gate A and the
+hand-off format of ``ms_load_records``.
+
+A typed mutation is what the reference's walk receives in its ``muts`` dict
+(mutator.py:26-47, :318-426): key, type, start, stop, reverse, plus the two RNG
+outputs the walk would draw itself (SNP ALT base, insert string).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+REC_DTYPE = np.dtype([("pos", "<u4"), ("cons", "<u4"), ("prod", "<u4"), ("out", "<u4"), ("src", "<i8"),
+                      ("kind", "u1"), ("type", "u1"), ("ref", "u1"), ("alt", "u1"), ("contig", "<u4")])
+assert REC_DTYPE.itemsize == 32
+
+T_SN, T_IN, T_DE, T_IV, T_DU, T_TL, T_TLI, T_IT = range(8)
+TYPE_CODE = {"SN": T_SN, "IN": T_IN, "DE": T_DE, "IV": T_IV, "DU": T_DU, "TL": T_TL, "TLI": T_TLI, "IT": T_IT}
+TYPE_NAME = {v: k for k, v in TYPE_CODE.items()}
+K_NONE, K_SNP, K_LIT, K_RAW, K_CONV, K_RC = range(6)
+
+# mutator.py:75 non_ambiguous as a 256-entry table
+CONV = np.arange(256, dtype=np.uint8)
+for _a, _b in zip(b"KSYMWRBDHV-", b"GCCAAACAAAN"):
+    CONV[_a] = _b
+
+
+def align16(n: int) -> int:
+    return (n + 15) & ~15
+
+
+def genome_offsets(lengths) -> np.ndarray:
+    """Index of base 0 of each contig in the padded genome array (16-byte aligned)."""
+    goff = np.zeros(len(lengths) + 1, dtype=np.int64)
+    acc = 0
+    for i, n in enumerate(lengths):
+        goff[i] = acc
+        acc = align16(acc + int(n))
+    goff[len(lengths)] = acc
+    return goff
+
+
+def pack_genome(seqs) -> tuple[np.ndarray, np.ndarray]:
+    """seqs: list of upper-cased uint8 arrays/bytes -> (padded genome with 64 trailing pad bytes, goff)."""
+    goff = genome_offsets([len(s) for s in seqs])
+    g = np.full(int(goff[-1]) + 64, ord("N"), dtype=np.uint8)
+    for i, s in enumerate(seqs):
+        a = np.frombuffer(s, dtype=np.uint8) if isinstance(s, (bytes, bytearray)) else np.asarray(s, dtype=np.uint8)
+        g[goff[i]:goff[i] + len(a)] = a
+    return g, goff
+
+
+def build_records(genome: np.ndarray, goff: np.ndarray, lengths, tables) -> tuple[np.ndarray, np.ndarray]:
+    """tables: per contig a list of dicts/objects with key,type,start,stop,reverse,alt,insert
+    (already restricted to the mutations the walk visits).  Returns (recs sorted by
+    (contig, pos) with ``out`` = 0, literal pool)."""
+    rows = []
+    lit = bytearray()
+    for ci, muts in enumerate(tables):
+        g0 = int(goff[ci])
+        L = int(lengths[ci])
+        for m in sorted(muts, key=lambda x: _get(x, "key")):
+            key, typ = int(_get(m, "key")), _get(m, "type")
+            t = TYPE_CODE[typ] if isinstance(typ, str) else int(typ)
+            start, stop = int(_get(m, "start")), int(_get(m, "stop"))
+            if not (0 <= key < L):
+                raise ValueError(f"mutation key {key} outside contig {ci} (length {L})")
+            ref = alt = 0
+            src = 0
+            if t == T_SN:
+                cons, prod, kind = 1, 1, K_SNP
+                ref = int(CONV[genome[g0 + key]])
+                a = _get(m, "alt")
+                alt = a[0] if isinstance(a, (bytes, bytearray)) else (ord(a) if isinstance(a, str) else int(a))
+            elif t == T_IN:
+                ins = _get(m, "insert")
+                ins = ins.encode() if isinstance(ins, str) else bytes(ins)
+                cons, prod, kind, src = 0, len(ins), K_LIT, len(lit)
+                lit += ins
+            elif t in (T_DE, T_TL):
+                cons, prod, kind = stop - start + 1, 0, K_NONE
+            elif t == T_IV:
+                n = stop - start + 1
+                cons, prod, kind, src = n, n, K_RC, g0 + key
+            elif t == T_DU:
+                cons, prod, kind, src = 0, stop - start + 1, K_RAW, g0 + key
+            elif t == T_TLI:
+                ins = _get(m, "insert", None)
+                if ins is not None:  # literal insert (VCF replay: the source TL is not recorded in the VCF)
+                    ins = ins.encode() if isinstance(ins, str) else bytes(ins)
+                    cons, prod, kind, src = 0, len(ins), K_LIT, len(lit)
+                    lit += ins
+                else:
+                    cons, prod, src = 0, stop - start + 1, g0 + start
+                    kind = K_RC if _get(m, "reverse", False) else K_CONV
+            else:
+                raise ValueError(f"unknown mutation type {typ}")
+            if key + cons > L:
+                raise ValueError(f"mutation at {key} of contig {ci} runs past the contig end")
+            rows.append((key, cons, prod, 0, src, kind, t, ref, alt, ci))
+    recs = np.array(rows, dtype=REC_DTYPE) if rows else np.zeros(0, dtype=REC_DTYPE)
+    return recs, np.frombuffer(bytes(lit) + b"\0" * 16, dtype=np.uint8).copy()
+
+
+def _get(m, name, default=KeyError):
+    if isinstance(m, dict):
+        if default is KeyError:
+            return m[name]
+        return m.get(name, default)
+    if default is KeyError:
+        return getattr(m, name)
+    return getattr(m, name, default)

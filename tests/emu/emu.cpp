@@ -1,0 +1,147 @@
+// emu.cpp — CPU emulation of the per-thread logic of the CUDA kernels.
+//
+// TEST TOOLING ONLY.  The build container has no GPU, so the index math that the
+// kernels share with this file through the host/device headers
+// (ms_rng.h, ms_splice_core.h, ms_vcf_core.h) is exercised here against the
+// oracle before GPU time is spent.  It is compiled by tests/test_emu.py with g++
+// and is never imported by the product package (which has no CPU fallback).
+#include <cstdint>
+#include <cstring>
+#include <vector>
+#include "../../mutation_simulator_b200/csrc/ms_rng.h"
+#include "../../mutation_simulator_b200/csrc/ms_records.h"
+#include "../../mutation_simulator_b200/csrc/ms_splice_core.h"
+#include "../../mutation_simulator_b200/csrc/ms_vcf_core.h"
+#include "../../mutation_simulator_b200/csrc/ms_sample_core.h"
+
+using namespace ms;
+
+extern "C" {
+
+void emu_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    U4 r = philox4x32_10(U4{ctr[0], ctr[1], ctr[2], ctr[3]}, key[0], key[1]);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+
+void emu_prp(uint64_t seed, uint32_t contig, uint32_t purpose, uint64_t idx, uint32_t n, uint32_t count, uint32_t* out) {
+    Prp p = make_prp(make_seed(seed), contig, purpose, idx, n);
+    for (uint32_t j = 0; j < count; ++j) out[j] = prp_apply(p, j);
+}
+
+// Layout + splice + VCF for a whole (small) genome.
+//   genome: concatenated contigs, contig c at goff[c] (16-aligned, >=32 pad bytes at the end)
+//   recs:   sorted by (contig, pos), `out` not yet filled
+// Returns 0, fills fasta (size *fasta_len) and vcf.
+int emu_apply(const uint8_t* genome, int32_t n_contigs, const int64_t* goff, const int64_t* clen, const int32_t* bpl,
+              const uint8_t* headers, const int64_t* hdr_off, const uint8_t* names, const int64_t* name_off,
+              Rec* recs, int64_t n_recs, const uint8_t* lit,
+              uint8_t* fasta, int64_t fasta_cap, int64_t* fasta_len, uint8_t* vcf, int64_t vcf_cap, int64_t* vcf_len,
+              int64_t tile_bytes, int64_t* n_fast_groups, int64_t* n_slow_groups) {
+    Tables tab; fill_tables(tab);
+    std::vector<Contig> C(n_contigs);
+    // delta scan + per-contig record ranges (K5)
+    int64_t ri = 0, file = 0, blk_total = 0, piece_total = 0;
+    for (int c = 0; c < n_contigs; ++c) {
+        Contig& k = C[c];
+        memset(&k, 0, sizeof(k));
+        k.goff = goff[c]; k.len = clen[c]; k.bpl = bpl[c] > 0 ? bpl[c] : 60; k.gid = c;
+        k.hdr_src = hdr_off[c]; k.hdr_len = (int32_t)(hdr_off[c + 1] - hdr_off[c]);
+        k.name_src = name_off[c]; k.name_len = (int32_t)(name_off[c + 1] - name_off[c]);
+        k.rec_lo = ri;
+        int64_t delta = 0;
+        while (ri < n_recs && recs[ri].contig == (uint32_t)c) {
+            recs[ri].out = (uint32_t)((int64_t)recs[ri].pos + delta);
+            delta += (int64_t)recs[ri].prod - (int64_t)recs[ri].cons;
+            ++ri;
+        }
+        k.rec_hi = ri;
+        k.out_len = k.len + delta;
+        k.body_bytes = k.out_len + k.out_len / k.bpl;
+        k.sep = (k.out_len % k.bpl != 0 && c != n_contigs - 1) ? 1 : 0;
+        k.hdr_off = file;
+        k.body_off = file + 1 + k.hdr_len + 1;
+        file = k.body_off + k.body_bytes + k.sep;
+        k.blk_lo = blk_total;
+        blk_total += (k.out_len >> BLK_SHIFT) + 1;
+        k.piece_lo = piece_total;
+        if (k.body_bytes > 0) piece_total += (k.body_off + k.body_bytes - 1) / tile_bytes - k.body_off / tile_bytes + 1;
+    }
+    if (file > fasta_cap) return -1;
+    *fasta_len = file;
+    // coarse block index
+    std::vector<uint32_t> blk(blk_total);
+    for (int c = 0; c < n_contigs; ++c) {
+        const Contig& k = C[c];
+        int64_t nb = (k.out_len >> BLK_SHIFT) + 1;
+        int64_t r = k.rec_lo;
+        for (int64_t b = 0; b < nb; ++b) {
+            while (r < k.rec_hi && (int64_t)recs[r].out < b * BLK_BASES) ++r;
+            blk[k.blk_lo + b] = (uint32_t)(r - k.rec_lo);
+        }
+    }
+    SpliceView v{genome, lit, recs, blk.data(), tab.conv, tab.comp};
+    memset(fasta, 0, (size_t)file);
+    int64_t nf = 0, ns = 0;
+    for (int c = 0; c < n_contigs; ++c) {
+        const Contig& k = C[c];
+        // header kernel
+        fasta[k.hdr_off] = '>';
+        memcpy(fasta + k.hdr_off + 1, headers + k.hdr_src, (size_t)k.hdr_len);
+        fasta[k.hdr_off + 1 + k.hdr_len] = '\n';
+        if (k.sep) fasta[k.body_off + k.body_bytes] = '\n';
+        if (k.body_bytes == 0) continue;
+        // pieces = tiles of the file image intersected with the contig body
+        int64_t t0 = k.body_off / tile_bytes, t1 = (k.body_off + k.body_bytes - 1) / tile_bytes;
+        for (int64_t t = t0; t <= t1; ++t) {
+            int64_t f_lo = t * tile_bytes, f_hi = f_lo + tile_bytes;
+            if (f_lo < k.body_off) f_lo = k.body_off;
+            if (f_hi > k.body_off + k.body_bytes) f_hi = k.body_off + k.body_bytes;
+            for (int64_t g = f_lo & ~(int64_t)15; g < f_hi; g += 16) {
+                int64_t a = g < f_lo ? f_lo : g, b = g + 16 > f_hi ? f_hi : g + 16;
+                uint32_t w[4] = {0, 0, 0, 0};
+                bool fast = false;
+                if (b - a == 16) {
+                    fast = group_fast(v, k, (uint32_t)(a - k.body_off), w, [&](int64_t idx, uint32_t win[8]) {
+                        memcpy(win, genome + idx, 32);
+                    });
+                }
+                if (fast) ++nf; else { ++ns; w[0] = w[1] = w[2] = w[3] = 0; group_slow(v, k, (uint32_t)(a - k.body_off), (int)(b - a), (int)(a - g), w); }
+                for (int64_t x = a; x < b; ++x) fasta[x] = (uint8_t)(w[(x - g) >> 2] >> (8 * ((x - g) & 3)));
+            }
+        }
+    }
+    *n_fast_groups = nf; *n_slow_groups = ns;
+    // VCF (K7): sizes -> offsets -> bytes
+    VcfView vv{genome, lit, names, tab.conv, tab.comp};
+    int64_t off = 0;
+    std::vector<int64_t> offs(n_recs + 1);
+    for (int64_t i = 0; i < n_recs; ++i) { offs[i] = off; off += vcf_line_size(vv, C[recs[i].contig], recs[i]); }
+    offs[n_recs] = off;
+    if (off > vcf_cap) return -2;
+    for (int64_t i = 0; i < n_recs; ++i) {
+        if (offs[i + 1] == offs[i]) continue;
+        WriteSink s{vcf + offs[i]};
+        vcf_emit(s, vv, C[recs[i].contig], recs[i]);
+        if (s.p != vcf + offs[i + 1]) return -3;
+    }
+    *vcf_len = off;
+    return 0;
+}
+
+// Sampling per-candidate logic (K2) and the chain walk (K3) on the CPU.
+int emu_type_len(uint64_t seed, uint32_t gid, uint32_t pos, const double cdf[7], const int32_t minlen[7],
+                 const int32_t maxlen[7], int64_t limit, uint8_t* type, uint32_t* len) {
+    RangeParams rp;
+    for (int t = 0; t < 7; ++t) { rp.cdf[t] = cdf[t]; rp.minlen[t] = minlen[t]; rp.maxlen[t] = maxlen[t]; }
+    rp.limit = limit;
+    draw_type_len(make_seed(seed), gid, pos, rp, *type, *len);
+    return 0;
+}
+
+int emu_snp(uint64_t seed, uint32_t gid, uint32_t pos, uint8_t ref, double p_ti, uint8_t* alt) {
+    Tables tab; fill_tables(tab);
+    *alt = draw_snp(make_seed(seed), gid, pos, ref, p_ti, tab.trans);
+    return 0;
+}
+
+}  // extern "C"

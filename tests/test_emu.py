@@ -1,0 +1,159 @@
+"""CPU emulation of the CUDA kernels' shared host/device logic (tests/emu/emu.cpp)
+against known answers and the golden vectors.  This is how index math is checked
+in the build container, which has no GPU; the product itself has no CPU path."""
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from mutation_simulator_b200 import records as R
+from tests.helpers import MS_CASES, load_case, load_muts, vcf_body
+
+HERE = Path(__file__).resolve().parent
+SRC = HERE / "emu" / "emu.cpp"
+LIB = HERE / "emu" / "_build" / "libemu.so"
+
+
+@pytest.fixture(scope="session")
+def emu():
+    LIB.parent.mkdir(exist_ok=True)
+    deps = [SRC] + list((HERE.parent / "mutation_simulator_b200" / "csrc").glob("*.h"))
+    if not LIB.exists() or LIB.stat().st_mtime < max(p.stat().st_mtime for p in deps):
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-o", str(LIB), str(SRC)])
+    return C.CDLL(str(LIB))
+
+
+def philox(emu, ctr, key):
+    c = (C.c_uint32 * 4)(*ctr)
+    k = (C.c_uint32 * 2)(*key)
+    o = (C.c_uint32 * 4)()
+    emu.emu_philox(c, k, o)
+    return list(o)
+
+
+def test_philox_known_answers(emu):
+    """Random123 kat_vectors for philox4x32-10."""
+    assert philox(emu, [0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert philox(emu, [0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert philox(emu, [0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def prp(emu, seed, n, count, contig=0, idx=0):
+    out = (C.c_uint32 * count)()
+    emu.emu_prp(C.c_uint64(seed), C.c_uint32(contig), C.c_uint32(1), C.c_uint64(idx), C.c_uint32(n), C.c_uint32(count), out)
+    return np.array(out)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 16, 17, 1000, 65537, 1_000_003])
+def test_prp_is_a_permutation(emu, n):
+    v = prp(emu, 123, n, n)
+    assert np.array_equal(np.sort(v), np.arange(n))
+
+
+def test_prp_small_domains_are_uniform(emu):
+    """Every arrangement of the first two images must be about equally likely over keys."""
+    from scipy import stats
+    for n in (2, 3, 4, 5, 7):
+        cnt = {}
+        trials = 6000
+        for s in range(trials):
+            v = prp(emu, 1000 + s, n, min(n, 2))
+            cnt[tuple(v)] = cnt.get(tuple(v), 0) + 1
+        cells = n * (n - 1) if n > 1 else 1
+        assert len(cnt) == cells
+        chi2, p = stats.chisquare(list(cnt.values()))
+        assert p > 1e-4, (n, cnt, p)
+
+
+def test_prp_subset_is_uniform_over_positions(emu):
+    from scipy import stats
+    n, k = 100000, 2000
+    hist = np.zeros(20)
+    for s in range(20):
+        v = prp(emu, s, n, k, contig=s)
+        hist += np.histogram(v, bins=20, range=(0, n))[0]
+    chi2, p = stats.chisquare(hist)
+    assert p > 1e-3
+
+
+def run_emu_apply(emu, contigs, tables, tile_bytes=4096):
+    seqs = [c[2] for c in contigs]
+    genome, goff = R.pack_genome(seqs)
+    lens = np.array([len(s) for s in seqs], dtype=np.int64)
+    bpl = np.array([c[3] for c in contigs], dtype=np.int32)
+    hdr = b"".join(c[1] for c in contigs)
+    hoff = np.cumsum([0] + [len(c[1]) for c in contigs]).astype(np.int64)
+    names = b"".join(c[0] for c in contigs)
+    noff = np.cumsum([0] + [len(c[0]) for c in contigs]).astype(np.int64)
+    recs, lit = R.build_records(genome, goff, lens, tables)
+    cap_f = int(lens.sum() * 3 + recs["prod"].sum() * 2 + 4096 + len(hdr) * 2)
+    cap_v = int(64 * len(recs) + 4 * (recs["prod"].sum() + recs["cons"].sum()) + len(names) * len(recs) + 4096)
+    fa = np.zeros(cap_f, dtype=np.uint8)
+    vcf = np.zeros(cap_v, dtype=np.uint8)
+    fl, vl, nf, ns = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = emu.emu_apply(P(genome), C.c_int32(len(contigs)), P(goff), P(lens), P(bpl), hdr, P(hoff), names, P(noff),
+                       P(recs), C.c_int64(len(recs)), P(lit), P(fa), C.c_int64(cap_f), C.byref(fl),
+                       P(vcf), C.c_int64(cap_v), C.byref(vl), C.c_int64(tile_bytes), C.byref(nf), C.byref(ns))
+    assert rc == 0
+    return fa[:fl.value].tobytes(), vcf[:vl.value].tobytes(), nf.value, ns.value
+
+
+def tables_from_golden(case):
+    out = []
+    for muts in load_muts(case):
+        out.append([dict(key=m.key, type=m.type, start=m.start, stop=m.stop, reverse=m.reverse,
+                         alt=m.alt, insert=m.insert) for m in muts])
+    return out
+
+
+@pytest.mark.parametrize("case", MS_CASES)
+@pytest.mark.parametrize("tile", [256, 4096])
+def test_emulated_splice_and_vcf_match_reference(emu, case, tile):
+    d, contigs = load_case(case)
+    fa, vcf, nf, ns = run_emu_apply(emu, contigs, tables_from_golden(case), tile)
+    assert fa == (d / "out.fa").read_bytes()
+    assert vcf == vcf_body((d / "out.vcf").read_bytes())
+    if case in ("args_all", "c1_small"):
+        assert nf > 2 * ns  # most groups take the vector path
+
+
+def oracle_tables(seqs, rates, minlen, maxlen, block, seed, titv=1.0):
+    """Sample with the C oracle's sampler; return per-contig typed tables."""
+    from oracle import c_oracle
+    tables = []
+    cdf = np.cumsum(np.array(rates) / sum(rates)).tolist()
+    for ci, s in enumerate(seqs):
+        L = len(s)
+        k = int(L * sum(rates))
+        rng = dict(start=0, stop=L - 1, k=k, cdf=cdf, minlen=minlen, maxlen=maxlen)
+        m, pool = c_oracle.sample_contig(bytes(s), [rng], block, min(block), titv, seed + ci)
+        t = []
+        for r in m:
+            d = dict(key=int(r["key"]), type=R.TYPE_NAME[int(r["type"])], start=int(r["start"]), stop=int(r["stop"]),
+                     reverse=bool(r["reverse"]), alt=bytes([r["alt"]]), insert=None)
+            if d["type"] == "IN":
+                n = d["stop"] - d["start"] + 1
+                d["insert"] = pool[int(r["lit_off"]):int(r["lit_off"]) + n]
+            t.append(d)
+        tables.append(t)
+    return tables
+
+
+@pytest.mark.parametrize("bpl,alphabet", [(60, b"ACGT"), (7, b"ACGT"), (16, b"ACGTNRYKMSWBDHV"), (61, b"ACGTN"), (1000, b"ACGT")])
+def test_emulated_apply_matches_c_oracle_randomized(emu, bpl, alphabet):
+    from oracle import c_oracle, pyref
+    rng = np.random.default_rng(bpl)
+    seqs = [bytes(rng.choice(np.frombuffer(alphabet, np.uint8), n)) for n in (120_000, 33_333, 17, 5_000)]
+    contigs = [(b"c%d" % i, b"c%d some description" % i, s, bpl) for i, s in enumerate(seqs)]
+    rates = [0.02, 0.004, 0.004, 0.003, 0.003, 0.003, 0.003]
+    tables = oracle_tables(seqs, rates, [1, 1, 1, 2, 1, 1, 1], [1, 12, 40, 30, 25, 20, 20], [1] * 7, seed=bpl)
+    muts = [[pyref.Mut(key=d["key"], type=d["type"], start=d["start"], stop=d["stop"], reverse=d["reverse"],
+                       alt=d["alt"], insert=d["insert"]) for d in t] for t in tables]
+    want_fa, want_vcf = c_oracle.mutate_genome(contigs, muts)
+    fa, vcf, nf, ns = run_emu_apply(emu, contigs, tables, tile_bytes=1024)
+    assert fa == want_fa
+    assert vcf == want_vcf
