@@ -1,0 +1,146 @@
+/*
+ * mutsim_b200.h — C ABI of libmutsim_b200.so, the B200 (sm_100a) implementation of
+ * Mutation-Simulator's mutation-injection hot path.
+ *
+ * The reference (mkpython3/Mutation-Simulator 3.0.2) is pure Python and has no
+ * FFI of its own; the boundary it exposes for this path is the class API
+ *   Mutator(args, fasta, sim).mutate()        mutation_simulator/mutator.py:79,105
+ *   ITMutator(args, fasta, sim).mutate()      mutation_simulator/it_mutator.py:25,215
+ * Each entry point below names the reference code it replaces.  The Python side
+ * (mutation_simulator_b200/) binds these with ctypes and mirrors the reference's
+ * classes on top; INTEGRATION.md shows the stub a maintainer of the reference
+ * would add.
+ *
+ * Conventions: plain pointers and sizes only; every call returns an int status
+ * (0 = MS_OK) and leaves a message retrievable with ms_last_error(); HOST
+ * pointers are caller-owned; device memory is owned by the context until
+ * ms_destroy(); all work is ordered on the context's CUDA stream; calls that
+ * return sizes or copy to the host synchronise that stream.
+ * There is no CPU fallback: without a CUDA device ms_create() fails.
+ *
+ * Mutation type codes (reference dict order, rmt.py:443-450 and :91-94):
+ *   0 SN  1 IN  2 DE  3 IV  4 DU  5 TL  6 TLI  (7 IT: interchromosomal segment)
+ */
+#ifndef MUTSIM_B200_H
+#define MUTSIM_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ms_ctx ms_ctx;
+
+enum {
+    MS_OK = 0,
+    MS_ERR_CUDA = 1,        /* a CUDA runtime call failed (message has file:line) */
+    MS_ERR_ARG = 2,         /* invalid argument */
+    MS_ERR_STATE = 3,       /* call order violated (e.g. apply before a genome is resident) */
+    MS_ERR_SAMPLE = 4,      /* k > population or k < 0: what random.sample raises as ValueError (util.py:104) */
+    MS_ERR_OVERLAP = 5,     /* records overlap / run past a contig end */
+    MS_ERR_LIMIT = 6,       /* size limit of this build exceeded (contig >= 2^31 bases, body >= 2^32 bytes) */
+    MS_ERR_INTERNAL = 7
+};
+
+/* 32-byte splice descriptor (mutation_simulator_b200/csrc/ms_records.h, `Rec`). */
+typedef struct {
+    uint32_t pos, cons, prod, out;
+    int64_t src;
+    uint8_t kind, type, ref, alt;
+    uint32_t contig;
+} ms_rec;
+
+/* One RMT range with mutations (rmt.py:166-189 RangeDefinition + :79-163 MutationSettings). */
+typedef struct {
+    uint32_t contig;       /* local contig index */
+    uint32_t start, stop;  /* 0-based inclusive */
+    uint32_t k;            /* int(((stop-start)+1)*sum(rates)) — computed by the caller in float64, mutator.py:225 */
+    int64_t limit;         /* exclusive end an SV may reach: contig length or start of the next None range */
+    double cdf[7];         /* cumulative mut_chances, canonical type order */
+    int32_t minlen[7];
+    int32_t maxlen[7];
+} ms_range;
+
+typedef struct {
+    int64_t n_candidates, n_accepted, n_records, lit_bytes, fasta_bytes, vcf_bytes, kernel_launches;
+    int64_t counts[8];           /* records per mutation type */
+    float stage_ms[16];          /* CUDA-event time of each pipeline stage of the last call (see ms_stage_name) */
+} ms_stats;
+
+/* ---- lifecycle --------------------------------------------------------- */
+int ms_create(int device, ms_ctx** ctx);
+int ms_destroy(ms_ctx* ctx);
+const char* ms_last_error(const ms_ctx* ctx);   /* ctx may be NULL: error of the last failed ms_create */
+int ms_abi_version(void);
+/* Run on an existing CUDA stream (e.g. torch's current stream) instead of the context's own. */
+int ms_set_stream(ms_ctx* ctx, void* cuda_stream);
+int ms_synchronize(ms_ctx* ctx);
+
+/* ---- genome ------------------------------------------------------------
+ * Replaces the per-base pyfaidx access of the walk (mutator.py:119,133-139,423;
+ * util.py:77-91 load_fasta).  `bases` = all contigs concatenated, upper-cased
+ * (util.py:87), no line breaks; bpl = bases per line of each input record
+ * (pyfaidx lenc, mutator.py:133-134); headers = full deflines without '>'
+ * (long_name, mutator.py:135-136); names = first token (VCF CHROM, mutator.py:341);
+ * gid = index of the contig in the whole FASTA — the RNG key, so that results do
+ * not depend on how contigs are partitioned over GPUs (NULL: 0..n-1).
+ * hdr_off / name_off have n_contigs+1 entries. */
+int ms_genome_upload(ms_ctx* ctx, const uint8_t* bases, int64_t total_bases, int32_t n_contigs,
+                     const int64_t* contig_len, const int32_t* bpl, const uint32_t* gid,
+                     const uint8_t* headers, const int64_t* hdr_off,
+                     const uint8_t* names, const int64_t* name_off);
+/* Same, from a DEVICE pointer (bases already resident, e.g. produced by ms_genome_synth). */
+int ms_genome_adopt(ms_ctx* ctx, const uint8_t* d_bases, int64_t total_bases, int32_t n_contigs,
+                    const int64_t* contig_len, const int32_t* bpl, const uint32_t* gid,
+                    const uint8_t* headers, const int64_t* hdr_off,
+                    const uint8_t* names, const int64_t* name_off);
+/* Synthetic iid-ACGT genome with N runs generated on the device (benchmarks). */
+int ms_genome_synth(ms_ctx* ctx, uint64_t seed, int32_t n_contigs, const int64_t* contig_len,
+                    const int32_t* bpl, double n_fraction, int64_t telomere_n,
+                    const uint8_t* headers, const int64_t* hdr_off,
+                    const uint8_t* names, const int64_t* name_off);
+int ms_genome_download(ms_ctx* ctx, uint8_t* bases, int64_t cap);
+
+/* ---- fresh sampling ----------------------------------------------------
+ * Replaces Mutator.__get_mutations / __get_mut_positions / __get_stop_position /
+ * __link_tls (mutator.py:144-316) and util.sample_with_minimum_distance
+ * (util.py:94-109) for all ranges of all contigs at once.
+ * block[7] = SimulationSettings.mut_block (rmt.py:326-345), min_dist = min(block)
+ * (mutator.py:161), p_ti = titv*(1/(titv+1)) (mutator.py:436). */
+int ms_set_ranges(ms_ctx* ctx, const ms_range* ranges, int32_t n_ranges, const int32_t* block,
+                  int32_t min_dist, double p_ti);
+int ms_sample(ms_ctx* ctx, uint64_t seed);
+
+/* ---- replay ------------------------------------------------------------
+ * Loads an explicit mutation table (what Mutator.__mutate_sequence receives as
+ * `muts`, mutator.py:318) as splice descriptors sorted by (contig, pos). */
+int ms_load_records(ms_ctx* ctx, const ms_rec* recs, int64_t n_recs, const uint8_t* lit, int64_t lit_bytes);
+
+/* ---- apply -------------------------------------------------------------
+ * Replaces Mutator.__mutate_sequence (mutator.py:318-426) with FastaWriter
+ * (fasta_writer.py:40-65) and VcfWriter.write (vcf_writer.py:118-126): builds the
+ * complete output FASTA image and the VCF body (no header) in device memory. */
+int ms_apply(ms_ctx* ctx, int64_t* fasta_bytes, int64_t* vcf_bytes);
+/* which: 0 FASTA image, 1 VCF body, 2 records (ms_rec[]), 3 literal pool */
+int ms_download(ms_ctx* ctx, int which, void* dst, int64_t cap, int64_t* nbytes);
+int ms_device_ptr(ms_ctx* ctx, int which, void** dptr, int64_t* nbytes);
+int ms_contig_out_len(ms_ctx* ctx, int64_t* out_len /* n_contigs */);
+
+/* ---- interchromosomal translocations ------------------------------------
+ * Replaces ITMutator.__get_breakpoints (it_mutator.py:94-118): for each pair p,
+ * n[p] breakpoints on each member, sample_with_minimum_distance(1, len, n, 1).
+ * bp_a/bp_b receive sum(n) sorted positions each (pair-major). */
+int ms_it_breakpoints(ms_ctx* ctx, uint64_t seed, int32_t n_pairs, const uint32_t* contig_a,
+                      const uint32_t* contig_b, const uint32_t* n, uint32_t* bp_a, uint32_t* bp_b);
+
+/* ---- introspection ------------------------------------------------------ */
+int ms_get_stats(ms_ctx* ctx, ms_stats* out);
+const char* ms_stage_name(int stage);
+/* Debug/validation taps used by the parity tests: candidates after K1..K3. */
+int ms_debug_candidates(ms_ctx* ctx, int64_t cap, int64_t* gpos, uint8_t* type, uint32_t* len, uint8_t* accept,
+                        int64_t* n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MUTSIM_B200_H */

@@ -1,0 +1,257 @@
+// ms_api.cu — extern "C" entry points of libmutsim_b200.so (include/mutsim_b200.h):
+// lifecycle, genome residency, record loading, downloads and introspection.
+#include <string.h>
+#include "ms_common.cuh"
+
+using namespace ms;
+
+static thread_local std::string g_create_error;
+
+static const char* STAGE_NAMES[ST_COUNT] = {"upload", "sample_positions", "sample_type_len", "sample_resolve",
+                                            "sample_link", "sample_finalize", "plan_scan_layout", "block_index",
+                                            "splice_emit_fasta", "vcf_format", "download"};
+
+extern "C" {
+
+int ms_abi_version(void) { return 1; }
+
+const char* ms_stage_name(int s) { return (s >= 0 && s < ST_COUNT) ? STAGE_NAMES[s] : ""; }
+
+const char* ms_last_error(const ms_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int ms_create(int device, ms_ctx** out) {
+    if (!out) return MS_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        g_create_error = std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                         "); libmutsim_b200 has no CPU fallback";
+        return MS_ERR_CUDA;
+    }
+    if (device < 0 || device >= n) { g_create_error = "device index out of range"; return MS_ERR_ARG; }
+    if ((e = cudaSetDevice(device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return MS_ERR_CUDA; }
+    ms_ctx* c = new ms_ctx();
+    c->device = device;
+    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        g_create_error = cudaGetErrorString(e); delete c; return MS_ERR_CUDA;
+    }
+    for (int s = 0; s < ST_COUNT; ++s) {
+        cudaEventCreate(&c->ev[s][0]); cudaEventCreate(&c->ev[s][1]);
+        c->ev_used[s] = false; c->stage_ms[s] = 0.f;
+    }
+    if ((e = cudaMallocHost((void**)&c->h_totals, sizeof(Totals))) != cudaSuccess) {
+        g_create_error = cudaGetErrorString(e); delete c; return MS_ERR_CUDA;
+    }
+    memset(c->h_totals, 0, sizeof(Totals));
+    Tables t; fill_tables(t);
+    if (c->tables.ensure(sizeof(Tables)) != cudaSuccess || c->totals.ensure(sizeof(Totals)) != cudaSuccess ||
+        cudaMemcpy(c->tables.p, &t, sizeof(Tables), cudaMemcpyHostToDevice) != cudaSuccess) {
+        g_create_error = "device allocation failed"; delete c; return MS_ERR_CUDA;
+    }
+    *out = c;
+    return MS_OK;
+}
+
+int ms_destroy(ms_ctx* c) {
+    if (!c) return MS_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    DevBuf* bufs[] = {&c->genome, &c->contigs, &c->headers, &c->names, &c->tables, &c->ranges, &c->cand_val, &c->cand_sorted,
+                      &c->bucket_cnt, &c->bucket_off, &c->cand_type, &c->cand_len, &c->cand_reach, &c->cand_pm, &c->cand_accept,
+                      &c->acc_idx, &c->tl_list, &c->tli_list, &c->link, &c->keep, &c->contig_tl, &c->scan_tmp, &c->scan_tmp2,
+                      &c->svec, &c->vvec, &c->lvec, &c->recs, &c->lit, &c->blk, &c->piece_lo, &c->long_gaps, &c->fasta, &c->vcf,
+                      &c->vcf_off, &c->totals};
+    for (DevBuf* b : bufs) b->release();
+    for (int s = 0; s < ST_COUNT; ++s) { cudaEventDestroy(c->ev[s][0]); cudaEventDestroy(c->ev[s][1]); }
+    if (c->h_totals) cudaFreeHost(c->h_totals);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return MS_OK;
+}
+
+int ms_set_stream(ms_ctx* c, void* stream) {
+    if (!c) return MS_ERR_ARG;
+    cudaStreamSynchronize(c->stream);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    c->stream = (cudaStream_t)stream;
+    c->own_stream = false;
+    return MS_OK;
+}
+
+int ms_synchronize(ms_ctx* c) {
+    if (!c) return MS_ERR_ARG;
+    MS_CUDA(c, cudaStreamSynchronize(c->stream));
+    return MS_OK;
+}
+
+// ---- genome ---------------------------------------------------------------------------
+static int set_contig_table(ms_ctx* c, int64_t total_bases, int32_t n_contigs, const int64_t* contig_len, const int32_t* bpl,
+                            const uint32_t* gid, const uint8_t* headers, const int64_t* hdr_off, const uint8_t* names,
+                            const int64_t* name_off) {
+    if (n_contigs <= 0 || !contig_len || !bpl || !headers || !hdr_off || !names || !name_off)
+        MS_FAIL(c, MS_ERR_ARG, "ms_genome: null argument or no contigs");
+    c->h_contigs.assign(n_contigs, Contig{});
+    int64_t off = 0;
+    for (int i = 0; i < n_contigs; ++i) {
+        Contig& k = c->h_contigs[i];
+        if (contig_len[i] < 0 || contig_len[i] >= (int64_t)0x7FFFFFF0)
+            MS_FAIL(c, MS_ERR_LIMIT, "contig %d has %lld bases; this build supports < 2^31 per contig", i, (long long)contig_len[i]);
+        k.goff = off; k.len = contig_len[i]; k.out_len = contig_len[i];
+        k.bpl = bpl[i] > 0 ? bpl[i] : 60;  // FastaWriter default (fasta_writer.py:26)
+        k.hdr_src = hdr_off[i]; k.hdr_len = (int32_t)(hdr_off[i + 1] - hdr_off[i]);
+        k.name_src = name_off[i]; k.name_len = (int32_t)(name_off[i + 1] - name_off[i]);
+        k.gid = gid ? gid[i] : (uint32_t)i;
+        off += contig_len[i];
+    }
+    if (off != total_bases) MS_FAIL(c, MS_ERR_ARG, "sum of contig lengths (%lld) != total_bases (%lld)", (long long)off, (long long)total_bases);
+    c->n_contigs = n_contigs;
+    c->total_bases = total_bases;
+    MS_CUDA(c, c->contigs.ensure(sizeof(Contig) * (size_t)n_contigs));
+    MS_CUDA(c, c->headers.ensure((size_t)hdr_off[n_contigs] + 16));
+    MS_CUDA(c, c->names.ensure((size_t)name_off[n_contigs] + 16));
+    MS_CUDA(c, cudaMemcpyAsync(c->contigs.p, c->h_contigs.data(), sizeof(Contig) * (size_t)n_contigs, cudaMemcpyHostToDevice, c->stream));
+    MS_CUDA(c, cudaMemcpyAsync(c->headers.p, headers, (size_t)hdr_off[n_contigs], cudaMemcpyHostToDevice, c->stream));
+    MS_CUDA(c, cudaMemcpyAsync(c->names.p, names, (size_t)name_off[n_contigs], cudaMemcpyHostToDevice, c->stream));
+    MS_CUDA(c, cudaStreamSynchronize(c->stream));  // h_contigs / caller buffers may be pageable
+    c->n_recs = 0; c->lit_bytes = 0; c->n_ranges = 0;
+    return MS_OK;
+}
+
+int ms_genome_upload(ms_ctx* c, const uint8_t* bases, int64_t total_bases, int32_t n_contigs, const int64_t* contig_len,
+                     const int32_t* bpl, const uint32_t* gid, const uint8_t* headers, const int64_t* hdr_off,
+                     const uint8_t* names, const int64_t* name_off) {
+    if (!c) return MS_ERR_ARG;
+    if (!bases && total_bases > 0) MS_FAIL(c, MS_ERR_ARG, "ms_genome_upload: bases is NULL");
+    MS_CUDA(c, cudaSetDevice(c->device));
+    stage_begin(c, ST_UPLOAD);
+    MS_CUDA(c, c->genome.ensure((size_t)total_bases + 64));
+    MS_CUDA(c, cudaMemcpyAsync(c->genome.p, bases, (size_t)total_bases, cudaMemcpyHostToDevice, c->stream));
+    MS_CUDA(c, cudaMemsetAsync(c->genome.as<uint8_t>() + total_bases, 'N', 64, c->stream));
+    stage_end(c, ST_UPLOAD);
+    return set_contig_table(c, total_bases, n_contigs, contig_len, bpl, gid, headers, hdr_off, names, name_off);
+}
+
+int ms_genome_adopt(ms_ctx* c, const uint8_t* d_bases, int64_t total_bases, int32_t n_contigs, const int64_t* contig_len,
+                    const int32_t* bpl, const uint32_t* gid, const uint8_t* headers, const int64_t* hdr_off,
+                    const uint8_t* names, const int64_t* name_off) {
+    if (!c) return MS_ERR_ARG;
+    MS_CUDA(c, cudaSetDevice(c->device));
+    if (d_bases != c->genome.p) {
+        MS_CUDA(c, c->genome.ensure((size_t)total_bases + 64));
+        MS_CUDA(c, cudaMemcpyAsync(c->genome.p, d_bases, (size_t)total_bases, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    MS_CUDA(c, cudaMemsetAsync(c->genome.as<uint8_t>() + total_bases, 'N', 64, c->stream));
+    return set_contig_table(c, total_bases, n_contigs, contig_len, bpl, gid, headers, hdr_off, names, name_off);
+}
+
+int ms_genome_download(ms_ctx* c, uint8_t* bases, int64_t cap) {
+    if (!c || !bases) return MS_ERR_ARG;
+    if (cap < c->total_bases) MS_FAIL(c, MS_ERR_ARG, "buffer too small");
+    MS_CUDA(c, cudaMemcpyAsync(bases, c->genome.p, (size_t)c->total_bases, cudaMemcpyDeviceToHost, c->stream));
+    MS_CUDA(c, cudaStreamSynchronize(c->stream));
+    return MS_OK;
+}
+
+// ---- replay ---------------------------------------------------------------------------
+int ms_load_records(ms_ctx* c, const ms_rec* recs, int64_t n_recs, const uint8_t* lit, int64_t lit_bytes) {
+    if (!c || n_recs < 0 || lit_bytes < 0 || (n_recs > 0 && !recs)) return MS_ERR_ARG;
+    if (c->n_contigs <= 0) MS_FAIL(c, MS_ERR_STATE, "ms_load_records: upload a genome first");
+    static_assert(sizeof(ms_rec) == sizeof(Rec), "ms_rec layout");
+    for (int64_t i = 0; i < n_recs; ++i) {
+        if (recs[i].contig >= (uint32_t)c->n_contigs) MS_FAIL(c, MS_ERR_ARG, "record %lld: contig out of range", (long long)i);
+        if (i && (recs[i].contig < recs[i - 1].contig || (recs[i].contig == recs[i - 1].contig && recs[i].pos <= recs[i - 1].pos)))
+            MS_FAIL(c, MS_ERR_OVERLAP, "record %lld: records must be sorted by (contig, pos) with distinct positions", (long long)i);
+        if (recs[i].kind == K_LIT && (recs[i].src < 0 || recs[i].src + recs[i].prod > lit_bytes))
+            MS_FAIL(c, MS_ERR_ARG, "record %lld: literal range outside the pool", (long long)i);
+        if ((recs[i].kind == K_RAW || recs[i].kind == K_CONV || recs[i].kind == K_RC) &&
+            (recs[i].src < 0 || recs[i].src + recs[i].prod > c->total_bases))
+            MS_FAIL(c, MS_ERR_ARG, "record %lld: source range outside the genome", (long long)i);
+    }
+    MS_CUDA(c, cudaSetDevice(c->device));
+    MS_CUDA(c, c->recs.ensure((size_t)(n_recs + 1) * sizeof(Rec)));
+    MS_CUDA(c, c->lit.ensure((size_t)lit_bytes + 64));
+    if (n_recs) MS_CUDA(c, cudaMemcpyAsync(c->recs.p, recs, (size_t)n_recs * sizeof(Rec), cudaMemcpyHostToDevice, c->stream));
+    if (lit_bytes) MS_CUDA(c, cudaMemcpyAsync(c->lit.p, lit, (size_t)lit_bytes, cudaMemcpyHostToDevice, c->stream));
+    MS_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->n_recs = n_recs;
+    c->lit_bytes = lit_bytes;
+    c->counts_valid = false;
+    return MS_OK;
+}
+
+// ---- apply ----------------------------------------------------------------------------
+int ms_apply(ms_ctx* c, int64_t* fasta_bytes, int64_t* vcf_bytes) {
+    if (!c) return MS_ERR_ARG;
+    MS_CUDA(c, cudaSetDevice(c->device));
+    int rc = apply_pipeline(c);
+    if (rc != MS_OK) return rc;
+    if (fasta_bytes) *fasta_bytes = c->fasta_bytes;
+    if (vcf_bytes) *vcf_bytes = c->vcf_bytes;
+    return MS_OK;
+}
+
+static int which_buffer(ms_ctx* c, int which, void** p, int64_t* n) {
+    switch (which) {
+        case 0: *p = c->fasta.p; *n = c->fasta_bytes; return MS_OK;
+        case 1: *p = c->vcf.p; *n = c->vcf_bytes; return MS_OK;
+        case 2: *p = c->recs.p; *n = c->n_recs * (int64_t)sizeof(Rec); return MS_OK;
+        case 3: *p = c->lit.p; *n = c->lit_bytes; return MS_OK;
+        case 4: *p = c->genome.p; *n = c->total_bases; return MS_OK;
+        default: MS_FAIL(c, MS_ERR_ARG, "unknown buffer id %d", which);
+    }
+}
+
+int ms_download(ms_ctx* c, int which, void* dst, int64_t cap, int64_t* nbytes) {
+    if (!c) return MS_ERR_ARG;
+    void* p; int64_t n;
+    int rc = which_buffer(c, which, &p, &n);
+    if (rc) return rc;
+    if (nbytes) *nbytes = n;
+    if (!dst) return MS_OK;  // size query
+    if (cap < n) MS_FAIL(c, MS_ERR_ARG, "ms_download: buffer too small (%lld < %lld)", (long long)cap, (long long)n);
+    MS_CUDA(c, cudaSetDevice(c->device));
+    stage_begin(c, ST_DOWNLOAD);
+    if (n) MS_CUDA(c, cudaMemcpyAsync(dst, p, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    stage_end(c, ST_DOWNLOAD);
+    MS_CUDA(c, cudaStreamSynchronize(c->stream));
+    return MS_OK;
+}
+
+int ms_device_ptr(ms_ctx* c, int which, void** dptr, int64_t* nbytes) {
+    if (!c || !dptr || !nbytes) return MS_ERR_ARG;
+    return which_buffer(c, which, dptr, nbytes);
+}
+
+int ms_contig_out_len(ms_ctx* c, int64_t* out_len) {
+    if (!c || !out_len) return MS_ERR_ARG;
+    MS_CUDA(c, cudaSetDevice(c->device));
+    MS_CUDA(c, cudaMemcpy(c->h_contigs.data(), c->contigs.p, sizeof(Contig) * (size_t)c->n_contigs, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < c->n_contigs; ++i) out_len[i] = c->h_contigs[i].out_len;
+    return MS_OK;
+}
+
+int ms_get_stats(ms_ctx* c, ms_stats* out) {
+    if (!c || !out) return MS_ERR_ARG;
+    memset(out, 0, sizeof(*out));
+    cudaStreamSynchronize(c->stream);
+    if (c->n_recs >= 0 && c->recs.p) { int rc = count_types(c); if (rc) return rc; }
+    for (int s = 0; s < ST_COUNT; ++s) {
+        if (c->ev_used[s]) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, c->ev[s][0], c->ev[s][1]) == cudaSuccess) c->stage_ms[s] = ms;
+        }
+        out->stage_ms[s] = c->stage_ms[s];
+    }
+    out->n_candidates = c->last_totals.n_candidates;
+    out->n_accepted = c->last_totals.n_accepted;
+    out->n_records = c->n_recs;
+    out->lit_bytes = c->lit_bytes;
+    out->fasta_bytes = c->fasta_bytes;
+    out->vcf_bytes = c->vcf_bytes;
+    out->kernel_launches = c->kernel_launches;
+    for (int t = 0; t < 8; ++t) out->counts[t] = c->last_totals.counts[t];
+    return MS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,127 @@
+// ms_common.cuh — context, device buffers and error plumbing of libmutsim_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "ms_records.h"
+#include "ms_sample_core.h"
+#include "../../include/mutsim_b200.h"
+
+namespace ms {
+
+constexpr int NUM_SMS_B200 = 148;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+    // grow-only; contents are NOT preserved
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { p = nullptr; return e; }
+        cap = want;
+        return cudaSuccess;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+// Device-side scalars a pipeline produces and the host needs (one small D2H copy).
+struct Totals {
+    int64_t fasta_bytes;
+    int64_t vcf_bytes;
+    int64_t n_blk;
+    int64_t n_pieces;
+    int64_t n_recs;       // records after sampling / linking
+    int64_t lit_bytes;
+    int64_t n_candidates;
+    int64_t n_accepted;
+    int64_t error;        // first error code raised by a kernel (0 = none)
+    int64_t error_arg;
+    int64_t n_long_gaps;
+    int64_t counts[8];    // accepted mutations per MutType
+    int64_t pad[5];
+};
+
+enum Stage { ST_UPLOAD = 0, ST_SAMPLE_POS, ST_SAMPLE_TYPE, ST_SAMPLE_RESOLVE, ST_SAMPLE_LINK, ST_SAMPLE_FINAL,
+             ST_PLAN, ST_INDEX, ST_SPLICE, ST_VCF, ST_DOWNLOAD, ST_COUNT };
+
+}  // namespace ms
+
+struct ms_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    std::string err;
+
+    // genome
+    ms::DevBuf genome, contigs, headers, names, tables;
+    std::vector<ms::Contig> h_contigs;
+    int32_t n_contigs = 0;
+    int64_t total_bases = 0;
+
+    // ranges / sampling
+    ms::DevBuf ranges, cand_val, cand_sorted, bucket_cnt, bucket_off, cand_type, cand_len, cand_reach, cand_pm,
+               cand_accept, acc_idx, tl_list, tli_list, link, keep, contig_tl, scan_tmp, scan_tmp2, svec, vvec, lvec;
+    std::vector<ms::Range> h_ranges;
+    int32_t n_ranges = 0;
+    int64_t n_candidates = 0;
+    int64_t n_buckets = 0;
+    int32_t block[7] = {1, 1, 1, 1, 1, 1, 1};
+    double p_ti = 0.5;
+    int32_t min_dist = 1;
+    bool counts_valid = false;
+
+    // records + outputs
+    ms::DevBuf recs, lit, blk, piece_lo, long_gaps, fasta, vcf, vcf_off, totals;
+    int64_t n_recs = 0, lit_bytes = 0, fasta_bytes = 0, vcf_bytes = 0, n_pieces = 0, n_blk = 0;
+    ms::Totals* h_totals = nullptr;  // pinned
+    ms::Totals last_totals{};
+
+    // timing
+    cudaEvent_t ev[ms::ST_COUNT][2];
+    bool ev_used[ms::ST_COUNT];
+    float stage_ms[ms::ST_COUNT];
+    int64_t kernel_launches = 0;
+    int tile_bytes = 16384;
+};
+
+#define MS_CUDA(ctx, call)                                                                        \
+    do {                                                                                          \
+        cudaError_t _e = (call);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            char _b[512];                                                                         \
+            snprintf(_b, sizeof(_b), "%s:%d: %s failed: %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+            (ctx)->err = _b;                                                                      \
+            return MS_ERR_CUDA;                                                                   \
+        }                                                                                         \
+    } while (0)
+
+#define MS_FAIL(ctx, code, ...)                                \
+    do {                                                       \
+        char _b[512];                                          \
+        snprintf(_b, sizeof(_b), __VA_ARGS__);                 \
+        (ctx)->err = _b;                                       \
+        return (code);                                         \
+    } while (0)
+
+#define MS_LAUNCH_CHECK(ctx)                                   \
+    do {                                                       \
+        (ctx)->kernel_launches++;                              \
+        MS_CUDA(ctx, cudaGetLastError());                      \
+    } while (0)
+
+namespace ms {
+inline void stage_begin(ms_ctx* c, Stage s) { cudaEventRecord(c->ev[s][0], c->stream); }
+inline void stage_end(ms_ctx* c, Stage s) { cudaEventRecord(c->ev[s][1], c->stream); c->ev_used[s] = true; }
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// pipeline entry points implemented in the .cu files
+int apply_pipeline(ms_ctx* c);
+int sample_pipeline(ms_ctx* c, uint64_t seed);
+int count_types(ms_ctx* c);
+}  // namespace ms

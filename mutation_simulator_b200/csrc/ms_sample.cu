@@ -1,0 +1,594 @@
+// ms_sample.cu — K1..K4: fresh sampling of mutations for all ranges of all contigs.
+//
+//   K1  positions   util.py:94-109 sample_with_minimum_distance: pi(0..k-1) of a
+//                   Philox-keyed permutation of range(n) (distinct by construction),
+//                   then a uniform bucket sort (count / scan / scatter / in-smem
+//                   bitonic) — keys are uniform, so equal-width buckets balance.
+//   K2  type+length mutator.py:166-182, 229-265 (fused into the sort's write-back)
+//   K3  rejection   mutator.py:184-213 first-come greedy acceptance, in parallel:
+//                   exclusive prefix-max of the blocking reach marks "anchors"
+//                   (candidates no earlier one can block); one thread walks the
+//                   short chain between two anchors.
+//   K4  linking     mutator.py:268-316 TL<->TLI: uniform random injection of the
+//                   smaller list into the larger one via a keyed permutation.
+//   K4b records     32-byte splice descriptors + SNP ALT (mutator.py:429-463) +
+//                   random insert strings (mutator.py:466-471).
+#include "ms_common.cuh"
+#include "ms_scan.cuh"
+
+namespace ms {
+
+constexpr int BUCKET_TARGET = 512;
+constexpr int SORT_CAP = 2048;
+constexpr int SORT_THREADS = 256;
+
+__device__ inline void raise_error_s(Totals* t, int64_t code, int64_t arg) {
+    if (atomicCAS((unsigned long long*)&t->error, 0ull, (unsigned long long)code) == 0ull) t->error_arg = arg;
+}
+
+// largest r in [0, n) with key[r] <= x   (key ascending, key[0] <= x)
+__device__ inline int upper_idx(const int64_t* key, int n, int64_t x) {
+    int lo = 0, hi = n;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (key[mid] <= x) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void k_make_prps(const Range* ranges, int32_t n_ranges, const Contig* contigs, Seed seed, uint32_t purpose, Prp* prps) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_ranges) return;
+    const Range& g = ranges[r];
+    prps[r] = make_prp(seed, contigs[g.contig].gid, purpose, g.start, g.n);
+}
+
+__device__ inline uint32_t bucket_of(const Range& g, uint32_t v) {
+    uint32_t b = (uint32_t)(((uint64_t)v * g.nb) / g.n);
+    return g.bucket_lo + (b < g.nb ? b : g.nb - 1);
+}
+
+// K1a: draw + histogram
+__global__ void __launch_bounds__(256)
+k_draw(const Range* ranges, const int64_t* cand_lo, int32_t n_ranges, const Prp* prps, int64_t K, uint32_t* cand_val, uint32_t* bucket_cnt) {
+    __shared__ int r0;
+    const int64_t s0 = (int64_t)blockIdx.x * blockDim.x;
+    if (threadIdx.x == 0) r0 = upper_idx(cand_lo, n_ranges, s0);
+    __syncthreads();
+    const int64_t s = s0 + threadIdx.x;
+    if (s >= K) return;
+    int r = r0;
+    while (s >= cand_lo[r + 1]) ++r;
+    const Range& g = ranges[r];
+    const Prp p = prps[r];
+    const uint32_t v = prp_apply(p, (uint32_t)(s - g.cand_lo));
+    cand_val[s] = v;
+    atomicAdd(&bucket_cnt[bucket_of(g, v)], 1u);
+}
+
+// K1c: scatter into buckets
+__global__ void __launch_bounds__(256)
+k_scatter(const Range* ranges, const int64_t* cand_lo, int32_t n_ranges, int64_t K, const uint32_t* cand_val,
+          const int64_t* bucket_off, uint32_t* cursor, uint32_t* sorted) {
+    __shared__ int r0;
+    const int64_t s0 = (int64_t)blockIdx.x * blockDim.x;
+    if (threadIdx.x == 0) r0 = upper_idx(cand_lo, n_ranges, s0);
+    __syncthreads();
+    const int64_t s = s0 + threadIdx.x;
+    if (s >= K) return;
+    int r = r0;
+    while (s >= cand_lo[r + 1]) ++r;
+    const uint32_t v = cand_val[s];
+    const uint32_t b = bucket_of(ranges[r], v);
+    sorted[bucket_off[b] + atomicAdd(&cursor[b], 1u)] = v;
+}
+
+// K1d + K2: sort one bucket in shared memory, then write position, type, length and reach.
+__global__ void __launch_bounds__(SORT_THREADS)
+k_sort_emit(const Range* ranges, const int64_t* bucket_lo_key, int32_t n_ranges, const Contig* contigs, const int64_t* bucket_off,
+            const uint32_t* sorted, Seed seed, int32_t min_dist, const int32_t* block7, int positions_only,
+            int64_t* cand_gpos, uint8_t* cand_type, uint32_t* cand_len, int64_t* cand_reach, uint32_t* cand_range, Totals* tot) {
+    __shared__ uint32_t sm[SORT_CAP];
+    __shared__ Range g;
+    __shared__ int32_t blk[7];
+    __shared__ uint32_t s_ridx;
+    const int tid = threadIdx.x;
+    const int64_t b = blockIdx.x;
+    const int64_t lo = bucket_off[b], hi = bucket_off[b + 1];
+    const int cnt = (int)(hi - lo);
+    if (cnt <= 0) return;
+    if (cnt > SORT_CAP) { if (tid == 0) raise_error_s(tot, MS_ERR_INTERNAL, 100 + b); return; }
+    if (tid == 0) { s_ridx = (uint32_t)upper_idx(bucket_lo_key, n_ranges, b); g = ranges[s_ridx]; }
+    if (tid < 7) blk[tid] = block7[tid];
+    int n2 = 32;
+    while (n2 < cnt) n2 <<= 1;
+    for (int i = tid; i < n2; i += SORT_THREADS) sm[i] = i < cnt ? sorted[lo + i] : 0xFFFFFFFFu;
+    __syncthreads();
+    for (int k = 2; k <= n2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < n2; i += SORT_THREADS) {
+                const int x = i ^ j;
+                if (x > i) {
+                    const uint32_t a = sm[i], c = sm[x];
+                    const bool asc = (i & k) == 0;
+                    if ((a > c) == asc) { sm[i] = c; sm[x] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    const Contig& ct = contigs[g.contig];
+    const uint32_t r_idx = s_ridx;
+    for (int i = tid; i < cnt; i += SORT_THREADS) {
+        const int64_t slot = lo + i;
+        const uint32_t rank = (uint32_t)(slot - g.cand_lo);
+        const uint32_t pos = g.start + sm[i] + (uint32_t)min_dist * rank;   // util.py:106-108
+        cand_gpos[slot] = ct.goff + pos;
+        if (positions_only) continue;
+        uint8_t type; uint32_t len;
+        draw_type_len(seed, ct.gid, pos, g, type, len);
+        int64_t reach = block_reach(type, pos, len, blk);
+        if (reach > ct.len) reach = ct.len;
+        cand_type[slot] = type;
+        cand_len[slot] = len;
+        cand_reach[slot] = type == T_DEAD ? 0 : ct.goff + reach;
+        cand_range[slot] = r_idx;
+    }
+}
+
+// K3b: walk the chain that starts at each anchor (mutator.py:184-213).
+__global__ void __launch_bounds__(256)
+k_resolve(int64_t K, const int64_t* gpos, const int64_t* reach, const uint8_t* type, const uint8_t* anchor, uint8_t* accept) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= K || !anchor[s]) return;
+    accept[s] = 1;
+    int64_t cur = reach[s];
+    for (int64_t t = s + 1; t < K && !anchor[t]; ++t) {
+        if (type[t] == T_DEAD) continue;           // inversion that does not fit: dropped, blocks nothing (:199-201)
+        if (gpos[t] >= cur) { accept[t] = 1; cur = reach[t]; }
+    }
+}
+
+__global__ void k_contig_tl_bounds(const Contig* contigs, int32_t n_contigs, const int64_t* gpos, const uint32_t* tl_list, int64_t n_tl,
+                                   const uint32_t* tli_list, int64_t n_tli, int64_t* tl_base, int64_t* tli_base) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > n_contigs) return;
+    if (c == n_contigs) { tl_base[c] = n_tl; tli_base[c] = n_tli; return; }
+    const int64_t key = contigs[c].goff;
+    int64_t lo = 0, hi = n_tl;
+    while (lo < hi) { const int64_t m = (lo + hi) >> 1; if (gpos[tl_list[m]] < key) lo = m + 1; else hi = m; }
+    tl_base[c] = lo;
+    lo = 0; hi = n_tli;
+    while (lo < hi) { const int64_t m = (lo + hi) >> 1; if (gpos[tli_list[m]] < key) lo = m + 1; else hi = m; }
+    tli_base[c] = lo;
+}
+
+// K4: element j of the smaller list is paired with element rho(j) of the larger one,
+// rho a keyed permutation of the larger list: a uniform random injection, which is
+// what "remove random surplus, shuffle, zip" (mutator.py:277-304) produces.
+// link[slot]: -1 unlinked (dropped), -2 kept TL, >= 0 (TLI) candidate slot of its TL.
+__global__ void __launch_bounds__(256)
+k_link(const Contig* contigs, const Range* ranges, const uint32_t* cand_range, const uint32_t* tl_list, int64_t n_tl,
+       const uint32_t* tli_list, int64_t n_tli, const int64_t* tl_base, const int64_t* tli_base, Seed seed, int32_t* link) {
+    const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= n_tl + n_tli) return;
+    const bool is_tl = x < n_tl;
+    const int64_t idx = is_tl ? x : x - n_tl;
+    const uint32_t slot = is_tl ? tl_list[idx] : tli_list[idx];
+    const uint32_t c = ranges[cand_range[slot]].contig;
+    const int64_t a = tl_base[c + 1] - tl_base[c], b = tli_base[c + 1] - tli_base[c];
+    if (a == 0 || b == 0) return;
+    // ties (a == b) are driven from the TL side
+    const bool tl_small = a <= b;
+    if (is_tl != tl_small) return;
+    const int64_t j = idx - (is_tl ? tl_base[c] : tli_base[c]);
+    const uint32_t m = (uint32_t)(tl_small ? b : a);
+    uint32_t rho;
+    if (m == 1) rho = 0;
+    else { const Prp p = make_prp(seed, contigs[c].gid, P_TL_PRP, 0, m); rho = prp_apply(p, (uint32_t)j); }
+    const uint32_t other = tl_small ? tli_list[tli_base[c] + rho] : tl_list[tl_base[c] + rho];
+    const uint32_t tl_slot = is_tl ? slot : other, tli_slot = is_tl ? other : slot;
+    link[tl_slot] = -2;
+    link[tli_slot] = (int32_t)tl_slot;
+}
+
+// K4b: one 32-byte record per kept mutation.
+__global__ void __launch_bounds__(256)
+k_build_records(int64_t n_acc, const uint32_t* acc_slot, const int64_t* rec_idx, const int64_t* lit_off, const int64_t* gpos,
+                const uint8_t* type, const uint32_t* len, const uint32_t* cand_range, const int32_t* link, const Range* ranges,
+                const Contig* contigs, const uint8_t* genome, const Tables* tab, Seed seed, double p_ti, Rec* recs, uint8_t* lit) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_acc) return;
+    if (rec_idx[e + 1] == rec_idx[e]) return;  // dropped TL / TLI
+    const uint32_t s = acc_slot[e];
+    const uint32_t cidx = ranges[cand_range[s]].contig;
+    const Contig& ct = contigs[cidx];
+    const uint32_t pos = (uint32_t)(gpos[s] - ct.goff);
+    const uint8_t t = type[s];
+    const uint32_t l = len[s];
+    Rec r;
+    r.pos = pos; r.out = 0; r.src = 0; r.type = t; r.ref = 0; r.alt = 0; r.contig = cidx;
+    switch (t) {
+        case T_SN: {
+            r.cons = 1; r.prod = 1; r.kind = K_SNP;
+            r.ref = tab->conv[genome[gpos[s]]];
+            r.alt = draw_snp(seed, ct.gid, pos, r.ref, p_ti, tab->trans);
+        } break;
+        case T_IN: {
+            r.cons = 0; r.prod = l; r.kind = K_LIT; r.src = lit_off[e];
+            U4 blk{0, 0, 0, 0};
+            for (uint32_t j = 0; j < l; ++j) {
+                if ((j & 63u) == 0) blk = draw(seed, ct.gid, P_INSERT | ((j >> 6) << 8), pos);
+                lit[r.src + j] = insert_base(blk, j);
+            }
+        } break;
+        case T_DE: case T_TL: r.cons = l; r.prod = 0; r.kind = K_NONE; break;
+        case T_IV: r.cons = l; r.prod = l; r.kind = K_RC; r.src = gpos[s]; break;
+        case T_DU: r.cons = 0; r.prod = l; r.kind = K_RAW; r.src = gpos[s]; break;
+        default: {  // T_TLI linked to the TL at candidate slot link[s]
+            const int32_t tl = link[s];
+            const uint32_t tl_len = len[tl];
+            r.cons = 0; r.prod = tl_len; r.src = gpos[tl];
+            r.kind = draw_tl_reverse(seed, ct.gid, pos, tl_len) ? K_RC : K_CONV;
+        } break;
+    }
+    recs[rec_idx[e]] = r;
+}
+
+__global__ void __launch_bounds__(256) k_count_types(const Rec* recs, int64_t n, Totals* tot) {
+    __shared__ unsigned int h[8];
+    if (threadIdx.x < 8) h[threadIdx.x] = 0;
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        atomicAdd(&h[recs[i].type & 7], 1u);
+    __syncthreads();
+    if (threadIdx.x < 8 && h[threadIdx.x]) atomicAdd((unsigned long long*)&tot->counts[threadIdx.x], (unsigned long long)h[threadIdx.x]);
+}
+
+template <class T> __global__ void k_copy_scalar(const T* src, T* dst) { *dst = *src; }
+
+// ---- host orchestration --------------------------------------------------------------
+static int draw_and_sort(ms_ctx* c, Seed seed, uint32_t purpose, int32_t min_dist, int positions_only) {
+    cudaStream_t st = c->stream;
+    const int64_t K = c->n_candidates;
+    const int32_t R = c->n_ranges;
+    const Range* d_ranges = c->ranges.as<Range>();
+    // side arrays kept right behind the Range table
+    int64_t* d_cand_lo = reinterpret_cast<int64_t*>(c->ranges.as<uint8_t>() + sizeof(Range) * (size_t)R);
+    int64_t* d_bucket_lo = d_cand_lo + (R + 1);
+    Prp* d_prps = reinterpret_cast<Prp*>(d_bucket_lo + (R + 1));
+    int32_t* d_block = reinterpret_cast<int32_t*>(d_prps + R);
+    Totals* d_tot = c->totals.as<Totals>();
+
+    MS_CUDA(c, c->cand_val.ensure((size_t)K * 4 + 16));
+    MS_CUDA(c, c->cand_sorted.ensure((size_t)K * 4 + 16));
+    MS_CUDA(c, c->bucket_cnt.ensure((size_t)(c->n_buckets + 1) * 4));
+    MS_CUDA(c, c->bucket_off.ensure((size_t)(c->n_buckets + 1) * 8));
+    MS_CUDA(c, c->cand_reach.ensure((size_t)K * 8 + 16));   // cand_gpos lives in svec
+    MS_CUDA(c, c->svec.ensure((size_t)(K + 1) * 8));
+    MS_CUDA(c, c->cand_type.ensure((size_t)K + 16));
+    MS_CUDA(c, c->cand_len.ensure((size_t)K * 4 + 16));
+    MS_CUDA(c, c->lvec.ensure((size_t)K * 4 + 16));         // cand_range
+    uint32_t* d_cnt = c->bucket_cnt.as<uint32_t>();
+    int64_t* d_boff = c->bucket_off.as<int64_t>();
+
+    stage_begin(c, ST_SAMPLE_POS);
+    k_make_prps<<<(unsigned)ceil_div(R, 128), 128, 0, st>>>(d_ranges, R, c->contigs.as<Contig>(), seed, purpose, d_prps);
+    MS_LAUNCH_CHECK(c);
+    MS_CUDA(c, cudaMemsetAsync(d_cnt, 0, (size_t)(c->n_buckets + 1) * 4, st));
+    k_draw<<<(unsigned)ceil_div(K, 256), 256, 0, st>>>(d_ranges, d_cand_lo, R, d_prps, K, c->cand_val.as<uint32_t>(), d_cnt);
+    MS_LAUNCH_CHECK(c);
+    {
+        const uint32_t* cnt = d_cnt;
+        auto in = [=] __device__(int64_t i) -> int64_t { return (int64_t)cnt[i]; };
+        auto out = [=] __device__(int64_t i, int64_t ex, int64_t) { d_boff[i] = ex; };
+        int64_t* d_total = nullptr;
+        MS_CUDA(c, (device_scan<int64_t>(c, in, out, c->n_buckets, (int64_t)0, SumOp(), c->scan_tmp, &d_total)));
+        k_copy_scalar<int64_t><<<1, 1, 0, st>>>(d_total, d_boff + c->n_buckets);
+        MS_LAUNCH_CHECK(c);
+    }
+    MS_CUDA(c, cudaMemsetAsync(d_cnt, 0, (size_t)(c->n_buckets + 1) * 4, st));
+    k_scatter<<<(unsigned)ceil_div(K, 256), 256, 0, st>>>(d_ranges, d_cand_lo, R, K, c->cand_val.as<uint32_t>(), d_boff, d_cnt,
+                                                          c->cand_sorted.as<uint32_t>());
+    MS_LAUNCH_CHECK(c);
+    stage_end(c, ST_SAMPLE_POS);
+
+    stage_begin(c, ST_SAMPLE_TYPE);
+    k_sort_emit<<<(unsigned)c->n_buckets, SORT_THREADS, 0, st>>>(d_ranges, d_bucket_lo, R, c->contigs.as<Contig>(), d_boff,
+                                                                 c->cand_sorted.as<uint32_t>(), seed, min_dist, d_block, positions_only,
+                                                                 c->svec.as<int64_t>(), c->cand_type.as<uint8_t>(), c->cand_len.as<uint32_t>(),
+                                                                 c->cand_reach.as<int64_t>(), c->lvec.as<uint32_t>(), d_tot);
+    MS_LAUNCH_CHECK(c);
+    stage_end(c, ST_SAMPLE_TYPE);
+    return MS_OK;
+}
+
+int sample_pipeline(ms_ctx* c, uint64_t seed64) {
+    if (c->n_contigs <= 0 || !c->genome.p) MS_FAIL(c, MS_ERR_STATE, "ms_sample: no genome resident");
+    if (c->n_ranges < 0) MS_FAIL(c, MS_ERR_STATE, "ms_sample: call ms_set_ranges first");
+    cudaStream_t st = c->stream;
+    const Seed seed = make_seed(seed64);
+    const int64_t K = c->n_candidates;
+    Totals* d_tot = c->totals.as<Totals>();
+    MS_CUDA(c, cudaMemsetAsync(d_tot, 0, sizeof(Totals), st));
+    c->last_totals = Totals{};
+    c->last_totals.n_candidates = K;
+    c->n_recs = 0; c->lit_bytes = 0;
+    MS_CUDA(c, c->recs.ensure(64));
+    MS_CUDA(c, c->lit.ensure(64));
+    if (K == 0 || c->n_ranges == 0) return MS_OK;
+
+    int rc = draw_and_sort(c, seed, P_RANGE_PRP, c->min_dist, 0);
+    if (rc) return rc;
+
+    const int64_t* d_gpos = c->svec.as<int64_t>();
+    const int64_t* d_reach = c->cand_reach.as<int64_t>();
+    const uint8_t* d_type = c->cand_type.as<uint8_t>();
+    const uint32_t* d_len = c->cand_len.as<uint32_t>();
+    const uint32_t* d_crange = c->lvec.as<uint32_t>();
+    const Range* d_ranges = c->ranges.as<Range>();
+    const Contig* d_contigs = c->contigs.as<Contig>();
+
+    // ---- K3: rejection -------------------------------------------------------------
+    stage_begin(c, ST_SAMPLE_RESOLVE);
+    MS_CUDA(c, c->cand_pm.ensure((size_t)K + 16));
+    MS_CUDA(c, c->cand_accept.ensure((size_t)K + 16));
+    uint8_t* d_anchor = c->cand_pm.as<uint8_t>();
+    uint8_t* d_accept = c->cand_accept.as<uint8_t>();
+    MS_CUDA(c, cudaMemsetAsync(d_accept, 0, (size_t)K, st));
+    {
+        auto in = [=] __device__(int64_t i) -> int64_t { return d_reach[i]; };
+        auto out = [=] __device__(int64_t i, int64_t ex, int64_t) {
+            d_anchor[i] = (d_type[i] != T_DEAD && d_gpos[i] >= ex) ? 1 : 0;
+        };
+        MS_CUDA(c, (device_scan<int64_t>(c, in, out, K, (int64_t)0, MaxOp(), c->scan_tmp, (int64_t**)nullptr)));
+    }
+    k_resolve<<<(unsigned)ceil_div(K, 256), 256, 0, st>>>(K, d_gpos, d_reach, d_type, d_anchor, d_accept);
+    MS_LAUNCH_CHECK(c);
+    // compaction of accepted candidates + TL / TLI lists in one pass
+    MS_CUDA(c, c->acc_idx.ensure((size_t)K * 4 + 16));
+    MS_CUDA(c, c->tl_list.ensure((size_t)K * 4 + 16));
+    MS_CUDA(c, c->tli_list.ensure((size_t)K * 4 + 16));
+    uint32_t* d_acc = c->acc_idx.as<uint32_t>();
+    uint32_t* d_tl = c->tl_list.as<uint32_t>();
+    uint32_t* d_tli = c->tli_list.as<uint32_t>();
+    {
+        auto in = [=] __device__(int64_t i) -> I64x3 {
+            const int64_t a = d_accept[i];
+            const uint8_t t = d_type[i];
+            return I64x3{a, (a && t == T_TL) ? 1 : 0, (a && t == T_TLI) ? 1 : 0};
+        };
+        auto out = [=] __device__(int64_t i, I64x3 ex, I64x3 v) {
+            if (v.a) d_acc[ex.a] = (uint32_t)i;
+            if (v.b) d_tl[ex.b] = (uint32_t)i;
+            if (v.c) d_tli[ex.c] = (uint32_t)i;
+        };
+        I64x3* d_total = nullptr;
+        MS_CUDA(c, (device_scan<I64x3>(c, in, out, K, I64x3{0, 0, 0}, SumOp(), c->scan_tmp, &d_total)));
+        MS_CUDA(c, cudaMemcpyAsync(c->h_totals, d_total, sizeof(I64x3), cudaMemcpyDeviceToHost, st));
+    }
+    stage_end(c, ST_SAMPLE_RESOLVE);
+    MS_CUDA(c, cudaStreamSynchronize(st));
+    const I64x3 cnt = *reinterpret_cast<const I64x3*>(c->h_totals);
+    const int64_t n_acc = cnt.a, n_tl = cnt.b, n_tli = cnt.c;
+    c->last_totals.n_accepted = n_acc;
+
+    // ---- K4: TL <-> TLI linking -------------------------------------------------------
+    stage_begin(c, ST_SAMPLE_LINK);
+    MS_CUDA(c, c->link.ensure((size_t)K * 4 + 16));
+    int32_t* d_link = c->link.as<int32_t>();
+    MS_CUDA(c, cudaMemsetAsync(d_link, 0xFF, (size_t)K * 4, st));
+    if (n_tl > 0 && n_tli > 0) {
+        MS_CUDA(c, c->contig_tl.ensure((size_t)(c->n_contigs + 1) * 16));
+        int64_t* d_tlb = c->contig_tl.as<int64_t>();
+        int64_t* d_tlib = d_tlb + (c->n_contigs + 1);
+        k_contig_tl_bounds<<<(unsigned)ceil_div(c->n_contigs + 1, 128), 128, 0, st>>>(d_contigs, c->n_contigs, d_gpos, d_tl, n_tl, d_tli,
+                                                                                     n_tli, d_tlb, d_tlib);
+        MS_LAUNCH_CHECK(c);
+        k_link<<<(unsigned)ceil_div(n_tl + n_tli, 256), 256, 0, st>>>(d_contigs, d_ranges, d_crange, d_tl, n_tl, d_tli, n_tli, d_tlb, d_tlib,
+                                                                      seed, d_link);
+        MS_LAUNCH_CHECK(c);
+    }
+    stage_end(c, ST_SAMPLE_LINK);
+
+    // ---- K4b: records -----------------------------------------------------------------
+    stage_begin(c, ST_SAMPLE_FINAL);
+    MS_CUDA(c, c->vvec.ensure((size_t)(n_acc + 1) * 8));
+    MS_CUDA(c, c->vcf_off.ensure((size_t)(n_acc + 1) * 8));
+    int64_t* d_recidx = c->vvec.as<int64_t>();
+    int64_t* d_litoff = c->vcf_off.as<int64_t>();
+    {
+        auto in = [=] __device__(int64_t e) -> I64x2 {
+            const uint32_t s = d_acc[e];
+            const uint8_t t = d_type[s];
+            const bool keep = (t != T_TL && t != T_TLI) || d_link[s] != -1;
+            return I64x2{keep ? 1 : 0, (keep && t == T_IN) ? (int64_t)d_len[s] : 0};
+        };
+        auto out = [=] __device__(int64_t e, I64x2 ex, I64x2) { d_recidx[e] = ex.a; d_litoff[e] = ex.b; };
+        I64x2* d_total = nullptr;
+        MS_CUDA(c, (device_scan<I64x2>(c, in, out, n_acc, I64x2{0, 0}, SumOp(), c->scan_tmp, &d_total)));
+        k_copy_scalar<int64_t><<<1, 1, 0, st>>>(&d_total->a, d_recidx + n_acc);
+        MS_LAUNCH_CHECK(c);
+        MS_CUDA(c, cudaMemcpyAsync(c->h_totals, d_total, sizeof(I64x2), cudaMemcpyDeviceToHost, st));
+    }
+    MS_CUDA(c, cudaStreamSynchronize(st));
+    const I64x2 fin = *reinterpret_cast<const I64x2*>(c->h_totals);
+    const int64_t n_recs = fin.a, lit_bytes = fin.b;
+    MS_CUDA(c, c->recs.ensure((size_t)(n_recs + 1) * sizeof(Rec)));
+    MS_CUDA(c, c->lit.ensure((size_t)lit_bytes + 64));
+    if (n_acc > 0) {
+        k_build_records<<<(unsigned)ceil_div(n_acc, 256), 256, 0, st>>>(n_acc, d_acc, d_recidx, d_litoff, d_gpos, d_type, d_len, d_crange,
+                                                                        d_link, d_ranges, d_contigs, c->genome.as<uint8_t>(),
+                                                                        c->tables.as<Tables>(), seed, c->p_ti, c->recs.as<Rec>(),
+                                                                        c->lit.as<uint8_t>());
+        MS_LAUNCH_CHECK(c);
+    }
+    MS_CUDA(c, cudaMemcpyAsync(c->h_totals, d_tot, sizeof(Totals), cudaMemcpyDeviceToHost, st));
+    stage_end(c, ST_SAMPLE_FINAL);
+    MS_CUDA(c, cudaStreamSynchronize(st));
+    if (c->h_totals->error) MS_FAIL(c, (int)c->h_totals->error, "ms_sample: kernel error %lld (arg %lld)", (long long)c->h_totals->error,
+                                    (long long)c->h_totals->error_arg);
+    c->n_recs = n_recs;
+    c->lit_bytes = lit_bytes;
+    c->last_totals.n_recs = n_recs;
+    c->last_totals.lit_bytes = lit_bytes;
+    c->counts_valid = false;
+    return MS_OK;
+}
+
+int count_types(ms_ctx* c) {
+    if (c->counts_valid) return MS_OK;
+    Totals* d_tot = c->totals.as<Totals>();
+    MS_CUDA(c, cudaMemsetAsync(d_tot->counts, 0, sizeof(d_tot->counts), c->stream));
+    if (c->n_recs > 0) {
+        k_count_types<<<NUM_SMS_B200 * 4, 256, 0, c->stream>>>(c->recs.as<Rec>(), c->n_recs, d_tot);
+        MS_LAUNCH_CHECK(c);
+    }
+    MS_CUDA(c, cudaMemcpyAsync(c->h_totals, d_tot, sizeof(Totals), cudaMemcpyDeviceToHost, c->stream));
+    MS_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int t = 0; t < 8; ++t) c->last_totals.counts[t] = c->h_totals->counts[t];
+    c->counts_valid = true;
+    return MS_OK;
+}
+
+// Range table upload shared by ms_set_ranges and ms_it_breakpoints.
+static int upload_ranges(ms_ctx* c, int32_t min_dist) {
+    const int32_t R = (int32_t)c->h_ranges.size();
+    std::vector<int64_t> cand_lo(R + 1), bucket_lo(R + 1);
+    int64_t K = 0, NB = 0;
+    for (int32_t r = 0; r < R; ++r) {
+        Range& g = c->h_ranges[r];
+        const int64_t n = (int64_t)g.stop - ((int64_t)g.k - 1) * min_dist - (int64_t)g.start;   // util.py:104
+        if ((int64_t)g.k > n || n <= 0)
+            MS_FAIL(c, MS_ERR_SAMPLE, "Sample larger than population or is negative (range %u-%u of contig %u: k=%u, population=%lld)",
+                    g.start + 1, g.stop + 1, g.contig + 1, g.k, (long long)n);
+        g.n = (uint32_t)n;
+        g.cand_lo = K;
+        g.nb = (uint32_t)std::max<int64_t>(1, ceil_div(g.k, BUCKET_TARGET));
+        g.bucket_lo = (uint32_t)NB;
+        g.gstart = c->h_contigs[g.contig].goff + g.start;
+        cand_lo[r] = K; bucket_lo[r] = NB;
+        K += g.k; NB += g.nb;
+    }
+    cand_lo[R] = K; bucket_lo[R] = NB;
+    if (K >= (int64_t)0x7FFFFFF0) MS_FAIL(c, MS_ERR_LIMIT, "more than 2^31 candidates in one call");
+    c->n_ranges = R; c->n_candidates = K; c->n_buckets = NB; c->min_dist = min_dist;
+    const size_t bytes = sizeof(Range) * (size_t)R + 2 * sizeof(int64_t) * (size_t)(R + 1) + sizeof(Prp) * (size_t)R + 64;
+    MS_CUDA(c, c->ranges.ensure(bytes));
+    uint8_t* base = c->ranges.as<uint8_t>();
+    cudaStream_t st = c->stream;
+    if (R > 0) MS_CUDA(c, cudaMemcpyAsync(base, c->h_ranges.data(), sizeof(Range) * (size_t)R, cudaMemcpyHostToDevice, st));
+    int64_t* d_cand_lo = reinterpret_cast<int64_t*>(base + sizeof(Range) * (size_t)R);
+    MS_CUDA(c, cudaMemcpyAsync(d_cand_lo, cand_lo.data(), sizeof(int64_t) * (size_t)(R + 1), cudaMemcpyHostToDevice, st));
+    MS_CUDA(c, cudaMemcpyAsync(d_cand_lo + (R + 1), bucket_lo.data(), sizeof(int64_t) * (size_t)(R + 1), cudaMemcpyHostToDevice, st));
+    int32_t* d_block = reinterpret_cast<int32_t*>(reinterpret_cast<Prp*>(d_cand_lo + 2 * (R + 1)) + R);
+    MS_CUDA(c, cudaMemcpyAsync(d_block, c->block, sizeof(int32_t) * 7, cudaMemcpyHostToDevice, st));
+    MS_CUDA(c, cudaStreamSynchronize(st));
+    return MS_OK;
+}
+
+}  // namespace ms
+
+using namespace ms;
+
+extern "C" {
+
+int ms_set_ranges(ms_ctx* c, const ms_range* ranges, int32_t n_ranges, const int32_t* block, int32_t min_dist, double p_ti) {
+    if (!c || n_ranges < 0 || (n_ranges > 0 && !ranges) || !block) return MS_ERR_ARG;
+    if (c->n_contigs <= 0) MS_FAIL(c, MS_ERR_STATE, "ms_set_ranges: upload a genome first");
+    if (min_dist < 0) MS_FAIL(c, MS_ERR_ARG, "min_dist must be >= 0");
+    MS_CUDA(c, cudaSetDevice(c->device));
+    for (int t = 0; t < 7; ++t) c->block[t] = block[t];
+    c->p_ti = p_ti;
+    c->h_ranges.clear();
+    c->n_ranges = -1;
+    for (int32_t r = 0; r < n_ranges; ++r) {
+        const ms_range& in = ranges[r];
+        if (in.contig >= (uint32_t)c->n_contigs) MS_FAIL(c, MS_ERR_ARG, "range %d: contig out of range", r);
+        const int64_t L = c->h_contigs[in.contig].len;
+        if (in.stop < in.start || (int64_t)in.stop > L) MS_FAIL(c, MS_ERR_ARG, "range %d: %u-%u outside contig of length %lld", r, in.start, in.stop, (long long)L);
+        if (r && (in.contig < ranges[r - 1].contig || (in.contig == ranges[r - 1].contig && in.start <= ranges[r - 1].stop)))
+            MS_FAIL(c, MS_ERR_ARG, "range %d: ranges must be sorted by (contig, start) and must not overlap", r);
+        if (in.k == 0) continue;  // random.sample(population, 0) == []
+        Range g{};
+        g.contig = in.contig; g.start = in.start; g.stop = in.stop; g.k = in.k;
+        g.limit = (in.limit > 0 && in.limit <= L) ? in.limit : L;
+        for (int t = 0; t < 7; ++t) {
+            g.cdf[t] = in.cdf[t]; g.minlen[t] = in.minlen[t]; g.maxlen[t] = in.maxlen[t];
+            if (g.maxlen[t] < g.minlen[t] || g.minlen[t] < 0) MS_FAIL(c, MS_ERR_ARG, "range %d: bad length bounds for type %d", r, t);
+        }
+        c->h_ranges.push_back(g);
+    }
+    return upload_ranges(c, min_dist);
+}
+
+int ms_sample(ms_ctx* c, uint64_t seed) {
+    if (!c) return MS_ERR_ARG;
+    MS_CUDA(c, cudaSetDevice(c->device));
+    return sample_pipeline(c, seed);
+}
+
+int ms_it_breakpoints(ms_ctx* c, uint64_t seed, int32_t n_pairs, const uint32_t* contig_a, const uint32_t* contig_b,
+                      const uint32_t* n, uint32_t* bp_a, uint32_t* bp_b) {
+    if (!c || n_pairs < 0 || !contig_a || !contig_b || !n || !bp_a || !bp_b) return MS_ERR_ARG;
+    if (c->n_contigs <= 0) MS_FAIL(c, MS_ERR_STATE, "ms_it_breakpoints: upload a genome first");
+    MS_CUDA(c, cudaSetDevice(c->device));
+    c->h_ranges.clear();
+    c->n_ranges = -1;
+    // pair-major: all of a's breakpoints then all of b's, per pair (it_mutator.py:108-111)
+    for (int32_t p = 0; p < n_pairs; ++p) {
+        for (int side = 0; side < 2; ++side) {
+            const uint32_t ci = side ? contig_b[p] : contig_a[p];
+            if (ci >= (uint32_t)c->n_contigs) MS_FAIL(c, MS_ERR_ARG, "pair %d: contig out of range", p);
+            if (n[p] == 0) continue;
+            Range g{};
+            g.contig = ci; g.start = 1; g.stop = (uint32_t)c->h_contigs[ci].len; g.k = n[p];   // sample_with_minimum_distance(1, len, n, 1)
+            g.limit = c->h_contigs[ci].len;
+            for (int t = 0; t < 7; ++t) { g.cdf[t] = 1.0; g.minlen[t] = 1; g.maxlen[t] = 1; }
+            c->h_ranges.push_back(g);
+        }
+    }
+    int rc = upload_ranges(c, 1);
+    if (rc) return rc;
+    const int64_t K = c->n_candidates;
+    const int32_t saved = c->n_ranges;
+    if (K > 0) {
+        MS_CUDA(c, cudaMemsetAsync(c->totals.p, 0, sizeof(Totals), c->stream));
+        rc = draw_and_sort(c, make_seed(seed), P_IT_PRP, 1, 1);
+        if (rc) return rc;
+        std::vector<int64_t> gpos((size_t)K);
+        MS_CUDA(c, cudaMemcpyAsync(gpos.data(), c->svec.p, (size_t)K * 8, cudaMemcpyDeviceToHost, c->stream));
+        MS_CUDA(c, cudaMemcpyAsync(c->h_totals, c->totals.p, sizeof(Totals), cudaMemcpyDeviceToHost, c->stream));
+        MS_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (c->h_totals->error) MS_FAIL(c, (int)c->h_totals->error, "ms_it_breakpoints: kernel error %lld", (long long)c->h_totals->error);
+        int64_t s = 0, o = 0;
+        for (int32_t p = 0; p < n_pairs; ++p) {
+            if (n[p] == 0) continue;
+            const int64_t ga = c->h_contigs[contig_a[p]].goff, gb = c->h_contigs[contig_b[p]].goff;
+            for (uint32_t i = 0; i < n[p]; ++i) bp_a[o + i] = (uint32_t)(gpos[s + i] - ga);
+            s += n[p];
+            for (uint32_t i = 0; i < n[p]; ++i) bp_b[o + i] = (uint32_t)(gpos[s + i] - gb);
+            s += n[p];
+            o += n[p];
+        }
+    }
+    (void)saved;
+    c->n_ranges = -1;  // the range table now holds breakpoint ranges: ms_sample needs ms_set_ranges again
+    return MS_OK;
+}
+
+int ms_debug_candidates(ms_ctx* c, int64_t cap, int64_t* gpos, uint8_t* type, uint32_t* len, uint8_t* accept, int64_t* n) {
+    if (!c || !n) return MS_ERR_ARG;
+    *n = c->n_candidates;
+    if (cap < c->n_candidates) return MS_OK;
+    const size_t K = (size_t)c->n_candidates;
+    MS_CUDA(c, cudaSetDevice(c->device));
+    if (gpos) MS_CUDA(c, cudaMemcpyAsync(gpos, c->svec.p, K * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (type) MS_CUDA(c, cudaMemcpyAsync(type, c->cand_type.p, K, cudaMemcpyDeviceToHost, c->stream));
+    if (len) MS_CUDA(c, cudaMemcpyAsync(len, c->cand_len.p, K * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (accept) MS_CUDA(c, cudaMemcpyAsync(accept, c->cand_accept.p, K, cudaMemcpyDeviceToHost, c->stream));
+    MS_CUDA(c, cudaStreamSynchronize(c->stream));
+    return MS_OK;
+}
+
+}  // extern "C"

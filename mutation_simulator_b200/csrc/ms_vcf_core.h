@@ -35,31 +35,31 @@ template <class S> MS_HD void put_uint(S& s, uint64_t v) {
     char buf[20];
     int n = 0;
     do { buf[n++] = (char)('0' + (v % 10)); v /= 10; } while (v);
-    if (S::counting) { s.skip((uint32_t)n); return; }
-    while (n) s.put((uint8_t)buf[--n]);
+    if constexpr (S::counting) s.skip((uint32_t)n);
+    else while (n) s.put((uint8_t)buf[--n]);
 }
 
 template <class S> MS_HD void put_str(S& s, const char* t, int n) {
-    if (S::counting) { s.skip((uint32_t)n); return; }
-    for (int i = 0; i < n; ++i) s.put((uint8_t)t[i]);
+    if constexpr (S::counting) s.skip((uint32_t)n);
+    else for (int i = 0; i < n; ++i) s.put((uint8_t)t[i]);
 }
 
 // n bytes of genome from g, optionally IUPAC-converted
 template <class S> MS_HD void put_bases(S& s, const VcfView& v, int64_t g, uint32_t n, bool convert) {
-    if (S::counting) { s.skip(n); return; }
-    for (uint32_t i = 0; i < n; ++i) { uint8_t c = v.genome[g + i]; s.put(convert ? v.conv[c] : c); }
+    if constexpr (S::counting) s.skip(n);
+    else for (uint32_t i = 0; i < n; ++i) { uint8_t c = v.genome[g + i]; s.put(convert ? v.conv[c] : c); }
 }
 
 // reverse complement of the converted bases [g, g+n)
 template <class S> MS_HD void put_rc(S& s, const VcfView& v, int64_t g, uint32_t n) {
-    if (S::counting) { s.skip(n); return; }
-    for (uint32_t i = 0; i < n; ++i) s.put(v.comp[v.conv[v.genome[g + (int64_t)(n - 1 - i)]]]);
+    if constexpr (S::counting) s.skip(n);
+    else for (uint32_t i = 0; i < n; ++i) s.put(v.comp[v.conv[v.genome[g + (int64_t)(n - 1 - i)]]]);
 }
 
 // payload bytes of a record as the FASTA shows them (insert of IN / TLI)
 template <class S> MS_HD void put_payload(S& s, const VcfView& v, const Rec& r) {
-    if (S::counting) { s.skip(r.prod); return; }
-    switch (r.kind) {
+    if constexpr (S::counting) { s.skip(r.prod); return; }
+    else switch (r.kind) {
         case K_LIT:  for (uint32_t i = 0; i < r.prod; ++i) s.put(v.lit[r.src + i]); break;
         case K_RAW:  put_bases(s, v, r.src, r.prod, false); break;
         case K_CONV: put_bases(s, v, r.src, r.prod, true); break;
@@ -95,7 +95,7 @@ template <class S> MS_HD void put_info(S& s, const char* sv, int svn, uint64_t e
 template <class S> MS_HD void vcf_emit(S& s, const VcfView& v, const Contig& c, const Rec& r) {
     const int64_t g0 = c.goff;
     const uint64_t p = r.pos;
-    if (S::counting) s.skip((uint32_t)c.name_len);
+    if constexpr (S::counting) s.skip((uint32_t)c.name_len);
     else for (int i = 0; i < c.name_len; ++i) s.put(v.names[c.name_src + i]);
     s.put('\t');
     const char* sv = ""; int svn = 0; uint64_t pos1 = 0, end = 0, svlen = 0;

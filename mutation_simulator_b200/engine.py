@@ -1,0 +1,198 @@
+"""Thin object wrapper over the C ABI: one ``Engine`` = one ms_ctx on one GPU.
+
+Host arrays go in as numpy arrays; every method maps 1:1 onto an entry point of
+include/mutsim_b200.h.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import MsRange, MsStats, MutSimError
+from .records import REC_DTYPE
+
+BUF_FASTA, BUF_VCF, BUF_RECS, BUF_LIT, BUF_GENOME = range(5)
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _blob(items: Sequence[bytes]):
+    off = np.zeros(len(items) + 1, dtype=np.int64)
+    np.cumsum([len(x) for x in items], out=off[1:])
+    return np.frombuffer(b"".join(items) + b"\0", dtype=np.uint8).copy(), off
+
+
+class Engine:
+    def __init__(self, device: int = 0):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        rc = self._lib.ms_create(device, C.byref(h))
+        if rc:
+            raise MutSimError(rc, (self._lib.ms_last_error(None) or b"").decode())
+        self._h = h
+        self.device = device
+        self.n_contigs = 0
+        self.total_bases = 0
+
+    # -- lifecycle ---------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.ms_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc: int):
+        if rc:
+            raise MutSimError(rc, (self._lib.ms_last_error(self._h) or b"").decode())
+
+    def set_stream(self, cuda_stream: int):
+        self._check(self._lib.ms_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def synchronize(self):
+        self._check(self._lib.ms_synchronize(self._h))
+
+    # -- genome ------------------------------------------------------------
+    def _contig_args(self, lengths, bpl, headers, names, gid):
+        self._len = np.ascontiguousarray(lengths, dtype=np.int64)
+        self._bpl = np.ascontiguousarray(bpl, dtype=np.int32)
+        self._hdr, self._hoff = _blob(headers)
+        self._nam, self._noff = _blob(names)
+        self._gid = None if gid is None else np.ascontiguousarray(gid, dtype=np.uint32)
+        self.n_contigs = len(self._len)
+        self.total_bases = int(self._len.sum())
+        self.names = list(names)
+
+    def upload_genome(self, bases: np.ndarray, lengths, bpl, headers: Sequence[bytes], names: Sequence[bytes], gid=None):
+        """bases: uint8, all contigs concatenated, upper-cased (ms_genome_upload)."""
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        self._contig_args(lengths, bpl, headers, names, gid)
+        self._check(self._lib.ms_genome_upload(self._h, _ptr(bases), self.total_bases, self.n_contigs, _ptr(self._len),
+                                               _ptr(self._bpl), _ptr(self._gid), _ptr(self._hdr), _ptr(self._hoff),
+                                               _ptr(self._nam), _ptr(self._noff)))
+
+    def adopt_genome(self, device_ptr: int, lengths, bpl, headers, names, gid=None):
+        self._contig_args(lengths, bpl, headers, names, gid)
+        self._check(self._lib.ms_genome_adopt(self._h, C.c_void_p(device_ptr), self.total_bases, self.n_contigs,
+                                              _ptr(self._len), _ptr(self._bpl), _ptr(self._gid), _ptr(self._hdr),
+                                              _ptr(self._hoff), _ptr(self._nam), _ptr(self._noff)))
+
+    def synth_genome(self, seed: int, lengths, bpl, headers, names, n_fraction=0.0, telomere_n=0):
+        self._contig_args(lengths, bpl, headers, names, None)
+        self._check(self._lib.ms_genome_synth(self._h, seed, self.n_contigs, _ptr(self._len), _ptr(self._bpl),
+                                              float(n_fraction), int(telomere_n), _ptr(self._hdr), _ptr(self._hoff),
+                                              _ptr(self._nam), _ptr(self._noff)))
+
+    def download_genome(self) -> np.ndarray:
+        out = np.empty(self.total_bases, dtype=np.uint8)
+        self._check(self._lib.ms_genome_download(self._h, _ptr(out), out.size))
+        return out
+
+    # -- sampling ----------------------------------------------------------
+    def set_ranges(self, ranges: Sequence[dict], block: Sequence[int], min_dist: int, p_ti: float):
+        """ranges: dicts with contig,start,stop,k,limit,cdf[7],minlen[7],maxlen[7] sorted by (contig,start)."""
+        arr = (MsRange * max(1, len(ranges)))()
+        for i, r in enumerate(ranges):
+            a = arr[i]
+            a.contig, a.start, a.stop, a.k, a.limit = r["contig"], r["start"], r["stop"], r["k"], r.get("limit", 0)
+            for t in range(7):
+                a.cdf[t], a.minlen[t], a.maxlen[t] = r["cdf"][t], r["minlen"][t], r["maxlen"][t]
+        blk = (C.c_int32 * 7)(*block)
+        self._check(self._lib.ms_set_ranges(self._h, arr, len(ranges), blk, int(min_dist), float(p_ti)))
+
+    def set_ranges_array(self, arr, n: int, block, min_dist: int, p_ti: float):
+        blk = (C.c_int32 * 7)(*block)
+        self._check(self._lib.ms_set_ranges(self._h, arr, n, blk, int(min_dist), float(p_ti)))
+
+    def sample(self, seed: int):
+        self._check(self._lib.ms_sample(self._h, C.c_uint64(seed & 0xFFFFFFFFFFFFFFFF)))
+
+    def debug_candidates(self):
+        n = C.c_int64()
+        self._check(self._lib.ms_debug_candidates(self._h, 0, None, None, None, None, C.byref(n)))
+        k = n.value
+        gpos = np.empty(k, np.int64); typ = np.empty(k, np.uint8); ln = np.empty(k, np.uint32); acc = np.empty(k, np.uint8)
+        self._check(self._lib.ms_debug_candidates(self._h, k, _ptr(gpos), _ptr(typ), _ptr(ln), _ptr(acc), C.byref(n)))
+        return gpos, typ, ln, acc
+
+    # -- replay / apply ----------------------------------------------------
+    def load_records(self, recs: np.ndarray, lit: Optional[np.ndarray] = None):
+        recs = np.ascontiguousarray(recs, dtype=REC_DTYPE)
+        lit = np.zeros(16, np.uint8) if lit is None else np.ascontiguousarray(lit, dtype=np.uint8)
+        nlit = int((recs["src"][recs["kind"] == 2] + recs["prod"][recs["kind"] == 2]).max()) if (recs["kind"] == 2).any() else 0
+        self._check(self._lib.ms_load_records(self._h, _ptr(recs), len(recs), _ptr(lit), max(nlit, 0)))
+
+    def apply(self) -> tuple[int, int]:
+        fb, vb = C.c_int64(), C.c_int64()
+        self._check(self._lib.ms_apply(self._h, C.byref(fb), C.byref(vb)))
+        return fb.value, vb.value
+
+    def download(self, which: int, out: Optional[np.ndarray] = None) -> np.ndarray:
+        n = C.c_int64()
+        self._check(self._lib.ms_download(self._h, which, None, 0, C.byref(n)))
+        if out is None:
+            out = np.empty(n.value, dtype=np.uint8)
+        self._check(self._lib.ms_download(self._h, which, _ptr(out), out.nbytes, C.byref(n)))
+        return out[:n.value] if out.dtype == np.uint8 else out
+
+    def fasta(self) -> bytes:
+        return self.download(BUF_FASTA).tobytes()
+
+    def vcf(self) -> bytes:
+        return self.download(BUF_VCF).tobytes()
+
+    def records(self) -> np.ndarray:
+        return self.download(BUF_RECS).view(REC_DTYPE)
+
+    def literals(self) -> np.ndarray:
+        return self.download(BUF_LIT)
+
+    def device_ptr(self, which: int) -> tuple[int, int]:
+        p, n = C.c_void_p(), C.c_int64()
+        self._check(self._lib.ms_device_ptr(self._h, which, C.byref(p), C.byref(n)))
+        return (p.value or 0), n.value
+
+    def contig_out_len(self) -> np.ndarray:
+        out = np.empty(self.n_contigs, dtype=np.int64)
+        self._check(self._lib.ms_contig_out_len(self._h, _ptr(out)))
+        return out
+
+    # -- IT ----------------------------------------------------------------
+    def it_breakpoints(self, seed: int, contig_a, contig_b, n):
+        a = np.ascontiguousarray(contig_a, dtype=np.uint32)
+        b = np.ascontiguousarray(contig_b, dtype=np.uint32)
+        n = np.ascontiguousarray(n, dtype=np.uint32)
+        tot = int(n.sum())
+        bpa = np.empty(max(tot, 1), np.uint32)
+        bpb = np.empty(max(tot, 1), np.uint32)
+        self._check(self._lib.ms_it_breakpoints(self._h, C.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), len(a), _ptr(a), _ptr(b),
+                                                _ptr(n), _ptr(bpa), _ptr(bpb)))
+        return bpa[:tot], bpb[:tot]
+
+    # -- stats -------------------------------------------------------------
+    def stats(self) -> dict:
+        s = MsStats()
+        self._check(self._lib.ms_get_stats(self._h, C.byref(s)))
+        stages = {}
+        for i in range(16):
+            name = self._lib.ms_stage_name(i)
+            if name:
+                stages[name.decode()] = float(s.stage_ms[i])
+        return {"n_candidates": s.n_candidates, "n_accepted": s.n_accepted, "n_records": s.n_records,
+                "lit_bytes": s.lit_bytes, "fasta_bytes": s.fasta_bytes, "vcf_bytes": s.vcf_bytes,
+                "kernel_launches": s.kernel_launches, "counts": list(s.counts), "stage_ms": stages}

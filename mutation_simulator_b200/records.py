@@ -30,13 +30,10 @@ def align16(n: int) -> int:
 
 
 def genome_offsets(lengths) -> np.ndarray:
-    """Index of base 0 of each contig in the padded genome array (16-byte aligned)."""
+    """Index of base 0 of each contig in the genome array (contigs are simply concatenated;
+    the device copy carries 64 pad bytes after the last base)."""
     goff = np.zeros(len(lengths) + 1, dtype=np.int64)
-    acc = 0
-    for i, n in enumerate(lengths):
-        goff[i] = acc
-        acc = align16(acc + int(n))
-    goff[len(lengths)] = acc
+    np.cumsum(np.asarray(lengths, dtype=np.int64), out=goff[1:])
     return goff
 
 

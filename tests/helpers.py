@@ -60,3 +60,44 @@ def vcf_body(text: bytes) -> bytes:
 
 def vcf_head(text: bytes) -> bytes:
     return b"".join(l for l in text.splitlines(keepends=True) if l.startswith(b"#"))
+
+
+# ---- GPU-side helpers -------------------------------------------------------------
+def engine_for(contigs, device=0):
+    """contigs: [(name, long_name, seq_upper, bpl)] -> (Engine with the genome resident, goff, lengths)"""
+    import numpy as np
+    from mutation_simulator_b200 import records as R
+    from mutation_simulator_b200.engine import Engine
+    eng = Engine(device)
+    seqs = [c[2] for c in contigs]
+    genome, goff = R.pack_genome(seqs)
+    lens = [len(s) for s in seqs]
+    eng.upload_genome(genome[:int(goff[-1])], lens, [c[3] for c in contigs], [c[1] for c in contigs], [c[0] for c in contigs])
+    return eng, genome, goff, np.array(lens)
+
+
+def recs_to_muts(recs, lit, goff):
+    """Decode device records back into per-contig lists of pyref.Mut (for the oracle)."""
+    from mutation_simulator_b200 import records as R
+    n_contigs = len(goff) - 1
+    out = [[] for _ in range(n_contigs)]
+    lit = bytes(lit.tobytes()) if hasattr(lit, "tobytes") else bytes(lit)
+    for r in recs:
+        c, pos, t = int(r["contig"]), int(r["pos"]), int(r["type"])
+        name = R.TYPE_NAME[t]
+        m = pyref.Mut(key=pos, type=name, start=pos, stop=pos)
+        if t == R.T_SN:
+            m.alt = bytes([int(r["alt"])])
+        elif t == R.T_IN:
+            m.insert = lit[int(r["src"]):int(r["src"]) + int(r["prod"])]
+            m.stop = pos + int(r["prod"]) - 1
+        elif t in (R.T_DE, R.T_TL, R.T_IV):
+            m.stop = pos + int(r["cons"]) - 1
+        elif t == R.T_DU:
+            m.stop = pos + int(r["prod"]) - 1
+        elif t == R.T_TLI:
+            m.start = int(r["src"]) - int(goff[c])
+            m.stop = m.start + int(r["prod"]) - 1
+            m.reverse = int(r["kind"]) == R.K_RC
+        out[c].append(m)
+    return out
