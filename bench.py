@@ -1,0 +1,369 @@
+#!/usr/bin/env python3
+"""bench.py — mutated genome Gbp/s on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2|c1|c5]
+
+A step = one pass of the hot path over the whole synthetic genome: sample ->
+resolve -> link -> plan -> splice/emit FASTA image -> format VCF, all on the GPU.
+`value`  : input bases / device time with the genome already resident in HBM.
+`e2e`    : the same through the C ABI with HOST buffers — pinned H2D of the genome,
+           D2H of the FASTA image and the VCF body inside the timed region.
+`roofline`: the splice/emit kernel's algorithmic bytes / its CUDA-event time vs the
+           measured HBM copy bandwidth (MEASURED_PEAKS.json).
+`cpu_baseline`: the C oracle port (oracle/ms_oracle.c) on a bounded sample, 1 thread.
+`--impl reference`: the reference's path on the host CPU = the oracle port on all host
+           threads (the reference is pure Python and cannot travel to the GPU box).
+N > 1 (torchrun): contigs are partitioned over ranks (LPT by length, no data-path
+collective); total work is fixed, so scaling is "strong".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+REPO = Path(__file__).resolve().parent
+sys.path.insert(0, str(REPO))
+
+GRCH38 = [248956422, 242193529, 198295559, 190214555, 181538259, 170805979, 159345973, 145138636, 138394717,
+          133797422, 135086622, 133275309, 114364328, 107043718, 101991189, 90338345, 83257441, 80373285,
+          58617616, 64444167, 46709983, 50818468, 156040895, 57227415]
+GRCH38_NAMES = [f"chr{i}" for i in range(1, 23)] + ["chrX", "chrY"]
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: ARGS, all mutation types, GRCh38-shaped 3.1 Gbp / 24 contigs
+    "c2": dict(desc="C2: ARGS all types (sn .01 titv 2 in/de .001 len<=10, du/iv/tl .0005 len<=50) on synthetic GRCh38-shaped 3.088 Gbp, 24 contigs",
+               lengths=GRCH38, names=GRCH38_NAMES, rates6=[0.01, 0.001, 0.001, 0.0005, 0.0005, 0.0005],
+               minlen=[1, 1, 1, 2, 1, 1, 1], maxlen=[1, 10, 10, 50, 50, 50, 50], titv=2.0, n_fraction=0.03, telomere=10000),
+    # BASELINE.json configs[0]: the reference's CPU-runnable case
+    "c1": dict(desc="C1: ARGS sn .01 in/de .001 len 1-10 on a synthetic 10 Mbp contig",
+               lengths=[10_000_000], names=["chr1"], rates6=[0.01, 0.001, 0.001, 0.0, 0.0, 0.0],
+               minlen=[1, 1, 1, 2, 1, 1, 1], maxlen=[1, 10, 10, 3, 2, 2, 2], titv=1.0, n_fraction=0.0, telomere=0),
+    # BASELINE.json configs[4]: many small contigs
+    "c5": dict(desc="C5: ARGS all types on 200k contigs x 5 kbp",
+               lengths=[5000] * 200_000, names=None, rates6=[0.01, 0.001, 0.001, 0.0005, 0.0005, 0.0005],
+               minlen=[1, 1, 1, 2, 1, 1, 1], maxlen=[1, 10, 10, 50, 50, 50, 50], titv=2.0, n_fraction=0.0, telomere=0),
+}
+
+
+def type_cdf(rates6):
+    rates = list(rates6[:5]) + [rates6[5] / 2, rates6[5] / 2]     # rmt.py:91-94
+    total = sum(rates)
+    cdf = np.cumsum(np.array(rates) / total)
+    return (cdf / cdf[-1]).tolist(), total
+
+
+def make_ranges(lengths, wl):
+    from mutation_simulator_b200._lib import MsRange
+    cdf, total = type_cdf(wl["rates6"])
+    arr = (MsRange * len(lengths))()
+    for i, L in enumerate(lengths):
+        a = arr[i]
+        a.contig, a.start, a.stop, a.k, a.limit = i, 0, L - 1, int(((L - 1) + 1) * total), L   # mutator.py:225
+        for t in range(7):
+            a.cdf[t], a.minlen[t], a.maxlen[t] = cdf[t], wl["minlen"][t], wl["maxlen"][t]
+    return arr
+
+
+def lpt_partition(lengths, n):
+    """Longest-processing-time bin packing of contigs onto n ranks."""
+    bins = [[] for _ in range(n)]
+    load = [0] * n
+    for i in sorted(range(len(lengths)), key=lambda i: -lengths[i]):
+        b = load.index(min(load))
+        bins[b].append(i)
+        load[b] += lengths[i]
+    return [sorted(b) for b in bins]
+
+
+class ClockSampler:
+    """nvidia-smi clocks line of B200_PROFILING.md, sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm = [float(r[1]) for r in rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            if len(r) >= 9:
+                for nme, v in zip(names, r[5:9]):
+                    if v.strip().lower() == "active":
+                        reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = REPO / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:  # noqa: BLE001
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---------------------------------------------------------------------------------------
+# CPU arm: the oracle port
+# ---------------------------------------------------------------------------------------
+def cpu_run(lengths, names, wl, seed, threads):
+    """One pass of the C oracle port (sample + walk + wrap + VCF) over a host genome."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import c_oracle
+    c_oracle.lib()
+    cdf, total = type_cdf(wl["rates6"])
+    rng = np.random.default_rng(12345)
+    seqs = [rng.choice(np.frombuffer(b"ACGT", np.uint8), L).tobytes() for L in lengths]
+
+    def one(i):
+        L = lengths[i]
+        r = dict(start=0, stop=L - 1, k=int(L * total), cdf=cdf, minlen=wl["minlen"], maxlen=wl["maxlen"])
+        fa, vcf, counts, _ = c_oracle.mutate_contig(seqs[i], names[i].encode(), names[i].encode(), 60, [r], [1] * 7, 1,
+                                                    wl["titv"], seed + i)
+        return len(fa) + len(vcf)
+
+    def run():
+        t0 = time.perf_counter()
+        if threads > 1:
+            with ThreadPoolExecutor(threads) as ex:
+                list(ex.map(one, range(len(lengths))))
+        else:
+            for i in range(len(lengths)):
+                one(i)
+        return time.perf_counter() - t0
+    return run
+
+
+def scaled_sample(wl, target_bases):
+    """Bounded sample of the workload: same contig count/shape, lengths scaled down."""
+    lengths = wl["lengths"]
+    tot = sum(lengths)
+    if tot <= target_bases:
+        return list(lengths), 1.0
+    f = target_bases / tot
+    return [max(1000, int(L * f)) for L in lengths], f
+
+
+def reference_arm(args, wl, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    lengths, f = scaled_sample(wl, 400_000_000)
+    names = wl["names"] or [f"ctg{i}" for i in range(len(lengths))]
+    threads = min(threads, len(lengths))
+    run = cpu_run(lengths, names, wl, 1, threads)
+    for _ in range(max(1, min(args.warmup, 1))):
+        run()
+    ts = [run() for _ in range(args.steps)]
+    t = float(np.mean(ts))
+    val = sum(lengths) / t / 1e9
+    line = {"impl": "reference", "metric": "mutated genome Gbp/s", "value": val, "unit": "Gbp/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": wl["desc"], "l2": "inputs larger than L2"},
+            "cpu_baseline": {"value": val, "unit": "Gbp/s", "cores": threads, "kind": "port",
+                             "sample": f"oracle/ms_oracle.c (C port of the reference's path; the reference itself is single-threaded "
+                                       f"Python, 9.4e-4 Gbp/s in BASELINE.md) on the workload scaled x{f:.3f} = {sum(lengths)/1e6:.0f} Mbp, "
+                                       f"one contig per thread"},
+            "e2e": {"value": val, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--verbose", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        reference_arm(args, wl, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from mutation_simulator_b200.engine import BUF_FASTA, BUF_VCF, Engine
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    lengths_all = wl["lengths"]
+    names_all = wl["names"] or [f"ctg{i}" for i in range(len(lengths_all))]
+    mine = lpt_partition(lengths_all, world)[rank] if world > 1 else list(range(len(lengths_all)))
+    lengths = [lengths_all[i] for i in mine]
+    names = [names_all[i].encode() for i in mine]
+    my_bases = sum(lengths)
+    total_bases = sum(lengths_all)
+
+    eng = Engine(local_rank)
+    stream = torch.cuda.Stream()
+    eng.set_stream(stream.cuda_stream)
+    eng.synth_genome(12345 + rank, lengths, [60] * len(lengths), names, names, wl["n_fraction"], wl["telomere"])
+    ranges = make_ranges(lengths, wl)
+    p_ti = wl["titv"] * (1 / (wl["titv"] + 1))
+    eng.set_ranges_array(ranges, len(lengths), [1] * 7, 1, p_ti)
+
+    def step(seed):
+        eng.sample(seed)
+        return eng.apply()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for w in range(args.warmup):
+        step(1000 + w)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = eng.stats()["kernel_launches"]
+    stage_acc = {}
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    t0 = time.perf_counter()
+    sizes = (0, 0)
+    for s in range(args.steps):
+        sizes = step(2000 + s)
+        if args.verbose or True:
+            st = eng.stats()
+            for k, v in st["stage_ms"].items():
+                stage_acc[k] = stage_acc.get(k, 0.0) + v
+    ev1.record(stream)
+    barrier()
+    wall = time.perf_counter() - t0
+    dev_ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    st = eng.stats()
+    launches = st["kernel_launches"] - launches0
+    t = torch.tensor([dev_ms, float(launches)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        dev_ms, launches = float(tmax[0]), int(tsum[1])
+    ms_per_step = dev_ms / args.steps
+    value = total_bases / (ms_per_step * 1e-3) / 1e9
+
+    # roofline of the dominant kernel (splice + SNP + line wrap -> FASTA image), rank 0's share
+    recs_n = st["n_records"]
+    fasta_bytes, vcf_bytes = sizes
+    hdr_bytes = sum(len(n) + 2 for n in names)
+    counts = st["counts"]
+    splice_ms = stage_acc.get("splice_emit_fasta", 0.0) / args.steps
+    tli_src = 25.5 * counts[6] if wl["maxlen"][5] == 50 else 0.0          # E[len] of the TLI gathers
+    alg_bytes = my_bases + (fasta_bytes - hdr_bytes) + 32 * recs_n + tli_src
+    peak, peak_src = measured_peak()
+    achieved = alg_bytes / (splice_ms * 1e-3) / 1e9 if splice_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "k_splice", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src,
+                "alg_bytes_per_launch": alg_bytes, "kernel_ms": splice_ms,
+                "all_kernels_frac": ((my_bases + fasta_bytes + vcf_bytes + 64 * recs_n) / (ms_per_step * 1e-3) / 1e9) / peak}
+
+    # e2e: HOST buffers through the C ABI
+    e2e = None
+    if not args.no_e2e:
+        g = torch.empty(my_bases, dtype=torch.uint8, pin_memory=True)
+        gn = g.numpy()
+        gn[:] = eng.download_genome()
+        fa_host = torch.empty(int(fasta_bytes * 1.02) + 4096, dtype=torch.uint8, pin_memory=True).numpy()
+        vcf_host = torch.empty(int(vcf_bytes * 1.05) + 4096, dtype=torch.uint8, pin_memory=True).numpy()
+        n_e2e = max(2, min(args.steps, 4))
+
+        def e2e_step(seed):
+            eng.upload_genome(gn, lengths, [60] * len(lengths), names, names, gid=mine)
+            eng.set_ranges_array(ranges, len(lengths), [1] * 7, 1, p_ti)
+            eng.sample(seed)
+            fb, vb = eng.apply()
+            eng.download(BUF_FASTA, fa_host)
+            eng.download(BUF_VCF, vcf_host)
+            return fb, vb
+        e2e_step(1)
+        barrier()
+        t0 = time.perf_counter()
+        for s in range(n_e2e):
+            fb, vb = e2e_step(3000 + s)
+        barrier()
+        dt = (time.perf_counter() - t0) / n_e2e
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": total_bases / float(tt[0]) / 1e9, "unit": "Gbp/s", "h2d_bytes_per_step": int(my_bases),
+               "d2h_bytes_per_step": int(fb + vb), "steps": n_e2e, "ms_per_step": float(tt[0]) * 1e3,
+               "note": "per-rank bytes; pinned host genome in, FASTA image + VCF body out"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        lens_s, f = scaled_sample(wl, 200_000_000)
+        nm = wl["names"] or [f"ctg{i}" for i in range(len(lens_s))]
+        run = cpu_run(lens_s, nm, wl, 1, 1)
+        tcpu = run()
+        cpu = {"value": sum(lens_s) / tcpu / 1e9, "unit": "Gbp/s", "cores": 1, "kind": "port",
+               "sample": f"oracle/ms_oracle.c, 1 thread, workload scaled x{f:.3f} = {sum(lens_s)/1e6:.0f} Mbp in {tcpu:.1f} s "
+                         f"(host has {os.cpu_count()} cores; the Python reference itself ran 9.4e-4 Gbp/s, BASELINE.md)"}
+
+    if rank == 0:
+        line = {"metric": "mutated genome Gbp/s", "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": {"workload": wl["desc"], "partition": f"contigs LPT over {world} rank(s)",
+                           "l2": "inputs (>=1 GB per rank) larger than the 126 MB L2; fresh seed every step",
+                           "timing": "CUDA events on the engine's stream, max over ranks"},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                "stage_ms": {k: v / args.steps for k, v in stage_acc.items()},
+                "records_per_step": int(recs_n), "wall_ms_per_step": wall / args.steps * 1e3}
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
