@@ -164,6 +164,131 @@ struct LoadWinGlobal {
     }
 };
 
+// Warp-cooperative vector path.  A warp owns 32 consecutive 16-byte groups (512 bytes
+// of the file image).  The records that can govern those bytes are loaded once, one
+// per lane, and every lookup is a shuffle, so control flow stays warp-uniform (the
+// per-thread record walk of group_fast() diverged to ~12 active lanes per
+// instruction, profiles/r1a).  Falls back to the generic queue when the span holds
+// more than 32 records or a group is not a plain shifted copy (+ <= 2 SNPs).
+__device__ __forceinline__ bool warp_fast_groups(const SpliceView& v, const Contig& k, bool full, uint32_t q0, int lane, uint32_t w[4]) {
+    const uint32_t FULL = 0xffffffffu;
+    const uint32_t bpl = (uint32_t)k.bpl, w1 = bpl + 1u;
+    const uint32_t line = q0 / w1;
+    const uint32_t col = q0 - line * w1;
+    const uint32_t j = bpl - col;                 // lane of the line break inside the group (if < 16)
+    const uint32_t nb = (j < 16u) ? 15u : 16u;
+    const uint32_t bF = q0 - line, bL = bF + nb - 1u;
+    const uint32_t fmask = __ballot_sync(FULL, full);
+    if (fmask == 0u) return false;
+    const uint32_t bFmin = __shfl_sync(FULL, bF, __ffs(fmask) - 1);
+    const uint32_t bLmax = __shfl_sync(FULL, bL, 31 - __clz(fmask));
+
+    // one record per lane, starting at the last record before the coarse block of bFmin
+    const int64_t r_base = k.rec_lo + (int64_t)__ldg(v.blk + k.blk_lo + (bFmin >> BLK_SHIFT)) - 1;
+    const int64_t my = r_base + lane;
+    uint32_t r_out, r_prod = 0u, r_run = 0u, r_ka = K_NONE;
+    int64_t r_src = 0;
+    if (my >= k.rec_lo && my < k.rec_hi) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(v.recs + my));
+        const uint4 b = __ldg(reinterpret_cast<const uint4*>(v.recs + my) + 1);
+        r_out = a.w; r_prod = a.z; r_run = a.x + a.y;          // pos + cons
+        r_src = (int64_t)(((uint64_t)b.y << 32) | b.x);
+        r_ka = (b.z & 0xffu) | ((b.z >> 16) & 0xff00u);          // kind | alt << 8
+    } else {
+        r_out = my < k.rec_lo ? 0u : 0xffffffffu;                // virtual record before the first / sentinel after the last
+    }
+    if (__shfl_sync(FULL, r_out, 31) <= bLmax) return false;    // span holds more than 32 records
+
+    const int n_need = __popc(__ballot_sync(FULL, r_out <= bLmax));   // sorted: these are lanes 0..n_need-1
+    int cnt = 0;
+    for (int t = 0; t < n_need; ++t) cnt += (__shfl_sync(FULL, r_out, t) <= bF) ? 1 : 0;
+    const int gl = cnt > 0 ? cnt - 1 : 0;                        // lane holding the governing record (cnt >= 1 for full lanes)
+    const uint32_t g_out = __shfl_sync(FULL, r_out, gl);
+    const uint32_t g_prod = __shfl_sync(FULL, r_prod, gl);
+    const uint32_t g_run = __shfl_sync(FULL, r_run, gl);
+    const uint32_t g_ka = __shfl_sync(FULL, r_ka, gl);
+    const uint32_t g_slo = __shfl_sync(FULL, (uint32_t)r_src, gl);
+    const uint32_t g_shi = __shfl_sync(FULL, (uint32_t)((uint64_t)r_src >> 32), gl);
+
+    bool clean = full;
+    bool scan_next = true;
+    uint32_t patch0 = 0xffu, patch1 = 0xffu;                     // lane | alt << 8, 0xff = none
+    int64_t src0;
+    const uint32_t rel = bF - g_out;
+    if (rel < g_prod) {
+        const uint32_t kind = g_ka & 0xffu;
+        if (kind == K_RAW && rel + nb <= g_prod) {
+            src0 = (int64_t)(((uint64_t)g_shi << 32) | g_slo) + rel;
+            scan_next = false;
+        } else if (kind == K_SNP) {
+            src0 = k.goff + (int64_t)g_run - 1;                   // SNP: pos = run - 1
+            patch0 = g_ka & 0xff00u;                              // lane 0
+        } else {
+            src0 = 0; clean = false;
+        }
+    } else {
+        src0 = k.goff + (int64_t)g_run + (int64_t)(rel - g_prod);
+    }
+    for (int t = 1; t < 32; ++t) {
+        const int nl = (gl + t) & 31;
+        const uint32_t o = __shfl_sync(FULL, r_out, nl);
+        const uint32_t ka = __shfl_sync(FULL, r_ka, nl);
+        const bool in = clean && scan_next && (gl + t < 32) && o <= bL;
+        if (!__any_sync(FULL, in)) break;
+        if (in) {
+            if ((ka & 0xffu) == K_SNP && patch1 == 0xffu) {
+                const uint32_t pv = (o - bF) | (ka & 0xff00u);
+                if (patch0 == 0xffu) patch0 = pv; else patch1 = pv;
+            } else {
+                clean = false;
+            }
+        }
+    }
+    if (!clean) return false;
+
+    // 16 (unaligned) source bytes
+    const uint4 wa = __ldg(reinterpret_cast<const uint4*>(v.genome + (src0 & ~(int64_t)15)));
+    const uint4 wb = __ldg(reinterpret_cast<const uint4*>(v.genome + (src0 & ~(int64_t)15) + 16));
+    const uint32_t o = (uint32_t)(src0 & 15);
+    const uint32_t bs = (o & 3u) * 8u;
+    uint32_t u0, u1, u2, u3, u4;
+    {   // word-level barrel shift by o>>2 (two select stages), then a byte-level funnel shift
+        const bool s2 = (o & 8u) != 0u, s1 = (o & 4u) != 0u;
+        const uint32_t t0 = s2 ? wa.z : wa.x, t1 = s2 ? wa.w : wa.y, t2 = s2 ? wb.x : wa.z, t3 = s2 ? wb.y : wa.w,
+                       t4 = s2 ? wb.z : wb.x, t5 = s2 ? wb.w : wb.y;
+        u0 = s1 ? t1 : t0; u1 = s1 ? t2 : t1; u2 = s1 ? t3 : t2; u3 = s1 ? t4 : t3; u4 = s1 ? t5 : t4;
+    }
+    uint32_t x0 = __funnelshift_r(u0, u1, bs), x1 = __funnelshift_r(u1, u2, bs), x2 = __funnelshift_r(u2, u3, bs),
+             x3 = __funnelshift_r(u3, u4, bs);
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        const uint32_t pv = p ? patch1 : patch0;
+        if ((pv & 0xffu) != 0xffu) {
+            const uint32_t t = pv & 0xffu, sh = (t & 3u) * 8u, m = ~(0xFFu << sh), val = (pv >> 8) << sh, wq = t >> 2;
+            x0 = wq == 0u ? (x0 & m) | val : x0;
+            x1 = wq == 1u ? (x1 & m) | val : x1;
+            x2 = wq == 2u ? (x2 & m) | val : x2;
+            x3 = wq == 3u ? (x3 & m) | val : x3;
+        }
+    }
+    if (j >= 16u) {
+        w[0] = x0; w[1] = x1; w[2] = x2; w[3] = x3;
+        return true;
+    }
+    // insert '\n' at lane j: lanes below keep x, lanes above take the byte one lane earlier
+    const uint32_t s0 = x0 << 8, s1 = __funnelshift_l(x0, x1, 8), s2 = __funnelshift_l(x1, x2, 8), s3 = __funnelshift_l(x2, x3, 8);
+    const uint32_t jw = j >> 2, t = j & 3u;
+    const uint32_t keep = t ? (0xFFFFFFFFu >> (32u - 8u * t)) : 0u;
+    const uint32_t nlm = 0xFFu << (8u * t);
+    const uint32_t hi = ~(keep | nlm);
+    const uint32_t nlv = 0x0Au << (8u * t);
+    w[0] = jw > 0u ? x0 : (x0 & keep) | nlv | (s0 & hi);
+    w[1] = jw > 1u ? x1 : (jw < 1u ? s1 : (x1 & keep) | nlv | (s1 & hi));
+    w[2] = jw > 2u ? x2 : (jw < 2u ? s2 : (x2 & keep) | nlv | (s2 & hi));
+    w[3] = jw < 3u ? s3 : (x3 & keep) | nlv | (s3 & hi);
+    return true;
+}
+
 __global__ void __launch_bounds__(SPLICE_THREADS)
 k_splice(SpliceView v, const Contig* contigs, int32_t n_contigs, const int64_t* piece_lo, const Tables* tables,
          uint8_t* fasta, int64_t tile_bytes) {
@@ -171,7 +296,7 @@ k_splice(SpliceView v, const Contig* contigs, int32_t n_contigs, const int64_t* 
     __shared__ uint16_t dirty[MAX_TILE_GROUPS];
     __shared__ int n_dirty;
     __shared__ uint8_t s_conv[256], s_comp[256];
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int64_t p = blockIdx.x;
     if (tid == 0) {
         int lo = 0, hi = n_contigs;  // last c with piece_lo[c] <= p
@@ -194,19 +319,28 @@ k_splice(SpliceView v, const Contig* contigs, int32_t n_contigs, const int64_t* 
     if (f_hi > k.body_off + k.body_bytes) f_hi = k.body_off + k.body_bytes;
     const int64_t g0 = f_lo & ~(int64_t)15;
     const int ngroups = (int)((f_hi - g0 + 15) >> 4);
-    const LoadWinGlobal loader{v.genome};
+    const bool vec_ok = k.bpl >= 16;   // at most one line break per group
 
-    for (int gi = tid; gi < ngroups; gi += SPLICE_THREADS) {
+    for (int gbase = tid - lane; gbase < ngroups; gbase += SPLICE_THREADS) {   // warp-uniform trip count
+        const int gi = gbase + lane;
         const int64_t g = g0 + ((int64_t)gi << 4);
+        const bool in_piece = gi < ngroups;
+        const bool full = in_piece && g >= f_lo && g + 16 <= f_hi;
         bool done = false;
-        if (g >= f_lo && g + 16 <= f_hi) {
+        if (vec_ok) {
             uint32_t w[4];
-            if (group_fast(v, k, (uint32_t)(g - k.body_off), w, loader)) {
-                *reinterpret_cast<uint4*>(fasta + g) = make_uint4(w[0], w[1], w[2], w[3]);
-                done = true;
-            }
+            done = warp_fast_groups(v, k, full, full ? (uint32_t)(g - k.body_off) : 0u, lane, w);
+            if (done) *reinterpret_cast<uint4*>(fasta + g) = make_uint4(w[0], w[1], w[2], w[3]);
         }
-        if (!done) dirty[atomicAdd(&n_dirty, 1)] = (uint16_t)gi;
+        const bool push = in_piece && !done;
+        const uint32_t pm = __ballot_sync(0xffffffffu, push);
+        if (pm) {
+            int base = 0;
+            const int leader = __ffs(pm) - 1;
+            if (lane == leader) base = atomicAdd(&n_dirty, __popc(pm));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (push) dirty[base + __popc(pm & ((1u << lane) - 1u))] = (uint16_t)gi;
+        }
     }
     __syncthreads();
     const int nd = n_dirty;
@@ -220,8 +354,8 @@ k_splice(SpliceView v, const Contig* contigs, int32_t n_contigs, const int64_t* 
             *reinterpret_cast<uint4*>(fasta + g) = make_uint4(w[0], w[1], w[2], w[3]);
         } else {
             for (int64_t x = a; x < b; ++x) {
-                const int lane = (int)(x - g);
-                fasta[x] = (uint8_t)(w[lane >> 2] >> (8 * (lane & 3)));
+                const int ln = (int)(x - g);
+                fasta[x] = (uint8_t)(w[ln >> 2] >> (8 * (ln & 3)));
             }
         }
     }
@@ -241,20 +375,45 @@ __global__ void k_headers(const Contig* contigs, int32_t n_contigs, const uint8_
 }
 
 // ---- K7: VCF lines -----------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+// One CTA formats 256 consecutive records.  Their lines are contiguous in the output,
+// so they are assembled in shared memory (placed at the same offset mod 16 as the
+// destination) and written out with aligned 16-byte stores; a CTA whose lines exceed
+// the staging buffer (long REF/ALT strings) writes straight to global memory.
+constexpr int VCF_THREADS = 256;
+constexpr int VCF_SMEM = 40 * 1024;
+
+__global__ void __launch_bounds__(VCF_THREADS)
 k_vcf_write(VcfView v, const Rec* recs, int64_t n_recs, const Contig* contigs, const Tables* tables, const int64_t* V, uint8_t* vcf) {
     __shared__ uint8_t s_conv[256], s_comp[256];
-    s_conv[threadIdx.x] = tables->conv[threadIdx.x];
-    s_comp[threadIdx.x] = tables->comp[threadIdx.x];
-    __syncthreads();
+    extern __shared__ __align__(16) uint8_t buf[];
+    const int tid = threadIdx.x;
+    s_conv[tid] = tables->conv[tid];
+    s_comp[tid] = tables->comp[tid];
     v.conv = s_conv; v.comp = s_comp;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_recs) return;
-    const int64_t a = V[i], b = V[i + 1];
-    if (b == a) return;
-    const Rec r = recs[i];
-    WriteSink s{vcf + a};
-    vcf_emit(s, v, contigs[r.contig], r);
+    const int64_t i0 = (int64_t)blockIdx.x * VCF_THREADS;
+    const int64_t i1 = i0 + VCF_THREADS < n_recs ? i0 + VCF_THREADS : n_recs;
+    const int64_t base = V[i0], end = V[i1];
+    const uint32_t shift = (uint32_t)(base & 15);
+    const bool staged = (end - base) + shift <= VCF_SMEM;
+    __syncthreads();
+    const int64_t i = i0 + tid;
+    if (i < i1) {
+        const int64_t a = V[i], b = V[i + 1];
+        if (b > a) {
+            const Rec r = recs[i];
+            WriteSink s{staged ? buf + shift + (a - base) : vcf + a};
+            vcf_emit(s, v, contigs[r.contig], r);
+        }
+    }
+    if (!staged) return;
+    __syncthreads();
+    int64_t al = (base + 15) & ~(int64_t)15;         // first 16-aligned destination offset
+    if (al > end) al = end;
+    const int64_t ah = al + ((end - al) & ~(int64_t)15);
+    for (int64_t x = base + tid; x < al; x += VCF_THREADS) vcf[x] = buf[shift + (x - base)];
+    for (int64_t x = al + 16 * (int64_t)tid; x < ah; x += 16 * VCF_THREADS)
+        *reinterpret_cast<uint4*>(vcf + x) = *reinterpret_cast<const uint4*>(buf + shift + (x - base));
+    for (int64_t x = ah + tid; x < end; x += VCF_THREADS) vcf[x] = buf[shift + (x - base)];
 }
 
 __global__ void k_store_total2(const I64x2* total, int64_t* S_end, int64_t* V_end) {
@@ -341,7 +500,9 @@ int apply_pipeline(ms_ctx* c) {
 
     stage_begin(c, ST_VCF);
     if (M > 0) {
-        k_vcf_write<<<(unsigned)ceil_div(M, 256), 256, 0, st>>>(vv, d_recs, M, d_contigs, d_tab, V, c->vcf.as<uint8_t>());
+        static bool attr_set = false;
+        if (!attr_set) { MS_CUDA(c, cudaFuncSetAttribute(k_vcf_write, cudaFuncAttributeMaxDynamicSharedMemorySize, VCF_SMEM + 32)); attr_set = true; }
+        k_vcf_write<<<(unsigned)ceil_div(M, VCF_THREADS), VCF_THREADS, VCF_SMEM + 32, st>>>(vv, d_recs, M, d_contigs, d_tab, V, c->vcf.as<uint8_t>());
         MS_LAUNCH_CHECK(c);
     }
     MS_CUDA(c, cudaMemcpyAsync(c->h_totals, d_tot, sizeof(Totals), cudaMemcpyDeviceToHost, st));

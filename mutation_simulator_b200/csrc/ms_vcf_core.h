@@ -31,12 +31,20 @@ struct WriteSink {
     static constexpr bool counting = false;
 };
 
-template <class S> MS_HD void put_uint(S& s, uint64_t v) {
-    char buf[20];
-    int n = 0;
-    do { buf[n++] = (char)('0' + (v % 10)); v /= 10; } while (v);
-    if constexpr (S::counting) s.skip((uint32_t)n);
-    else while (n) s.put((uint8_t)buf[--n]);
+MS_HD uint32_t ndigits(uint32_t v) {
+    return v < 10u ? 1u : v < 100u ? 2u : v < 1000u ? 3u : v < 10000u ? 4u : v < 100000u ? 5u : v < 1000000u ? 6u
+         : v < 10000000u ? 7u : v < 100000000u ? 8u : v < 1000000000u ? 9u : 10u;
+}
+
+// every POS / END / SVLEN of this build is < 2^32 (contigs < 2^31 bases)
+template <class S> MS_HD void put_uint(S& s, uint32_t v) {
+    if constexpr (S::counting) s.skip(ndigits(v));
+    else {
+        char buf[10];
+        int n = 0;
+        do { const uint32_t q = v / 10u; buf[n++] = (char)('0' + (v - q * 10u)); v = q; } while (v);
+        while (n) s.put((uint8_t)buf[--n]);
+    }
 }
 
 template <class S> MS_HD void put_str(S& s, const char* t, int n) {
@@ -85,7 +93,7 @@ MS_HD bool vcf_omitted(const VcfView& v, const Contig& c, const Rec& r) {
     }
 }
 
-template <class S> MS_HD void put_info(S& s, const char* sv, int svn, uint64_t end, uint64_t len) {
+template <class S> MS_HD void put_info(S& s, const char* sv, int svn, uint32_t end, uint32_t len) {
     put_str(s, "SVTYPE=", 7); put_str(s, sv, svn);
     put_str(s, ";END=", 5); put_uint(s, end);
     put_str(s, ";SVLEN=", 7); put_uint(s, len);
@@ -94,18 +102,18 @@ template <class S> MS_HD void put_info(S& s, const char* sv, int svn, uint64_t e
 // Emits the whole line (caller has checked vcf_omitted).
 template <class S> MS_HD void vcf_emit(S& s, const VcfView& v, const Contig& c, const Rec& r) {
     const int64_t g0 = c.goff;
-    const uint64_t p = r.pos;
+    const uint32_t p = r.pos;
     if constexpr (S::counting) s.skip((uint32_t)c.name_len);
     else for (int i = 0; i < c.name_len; ++i) s.put(v.names[c.name_src + i]);
     s.put('\t');
-    const char* sv = ""; int svn = 0; uint64_t pos1 = 0, end = 0, svlen = 0;
+    const char* sv = ""; int svn = 0; uint32_t pos1 = 0, end = 0, svlen = 0;
     // POS first, REF/ALT below
     switch (r.type) {
         case T_SN: pos1 = p + 1; break;
         case T_IN: pos1 = p > 0 ? p : 1; end = pos1; svlen = r.prod; sv = "INS"; svn = 3; break;
         case T_TLI: pos1 = p > 0 ? p : 1; end = pos1; svlen = r.prod; sv = "INS:ME"; svn = 6; break;
         case T_DE: case T_TL:
-            pos1 = p > 0 ? p : 1; end = p > 0 ? p + r.cons : (uint64_t)r.cons + 1; svlen = r.cons;
+            pos1 = p > 0 ? p : 1; end = p > 0 ? p + r.cons : r.cons + 1u; svlen = r.cons;
             if (r.type == T_DE) { sv = "DEL"; svn = 3; } else { sv = "DEL:ME"; svn = 6; }
             break;
         case T_IV: pos1 = p + 1; end = p + r.cons; svlen = 0; sv = "INV"; svn = 3; break;
