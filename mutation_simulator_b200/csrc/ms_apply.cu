@@ -379,30 +379,208 @@ __global__ void k_headers(const Contig* contigs, int32_t n_contigs, const uint8_
 // so they are assembled in shared memory (placed at the same offset mod 16 as the
 // destination) and written out with aligned 16-byte stores; a CTA whose lines exceed
 // the staging buffer (long REF/ALT strings) writes straight to global memory.
+//
+// Emission is data driven: every record type runs the same instruction stream over a
+// table of up to four sequence segments (REF, ALT1..3), so a warp does not serialise
+// over the type switch of vcf_emit(); segments longer than one byte are queued as
+// copy jobs and moved by whole warps afterwards (profiles/r1b: the per-byte REF/ALT
+// loops ran on 1.5 lanes and were half of all instructions).
 constexpr int VCF_THREADS = 256;
-constexpr int VCF_SMEM = 40 * 1024;
+constexpr int VCF_SMEM = 32 * 1024;
+constexpr int VCF_MAX_JOBS = 2 * VCF_THREADS;
+enum SegMode : uint32_t { SM_IMM = 0, SM_RAW = 1, SM_CONV = 2, SM_RC = 3, SM_LIT = 4 };
+struct Seg { int64_t src; uint32_t len; uint32_t mode; };
+struct CopyJob { int64_t src; uint32_t dst; uint32_t len_mode; };   // len | mode << 29
+
+__device__ __forceinline__ uint8_t seg_byte(const VcfView& v, uint32_t mode, int64_t src, uint32_t len, uint32_t i) {
+    switch (mode) {
+        case SM_IMM:  return (uint8_t)src;
+        case SM_RAW:  return v.genome[src + i];
+        case SM_CONV: return v.conv[v.genome[src + i]];
+        case SM_RC:   return v.comp[v.conv[v.genome[src + (int64_t)(len - 1 - i)]]];
+        default:      return v.lit[src + i];
+    }
+}
+
+__device__ __forceinline__ uint8_t* put_u32(uint8_t* p, uint32_t v) {
+    const uint32_t n = ndigits(v);
+    uint8_t* e = p + n;
+    uint8_t* q = e;
+    do { const uint32_t d = v / 10u; *--q = (uint8_t)('0' + (v - d * 10u)); v = d; } while (v);
+    return e;
+}
+
+__device__ __forceinline__ uint8_t* put_lit(uint8_t* p, const char* t, int n) {
+    for (int i = 0; i < n; ++i) p[i] = (uint8_t)t[i];
+    return p + n;
+}
+
+// Segment table of one record: mutator.py:334-421 (REF/ALT per type).
+__device__ __forceinline__ void vcf_segments(const VcfView& v, const Contig& c, const Rec& r, Seg sg[4], uint32_t& pos1, uint32_t& end,
+                                             uint32_t& svlen, uint32_t& svt) {
+    const int64_t g0 = c.goff;
+    const uint32_t p = r.pos;
+    const Seg none{0, 0u, SM_IMM};
+    sg[0] = sg[1] = sg[2] = sg[3] = none;
+    const uint32_t pmode = r.kind == K_LIT ? SM_LIT : r.kind == K_RAW ? SM_RAW : r.kind == K_CONV ? SM_CONV : SM_RC;
+    switch (r.type) {
+        case T_SN:
+            pos1 = p + 1u; end = 0u; svlen = 0u; svt = 0u;
+            sg[0] = Seg{(int64_t)r.ref, 1u, SM_IMM}; sg[1] = Seg{(int64_t)r.alt, 1u, SM_IMM};
+            break;
+        case T_IN: case T_TLI: {
+            pos1 = p > 0u ? p : 1u; end = pos1; svlen = r.prod; svt = r.type == T_IN ? 1u : 6u;
+            const Seg anchor{g0 + (p > 0u ? (int64_t)p - 1 : 0), 1u, SM_CONV};
+            const Seg pay{r.src, r.prod, pmode};
+            sg[0] = anchor;
+            if (p > 0u) { sg[1] = anchor; sg[2] = pay; } else { sg[1] = pay; sg[2] = anchor; }
+        } break;
+        case T_DE: case T_TL: {
+            pos1 = p > 0u ? p : 1u; end = p > 0u ? p + r.cons : r.cons + 1u; svlen = r.cons; svt = r.type == T_DE ? 2u : 5u;
+            if (p > 0u) {
+                sg[0] = Seg{g0 + (int64_t)p - 1, r.cons + 1u, SM_CONV};
+                sg[1] = Seg{g0 + (int64_t)p - 1, 1u, SM_CONV};
+            } else {
+                uint32_t rl = r.cons + 1u;
+                if ((int64_t)rl > c.len) rl = (uint32_t)c.len;
+                sg[0] = Seg{g0, rl, SM_CONV};
+                sg[1] = Seg{g0 + (int64_t)rl - 1, 1u, SM_CONV};
+            }
+        } break;
+        case T_IV:
+            pos1 = p + 1u; end = p + r.cons; svlen = 0u; svt = 3u;
+            sg[0] = Seg{g0 + (int64_t)p, r.cons, SM_CONV}; sg[1] = Seg{g0 + (int64_t)p, r.cons, SM_RC};
+            break;
+        default:  // T_DU
+            pos1 = p + 1u; end = p + r.prod; svlen = r.prod; svt = 4u;
+            sg[0] = sg[1] = sg[2] = Seg{g0 + (int64_t)p, r.prod, SM_RAW};
+            break;
+    }
+}
+
+template <bool STAGED>
+__device__ __forceinline__ void vcf_emit_uniform(const VcfView& v, const Contig& c, const Rec& r, uint8_t* line0, uint8_t* p,
+                                                 CopyJob* jobs, int* n_jobs) {
+    Seg sg[4];
+    uint32_t pos1, end, svlen, svt;
+    vcf_segments(v, c, r, sg, pos1, end, svlen, svt);
+    for (int i = 0; i < c.name_len; ++i) p[i] = v.names[c.name_src + i];
+    p += c.name_len;
+    *p++ = '\t';
+    p = put_u32(p, pos1);
+    p = put_lit(p, "\t.\t", 3);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if (q == 1) *p++ = '\t';
+        const Seg g = sg[q];
+        if (g.len <= 3u) {
+            for (uint32_t i = 0; i < g.len; ++i) *p++ = seg_byte(v, g.mode, g.src, g.len, i);
+        } else {
+            const int slot = atomicAdd(n_jobs, 1);
+            if (slot < VCF_MAX_JOBS) jobs[slot] = CopyJob{g.src, (uint32_t)(p - line0), g.len | (g.mode << 29)};
+            else for (uint32_t i = 0; i < g.len; ++i) p[i] = seg_byte(v, g.mode, g.src, g.len, i);   // queue full (never at sane densities)
+            p += g.len;
+        }
+    }
+    p = put_lit(p, "\t.\t.\t", 5);
+    if (svt == 0u) {
+        *p++ = '.';
+    } else {
+        const char* names = "INS\0\0\0\0\0DEL\0\0\0\0\0INV\0\0\0\0\0DUP\0\0\0\0\0DEL:ME\0\0INS:ME\0\0";
+        const char* nm = names + 8 * (svt - 1u);
+        p = put_lit(p, "SVTYPE=", 7);
+        const int nn = svt >= 5u ? 6 : 3;
+        p = put_lit(p, nm, nn);
+        p = put_lit(p, ";END=", 5);
+        p = put_u32(p, end);
+        p = put_lit(p, ";SVLEN=", 7);
+        p = put_u32(p, svlen);
+    }
+    put_lit(p, "\tGT\t1\n", 6);
+}
 
 __global__ void __launch_bounds__(VCF_THREADS)
 k_vcf_write(VcfView v, const Rec* recs, int64_t n_recs, const Contig* contigs, const Tables* tables, const int64_t* V, uint8_t* vcf) {
     __shared__ uint8_t s_conv[256], s_comp[256];
+    __shared__ int n_jobs, n_sv;
+    __shared__ uint8_t sv_list[VCF_THREADS];
+    __shared__ CopyJob jobs[VCF_MAX_JOBS];
     extern __shared__ __align__(16) uint8_t buf[];
     const int tid = threadIdx.x;
     s_conv[tid] = tables->conv[tid];
     s_comp[tid] = tables->comp[tid];
+    if (tid == 0) { n_jobs = 0; n_sv = 0; }
     v.conv = s_conv; v.comp = s_comp;
     const int64_t i0 = (int64_t)blockIdx.x * VCF_THREADS;
     const int64_t i1 = i0 + VCF_THREADS < n_recs ? i0 + VCF_THREADS : n_recs;
     const int64_t base = V[i0], end = V[i1];
     const uint32_t shift = (uint32_t)(base & 15);
     const bool staged = (end - base) + shift <= VCF_SMEM;
+    uint8_t* line0 = staged ? buf + shift : vcf + base;   // byte 0 of this CTA's lines
     __syncthreads();
     const int64_t i = i0 + tid;
+    // pass 1: SNP lines (three quarters of all records) in lock step; everything else is queued
+    bool is_sv = false;
     if (i < i1) {
         const int64_t a = V[i], b = V[i + 1];
         if (b > a) {
-            const Rec r = recs[i];
-            WriteSink s{staged ? buf + shift + (a - base) : vcf + a};
-            vcf_emit(s, v, contigs[r.contig], r);
+            const uint4 hi = __ldg(reinterpret_cast<const uint4*>(recs + i) + 1);   // src, kind/type/ref/alt, contig
+            const uint32_t type = (hi.z >> 8) & 0xffu;
+            if (type == T_SN) {
+                const uint32_t pos = __ldg(&recs[i].pos);
+                const Contig& c = contigs[hi.w];
+                uint8_t* p = staged ? buf + shift + (a - base) : vcf + a;
+                for (int q = 0; q < c.name_len; ++q) p[q] = v.names[c.name_src + q];
+                p += c.name_len;
+                *p++ = '\t';
+                p = put_u32(p, pos + 1u);
+                p[0] = '\t'; p[1] = '.'; p[2] = '\t'; p[3] = (uint8_t)(hi.z >> 16); p[4] = '\t'; p[5] = (uint8_t)(hi.z >> 24);
+                p[6] = '\t'; p[7] = '.'; p[8] = '\t'; p[9] = '.'; p[10] = '\t'; p[11] = '.'; p[12] = '\t'; p[13] = 'G'; p[14] = 'T';
+                p[15] = '\t'; p[16] = '1'; p[17] = '\n';
+            } else {
+                is_sv = true;
+            }
+        }
+    }
+    {
+        const uint32_t m = __ballot_sync(0xffffffffu, is_sv);
+        const int lane = tid & 31;
+        if (m) {
+            int b0 = 0;
+            const int leader = __ffs(m) - 1;
+            if (lane == leader) b0 = atomicAdd(&n_sv, __popc(m));
+            b0 = __shfl_sync(0xffffffffu, b0, leader);
+            if (is_sv) sv_list[b0 + __popc(m & ((1u << lane) - 1u))] = (uint8_t)tid;
+        }
+    }
+    __syncthreads();
+    // pass 2: the remaining record types, densely packed over the threads
+    for (int e = tid; e < n_sv; e += VCF_THREADS) {
+        const int64_t ii = i0 + sv_list[e];
+        const int64_t a = V[ii];
+        const Rec r = recs[ii];
+        if (staged) vcf_emit_uniform<true>(v, contigs[r.contig], r, line0, buf + shift + (a - base), jobs, &n_jobs);
+        else vcf_emit_uniform<false>(v, contigs[r.contig], r, line0, vcf + a, jobs, &n_jobs);
+    }
+    __syncthreads();
+    // pass 3: copy jobs, one warp per job; all warps together on jobs longer than 2 KiB
+    const int nj = n_jobs < VCF_MAX_JOBS ? n_jobs : VCF_MAX_JOBS;
+    const int warp = tid >> 5, lane = tid & 31;
+    bool any_big = false;
+    for (int jb = warp; jb < nj; jb += VCF_THREADS / 32) {
+        const CopyJob job = jobs[jb];
+        const uint32_t len = job.len_mode & 0x1FFFFFFFu, mode = job.len_mode >> 29;
+        if (len > 2048u) { any_big = true; continue; }
+        uint8_t* d = line0 + job.dst;
+        for (uint32_t x = lane; x < len; x += 32u) d[x] = seg_byte(v, mode, job.src, len, x);
+    }
+    if (__syncthreads_or(any_big)) {
+        for (int jb = 0; jb < nj; ++jb) {
+            const CopyJob job = jobs[jb];
+            const uint32_t len = job.len_mode & 0x1FFFFFFFu, mode = job.len_mode >> 29;
+            if (len <= 2048u) continue;
+            uint8_t* d = line0 + job.dst;
+            for (uint32_t x = tid; x < len; x += VCF_THREADS) d[x] = seg_byte(v, mode, job.src, len, x);
         }
     }
     if (!staged) return;

@@ -10,8 +10,9 @@ rows = list(csv.reader(txt.splitlines()))
 cur = None; out = []; tot = 0; tots = 0
 for r in rows:
     if r and r[0] == "File Path": cur = r[1].split("/")[-1]; continue
-    if len(r) > 9 and r[0].isdigit() and r[7].isdigit():
-        n, t, s = int(r[7]), int(r[8]), int(r[6] or 0)
+    if len(r) > 9 and r[0].isdigit():
+        I = lambda x: int(x) if x.strip().lstrip("-").isdigit() else 0
+        n, t, s = I(r[7]), I(r[8]), I(r[6])
         if n or s: out.append((n, t, s, cur, r[0], r[1].strip()[:100])); tot += n; tots += s
 print(f"kernel {kern}: {tot} warp-instructions, {tots} samples")
 for n, t, s, f, ln, src in sorted(out, key=lambda x: -x[0])[:top]:
