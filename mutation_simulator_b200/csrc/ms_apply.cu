@@ -164,148 +164,102 @@ struct LoadWinGlobal {
     }
 };
 
-// Warp-cooperative vector path.  A warp owns 32 consecutive 16-byte groups (512 bytes
-// of the file image).  The records that can govern those bytes are loaded once, one
-// per lane, and every lookup is a shuffle, so control flow stays warp-uniform (the
-// per-thread record walk of group_fast() diverged to ~12 active lanes per
-// instruction, profiles/r1a).  Falls back to the generic queue when the span holds
-// more than 32 records or a group is not a plain shifted copy (+ <= 2 SNPs).
-__device__ __forceinline__ bool warp_fast_groups(const SpliceView& v, const Contig& k, bool full, uint32_t q0, int lane, uint32_t w[4]) {
-    const uint32_t FULL = 0xffffffffu;
-    const uint32_t bpl = (uint32_t)k.bpl, w1 = bpl + 1u;
-    const uint32_t line = q0 / w1;
-    const uint32_t col = q0 - line * w1;
-    const uint32_t j = bpl - col;                 // lane of the line break inside the group (if < 16)
-    const uint32_t nb = (j < 16u) ? 15u : 16u;
-    const uint32_t bF = q0 - line, bL = bF + nb - 1u;
-    const uint32_t fmask = __ballot_sync(FULL, full);
-    if (fmask == 0u) return false;
-    const uint32_t bFmin = __shfl_sync(FULL, bF, __ffs(fmask) - 1);
-    const uint32_t bLmax = __shfl_sync(FULL, bL, 31 - __clz(fmask));
+// Run-centric splice.  SNPs do not move anything, so between two consecutive non-SNP
+// records the output is one shifted copy of the input ("run", ~290 bases at human-like
+// rates).  A CTA assembles the mutated bases of its tile in shared memory:
+//   S1  every run (and every raw payload: tandem duplications, interchromosomal
+//       segments) is a warp-level shifted copy global -> shared, 16 bytes per lane;
+//   S2  one thread per record scatters SNP bases and queues the remaining payloads
+//       (random inserts, inversions, translocation inserts) as byte jobs for warps;
+//   S3  line breaks are inserted while the tile is written out, 16 aligned bytes per
+//       lane (2 x LDS.128 -> 1 x STG.128).
+// The group-centric version it replaces spent ~490 warp-instructions per 512 bytes on
+// per-group record lookups (profiles/r1b); here lookups are per run.
+constexpr int SP_TILE_MAX = 16384;
+constexpr int SP_RUN_CAP = 512;
+constexpr int SP_SEG_CAP = 640;
+constexpr int SP_JOB_CAP = 192;
+constexpr uint32_t SP_SEG_SPLIT = 2048;
+struct SegC { int64_t src; uint32_t dst; uint32_t n; };   // copy n bytes genome[src..] -> tile[dst..]; jobs: n | kind << 24
 
-    // one record per lane, starting at the last record before the coarse block of bFmin
-    const int64_t r_base = k.rec_lo + (int64_t)__ldg(v.blk + k.blk_lo + (bFmin >> BLK_SHIFT)) - 1;
-    const int64_t my = r_base + lane;
-    uint32_t r_out, r_prod = 0u, r_run = 0u, r_ka = K_NONE;
-    int64_t r_src = 0;
-    if (my >= k.rec_lo && my < k.rec_hi) {
-        const uint4 a = __ldg(reinterpret_cast<const uint4*>(v.recs + my));
-        const uint4 b = __ldg(reinterpret_cast<const uint4*>(v.recs + my) + 1);
-        r_out = a.w; r_prod = a.z; r_run = a.x + a.y;          // pos + cons
-        r_src = (int64_t)(((uint64_t)b.y << 32) | b.x);
-        r_ka = (b.z & 0xffu) | ((b.z >> 16) & 0xff00u);          // kind | alt << 8
-    } else {
-        r_out = my < k.rec_lo ? 0u : 0xffffffffu;                // virtual record before the first / sentinel after the last
-    }
-    if (__shfl_sync(FULL, r_out, 31) <= bLmax) return false;    // span holds more than 32 records
-
-    const int n_need = __popc(__ballot_sync(FULL, r_out <= bLmax));   // sorted: these are lanes 0..n_need-1
-    int cnt = 0;
-    for (int t = 0; t < n_need; ++t) cnt += (__shfl_sync(FULL, r_out, t) <= bF) ? 1 : 0;
-    const int gl = cnt > 0 ? cnt - 1 : 0;                        // lane holding the governing record (cnt >= 1 for full lanes)
-    const uint32_t g_out = __shfl_sync(FULL, r_out, gl);
-    const uint32_t g_prod = __shfl_sync(FULL, r_prod, gl);
-    const uint32_t g_run = __shfl_sync(FULL, r_run, gl);
-    const uint32_t g_ka = __shfl_sync(FULL, r_ka, gl);
-    const uint32_t g_slo = __shfl_sync(FULL, (uint32_t)r_src, gl);
-    const uint32_t g_shi = __shfl_sync(FULL, (uint32_t)((uint64_t)r_src >> 32), gl);
-
-    bool clean = full;
-    bool scan_next = true;
-    uint32_t patch0 = 0xffu, patch1 = 0xffu;                     // lane | alt << 8, 0xff = none
-    int64_t src0;
-    const uint32_t rel = bF - g_out;
-    if (rel < g_prod) {
-        const uint32_t kind = g_ka & 0xffu;
-        if (kind == K_RAW && rel + nb <= g_prod) {
-            src0 = (int64_t)(((uint64_t)g_shi << 32) | g_slo) + rel;
-            scan_next = false;
-        } else if (kind == K_SNP) {
-            src0 = k.goff + (int64_t)g_run - 1;                   // SNP: pos = run - 1
-            patch0 = g_ka & 0xff00u;                              // lane 0
-        } else {
-            src0 = 0; clean = false;
-        }
-    } else {
-        src0 = k.goff + (int64_t)g_run + (int64_t)(rel - g_prod);
-    }
-    for (int t = 1; t < 32; ++t) {
-        const int nl = (gl + t) & 31;
-        const uint32_t o = __shfl_sync(FULL, r_out, nl);
-        const uint32_t ka = __shfl_sync(FULL, r_ka, nl);
-        const bool in = clean && scan_next && (gl + t < 32) && o <= bL;
-        if (!__any_sync(FULL, in)) break;
-        if (in) {
-            if ((ka & 0xffu) == K_SNP && patch1 == 0xffu) {
-                const uint32_t pv = (o - bF) | (ka & 0xff00u);
-                if (patch0 == 0xffu) patch0 = pv; else patch1 = pv;
-            } else {
-                clean = false;
-            }
-        }
-    }
-    if (!clean) return false;
-
-    // 16 (unaligned) source bytes
-    const uint4 wa = __ldg(reinterpret_cast<const uint4*>(v.genome + (src0 & ~(int64_t)15)));
-    const uint4 wb = __ldg(reinterpret_cast<const uint4*>(v.genome + (src0 & ~(int64_t)15) + 16));
-    const uint32_t o = (uint32_t)(src0 & 15);
+// bytes [o, o+16) of the 32-byte window (a, b)
+__device__ __forceinline__ uint4 shift16(const uint4 a, const uint4 b, uint32_t o) {
+    const bool s2 = (o & 8u) != 0u, s1 = (o & 4u) != 0u;
+    const uint32_t t0 = s2 ? a.z : a.x, t1 = s2 ? a.w : a.y, t2 = s2 ? b.x : a.z, t3 = s2 ? b.y : a.w,
+                   t4 = s2 ? b.z : b.x, t5 = s2 ? b.w : b.y;
+    const uint32_t u0 = s1 ? t1 : t0, u1 = s1 ? t2 : t1, u2 = s1 ? t3 : t2, u3 = s1 ? t4 : t3, u4 = s1 ? t5 : t4;
     const uint32_t bs = (o & 3u) * 8u;
-    uint32_t u0, u1, u2, u3, u4;
-    {   // word-level barrel shift by o>>2 (two select stages), then a byte-level funnel shift
-        const bool s2 = (o & 8u) != 0u, s1 = (o & 4u) != 0u;
-        const uint32_t t0 = s2 ? wa.z : wa.x, t1 = s2 ? wa.w : wa.y, t2 = s2 ? wb.x : wa.z, t3 = s2 ? wb.y : wa.w,
-                       t4 = s2 ? wb.z : wb.x, t5 = s2 ? wb.w : wb.y;
-        u0 = s1 ? t1 : t0; u1 = s1 ? t2 : t1; u2 = s1 ? t3 : t2; u3 = s1 ? t4 : t3; u4 = s1 ? t5 : t4;
-    }
-    uint32_t x0 = __funnelshift_r(u0, u1, bs), x1 = __funnelshift_r(u1, u2, bs), x2 = __funnelshift_r(u2, u3, bs),
-             x3 = __funnelshift_r(u3, u4, bs);
-#pragma unroll
-    for (int p = 0; p < 2; ++p) {
-        const uint32_t pv = p ? patch1 : patch0;
-        if ((pv & 0xffu) != 0xffu) {
-            const uint32_t t = pv & 0xffu, sh = (t & 3u) * 8u, m = ~(0xFFu << sh), val = (pv >> 8) << sh, wq = t >> 2;
-            x0 = wq == 0u ? (x0 & m) | val : x0;
-            x1 = wq == 1u ? (x1 & m) | val : x1;
-            x2 = wq == 2u ? (x2 & m) | val : x2;
-            x3 = wq == 3u ? (x3 & m) | val : x3;
-        }
-    }
-    if (j >= 16u) {
-        w[0] = x0; w[1] = x1; w[2] = x2; w[3] = x3;
-        return true;
-    }
-    // insert '\n' at lane j: lanes below keep x, lanes above take the byte one lane earlier
-    const uint32_t s0 = x0 << 8, s1 = __funnelshift_l(x0, x1, 8), s2 = __funnelshift_l(x1, x2, 8), s3 = __funnelshift_l(x2, x3, 8);
-    const uint32_t jw = j >> 2, t = j & 3u;
-    const uint32_t keep = t ? (0xFFFFFFFFu >> (32u - 8u * t)) : 0u;
-    const uint32_t nlm = 0xFFu << (8u * t);
-    const uint32_t hi = ~(keep | nlm);
-    const uint32_t nlv = 0x0Au << (8u * t);
-    w[0] = jw > 0u ? x0 : (x0 & keep) | nlv | (s0 & hi);
-    w[1] = jw > 1u ? x1 : (jw < 1u ? s1 : (x1 & keep) | nlv | (s1 & hi));
-    w[2] = jw > 2u ? x2 : (jw < 2u ? s2 : (x2 & keep) | nlv | (s2 & hi));
-    w[3] = jw < 3u ? s3 : (x3 & keep) | nlv | (s3 & hi);
-    return true;
+    return make_uint4(__funnelshift_r(u0, u1, bs), __funnelshift_r(u1, u2, bs), __funnelshift_r(u2, u3, bs),
+                      __funnelshift_r(u3, u4, bs));
 }
 
-__global__ void __launch_bounds__(SPLICE_THREADS)
+__device__ __forceinline__ void warp_copy_to_tile(uint8_t* tile, const uint8_t* __restrict__ genome, const SegC sg, int lane) {
+    const uint32_t d0 = sg.dst, d1 = sg.dst + sg.n;
+    const uint32_t a0 = (d0 + 15u) & ~15u, a1 = d1 & ~15u;
+    if (a0 >= a1) {   // no aligned 16-byte chunk inside: at most 30 bytes
+        const uint32_t x = d0 + lane;
+        if (x < d1) tile[x] = __ldg(genome + sg.src + lane);
+        return;
+    }
+    {   // <= 15 head bytes on lanes 0..15, <= 15 tail bytes on lanes 16..31
+        const uint32_t x = lane < 16 ? d0 + lane : a1 + (lane - 16);
+        if (x < (lane < 16 ? a0 : d1)) tile[x] = __ldg(genome + sg.src + (x - d0));
+    }
+    for (uint32_t c = a0 + 16u * lane; c < a1; c += 512u) {
+        const int64_t s = sg.src + (int64_t)(c - d0);
+        const uint4* w = reinterpret_cast<const uint4*>(genome + (s & ~(int64_t)15));
+        const uint4 wa = __ldg(w), wb = __ldg(w + 1);
+        *reinterpret_cast<uint4*>(tile + c) = shift16(wa, wb, (uint32_t)(s & 15));
+    }
+}
+
+// number of records among recs[r0 .. ) (r0 may be rec_lo-1 = the virtual record with out 0) whose out <= target,
+// minus one, as an absolute index: the last record with out <= target.
+__device__ __forceinline__ int64_t warp_last_le(const Rec* recs, const Contig& k, int64_t r0, uint32_t target, int lane) {
+    int64_t r = r0;
+    for (;;) {
+        const int64_t my = r + lane;
+        uint32_t o;
+        if (my < k.rec_lo) o = 0u;
+        else if (my < k.rec_hi) o = __ldg(&recs[my].out);
+        else o = 0xffffffffu;
+        const int cnt = __popc(__ballot_sync(0xffffffffu, o <= target && my < k.rec_hi));
+        if (cnt < 32) return r + cnt - 1;
+        r += 32;
+    }
+}
+
+__global__ void __launch_bounds__(SPLICE_THREADS, 6)
 k_splice(SpliceView v, const Contig* contigs, int32_t n_contigs, const int64_t* piece_lo, const Tables* tables,
          uint8_t* fasta, int64_t tile_bytes) {
     __shared__ Contig sc;
-    __shared__ uint16_t dirty[MAX_TILE_GROUPS];
-    __shared__ int n_dirty;
+    __shared__ __align__(16) uint8_t tile[SP_TILE_MAX + 64];
+    __shared__ SegC segs[SP_SEG_CAP];
+    __shared__ SegC jobs[SP_JOB_CAP];
+    __shared__ uint32_t nout[SP_RUN_CAP + 1], nidx[SP_RUN_CAP];
+    __shared__ uint32_t warp_tot[SPLICE_THREADS / 32];
+    __shared__ int n_segs, n_jobs, fallback;
+    __shared__ long long s_first, s_last;
     __shared__ uint8_t s_conv[256], s_comp[256];
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t p = blockIdx.x;
-    if (tid == 0) {
-        int lo = 0, hi = n_contigs;  // last c with piece_lo[c] <= p
+    if (warp == 0) {
+        // last c with piece_lo[c] <= p, by a 32-ary search (one round for a human-sized contig table)
+        int lo = 0, hi = n_contigs;
         while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (piece_lo[mid] <= p) lo = mid; else hi = mid;
+            const int step = (hi - lo + 31) >> 5;
+            const int probe = lo + step * (lane + 1);
+            const bool le = probe < hi && __ldg(piece_lo + probe) <= p;
+            const int cnt = __popc(__ballot_sync(0xffffffffu, le));   // probes are ascending: the first cnt are <= p
+            const int nlo = lo + step * cnt;
+            const int nhi = lo + step * (cnt + 1);
+            lo = nlo; hi = nhi < hi ? nhi : hi;
         }
-        sc = contigs[lo];
-        n_dirty = 0;
+        // copy the contig descriptor with the whole warp
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(contigs + lo);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&sc);
+        if (lane < (int)(sizeof(Contig) / 4)) dst[lane] = __ldg(src + lane);
+        if (lane == 0) { n_segs = 0; n_jobs = 0; fallback = 0; }
     }
     s_conv[tid] = tables->conv[tid];
     s_comp[tid] = tables->comp[tid];
@@ -313,46 +267,219 @@ k_splice(SpliceView v, const Contig* contigs, int32_t n_contigs, const int64_t* 
     const Contig& k = sc;
     v.conv = s_conv;
     v.comp = s_comp;
-    const int64_t tile = k.body_off / tile_bytes + (p - k.piece_lo);
-    int64_t f_lo = tile * tile_bytes, f_hi = f_lo + tile_bytes;
+    const int64_t tile_i = k.body_off / tile_bytes + (p - k.piece_lo);
+    int64_t f_lo = tile_i * tile_bytes, f_hi = f_lo + tile_bytes;
     if (f_lo < k.body_off) f_lo = k.body_off;
     if (f_hi > k.body_off + k.body_bytes) f_hi = k.body_off + k.body_bytes;
     const int64_t g0 = f_lo & ~(int64_t)15;
     const int ngroups = (int)((f_hi - g0 + 15) >> 4);
-    const bool vec_ok = k.bpl >= 16;   // at most one line break per group
+    const uint32_t bpl = (uint32_t)k.bpl, w1 = bpl + 1u;
+    const uint32_t q_lo = (uint32_t)(f_lo - k.body_off), q_hi = (uint32_t)(f_hi - k.body_off);
+    const uint32_t b_lo = q_lo - q_lo / w1, b_hi = q_hi - q_hi / w1;   // mutated bases [b_lo, b_hi) live in this tile
+    const Rec* recs = v.recs;
 
-    for (int gbase = tid - lane; gbase < ngroups; gbase += SPLICE_THREADS) {   // warp-uniform trip count
-        const int gi = gbase + lane;
-        const int64_t g = g0 + ((int64_t)gi << 4);
-        const bool in_piece = gi < ngroups;
-        const bool full = in_piece && g >= f_lo && g + 16 <= f_hi;
-        bool done = false;
-        if (vec_ok) {
-            uint32_t w[4];
-            done = warp_fast_groups(v, k, full, full ? (uint32_t)(g - k.body_off) : 0u, lane, w);
-            if (done) *reinterpret_cast<uint4*>(fasta + g) = make_uint4(w[0], w[1], w[2], w[3]);
+    // ---- records of the tile: [i_first, i_last], i_first = governing record of b_lo (may be the virtual rec_lo-1)
+    if (warp == 0) {
+        const int64_t r0 = k.rec_lo + (int64_t)__ldg(v.blk + k.blk_lo + (b_lo >> BLK_SHIFT)) - 1;
+        const int64_t r = warp_last_le(recs, k, r0, b_lo, lane);
+        if (lane == 0) s_first = r;
+    } else if (warp == 1) {
+        const uint32_t t = b_hi > b_lo ? b_hi - 1u : b_lo;
+        const int64_t r0 = k.rec_lo + (int64_t)__ldg(v.blk + k.blk_lo + (t >> BLK_SHIFT)) - 1;
+        const int64_t r = warp_last_le(recs, k, r0, t, lane);
+        if (lane == 0) s_last = r;
+    }
+    __syncthreads();
+    const int64_t i_first = s_first, i_last = s_last;
+    const int n_rec = (int)(i_last - i_first + 1);
+
+    // ---- pass 1: ordered list of the run-starting records (the governing one + every non-SNP record)
+    int n_runs = 0;
+    for (int base = 0; base < n_rec; base += SPLICE_THREADS) {
+        const int t = base + tid;
+        const int64_t j = i_first + t;
+        bool flag = false;
+        uint32_t o = 0u;
+        if (t < n_rec) {
+            if (j < k.rec_lo) flag = true;   // virtual record before the first one
+            else {
+                const uint4 lo4 = __ldg(reinterpret_cast<const uint4*>(recs + j));
+                const uint32_t kk = __ldg(reinterpret_cast<const uint32_t*>(recs + j) + 6) & 0xffu;
+                o = lo4.w;
+                flag = (kk != K_SNP) || t == 0;
+            }
         }
-        const bool push = in_piece && !done;
-        const uint32_t pm = __ballot_sync(0xffffffffu, push);
-        if (pm) {
-            int base = 0;
-            const int leader = __ffs(pm) - 1;
-            if (lane == leader) base = atomicAdd(&n_dirty, __popc(pm));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (push) dirty[base + __popc(pm & ((1u << lane) - 1u))] = (uint16_t)gi;
+        const uint32_t m = __ballot_sync(0xffffffffu, flag);
+        if (lane == 0) warp_tot[warp] = __popc(m);
+        __syncthreads();
+        int before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < SPLICE_THREADS / 32; ++w) { const int c = (int)warp_tot[w]; if (w < warp) before += c; total += c; }
+        if (flag) {
+            const int pos = n_runs + before + __popc(m & ((1u << lane) - 1u));
+            if (pos < SP_RUN_CAP) { nout[pos] = o; nidx[pos] = (uint32_t)t; }
+        }
+        n_runs += total;
+        __syncthreads();
+    }
+    if (n_runs > SP_RUN_CAP) { if (tid == 0) fallback = 1; n_runs = 0; }
+    if (tid == 0 && n_runs <= SP_RUN_CAP) nout[n_runs] = b_hi;
+    __syncthreads();
+
+    // ---- pass 2: copy segments of every run (raw payload + trailing shifted copy), clipped to the tile
+    for (int r = tid; r < n_runs; r += SPLICE_THREADS) {
+        const int64_t j = i_first + nidx[r];
+        uint32_t o = 0u, pr = 0u, kind = K_NONE;
+        int64_t run_src = k.goff, psrc = 0;   // source of the base right after the payload
+        if (j >= k.rec_lo) {
+            const uint4 a = __ldg(reinterpret_cast<const uint4*>(recs + j));
+            const uint4 b = __ldg(reinterpret_cast<const uint4*>(recs + j) + 1);
+            o = a.w; pr = a.z; kind = b.z & 0xffu;
+            run_src = k.goff + (int64_t)a.x + (int64_t)a.y;
+            psrc = (int64_t)(((uint64_t)b.y << 32) | b.x);
+        }
+        uint32_t end = nout[r + 1];
+        if (end > b_hi) end = b_hi;
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {
+            uint32_t lo, hi;
+            int64_t src;
+            if (part == 0) {  // raw payload [o, o+pr)
+                if (kind != K_RAW || pr == 0u) continue;
+                lo = o > b_lo ? o : b_lo;
+                hi = o + pr < b_hi ? o + pr : b_hi;
+                src = psrc + (int64_t)(lo - o);
+            } else {          // trailing run [o+pr, end)
+                lo = o + pr > b_lo ? o + pr : b_lo;
+                hi = end;
+                src = run_src + (int64_t)(lo - (o + pr));
+            }
+            while (lo < hi) {
+                const uint32_t n = hi - lo < SP_SEG_SPLIT ? hi - lo : SP_SEG_SPLIT;
+                const int slot = atomicAdd(&n_segs, 1);
+                if (slot < SP_SEG_CAP) segs[slot] = SegC{src, lo - b_lo, n}; else fallback = 1;
+                lo += n; src += n;
+            }
         }
     }
     __syncthreads();
-    const int nd = n_dirty;
-    for (int e = tid; e < nd; e += SPLICE_THREADS) {
-        const int64_t g = g0 + ((int64_t)dirty[e] << 4);
-        const int64_t a = g < f_lo ? f_lo : g;
-        const int64_t b = g + 16 > f_hi ? f_hi : g + 16;
-        uint32_t w[4] = {0u, 0u, 0u, 0u};
-        group_slow(v, k, (uint32_t)(a - k.body_off), (int)(b - a), (int)(a - g), w);
-        if (b - a == 16) {
-            *reinterpret_cast<uint4*>(fasta + g) = make_uint4(w[0], w[1], w[2], w[3]);
-        } else {
+
+    if (!fallback) {
+        // ---- S1: shifted copies, one warp per segment
+        const int ns = n_segs;
+        for (int sidx = warp; sidx < ns; sidx += SPLICE_THREADS / 32) warp_copy_to_tile(tile, v.genome, segs[sidx], lane);
+        __syncthreads();
+        // ---- S2: SNP bases and non-raw payloads
+        for (int t = tid; t < n_rec; t += SPLICE_THREADS) {
+            const int64_t j = i_first + t;
+            if (j < k.rec_lo) continue;
+            const uint4 a = __ldg(reinterpret_cast<const uint4*>(recs + j));
+            const uint4 b = __ldg(reinterpret_cast<const uint4*>(recs + j) + 1);
+            const uint32_t o = a.w, pr = a.z, kind = b.z & 0xffu;
+            if (kind == K_SNP) {
+                if (o >= b_lo && o < b_hi) tile[o - b_lo] = (uint8_t)(b.z >> 24);
+            } else if (pr > 0u && kind != K_RAW) {
+                const uint32_t lo = o > b_lo ? o : b_lo, hi = o + pr < b_hi ? o + pr : b_hi;
+                if (lo < hi) {
+                    const int64_t src = (int64_t)(((uint64_t)b.y << 32) | b.x);
+                    const uint32_t rel = lo - o, n = hi - lo;
+                    const int64_t s0 = kind == K_RC ? src + (int64_t)(pr - 1u - rel) : src + rel;   // RC walks backwards
+                    if (n <= 3u) {
+                        for (uint32_t x = 0; x < n; ++x) {
+                            const uint8_t ch = kind == K_LIT ? v.lit[s0 + x]
+                                             : kind == K_CONV ? s_conv[v.genome[s0 + x]] : s_comp[s_conv[v.genome[s0 - (int64_t)x]]];
+                            tile[lo - b_lo + x] = ch;
+                        }
+                    } else {
+                        const int slot = atomicAdd(&n_jobs, 1);
+                        if (slot < SP_JOB_CAP) jobs[slot] = SegC{s0, lo - b_lo, n | (kind << 24)};
+                        else {
+                            for (uint32_t x = 0; x < n; ++x) {
+                                const uint8_t ch = kind == K_LIT ? v.lit[s0 + x]
+                                                 : kind == K_CONV ? s_conv[v.genome[s0 + x]] : s_comp[s_conv[v.genome[s0 - (int64_t)x]]];
+                                tile[lo - b_lo + x] = ch;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        const int nj = n_jobs < SP_JOB_CAP ? n_jobs : SP_JOB_CAP;
+        for (int jb = warp; jb < nj; jb += SPLICE_THREADS / 32) {
+            const SegC job = jobs[jb];
+            const uint32_t n = job.n & 0xFFFFFFu, kind = job.n >> 24;
+            for (uint32_t x = lane; x < n; x += 32u) {
+                const uint8_t ch = kind == K_LIT ? v.lit[job.src + x]
+                                 : kind == K_CONV ? s_conv[v.genome[job.src + x]] : s_comp[s_conv[v.genome[job.src - (int64_t)x]]];
+                tile[job.dst + x] = ch;
+            }
+        }
+        __syncthreads();
+        // ---- S3: insert line breaks, write the file image
+        // line / column of a thread's groups advance by a constant per iteration: one division per thread
+        const int g_first = (int)((f_lo - g0 + 15) >> 4);                 // first full group
+        const int g_end = (int)((f_hi - g0) >> 4);                        // one past the last full group
+        if (bpl >= 16u && g_end > g_first) {
+            const uint32_t step_q = 16u * SPLICE_THREADS;
+            const uint32_t step_line = step_q / w1, step_col = step_q - step_line * w1;
+            int gi = g_first + tid;
+            uint32_t q0 = (uint32_t)(g0 - k.body_off) + ((uint32_t)gi << 4);
+            uint32_t line = q0 / w1, col = q0 - line * w1;
+            uint8_t* out = fasta + g0 + ((int64_t)gi << 4);
+            for (; gi < g_end; gi += SPLICE_THREADS) {
+                const uint32_t j = bpl - col;                             // lane of the line break (if < 16)
+                const uint32_t so = (q0 - line) - b_lo;                   // tile offset of the group's first base
+                const uint32_t* w = reinterpret_cast<const uint32_t*>(tile + (so & ~3u));
+                const uint32_t bs = (so & 3u) * 8u;
+                const uint32_t u0 = w[0], u1 = w[1], u2 = w[2], u3 = w[3], u4 = w[4];
+                uint4 y = make_uint4(__funnelshift_r(u0, u1, bs), __funnelshift_r(u1, u2, bs), __funnelshift_r(u2, u3, bs),
+                                     __funnelshift_r(u3, u4, bs));
+                if (j < 16u) {
+                    // word q of the result: untouched below the break, shifted up by one byte above it,
+                    // and a 4-way byte permute (with '\n') in the word that holds the break
+                    const uint32_t jw = j >> 2;
+                    const uint32_t t = j & 3u;
+                    // selectors for prmt(cur, '\n' word): byte t becomes '\n' (index 4), bytes above take cur[t..]
+                    const uint32_t selnl = t == 0u ? 0x2104u : t == 1u ? 0x2140u : t == 2u ? 0x2410u : 0x4210u;
+                    const uint32_t NL = 0x0Au;
+                    const uint32_t x0 = y.x, x1 = y.y, x2 = y.z, x3 = y.w;
+                    // bytes that fall off the top of the break word when '\n' is inserted
+                    const uint32_t sh1 = __byte_perm(x0, x1, 0x6543u), sh2 = __byte_perm(x1, x2, 0x6543u), sh3 = __byte_perm(x2, x3, 0x6543u);
+                    y.x = jw == 0u ? __byte_perm(x0, NL, selnl) : x0;
+                    y.y = jw > 1u ? x1 : (jw == 1u ? __byte_perm(x1, NL, selnl) : sh1);
+                    y.z = jw > 2u ? x2 : (jw == 2u ? __byte_perm(x2, NL, selnl) : sh2);
+                    y.w = jw == 3u ? __byte_perm(x3, NL, selnl) : sh3;
+                }
+                __stcs(reinterpret_cast<uint4*>(out), y);
+                out += step_q;
+                q0 += step_q;
+                line += step_line; col += step_col;
+                if (col >= w1) { col -= w1; ++line; }
+            }
+        }
+        // edge bytes of the piece (and everything when lines are shorter than a group)
+        {
+            const int64_t e0 = bpl >= 16u ? g0 + ((int64_t)g_first << 4) : f_lo;   // [f_lo, e0) and [e1, f_hi) go byte-wise
+            const int64_t e1 = bpl >= 16u ? (g_end > g_first ? g0 + ((int64_t)g_end << 4) : e0) : f_lo;
+            const int64_t n_head = (e0 < f_hi ? e0 : f_hi) - f_lo;
+            const int64_t n_tail = f_hi - (e1 > f_lo ? e1 : f_lo);
+            for (int64_t y = tid; y < n_head + (n_tail > 0 ? n_tail : 0); y += SPLICE_THREADS) {
+                const int64_t x = y < n_head ? f_lo + y : e1 + (y - n_head);
+                if (x >= f_hi) continue;
+                const uint32_t q = (uint32_t)(x - k.body_off);
+                const uint32_t ln = q / w1;
+                fasta[x] = (q - ln * w1 == bpl) ? (uint8_t)'\n' : tile[(q - ln) - b_lo];
+            }
+        }
+    } else {
+        // ---- fallback for tiles with more runs than the staging lists hold: generic per-byte path
+        for (int gi = tid; gi < ngroups; gi += SPLICE_THREADS) {
+            const int64_t g = g0 + ((int64_t)gi << 4);
+            const int64_t a = g < f_lo ? f_lo : g;
+            const int64_t b = g + 16 > f_hi ? f_hi : g + 16;
+            uint32_t w[4] = {0u, 0u, 0u, 0u};
+            group_slow(v, k, (uint32_t)(a - k.body_off), (int)(b - a), (int)(a - g), w);
             for (int64_t x = a; x < b; ++x) {
                 const int ln = (int)(x - g);
                 fasta[x] = (uint8_t)(w[ln >> 2] >> (8 * (ln & 3)));
