@@ -1,0 +1,74 @@
+"""``python -m mutation_simulator_b200`` / ``mutation-simulator``: the reference's
+entry point (__main__.py:34-107) — same modes, messages and exit codes."""
+from __future__ import annotations
+
+from timeit import default_timer as timer
+
+from . import (BedpeWriterError, ChromNotExistError, FastaDuplicateHeaderError, FastaIndexingError, FastaNotFoundError,
+               FastaWriterError, ITMutator, ITNotEnoughAvailChromsError, ItRateTooHighError, ItRateTooLowError,
+               MinimumLengthHigherThanMaximumError, MinimumLengthTooLowError, MissingLengthError, Mutator, MutSimError,
+               RangeDefinitionOutOfBoundsError, RangeOverlapError, RatesTooHighError, RatesTooLowError, RMTParseError,
+               SimulationSettings, TitvTooLowError, VcfWriterError, exit_with_error, get_args, get_md5, load_fasta,
+               print_success, print_warning)
+
+_SETUP_ERRORS = (FileNotFoundError, ITNotEnoughAvailChromsError, RatesTooHighError, RatesTooLowError, FastaIndexingError,
+                 FastaNotFoundError, ItRateTooHighError, ItRateTooLowError, RMTParseError, MissingLengthError,
+                 MinimumLengthTooLowError, TitvTooLowError, ChromNotExistError, RangeDefinitionOutOfBoundsError,
+                 FastaDuplicateHeaderError, MinimumLengthHigherThanMaximumError)
+
+
+def initialize():
+    args = get_args()
+    try:
+        fasta = load_fasta(args.infile)
+        if args.mode == "args":
+            sim = SimulationSettings.from_args(args, fasta, args.ignore_warnings)
+        elif args.mode == "it":
+            sim = SimulationSettings.from_it(args.interchromosomalrate, fasta, args.ignore_warnings)
+        else:
+            sim = SimulationSettings.from_rmt(args.rmtfile, fasta, args.ignore_warnings)
+    except _SETUP_ERRORS as e:
+        exit_with_error(e, args.no_color)
+    if not args.ignore_warnings:
+        warn_user(args, sim)
+    return args, fasta, sim
+
+
+def warn_user(args, sim):
+    if sim.fasta and args.infile.name != sim.fasta:
+        print_warning("Fasta filename does not match RMT", args.no_color)
+    if sim.md5 and get_md5(args.infile) != sim.md5:
+        print_warning("Fasta md5 hash does not match RMT", args.no_color)
+
+
+def main():
+    start = timer()
+    args, fasta, sim = initialize()
+    if sim.has_mutations:
+        try:
+            mutator = Mutator(args, fasta, sim)
+            mutator.mutate()
+            mutator.close()
+            fasta.close()
+        except (FastaWriterError, VcfWriterError, MutSimError, RangeOverlapError) as e:
+            exit_with_error(e, args.no_color)
+    if sim.has_it:
+        if sim.has_mutations:   # IT runs on the mutated genome (__main__.py:88-95)
+            try:
+                fasta = load_fasta(args.outfasta)
+            except (FastaDuplicateHeaderError, FastaIndexingError, FastaNotFoundError) as e:
+                exit_with_error(e, args.no_color)
+        try:
+            it_mutator = ITMutator(args, fasta, sim)
+            it_mutator.mutate()
+            it_mutator.close()
+            fasta.close()
+        except (FastaWriterError, BedpeWriterError, MutSimError) as e:
+            exit_with_error(e, args.no_color)
+    runtime = round(timer() - start, 4)
+    if not args.quiet:
+        print_success(f"Mutation-Simulator finished in: {runtime}s", args.no_color)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,226 @@
+"""Bulk FASTA loader with the ``pyfaidx.Fasta`` surface the reference uses.
+
+Replaces util.load_fasta's ``pyfaidx.Fasta(..., as_raw=True,
+sequence_always_upper=True)`` (util.py:77-91).  The whole file is parsed at once
+with numpy into one upper-cased base array (what the GPU consumes); the objects
+below are thin host views over it exposing exactly what reference-style code
+reads: ``fasta[int|str]``, ``keys()``, ``get_seq(name, start1, end1)``,
+``faidx.index[name].lenc``, ``close()``; records: ``len()``, ``[int]``, ``[a:b]``,
+``.name``, ``.long_name``, iteration by line.
+"""
+from __future__ import annotations
+
+from pathlib import Path
+
+import numpy as np
+
+_UPPER = np.arange(256, dtype=np.uint8)
+_UPPER[ord("a"):ord("z") + 1] -= 32
+
+
+class FastaIndexingError(Exception):
+    """Malformed FASTA (same role as pyfaidx.FastaIndexingError)."""
+
+
+class FastaNotFoundError(Exception):
+    """FASTA file cannot be read (same role as pyfaidx.FastaNotFoundError)."""
+
+
+class IndexEntry:
+    __slots__ = ("rlen", "offset", "lenc", "lenb")
+
+    def __init__(self, rlen, offset, lenc, lenb):
+        self.rlen, self.offset, self.lenc, self.lenb = rlen, offset, lenc, lenb
+
+
+class _Faidx:
+    def __init__(self):
+        self.index = {}
+
+
+class FastaRecord:
+    """One contig; a view into the genome array."""
+
+    def __init__(self, name: str, long_name: str, bases: np.ndarray, lenc: int):
+        self.name = name
+        self.long_name = long_name
+        self._b = bases
+        self._lenc = lenc
+
+    def __len__(self):
+        return int(self._b.size)
+
+    def __getitem__(self, n):
+        if isinstance(n, slice):
+            start, stop, step = n.start, n.stop, n.step
+            size = len(self)
+            if not start:
+                start = 0
+            if not stop:  # pyfaidx: a falsy stop means "to the end"
+                stop = size
+            if stop < 0:
+                stop += size
+            if start < 0:
+                start += size
+            return self._b[start:stop][::step].tobytes().decode("latin-1")
+        if n < 0:
+            n += len(self)
+        return chr(self._b[n])
+
+    def __iter__(self):
+        w = self._lenc if self._lenc > 0 else max(1, len(self))
+        for i in range(0, len(self), w):
+            yield self._b[i:i + w].tobytes().decode("latin-1")
+
+    def __str__(self):
+        return self._b.tobytes().decode("latin-1")
+
+    @property
+    def array(self) -> np.ndarray:
+        """The upper-cased bases as uint8 (no copy)."""
+        return self._b
+
+
+class Fasta:
+    """All contigs of one FASTA file, upper-cased, resident in host memory."""
+
+    def __init__(self, filename, one_based_attributes=False, as_raw=True, sequence_always_upper=True,
+                 read_ahead=None, build_index=True, **_):
+        self.filename = str(filename)
+        try:
+            data = np.fromfile(self.filename, dtype=np.uint8)
+        except (FileNotFoundError, IsADirectoryError, PermissionError):
+            raise FastaNotFoundError(f"Cannot read FASTA from file {self.filename}")
+        self._parse(data, sequence_always_upper)
+        self.faidx = _Faidx()
+        self._records = {}
+        for i, nm in enumerate(self.names):
+            if nm in self._records:
+                raise ValueError(f"Duplicate key \"{nm}\"")  # util.py:89-91 maps this to FastaDuplicateHeaderError
+            self._records[nm] = FastaRecord(nm, self.long_names[i], self.genome[self.goff[i]:self.goff[i + 1]], int(self.bpl[i]))
+            self.faidx.index[nm] = IndexEntry(int(self.lengths[i]), int(self._seq_off[i]), int(self.bpl[i]), int(self._lenb[i]))
+        if build_index:
+            self._write_fai()
+
+    # -- parsing -----------------------------------------------------------
+    def _parse(self, data: np.ndarray, upper: bool):
+        n = data.size
+        nl = np.flatnonzero(data == 10)
+        gt = np.flatnonzero(data == ord(">"))
+        if gt.size:
+            at_line_start = np.ones(gt.size, dtype=bool)
+            nz = gt > 0
+            at_line_start[nz] = data[gt[nz] - 1] == 10
+            hdr = gt[at_line_start]
+        else:
+            hdr = gt
+        if hdr.size == 0:
+            raise FastaIndexingError(f"No sequences found in {self.filename}")
+        # end of each header line
+        k = np.searchsorted(nl, hdr)
+        hdr_end = np.where(k < nl.size, nl[np.minimum(k, max(nl.size - 1, 0))] if nl.size else n, n).astype(np.int64)
+        seq_lo = np.minimum(hdr_end + 1, n)
+        seq_hi = np.append(hdr[1:], n).astype(np.int64)
+        keep = (data != 10) & (data != 13)
+        for a, b in zip(hdr.tolist(), seq_lo.tolist()):
+            keep[a:b] = False
+        if hdr[0] > 0:
+            keep[:hdr[0]] = False  # anything before the first header is ignored
+        lengths = np.add.reduceat(keep, hdr.astype(np.intp)).astype(np.int64) if n else np.zeros(0, np.int64)
+        genome = data[keep]
+        if upper:
+            genome = _UPPER[genome]
+        # bases per line of the first sequence line (pyfaidx lenc) and bytes per line (lenb)
+        k1 = np.searchsorted(nl, seq_lo)
+        first_nl = np.where(k1 < nl.size, nl[np.minimum(k1, max(nl.size - 1, 0))] if nl.size else n, n)
+        first_end = np.minimum(first_nl, seq_hi)
+        lenb = np.where(first_nl < seq_hi, first_end - seq_lo + 1, first_end - seq_lo)
+        cr = np.zeros(hdr.size, dtype=np.int64)
+        has = first_end > seq_lo
+        cr[has] = data[np.maximum(first_end[has] - 1, 0)] == 13
+        lenc = np.maximum(first_end - seq_lo - cr, 0)
+        self._check_line_widths(data, nl, seq_lo, seq_hi, lenb)
+        self.names, self.long_names = [], []
+        for a, b in zip(hdr.tolist(), hdr_end.tolist()):
+            line = data[a + 1:b].tobytes().decode("latin-1").rstrip("\r")
+            self.long_names.append(line)
+            tok = line.split()
+            self.names.append(tok[0] if tok else "")
+        self.lengths = lengths
+        self.bpl = lenc.astype(np.int32)
+        self._lenb = lenb
+        self._seq_off = seq_lo
+        self.goff = np.zeros(hdr.size + 1, dtype=np.int64)
+        np.cumsum(lengths, out=self.goff[1:])
+        self.genome = genome
+
+    def _check_line_widths(self, data, nl, seq_lo, seq_hi, lenb):
+        """pyfaidx refuses records whose lines (all but the last) differ in length."""
+        if nl.size == 0:
+            return
+        starts = np.concatenate(([0], nl[:-1] + 1))
+        widths = nl - starts + 1                       # bytes per line incl. '\n'
+        rec = np.searchsorted(seq_lo, starts, side="right") - 1
+        ok = (rec >= 0)
+        inside = ok & (starts >= seq_lo[np.maximum(rec, 0)]) & (starts < seq_hi[np.maximum(rec, 0)])
+        if not inside.any():
+            return
+        r = rec[inside]
+        w = widths[inside]
+        e = nl[inside] + 1
+        last = e >= seq_hi[r]                          # last line of the record may be shorter
+        bad = (~last) & (w != lenb[r])
+        long_last = last & (w > lenb[r])
+        if bad.any() or long_last.any():
+            i = int(r[np.flatnonzero(bad | long_last)[0]])
+            raise FastaIndexingError(f"Line length of fasta file is not consistent! Inconsistent line found in record {i + 1}")
+
+    def _write_fai(self):
+        """pyfaidx leaves <file>.fai next to the input (README 'Notes'); keep that side effect when the directory is writable."""
+        p = Path(self.filename + ".fai")
+        if p.exists():
+            return
+        try:
+            with open(p, "w") as fh:
+                for nm in self.names:
+                    e = self.faidx.index[nm]
+                    fh.write(f"{nm}\t{e.rlen}\t{e.offset}\t{e.lenc}\t{e.lenb}\n")
+        except OSError:
+            pass
+
+    # -- pyfaidx surface ---------------------------------------------------
+    def keys(self):
+        return list(self.names)
+
+    def __len__(self):
+        return len(self.names)
+
+    def __iter__(self):
+        return iter(self._records[nm] for nm in self.names)
+
+    def __contains__(self, key):
+        return key in self._records
+
+    def __getitem__(self, key):
+        if isinstance(key, (int, np.integer)):
+            return self._records[self.names[key]]
+        return self._records[key]
+
+    def get_seq(self, name, start, end, rc=False):
+        return self._records[name]._b[start - 1:end].tobytes().decode("latin-1")
+
+    def close(self):
+        pass
+
+    # -- engine side -------------------------------------------------------
+    def upload(self, engine, contig_ids=None):
+        """Make this genome (or a subset of its contigs) resident on the engine's GPU."""
+        ids = list(range(len(self.names))) if contig_ids is None else list(contig_ids)
+        if contig_ids is None:
+            bases = self.genome
+        else:
+            bases = np.concatenate([self.genome[self.goff[i]:self.goff[i + 1]] for i in ids]) if ids else np.zeros(0, np.uint8)
+        engine.upload_genome(bases, [int(self.lengths[i]) for i in ids], [int(self.bpl[i]) for i in ids],
+                             [self.long_names[i].encode("latin-1") for i in ids],
+                             [self.names[i].encode("latin-1") for i in ids], gid=ids)
+        return ids

@@ -1,0 +1,141 @@
+"""The drop-in class API and CLI on the GPU: Mutator / ITMutator / main()."""
+import json
+import shutil
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import pyref
+from tests.helpers import GOLDEN, read_fasta_simple, vcf_body, vcf_head
+
+pytestmark = pytest.mark.gpu
+
+
+def run_main(argv):
+    from mutation_simulator_b200.__main__ import main
+    old = sys.argv
+    sys.argv = ["mutation-simulator"] + [str(a) for a in argv]
+    try:
+        main()
+    finally:
+        sys.argv = old
+
+
+def replay_plain(contigs, vcf_text):
+    """Reference-independent check of a produced (FASTA, VCF) pair: REF->ALT replay."""
+    recs = {}
+    for line in vcf_body(vcf_text).splitlines():
+        f = line.split(b"\t")
+        recs.setdefault(f[0], []).append((int(f[1]), f[3], f[4]))
+    fa = pyref.FastaOut()
+    for name, long_name, seq, bpl in contigs:
+        fa.set_bpl(bpl)
+        fa.write_header(long_name)
+        pos, out = 0, []
+        for p, ref, alt in recs.get(name, []):
+            assert p - 1 >= pos, "overlapping VCF records"
+            out.append(seq[pos:p - 1])
+            assert seq[p - 1:p - 1 + len(ref)] == ref
+            out.append(alt)
+            pos = p - 1 + len(ref)
+        out.append(seq[pos:])
+        fa.write_multi(b"".join(out))
+    return fa.getvalue()
+
+
+def test_cli_args_mode_is_self_consistent_and_reproducible(tmp_path):
+    shutil.copy(GOLDEN / "args_all" / "in.fa", tmp_path / "in.fa")
+    cmd = json.loads((GOLDEN / "args_all" / "cmd.json").read_text())["argv"]
+    argv = [tmp_path / "in.fa", "-o", tmp_path / "in", "-q", "--seed", "11"] + cmd[4:]
+    run_main(argv)
+    fa1, vcf1 = (tmp_path / "in_ms.fa").read_bytes(), (tmp_path / "in_ms.vcf").read_bytes()
+    # header identical to the reference's for the same command (minus the wall-clock line)
+    head = b"".join(l for l in vcf_head(vcf1).splitlines(keepends=True) if not l.startswith(b"##filedate="))
+    assert head == vcf_head((GOLDEN / "args_all" / "out.vcf").read_bytes())
+    contigs = read_fasta_simple(tmp_path / "in.fa")
+    assert replay_plain(contigs, vcf1) == fa1
+    assert len(vcf_body(vcf1).splitlines()) > 100
+    run_main(argv)
+    assert (tmp_path / "in_ms.fa").read_bytes() == fa1 and (tmp_path / "in_ms.vcf").read_bytes() == vcf1
+    argv[argv.index("11")] = "12"
+    run_main(argv)
+    assert (tmp_path / "in_ms.fa").read_bytes() != fa1
+
+
+def test_cli_rmt_mode_respects_blocked_ranges(tmp_path):
+    shutil.copy(GOLDEN / "rmt_ranges" / "in.fa", tmp_path / "in.fa")
+    shutil.copy(GOLDEN / "rmt_ranges" / "in.rmt", tmp_path / "in.rmt")
+    run_main([tmp_path / "in.fa", "-o", tmp_path / "in", "-q", "--seed", "5", "rmt", tmp_path / "in.rmt"])
+    vcf = (tmp_path / "in_ms.vcf").read_bytes()
+    assert b'species="test species"' in vcf and vcf_head(vcf).splitlines()[-1].endswith(b"\tsample")
+    contigs = read_fasta_simple(tmp_path / "in.fa")
+    assert replay_plain(contigs, vcf) == (tmp_path / "in_ms.fa").read_bytes()
+    n = 0
+    for line in vcf_body(vcf).splitlines():
+        f = line.split(b"\t")
+        if f[0] == b"seq1":
+            p = int(f[1])
+            end = p + len(f[3])
+            for lo, hi in ((1, 500), (3001, 4000)):   # None ranges of chr 1 (1-based inclusive)
+                assert not (p <= hi and end - 1 >= lo and len(f[3]) > 1 and p >= lo), line
+                assert not (lo <= p <= hi and f[7] == b"."), line
+            n += 1
+    assert n > 50
+
+
+def test_it_replay_of_reference_breakpoints_is_bit_exact():
+    """Gate A for IT: the reference's breakpoints + partners -> the reference's *_it.fa and .bedpe."""
+    from argparse import Namespace
+    import tempfile
+    from mutation_simulator_b200 import ITMutator, SimulationSettings, load_fasta
+    d = GOLDEN / "it_basic"
+    bp = json.loads((d / "bp.json").read_text())
+    with tempfile.TemporaryDirectory() as t:
+        t = Path(t)
+        shutil.copy(d / "in.fa", t / "in.fa")
+        fasta = load_fasta(t / "in.fa")
+        sim = SimulationSettings.from_it(0.004, fasta, True)
+        args = Namespace(outfastait=t / "o.fa", outbedpe=t / "o.bedpe", ignore_warnings=True, no_color=True, seed=1, device=0)
+        it = ITMutator(args, fasta, sim)
+        it._partners = {int(k): v for k, v in bp["partners"].items()}
+        bps = {int(k): {"self": np.array(v["self"], np.uint32), "partner": np.array(v["partner"], np.uint32)}
+               for k, v in bp["breakpoints"].items()}
+        it._generate_all_breakpoints = lambda eng: bps
+        it.mutate()
+        it.close()
+        assert (t / "o.fa").read_bytes() == (d / "out_it.fa").read_bytes()
+        assert (t / "o.bedpe").read_bytes() == (d / "out.bedpe").read_bytes()
+
+
+def test_cli_it_mode_and_rmt_with_it(tmp_path):
+    shutil.copy(GOLDEN / "it_basic" / "in.fa", tmp_path / "in.fa")
+    run_main([tmp_path / "in.fa", "-o", tmp_path / "in", "-q", "--seed", "3", "it", "0.004"])
+    contigs = read_fasta_simple(tmp_path / "in.fa")
+    out = read_fasta_simple(tmp_path / "in_ms_it.fa")
+    bed = (tmp_path / "in_ms_it.bedpe").read_bytes().splitlines()
+    assert [c[1] for c in out] == [c[1] for c in contigs]
+    assert sum(len(c[2]) for c in out) == sum(len(c[2]) for c in contigs)   # swaps conserve bases
+    assert len(bed) > 4
+    # rebuild the output from the BEDPE rows with the oracle
+    names = {c[0]: i for i, c in enumerate(contigs)}
+    bps, partners = {}, {}
+    for row in bed:
+        a, s1, e1, b, s2, e2 = row.split(b"\t")
+        i, j = names[a], names[b]
+        partners[i] = j
+        d = bps.setdefault(i, {"self": [], "partner": []})
+        for x, y in ((int(s1), int(s2)), (int(e1), int(e2))):
+            if x != len(contigs[i][2]):
+                d["self"].append(x); d["partner"].append(y)
+    want, _ = pyref.it_genome(contigs, bps, partners)
+    assert want == (tmp_path / "in_ms_it.fa").read_bytes()
+    # combined mode: Mutator first, IT on the mutated genome (__main__.py:88-102)
+    shutil.copy(GOLDEN / "rmt_it" / "in.fa", tmp_path / "k.fa")
+    shutil.copy(GOLDEN / "rmt_it" / "in.rmt", tmp_path / "k.rmt")
+    run_main([tmp_path / "k.fa", "-o", tmp_path / "k", "-q", "--seed", "4", "rmt", tmp_path / "k.rmt"])
+    ms = read_fasta_simple(tmp_path / "k_ms.fa")
+    it = read_fasta_simple(tmp_path / "k_ms_it.fa")
+    assert sum(len(c[2]) for c in it) == sum(len(c[2]) for c in ms)
+    assert (tmp_path / "k_ms_it.bedpe").stat().st_size > 0

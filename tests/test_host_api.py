@@ -1,0 +1,137 @@
+"""Host-side pieces of the drop-in API that need no GPU: VCF header, BEDPE rows,
+range planning, output naming, C-ABI symbol table."""
+import ctypes as C
+import json
+import re
+import sys
+from datetime import datetime
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from mutation_simulator_b200 import _lib, bedpe_writer, plan, vcf_writer
+from mutation_simulator_b200.argument_parser import get_args
+from mutation_simulator_b200.fasta import Fasta, FastaIndexingError, FastaNotFoundError
+from mutation_simulator_b200.rmt import SimulationSettings
+from tests.helpers import GOLDEN, vcf_head
+
+REPO = Path(__file__).resolve().parent.parent
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    hdr = (REPO / "include" / "mutsim_b200.h").read_text()
+    declared = set(re.findall(r"\b(ms_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
+    lib = _lib.load()
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.ms_abi_version() == 1
+    assert lib.ms_stage_name(8) == b"splice_emit_fasta"
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from mutation_simulator_b200.engine import Engine
+    with pytest.raises(_lib.MutSimError):
+        Engine(0)
+
+
+def test_vcf_header_matches_reference():
+    f = Fasta(GOLDEN / "args_all" / "in.fa", build_index=False)
+    txt = vcf_writer.header_text("in.fa", [(f[n].name, len(f[n])) for n in f.keys()], "asmX", "Some species", "smp1",
+                                 now=datetime(2026, 1, 5))
+    assert "##filedate=202615\n" in txt           # un-padded YYYYMD (vcf_writer.py:85)
+    txt = "".join(l for l in txt.splitlines(keepends=True) if not l.startswith("##filedate="))
+    assert txt.encode() == vcf_head((GOLDEN / "args_all" / "out.vcf").read_bytes())
+
+
+@pytest.mark.parametrize("case", ["it_basic", "rmt_it"])
+def test_bedpe_rows_match_reference(case):
+    d = GOLDEN / case
+    f = Fasta(d / ("out.fa" if (d / "out.fa").exists() else "in.fa"), build_index=False)
+    bp = json.loads((d / "bp.json").read_text())
+    out = b""
+    for i in range(len(f.names)):
+        if str(i) in bp["breakpoints"]:
+            p = bp["partners"][str(i)]
+            b = bp["breakpoints"][str(i)]
+            out += bedpe_writer.rows(f[i].name, b["self"], len(f[i]), f[p].name, b["partner"], len(f[p]))
+    assert out == (d / "out.bedpe").read_bytes()
+
+
+def _args(argv):
+    old = sys.argv
+    sys.argv = ["mutation-simulator"] + argv
+    try:
+        return get_args()
+    finally:
+        sys.argv = old
+
+
+def test_output_names_follow_reference():
+    a = _args(["dir/genome.fa", "it", "0.1"])
+    assert (str(a.outfasta), str(a.outvcf), str(a.outfastait), str(a.outbedpe)) == \
+        ("genome_ms.fa", "genome_ms.vcf", "genome_ms_it.fa", "genome_ms_it.bedpe")
+    a = _args(["dir/genome.fasta", "-o", "out/base", "-q", "it", "0.1"])
+    assert (str(a.outfasta), str(a.outvcf), str(a.outfastait), str(a.outbedpe)) == \
+        ("out/base_ms.fasta", "out/base_ms.vcf", "out/base_ms_it.fasta", "out/base_ms_it.bedpe")
+    assert a.ignore_warnings and a.no_progress and a.seed is None
+
+
+def test_plan_candidate_counts_match_reference_runs():
+    g = json.loads((GOLDEN / "stats_all.json").read_text())
+    lengths = g["lengths"]
+
+    class F:  # minimal fasta stand-in for from_args
+        def keys(self):
+            return [f"c{i}" for i in range(len(lengths))]
+
+        def __getitem__(self, i):
+            return "x" * 0 if False else type("R", (), {"__len__": lambda s: lengths[i if isinstance(i, int) else int(i[1:])]})()
+    a = _args(["g.fa", "args"] + g["args"])
+    sim = SimulationSettings.from_args(a, F(), True)
+    arr, n = plan.build_ranges(sim, lengths)
+    assert n == len(lengths)
+    for i in range(n):
+        assert arr[i].k == g["runs"][0]["contigs"][i]["candidates"]
+        assert arr[i].start == 0 and arr[i].stop == lengths[i] - 1 and arr[i].limit == lengths[i]
+        assert abs(arr[i].cdf[6] - 1.0) < 1e-12
+    assert plan.block_list(sim) == [1] * 7
+    assert plan.p_transition(2.0) == 2.0 * (1 / 3.0)
+
+
+def test_plan_rmt_limits_and_overlap(tmp_path):
+    f = Fasta(GOLDEN / "rmt" / "g.fa", build_index=False)
+    sim = SimulationSettings.from_rmt(GOLDEN / "rmt" / "ok_ranges.rmt".replace("ok_ranges", "ok_unsorted_ranges"), f, True)
+    arr, n = plan.build_ranges(sim, f.lengths)
+    rows = [(arr[i].contig, arr[i].start, arr[i].stop, arr[i].limit) for i in range(n)]
+    # chr 2: 1-100 sn 0.1 | 101-200 std | 201-300 None: SVs of the first two ranges may not reach base 200
+    assert (1, 0, 99, 200) in rows and (1, 100, 199, 200) in rows
+    p = tmp_path / "o.rmt"
+    p.write_text("std\nit None\nsn 0.01\nchr 1\n10-200 sn 0.1\n150-300 sn 0.1\n")
+    sim = SimulationSettings.from_rmt(p, f, True)
+    with pytest.raises(plan.RangeOverlapError):
+        plan.build_ranges(sim, f.lengths)
+
+
+def test_fasta_loader_errors(tmp_path):
+    with pytest.raises(FastaNotFoundError):
+        Fasta(tmp_path / "nope.fa")
+    p = tmp_path / "ragged.fa"
+    p.write_text(">a\nACGT\nAC\nACGT\n")
+    with pytest.raises(FastaIndexingError):
+        Fasta(p)
+    p = tmp_path / "dup.fa"
+    p.write_text(">a x\nACGT\n>a y\nAC\n")
+    from mutation_simulator_b200.util import FastaDuplicateHeaderError, load_fasta
+    with pytest.raises(FastaDuplicateHeaderError):
+        load_fasta(p)
+    p = tmp_path / "ok.fa"
+    p.write_text(">a desc\nacgtn\nAC\n>b\nGG\n")
+    f = load_fasta(p)
+    assert f.keys() == ["a", "b"] and str(f["a"]) == "ACGTNAC" and f[1].long_name == "b"
+    assert f.faidx.index["a"].lenc == 5 and (tmp_path / "ok.fa.fai").exists()
+    assert f["a"][1:3] == "CG" and f["a"][0:0] == "ACGTNAC" and list(f["a"]) == ["ACGTN", "AC"]
