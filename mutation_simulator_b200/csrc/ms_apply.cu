@@ -721,6 +721,16 @@ k_vcf_write(VcfView v, const Rec* recs, int64_t n_recs, const Contig* contigs, c
     for (int64_t x = ah + tid; x < end; x += VCF_THREADS) vcf[x] = buf[shift + (x - base)];
 }
 
+// delta (prod - cons) and VCF line size of every record, computed once (the scan reads 8 bytes per record)
+__global__ void __launch_bounds__(256)
+k_rec_sizes(VcfView v, const Rec* recs, int64_t n, const Contig* contigs, int32_t* delta, uint32_t* vsize) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Rec r = recs[i];
+    delta[i] = (int32_t)r.prod - (int32_t)r.cons;
+    vsize[i] = vcf_line_size(v, contigs[r.contig], r);
+}
+
 __global__ void k_store_total2(const I64x2* total, int64_t* S_end, int64_t* V_end) {
     *S_end = total->a;
     *V_end = total->b;
@@ -751,12 +761,15 @@ int apply_pipeline(ms_ctx* c) {
 
     VcfView vv{c->genome.as<uint8_t>(), c->lit.as<uint8_t>(), c->names.as<uint8_t>(), d_tab->conv, d_tab->comp};
     {
-        const Rec* recs = d_recs;
-        const Contig* contigs = d_contigs;
-        auto in = [=] __device__(int64_t i) -> I64x2 {
-            const Rec r = recs[i];
-            return I64x2{(int64_t)r.prod - (int64_t)r.cons, (int64_t)vcf_line_size(vv, contigs[r.contig], r)};
-        };
+        MS_CUDA(c, c->lvec.ensure((size_t)(M + 1) * 4));
+        MS_CUDA(c, c->vvec.ensure((size_t)(M + 1) * 4));
+        int32_t* d_delta = c->lvec.as<int32_t>();
+        uint32_t* d_vsize = c->vvec.as<uint32_t>();
+        if (M > 0) {
+            k_rec_sizes<<<(unsigned)ceil_div(M, 256), 256, 0, st>>>(vv, d_recs, M, d_contigs, d_delta, d_vsize);
+            MS_LAUNCH_CHECK(c);
+        }
+        auto in = [=] __device__(int64_t i) -> I64x2 { return I64x2{(int64_t)d_delta[i], (int64_t)d_vsize[i]}; };
         auto out = [=] __device__(int64_t i, I64x2 ex, I64x2) { S[i] = ex.a; V[i] = ex.b; };
         I64x2* d_total = nullptr;
         MS_CUDA(c, (device_scan<I64x2>(c, in, out, M, I64x2{0, 0}, SumOp(), c->scan_tmp, &d_total)));

@@ -71,6 +71,7 @@ struct ms_ctx {
     int32_t n_ranges = 0;
     int64_t n_candidates = 0;
     int64_t n_buckets = 0;
+    int64_t store_entries = 0;
     int32_t block[7] = {1, 1, 1, 1, 1, 1, 1};
     double p_ti = 0.5;
     int32_t min_dist = 1;

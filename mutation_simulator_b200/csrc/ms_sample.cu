@@ -18,9 +18,10 @@
 
 namespace ms {
 
-constexpr int BUCKET_TARGET = 512;
-constexpr int SORT_CAP = 2048;
-constexpr int SORT_THREADS = 256;
+constexpr int BUCKET_TARGET = 384;   // mean keys per sort bucket of a multi-bucket range
+constexpr int BUCKET_CAP = 640;      // storage per such bucket: mean + 13 sigma of Binomial(k, 1/nb); overflow raises MS_ERR_INTERNAL
+constexpr int SORT_CAP = 1024;
+constexpr int SORT_THREADS = 512;
 
 __device__ inline void raise_error_s(Totals* t, int64_t code, int64_t arg) {
     if (atomicCAS((unsigned long long*)&t->error, 0ull, (unsigned long long)code) == 0ull) t->error_arg = arg;
@@ -44,13 +45,20 @@ __global__ void k_make_prps(const Range* ranges, int32_t n_ranges, const Contig*
 }
 
 __device__ inline uint32_t bucket_of(const Range& g, uint32_t v) {
-    uint32_t b = (uint32_t)(((uint64_t)v * g.nb) / g.n);
+    uint32_t b = g.nb == 1u ? 0u : (uint32_t)(((uint64_t)v * g.nb) / g.n);
     return g.bucket_lo + (b < g.nb ? b : g.nb - 1);
 }
 
-// K1a: draw + histogram
+// K1a: draw and drop each value straight into its sort bucket.  Keys are uniform, so equal-width buckets
+// are balanced and a fixed capacity per bucket replaces the usual count / scan / scatter passes.
+__device__ inline int64_t bucket_store(const Range& g, uint32_t b) {
+    const uint32_t cap = g.nb == 1u ? g.k : (uint32_t)BUCKET_CAP;
+    return g.store_lo + (int64_t)(b - g.bucket_lo) * cap;
+}
+
 __global__ void __launch_bounds__(256)
-k_draw(const Range* ranges, const int64_t* cand_lo, int32_t n_ranges, const Prp* prps, int64_t K, uint32_t* cand_val, uint32_t* bucket_cnt) {
+k_draw(const Range* ranges, const int64_t* cand_lo, int32_t n_ranges, const Prp* prps, int64_t K, uint32_t* store, uint32_t* bucket_cnt,
+       Totals* tot) {
     __shared__ int r0;
     const int64_t s0 = (int64_t)blockIdx.x * blockDim.x;
     if (threadIdx.x == 0) r0 = upper_idx(cand_lo, n_ranges, s0);
@@ -62,31 +70,17 @@ k_draw(const Range* ranges, const int64_t* cand_lo, int32_t n_ranges, const Prp*
     const Range& g = ranges[r];
     const Prp p = prps[r];
     const uint32_t v = prp_apply(p, (uint32_t)(s - g.cand_lo));
-    cand_val[s] = v;
-    atomicAdd(&bucket_cnt[bucket_of(g, v)], 1u);
-}
-
-// K1c: scatter into buckets
-__global__ void __launch_bounds__(256)
-k_scatter(const Range* ranges, const int64_t* cand_lo, int32_t n_ranges, int64_t K, const uint32_t* cand_val,
-          const int64_t* bucket_off, uint32_t* cursor, uint32_t* sorted) {
-    __shared__ int r0;
-    const int64_t s0 = (int64_t)blockIdx.x * blockDim.x;
-    if (threadIdx.x == 0) r0 = upper_idx(cand_lo, n_ranges, s0);
-    __syncthreads();
-    const int64_t s = s0 + threadIdx.x;
-    if (s >= K) return;
-    int r = r0;
-    while (s >= cand_lo[r + 1]) ++r;
-    const uint32_t v = cand_val[s];
-    const uint32_t b = bucket_of(ranges[r], v);
-    sorted[bucket_off[b] + atomicAdd(&cursor[b], 1u)] = v;
+    const uint32_t b = bucket_of(g, v);
+    const uint32_t slot = atomicAdd(&bucket_cnt[b], 1u);
+    const uint32_t cap = g.nb == 1u ? g.k : (uint32_t)BUCKET_CAP;
+    if (slot < cap) store[bucket_store(g, b) + slot] = v;
+    else raise_error_s(tot, MS_ERR_INTERNAL, 200 + b);
 }
 
 // K1d + K2: sort one bucket in shared memory, then write position, type, length and reach.
 __global__ void __launch_bounds__(SORT_THREADS)
 k_sort_emit(const Range* ranges, const int64_t* bucket_lo_key, int32_t n_ranges, const Contig* contigs, const int64_t* bucket_off,
-            const uint32_t* sorted, Seed seed, int32_t min_dist, const int32_t* block7, int positions_only,
+            const uint32_t* store, Seed seed, int32_t min_dist, const int32_t* block7, int positions_only,
             int64_t* cand_gpos, uint8_t* cand_type, uint32_t* cand_len, int64_t* cand_reach, uint32_t* cand_range, Totals* tot) {
     __shared__ uint32_t sm[SORT_CAP];
     __shared__ Range g;
@@ -102,19 +96,45 @@ k_sort_emit(const Range* ranges, const int64_t* bucket_lo_key, int32_t n_ranges,
     if (tid < 7) blk[tid] = block7[tid];
     int n2 = 32;
     while (n2 < cnt) n2 <<= 1;
-    for (int i = tid; i < n2; i += SORT_THREADS) sm[i] = i < cnt ? sorted[lo + i] : 0xFFFFFFFFu;
     __syncthreads();
-    for (int k = 2; k <= n2; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < n2; i += SORT_THREADS) {
-                const int x = i ^ j;
-                if (x > i) {
-                    const uint32_t a = sm[i], c = sm[x];
-                    const bool asc = (i & k) == 0;
-                    if ((a > c) == asc) { sm[i] = c; sm[x] = a; }
+    const uint32_t* src = store + bucket_store(g, (uint32_t)b);
+    if (n2 <= SORT_THREADS) {
+        // one key per thread: strides below 32 are exchanged with shuffles, only the
+        // 10 cross-warp phases of a 512-key bitonic network go through shared memory
+        uint32_t v = tid < cnt ? src[tid] : 0xFFFFFFFFu;
+        for (int k = 2; k <= n2; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                uint32_t other;
+                if (j >= 32) {
+                    sm[tid] = v;
+                    __syncthreads();
+                    other = sm[tid ^ j];
+                    __syncthreads();
+                } else {
+                    other = __shfl_xor_sync(0xffffffffu, v, j);
                 }
+                const bool keep_min = ((tid & j) == 0) == ((tid & k) == 0);
+                const uint32_t mn = v < other ? v : other, mx = v < other ? other : v;
+                v = keep_min ? mn : mx;
             }
-            __syncthreads();
+        }
+        sm[tid] = v;
+        __syncthreads();
+    } else {
+        for (int i = tid; i < n2; i += SORT_THREADS) sm[i] = i < cnt ? src[i] : 0xFFFFFFFFu;
+        __syncthreads();
+        for (int k = 2; k <= n2; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = tid; i < n2; i += SORT_THREADS) {
+                    const int x = i ^ j;
+                    if (x > i) {
+                        const uint32_t a = sm[i], c = sm[x];
+                        const bool asc = (i & k) == 0;
+                        if ((a > c) == asc) { sm[i] = c; sm[x] = a; }
+                    }
+                }
+                __syncthreads();
+            }
         }
     }
     const Contig& ct = contigs[g.contig];
@@ -260,8 +280,7 @@ static int draw_and_sort(ms_ctx* c, Seed seed, uint32_t purpose, int32_t min_dis
     int32_t* d_block = reinterpret_cast<int32_t*>(d_prps + R);
     Totals* d_tot = c->totals.as<Totals>();
 
-    MS_CUDA(c, c->cand_val.ensure((size_t)K * 4 + 16));
-    MS_CUDA(c, c->cand_sorted.ensure((size_t)K * 4 + 16));
+    MS_CUDA(c, c->cand_sorted.ensure((size_t)c->store_entries * 4 + 16));
     MS_CUDA(c, c->bucket_cnt.ensure((size_t)(c->n_buckets + 1) * 4));
     MS_CUDA(c, c->bucket_off.ensure((size_t)(c->n_buckets + 1) * 8));
     MS_CUDA(c, c->cand_reach.ensure((size_t)K * 8 + 16));   // cand_gpos lives in svec
@@ -276,7 +295,7 @@ static int draw_and_sort(ms_ctx* c, Seed seed, uint32_t purpose, int32_t min_dis
     k_make_prps<<<(unsigned)ceil_div(R, 128), 128, 0, st>>>(d_ranges, R, c->contigs.as<Contig>(), seed, purpose, d_prps);
     MS_LAUNCH_CHECK(c);
     MS_CUDA(c, cudaMemsetAsync(d_cnt, 0, (size_t)(c->n_buckets + 1) * 4, st));
-    k_draw<<<(unsigned)ceil_div(K, 256), 256, 0, st>>>(d_ranges, d_cand_lo, R, d_prps, K, c->cand_val.as<uint32_t>(), d_cnt);
+    k_draw<<<(unsigned)ceil_div(K, 256), 256, 0, st>>>(d_ranges, d_cand_lo, R, d_prps, K, c->cand_sorted.as<uint32_t>(), d_cnt, d_tot);
     MS_LAUNCH_CHECK(c);
     {
         const uint32_t* cnt = d_cnt;
@@ -287,10 +306,6 @@ static int draw_and_sort(ms_ctx* c, Seed seed, uint32_t purpose, int32_t min_dis
         k_copy_scalar<int64_t><<<1, 1, 0, st>>>(d_total, d_boff + c->n_buckets);
         MS_LAUNCH_CHECK(c);
     }
-    MS_CUDA(c, cudaMemsetAsync(d_cnt, 0, (size_t)(c->n_buckets + 1) * 4, st));
-    k_scatter<<<(unsigned)ceil_div(K, 256), 256, 0, st>>>(d_ranges, d_cand_lo, R, K, c->cand_val.as<uint32_t>(), d_boff, d_cnt,
-                                                          c->cand_sorted.as<uint32_t>());
-    MS_LAUNCH_CHECK(c);
     stage_end(c, ST_SAMPLE_POS);
 
     stage_begin(c, ST_SAMPLE_TYPE);
@@ -455,7 +470,7 @@ int count_types(ms_ctx* c) {
 static int upload_ranges(ms_ctx* c, int32_t min_dist) {
     const int32_t R = (int32_t)c->h_ranges.size();
     std::vector<int64_t> cand_lo(R + 1), bucket_lo(R + 1);
-    int64_t K = 0, NB = 0;
+    int64_t K = 0, NB = 0, STORE = 0;
     for (int32_t r = 0; r < R; ++r) {
         Range& g = c->h_ranges[r];
         const int64_t n = (int64_t)g.stop - ((int64_t)g.k - 1) * min_dist - (int64_t)g.start;   // util.py:104
@@ -466,13 +481,15 @@ static int upload_ranges(ms_ctx* c, int32_t min_dist) {
         g.cand_lo = K;
         g.nb = (uint32_t)std::max<int64_t>(1, ceil_div(g.k, BUCKET_TARGET));
         g.bucket_lo = (uint32_t)NB;
+        g.store_lo = STORE;
+        STORE += (int64_t)g.nb * (g.nb == 1u ? g.k : (uint32_t)BUCKET_CAP);
         g.gstart = c->h_contigs[g.contig].goff + g.start;
         cand_lo[r] = K; bucket_lo[r] = NB;
         K += g.k; NB += g.nb;
     }
     cand_lo[R] = K; bucket_lo[R] = NB;
     if (K >= (int64_t)0x7FFFFFF0) MS_FAIL(c, MS_ERR_LIMIT, "more than 2^31 candidates in one call");
-    c->n_ranges = R; c->n_candidates = K; c->n_buckets = NB; c->min_dist = min_dist;
+    c->n_ranges = R; c->n_candidates = K; c->n_buckets = NB; c->min_dist = min_dist; c->store_entries = STORE;
     const size_t bytes = sizeof(Range) * (size_t)R + 2 * sizeof(int64_t) * (size_t)(R + 1) + sizeof(Prp) * (size_t)R + 64;
     MS_CUDA(c, c->ranges.ensure(bytes));
     uint8_t* base = c->ranges.as<uint8_t>();

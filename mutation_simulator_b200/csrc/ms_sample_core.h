@@ -11,6 +11,7 @@ namespace ms {
 struct Range {
     int64_t gstart;     // genome index of the range's first base
     int64_t cand_lo;    // first candidate slot of this range
+    int64_t store_lo;   // first slot of this range's sort buckets in the bucket store
     int64_t limit;      // contig-relative end (exclusive) an SV may extend to: contig length,
                         // or the start of the next blocked (None) range — SURVEY.md Q3 stance
     uint32_t start;     // contig-relative, inclusive
