@@ -85,44 +85,62 @@ def lpt_partition(lengths, n):
 
 
 class ClockSampler:
-    """nvidia-smi clocks line of B200_PROFILING.md, sampled during the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed region, polled through NVML every ~2 ms
+    (the timed region is tens of milliseconds, too short for `nvidia-smi -lms`)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, device):
-        self.device = device
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+        self.device, self.samples, self.mask, self.max_mhz, self._stop, self._t = device, [], 0, None, False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            # torch's device order follows CUDA_VISIBLE_DEVICES; map through the UUID-less common case (same order)
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[device]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else device
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # noqa: BLE001
+            self.nv, self.err = None, str(e)
+
+    def _loop(self):
+        nv = self.nv
+        while not self._stop:
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:  # noqa: BLE001
+                    self.mask |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.002)
 
     def start(self):
-        try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
-        except OSError:
-            self.p = None
+        if self.nv is not None:
+            self._t = threading.Thread(target=self._loop, daemon=True)
+            self._t.start()
 
     def stop(self):
-        if self.p is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.p.kill()
-        self.f.flush()
-        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
-        os.unlink(self.f.name)
-        sm = [float(r[1]) for r in rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
-        reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in rows:
-            if len(r) >= 9:
-                for nme, v in zip(names, r[5:9]):
-                    if v.strip().lower() == "active":
-                        reasons.add(nme)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"nvml unavailable: {getattr(self, 'err', '')}"], "samples": 0}
+        self._stop = True
+        self._t.join(timeout=2)
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(n for bit, n in self.REASONS.items() if self.mask & bit), "samples": len(self.samples)}
+
+
+def reduce_over_ranks(values, op, world):
+    """max / sum of a list of floats over the ranks (device-timed numbers are the max over ranks)."""
+    if world == 1:
+        return list(values)
+    import torch
+    import torch.distributed as dist
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor(values, dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM)
+    return t.tolist()
 
 
 def measured_peak():
@@ -282,13 +300,8 @@ def main():
     clocks = sampler.stop()
     st = eng.stats()
     launches = st["kernel_launches"] - launches0
-    t = torch.tensor([dev_ms, float(launches)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        tmax = t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone()
-        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        dev_ms, launches = float(tmax[0]), int(tsum[1])
+    dev_ms = reduce_over_ranks([dev_ms], "max", world)[0]
+    launches = int(reduce_over_ranks([float(launches)], "sum", world)[0])
     ms_per_step = dev_ms / args.steps
     value = total_bases / (ms_per_step * 1e-3) / 1e9
 
@@ -332,11 +345,9 @@ def main():
             fb, vb = e2e_step(3000 + s)
         barrier()
         dt = (time.perf_counter() - t0) / n_e2e
-        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": total_bases / float(tt[0]) / 1e9, "unit": "Gbp/s", "h2d_bytes_per_step": int(my_bases),
-               "d2h_bytes_per_step": int(fb + vb), "steps": n_e2e, "ms_per_step": float(tt[0]) * 1e3,
+        dt = reduce_over_ranks([dt], "max", world)[0]
+        e2e = {"value": total_bases / dt / 1e9, "unit": "Gbp/s", "h2d_bytes_per_step": int(my_bases),
+               "d2h_bytes_per_step": int(fb + vb), "steps": n_e2e, "ms_per_step": dt * 1e3,
                "note": "per-rank bytes; pinned host genome in, FASTA image + VCF body out"}
 
     cpu = None
