@@ -75,13 +75,8 @@ def make_ranges(lengths, wl):
 
 def lpt_partition(lengths, n):
     """Longest-processing-time bin packing of contigs onto n ranks."""
-    bins = [[] for _ in range(n)]
-    load = [0] * n
-    for i in sorted(range(len(lengths)), key=lambda i: -lengths[i]):
-        b = load.index(min(load))
-        bins[b].append(i)
-        load[b] += lengths[i]
-    return [sorted(b) for b in bins]
+    from mutation_simulator_b200.distributed import lpt_partition as f
+    return f(lengths, n)
 
 
 class ClockSampler:

@@ -100,6 +100,11 @@ int ms_genome_synth(ms_ctx* ctx, uint64_t seed, int32_t n_contigs, const int64_t
                     const uint8_t* headers, const int64_t* hdr_off,
                     const uint8_t* names, const int64_t* name_off);
 int ms_genome_download(ms_ctx* ctx, uint8_t* bases, int64_t cap);
+/* Reserve `extra_bytes` of staging space behind the genome for bases of contigs that live on another GPU
+ * (interchromosomal partners, it_mutator.py:133-137).  Call before ms_genome_upload.  The region starts at
+ * genome index total_bases + 64 (ms_device_ptr(4) gives the base pointer); K_RAW records may point into it,
+ * so a peer's ncclSend can land directly where the splice kernel gathers from. */
+int ms_genome_reserve(ms_ctx* ctx, int64_t extra_bytes);
 
 /* ---- fresh sampling ----------------------------------------------------
  * Replaces Mutator.__get_mutations / __get_mut_positions / __get_stop_position /
@@ -125,6 +130,12 @@ int ms_apply(ms_ctx* ctx, int64_t* fasta_bytes, int64_t* vcf_bytes);
 int ms_download(ms_ctx* ctx, int which, void* dst, int64_t cap, int64_t* nbytes);
 int ms_device_ptr(ms_ctx* ctx, int which, void** dptr, int64_t* nbytes);
 int ms_contig_out_len(ms_ctx* ctx, int64_t* out_len /* n_contigs */);
+/* Per-contig slices of the last ms_apply outputs, for assembling one file from several GPUs:
+ * fasta_off[c]..fasta_off[c+1] = header + body (+ separator) bytes of contig c in the FASTA image,
+ * vcf_off[c]..vcf_off[c+1] = its VCF lines; sep[c] = 1 if the slice ends with the '\n' that closes a partial
+ * last line (fasta_writer.py:44-45); partial[c] = 1 if the last line is partial.  Arrays have n_contigs+1 /
+ * n_contigs entries. */
+int ms_contig_layout(ms_ctx* ctx, int64_t* fasta_off, int64_t* vcf_off, uint8_t* sep, uint8_t* partial);
 
 /* ---- interchromosomal translocations ------------------------------------
  * Replaces ITMutator.__get_breakpoints (it_mutator.py:94-118): for each pair p,
@@ -132,6 +143,11 @@ int ms_contig_out_len(ms_ctx* ctx, int64_t* out_len /* n_contigs */);
  * bp_a/bp_b receive sum(n) sorted positions each (pair-major). */
 int ms_it_breakpoints(ms_ctx* ctx, uint64_t seed, int32_t n_pairs, const uint32_t* contig_a,
                       const uint32_t* contig_b, const uint32_t* n, uint32_t* bp_a, uint32_t* bp_b);
+/* util.sample_with_minimum_distance (util.py:94-109) for many ranges at once, independent of the resident
+ * genome: range i = (gid[i], start[i], stop[i], k[i]); out receives sum(k) sorted positions, range-major.
+ * The stream is keyed by (seed, gid, start), so any GPU computes the same positions. */
+int ms_sample_positions(ms_ctx* ctx, uint64_t seed, int32_t n, const uint32_t* gid, const uint32_t* start,
+                        const uint32_t* stop, const uint32_t* k, int32_t min_dist, uint32_t* out);
 
 /* ---- introspection ------------------------------------------------------ */
 int ms_get_stats(ms_ctx* ctx, ms_stats* out);

@@ -54,6 +54,8 @@ def main():
             exit_with_error(e, args.no_color)
     if sim.has_it:
         if sim.has_mutations:   # IT runs on the mutated genome (__main__.py:88-95)
+            from . import distributed
+            distributed.barrier()   # all ranks have written their slices of *_ms.fa
             try:
                 fasta = load_fasta(args.outfasta)
             except (FastaDuplicateHeaderError, FastaIndexingError, FastaNotFoundError) as e:
@@ -66,6 +68,9 @@ def main():
         except (FastaWriterError, BedpeWriterError, MutSimError) as e:
             exit_with_error(e, args.no_color)
     runtime = round(timer() - start, 4)
+    from . import distributed
+    if distributed.rank_world()[0] != 0:
+        return
     if not args.quiet:
         print_success(f"Mutation-Simulator finished in: {runtime}s", args.no_color)
 

@@ -60,7 +60,7 @@ int ms_destroy(ms_ctx* c) {
     DevBuf* bufs[] = {&c->genome, &c->contigs, &c->headers, &c->names, &c->tables, &c->ranges, &c->cand_val, &c->cand_sorted,
                       &c->bucket_cnt, &c->bucket_off, &c->cand_type, &c->cand_len, &c->cand_reach, &c->cand_pm, &c->cand_accept,
                       &c->acc_idx, &c->tl_list, &c->tli_list, &c->link, &c->keep, &c->contig_tl, &c->scan_tmp, &c->scan_tmp2,
-                      &c->svec, &c->vvec, &c->lvec, &c->recs, &c->lit, &c->blk, &c->piece_lo, &c->long_gaps, &c->fasta, &c->vcf,
+                      &c->svec, &c->vvec, &c->lvec, &c->tmp_contigs, &c->recs, &c->lit, &c->blk, &c->piece_lo, &c->long_gaps, &c->fasta, &c->vcf,
                       &c->vcf_off, &c->totals};
     for (DevBuf* b : bufs) b->release();
     for (int s = 0; s < ST_COUNT; ++s) { cudaEventDestroy(c->ev[s][0]); cudaEventDestroy(c->ev[s][1]); }
@@ -125,7 +125,7 @@ int ms_genome_upload(ms_ctx* c, const uint8_t* bases, int64_t total_bases, int32
     if (!bases && total_bases > 0) MS_FAIL(c, MS_ERR_ARG, "ms_genome_upload: bases is NULL");
     MS_CUDA(c, cudaSetDevice(c->device));
     stage_begin(c, ST_UPLOAD);
-    MS_CUDA(c, c->genome.ensure((size_t)total_bases + 64));
+    MS_CUDA(c, c->genome.ensure((size_t)total_bases + 64 + (size_t)c->foreign_cap + 64));
     MS_CUDA(c, cudaMemcpyAsync(c->genome.p, bases, (size_t)total_bases, cudaMemcpyHostToDevice, c->stream));
     MS_CUDA(c, cudaMemsetAsync(c->genome.as<uint8_t>() + total_bases, 'N', 64, c->stream));
     stage_end(c, ST_UPLOAD);
@@ -143,6 +143,12 @@ int ms_genome_adopt(ms_ctx* c, const uint8_t* d_bases, int64_t total_bases, int3
     }
     MS_CUDA(c, cudaMemsetAsync(c->genome.as<uint8_t>() + total_bases, 'N', 64, c->stream));
     return set_contig_table(c, total_bases, n_contigs, contig_len, bpl, gid, headers, hdr_off, names, name_off);
+}
+
+int ms_genome_reserve(ms_ctx* c, int64_t extra_bytes) {
+    if (!c || extra_bytes < 0) return MS_ERR_ARG;
+    c->foreign_cap = extra_bytes;
+    return MS_OK;
 }
 
 int ms_genome_download(ms_ctx* c, uint8_t* bases, int64_t cap) {
@@ -165,7 +171,7 @@ int ms_load_records(ms_ctx* c, const ms_rec* recs, int64_t n_recs, const uint8_t
         if (recs[i].kind == K_LIT && (recs[i].src < 0 || recs[i].src + recs[i].prod > lit_bytes))
             MS_FAIL(c, MS_ERR_ARG, "record %lld: literal range outside the pool", (long long)i);
         if ((recs[i].kind == K_RAW || recs[i].kind == K_CONV || recs[i].kind == K_RC) &&
-            (recs[i].src < 0 || recs[i].src + recs[i].prod > c->total_bases))
+            (recs[i].src < 0 || recs[i].src + recs[i].prod > c->total_bases + 64 + c->foreign_cap))
             MS_FAIL(c, MS_ERR_ARG, "record %lld: source range outside the genome", (long long)i);
     }
     MS_CUDA(c, cudaSetDevice(c->device));
@@ -228,6 +234,36 @@ int ms_contig_out_len(ms_ctx* c, int64_t* out_len) {
     MS_CUDA(c, cudaSetDevice(c->device));
     MS_CUDA(c, cudaMemcpy(c->h_contigs.data(), c->contigs.p, sizeof(Contig) * (size_t)c->n_contigs, cudaMemcpyDeviceToHost));
     for (int i = 0; i < c->n_contigs; ++i) out_len[i] = c->h_contigs[i].out_len;
+    return MS_OK;
+}
+
+int ms_contig_layout(ms_ctx* c, int64_t* fasta_off, int64_t* vcf_off, uint8_t* sep, uint8_t* partial) {
+    if (!c || !fasta_off || !vcf_off) return MS_ERR_ARG;
+    MS_CUDA(c, cudaSetDevice(c->device));
+    MS_CUDA(c, cudaStreamSynchronize(c->stream));
+    MS_CUDA(c, cudaMemcpy(c->h_contigs.data(), c->contigs.p, sizeof(Contig) * (size_t)c->n_contigs, cudaMemcpyDeviceToHost));
+    std::vector<int64_t> V;
+    for (int i = 0; i < c->n_contigs; ++i) {
+        const Contig& k = c->h_contigs[i];
+        fasta_off[i] = k.hdr_off;
+        if (sep) sep[i] = (uint8_t)k.sep;
+        if (partial) partial[i] = (uint8_t)(k.out_len % k.bpl != 0);
+        // V[rec_lo] of each contig: one 8-byte copy per contig is fine for genome-scale contig counts; batch for many
+        vcf_off[i] = 0;
+    }
+    fasta_off[c->n_contigs] = c->fasta_bytes;
+    if (c->n_recs > 0) {
+        // gather V[rec_lo[c]] with a strided 2D copy when contigs are few, else download V once
+        if (c->n_contigs <= 4096) {
+            for (int i = 0; i < c->n_contigs; ++i)
+                MS_CUDA(c, cudaMemcpy(&vcf_off[i], c->vcf_off.as<int64_t>() + c->h_contigs[i].rec_lo, 8, cudaMemcpyDeviceToHost));
+        } else {
+            V.resize((size_t)c->n_recs + 1);
+            MS_CUDA(c, cudaMemcpy(V.data(), c->vcf_off.p, (size_t)(c->n_recs + 1) * 8, cudaMemcpyDeviceToHost));
+            for (int i = 0; i < c->n_contigs; ++i) vcf_off[i] = V[(size_t)c->h_contigs[i].rec_lo];
+        }
+    }
+    vcf_off[c->n_contigs] = c->vcf_bytes;
     return MS_OK;
 }
 

@@ -63,6 +63,8 @@ struct ms_ctx {
     std::vector<ms::Contig> h_contigs;
     int32_t n_contigs = 0;
     int64_t total_bases = 0;
+    int64_t foreign_cap = 0;   // staging bytes behind the genome (ms_genome_reserve)
+    ms::DevBuf tmp_contigs;
 
     // ranges / sampling
     ms::DevBuf ranges, cand_val, cand_sorted, bucket_cnt, bucket_off, cand_type, cand_len, cand_reach, cand_pm,

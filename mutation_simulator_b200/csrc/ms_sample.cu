@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(256) k_count_types(const Rec* recs, int64_t n,
 template <class T> __global__ void k_copy_scalar(const T* src, T* dst) { *dst = *src; }
 
 // ---- host orchestration --------------------------------------------------------------
-static int draw_and_sort(ms_ctx* c, Seed seed, uint32_t purpose, int32_t min_dist, int positions_only) {
+static int draw_and_sort(ms_ctx* c, Seed seed, uint32_t purpose, int32_t min_dist, int positions_only, const Contig* d_ctg) {
     cudaStream_t st = c->stream;
     const int64_t K = c->n_candidates;
     const int32_t R = c->n_ranges;
@@ -292,7 +292,7 @@ static int draw_and_sort(ms_ctx* c, Seed seed, uint32_t purpose, int32_t min_dis
     int64_t* d_boff = c->bucket_off.as<int64_t>();
 
     stage_begin(c, ST_SAMPLE_POS);
-    k_make_prps<<<(unsigned)ceil_div(R, 128), 128, 0, st>>>(d_ranges, R, c->contigs.as<Contig>(), seed, purpose, d_prps);
+    k_make_prps<<<(unsigned)ceil_div(R, 128), 128, 0, st>>>(d_ranges, R, d_ctg, seed, purpose, d_prps);
     MS_LAUNCH_CHECK(c);
     MS_CUDA(c, cudaMemsetAsync(d_cnt, 0, (size_t)(c->n_buckets + 1) * 4, st));
     k_draw<<<(unsigned)ceil_div(K, 256), 256, 0, st>>>(d_ranges, d_cand_lo, R, d_prps, K, c->cand_sorted.as<uint32_t>(), d_cnt, d_tot);
@@ -309,7 +309,7 @@ static int draw_and_sort(ms_ctx* c, Seed seed, uint32_t purpose, int32_t min_dis
     stage_end(c, ST_SAMPLE_POS);
 
     stage_begin(c, ST_SAMPLE_TYPE);
-    k_sort_emit<<<(unsigned)c->n_buckets, SORT_THREADS, 0, st>>>(d_ranges, d_bucket_lo, R, c->contigs.as<Contig>(), d_boff,
+    k_sort_emit<<<(unsigned)c->n_buckets, SORT_THREADS, 0, st>>>(d_ranges, d_bucket_lo, R, d_ctg, d_boff,
                                                                  c->cand_sorted.as<uint32_t>(), seed, min_dist, d_block, positions_only,
                                                                  c->svec.as<int64_t>(), c->cand_type.as<uint8_t>(), c->cand_len.as<uint32_t>(),
                                                                  c->cand_reach.as<int64_t>(), c->lvec.as<uint32_t>(), d_tot);
@@ -333,7 +333,7 @@ int sample_pipeline(ms_ctx* c, uint64_t seed64) {
     MS_CUDA(c, c->lit.ensure(64));
     if (K == 0 || c->n_ranges == 0) return MS_OK;
 
-    int rc = draw_and_sort(c, seed, P_RANGE_PRP, c->min_dist, 0);
+    int rc = draw_and_sort(c, seed, P_RANGE_PRP, c->min_dist, 0, c->contigs.as<Contig>());
     if (rc) return rc;
 
     const int64_t* d_gpos = c->svec.as<int64_t>();
@@ -467,7 +467,7 @@ int count_types(ms_ctx* c) {
 }
 
 // Range table upload shared by ms_set_ranges and ms_it_breakpoints.
-static int upload_ranges(ms_ctx* c, int32_t min_dist) {
+static int upload_ranges(ms_ctx* c, int32_t min_dist, const std::vector<Contig>& ctg) {
     const int32_t R = (int32_t)c->h_ranges.size();
     std::vector<int64_t> cand_lo(R + 1), bucket_lo(R + 1);
     int64_t K = 0, NB = 0, STORE = 0;
@@ -483,7 +483,7 @@ static int upload_ranges(ms_ctx* c, int32_t min_dist) {
         g.bucket_lo = (uint32_t)NB;
         g.store_lo = STORE;
         STORE += (int64_t)g.nb * (g.nb == 1u ? g.k : (uint32_t)BUCKET_CAP);
-        g.gstart = c->h_contigs[g.contig].goff + g.start;
+        g.gstart = ctg[g.contig].goff + g.start;
         cand_lo[r] = K; bucket_lo[r] = NB;
         K += g.k; NB += g.nb;
     }
@@ -536,7 +536,7 @@ int ms_set_ranges(ms_ctx* c, const ms_range* ranges, int32_t n_ranges, const int
         }
         c->h_ranges.push_back(g);
     }
-    return upload_ranges(c, min_dist);
+    return upload_ranges(c, min_dist, c->h_contigs);
 }
 
 int ms_sample(ms_ctx* c, uint64_t seed) {
@@ -545,52 +545,75 @@ int ms_sample(ms_ctx* c, uint64_t seed) {
     return sample_pipeline(c, seed);
 }
 
+int ms_sample_positions(ms_ctx* c, uint64_t seed, int32_t n, const uint32_t* gid, const uint32_t* start, const uint32_t* stop,
+                        const uint32_t* k, int32_t min_dist, uint32_t* out) {
+    if (!c || n < 0 || (n > 0 && (!gid || !start || !stop || !k || !out)) || min_dist < 0) return MS_ERR_ARG;
+    MS_CUDA(c, cudaSetDevice(c->device));
+    // a private contig table: one pseudo contig per range, long enough to hold it
+    std::vector<Contig> ctg((size_t)n);
+    c->h_ranges.clear();
+    c->n_ranges = -1;
+    int64_t off = 0;
+    for (int32_t i = 0; i < n; ++i) {
+        Contig& q = ctg[i];
+        q = Contig{};
+        q.goff = off; q.len = (int64_t)stop[i] + 1; q.gid = gid[i]; q.bpl = 60;
+        off += q.len;
+        if (k[i] == 0) continue;
+        Range g{};
+        g.contig = (uint32_t)i; g.start = start[i]; g.stop = stop[i]; g.k = k[i]; g.limit = q.len;
+        for (int t = 0; t < 7; ++t) { g.cdf[t] = 1.0; g.minlen[t] = 1; g.maxlen[t] = 1; }
+        c->h_ranges.push_back(g);
+    }
+    int rc = upload_ranges(c, min_dist, ctg);
+    c->n_ranges = -1;  // the range table now holds position-only ranges: ms_sample needs ms_set_ranges again
+    if (rc) return rc;
+    const int64_t K = c->n_candidates;
+    if (K == 0) return MS_OK;
+    MS_CUDA(c, c->tmp_contigs.ensure(sizeof(Contig) * (size_t)n));
+    MS_CUDA(c, cudaMemcpyAsync(c->tmp_contigs.p, ctg.data(), sizeof(Contig) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    MS_CUDA(c, cudaMemsetAsync(c->totals.p, 0, sizeof(Totals), c->stream));
+    rc = draw_and_sort(c, make_seed(seed), P_IT_PRP, min_dist, 1, c->tmp_contigs.as<Contig>());
+    if (rc) return rc;
+    std::vector<int64_t> gpos((size_t)K);
+    MS_CUDA(c, cudaMemcpyAsync(gpos.data(), c->svec.p, (size_t)K * 8, cudaMemcpyDeviceToHost, c->stream));
+    MS_CUDA(c, cudaMemcpyAsync(c->h_totals, c->totals.p, sizeof(Totals), cudaMemcpyDeviceToHost, c->stream));
+    MS_CUDA(c, cudaStreamSynchronize(c->stream));   // also keeps ctg alive until the async copy is done
+    if (c->h_totals->error) MS_FAIL(c, (int)c->h_totals->error, "ms_sample_positions: kernel error %lld", (long long)c->h_totals->error);
+    int64_t s = 0;
+    for (int32_t i = 0; i < n; ++i) {
+        for (uint32_t j = 0; j < k[i]; ++j) out[s + j] = (uint32_t)(gpos[(size_t)(s + j)] - ctg[i].goff);
+        s += k[i];
+    }
+    return MS_OK;
+}
+
 int ms_it_breakpoints(ms_ctx* c, uint64_t seed, int32_t n_pairs, const uint32_t* contig_a, const uint32_t* contig_b,
                       const uint32_t* n, uint32_t* bp_a, uint32_t* bp_b) {
     if (!c || n_pairs < 0 || !contig_a || !contig_b || !n || !bp_a || !bp_b) return MS_ERR_ARG;
     if (c->n_contigs <= 0) MS_FAIL(c, MS_ERR_STATE, "ms_it_breakpoints: upload a genome first");
-    MS_CUDA(c, cudaSetDevice(c->device));
-    c->h_ranges.clear();
-    c->n_ranges = -1;
-    // pair-major: all of a's breakpoints then all of b's, per pair (it_mutator.py:108-111)
+    // pair-major: all of a's breakpoints, then all of b's: sample_with_minimum_distance(1, len, n, 1) each (it_mutator.py:108-111)
+    std::vector<uint32_t> gid, start, stop, k;
+    int64_t total = 0;
     for (int32_t p = 0; p < n_pairs; ++p) {
         for (int side = 0; side < 2; ++side) {
             const uint32_t ci = side ? contig_b[p] : contig_a[p];
             if (ci >= (uint32_t)c->n_contigs) MS_FAIL(c, MS_ERR_ARG, "pair %d: contig out of range", p);
-            if (n[p] == 0) continue;
-            Range g{};
-            g.contig = ci; g.start = 1; g.stop = (uint32_t)c->h_contigs[ci].len; g.k = n[p];   // sample_with_minimum_distance(1, len, n, 1)
-            g.limit = c->h_contigs[ci].len;
-            for (int t = 0; t < 7; ++t) { g.cdf[t] = 1.0; g.minlen[t] = 1; g.maxlen[t] = 1; }
-            c->h_ranges.push_back(g);
+            gid.push_back(c->h_contigs[ci].gid); start.push_back(1u); stop.push_back((uint32_t)c->h_contigs[ci].len); k.push_back(n[p]);
         }
+        total += n[p];
     }
-    int rc = upload_ranges(c, 1);
+    std::vector<uint32_t> out((size_t)(2 * total) + 1);
+    int rc = ms_sample_positions(c, seed, (int32_t)gid.size(), gid.data(), start.data(), stop.data(), k.data(), 1, out.data());
     if (rc) return rc;
-    const int64_t K = c->n_candidates;
-    const int32_t saved = c->n_ranges;
-    if (K > 0) {
-        MS_CUDA(c, cudaMemsetAsync(c->totals.p, 0, sizeof(Totals), c->stream));
-        rc = draw_and_sort(c, make_seed(seed), P_IT_PRP, 1, 1);
-        if (rc) return rc;
-        std::vector<int64_t> gpos((size_t)K);
-        MS_CUDA(c, cudaMemcpyAsync(gpos.data(), c->svec.p, (size_t)K * 8, cudaMemcpyDeviceToHost, c->stream));
-        MS_CUDA(c, cudaMemcpyAsync(c->h_totals, c->totals.p, sizeof(Totals), cudaMemcpyDeviceToHost, c->stream));
-        MS_CUDA(c, cudaStreamSynchronize(c->stream));
-        if (c->h_totals->error) MS_FAIL(c, (int)c->h_totals->error, "ms_it_breakpoints: kernel error %lld", (long long)c->h_totals->error);
-        int64_t s = 0, o = 0;
-        for (int32_t p = 0; p < n_pairs; ++p) {
-            if (n[p] == 0) continue;
-            const int64_t ga = c->h_contigs[contig_a[p]].goff, gb = c->h_contigs[contig_b[p]].goff;
-            for (uint32_t i = 0; i < n[p]; ++i) bp_a[o + i] = (uint32_t)(gpos[s + i] - ga);
-            s += n[p];
-            for (uint32_t i = 0; i < n[p]; ++i) bp_b[o + i] = (uint32_t)(gpos[s + i] - gb);
-            s += n[p];
-            o += n[p];
-        }
+    int64_t s = 0, o = 0;
+    for (int32_t p = 0; p < n_pairs; ++p) {
+        for (uint32_t i = 0; i < n[p]; ++i) bp_a[o + i] = out[(size_t)(s + i)];
+        s += n[p];
+        for (uint32_t i = 0; i < n[p]; ++i) bp_b[o + i] = out[(size_t)(s + i)];
+        s += n[p];
+        o += n[p];
     }
-    (void)saved;
-    c->n_ranges = -1;  // the range table now holds breakpoint ranges: ms_sample needs ms_set_ranges again
     return MS_OK;
 }
 

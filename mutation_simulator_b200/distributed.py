@@ -1,0 +1,166 @@
+"""One process per GPU (torchrun): contig partitioning, peer exchange and output assembly.
+
+ARGS/RMT need no data-path collective: contigs are independent (mutator.py:111 carries no
+state between them) and the RNG is keyed by the global contig index, so every rank simply
+processes its share and the ranks' slices are written into one file at offsets derived
+from an all-gather of their sizes.  IT needs one exchange step: for a pair whose members
+live on different GPUs each owner sends its contig to the other (NCCL send/recv, grouped)
+straight into the staging region behind the receiver's genome, which is where the splice
+kernel's raw far-copy records point (it_mutator.py:133-142)."""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+_pg_ready = False
+
+
+def rank_world():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def local_device(default: int = 0) -> int:
+    return int(os.environ.get("LOCAL_RANK", default))
+
+
+def init():
+    """Initialise torch.distributed (NCCL) when launched with WORLD_SIZE > 1."""
+    global _pg_ready
+    rank, world = rank_world()
+    if world > 1 and not _pg_ready:
+        import torch
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            torch.cuda.set_device(local_device())
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_device()))
+        _pg_ready = True
+    return rank, world
+
+
+def barrier():
+    if rank_world()[1] > 1:
+        import torch.distributed as dist
+        dist.barrier()
+
+
+def broadcast_object(obj):
+    if rank_world()[1] == 1:
+        return obj
+    import torch.distributed as dist
+    box = [obj]
+    dist.broadcast_object_list(box, src=0)
+    return box[0]
+
+
+def all_gather_object(obj):
+    world = rank_world()[1]
+    if world == 1:
+        return [obj]
+    import torch.distributed as dist
+    out = [None] * world
+    dist.all_gather_object(out, obj)
+    return out
+
+
+def lpt_partition(lengths, n):
+    """Longest-processing-time bin packing of contigs onto n ranks; deterministic."""
+    bins = [[] for _ in range(n)]
+    load = [0] * n
+    for i in sorted(range(len(lengths)), key=lambda i: (-int(lengths[i]), i)):
+        b = load.index(min(load))
+        bins[b].append(i)
+        load[b] += int(lengths[i])
+    return [sorted(b) for b in bins]
+
+
+def owners(parts, n_contigs):
+    own = np.zeros(n_contigs, dtype=np.int64)
+    for r, ids in enumerate(parts):
+        own[ids] = r
+    return own
+
+
+class _DevMem:
+    """Zero-copy torch view of engine-owned device memory (for NCCL send/recv)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+def device_view(ptr: int, nbytes: int, device: int):
+    import torch
+    return torch.as_tensor(_DevMem(ptr, nbytes), device=f"cuda:{device}")
+
+
+def exchange_contigs(engine, device, sends, recvs):
+    """sends: [(peer, genome_index, nbytes)], recvs: [(peer, genome_index, nbytes)] in a globally agreed order.
+    One grouped NCCL call (ncclGroupStart/End under batch_isend_irecv)."""
+    if not sends and not recvs:
+        return
+    import torch
+    import torch.distributed as dist
+    from .engine import BUF_GENOME
+    base, _ = engine.device_ptr(BUF_GENOME)
+    ops = []
+    keep = []
+    for peer, idx, n in sends:
+        t = device_view(base + idx, n, device)
+        keep.append(t)
+        ops.append(dist.P2POp(dist.isend, t, peer))
+    for peer, idx, n in recvs:
+        t = device_view(base + idx, n, device)
+        keep.append(t)
+        ops.append(dist.P2POp(dist.irecv, t, peer))
+    for w in dist.batch_isend_irecv(ops):
+        w.wait()
+    torch.cuda.synchronize()
+
+
+def write_partitioned(path, my_ids, chunks, n_contigs, prefix: bytes = b""):
+    """Every rank writes the byte chunks of its contigs (chunks[i] belongs to global contig my_ids[i]) into
+    one file, contigs in global order, after `prefix` (written by rank 0)."""
+    rank, world = rank_world()
+    sizes = np.zeros(n_contigs, dtype=np.int64)
+    for r_ids, r_sizes in all_gather_object((list(my_ids), [len(c) for c in chunks])):
+        sizes[r_ids] = r_sizes
+    off = np.zeros(n_contigs + 1, dtype=np.int64)
+    np.cumsum(sizes, out=off[1:])
+    off += len(prefix)
+    if rank == 0:
+        with open(path, "wb") as fh:
+            fh.write(prefix)
+            fh.truncate(int(off[-1]))
+    barrier()
+    fd = os.open(path, os.O_WRONLY)
+    try:
+        for g, c in zip(my_ids, chunks):
+            if len(c):
+                os.pwrite(fd, c, int(off[g]))
+    finally:
+        os.close(fd)
+    barrier()
+
+
+def fasta_chunks(engine, my_ids, n_contigs_global):
+    """Per-contig slices of the engine's FASTA image with the separator fixed up for the global file:
+    a '\\n' follows a partial last line unless the contig is the last one of the whole file."""
+    from .engine import BUF_FASTA
+    image = engine.download(BUF_FASTA)
+    fo, vo, sep, partial = engine.contig_layout()
+    out = []
+    for i, g in enumerate(my_ids):
+        a, b = int(fo[i]), int(fo[i + 1])
+        if sep[i]:
+            b -= 1
+        chunk = image[a:b].tobytes()
+        if partial[i] and g != n_contigs_global - 1:
+            chunk += b"\n"
+        out.append(chunk)
+    return out, vo
+
+
+def vcf_chunks(engine, my_ids, vcf_off):
+    from .engine import BUF_VCF
+    body = engine.download(BUF_VCF)
+    return [body[int(vcf_off[i]):int(vcf_off[i + 1])].tobytes() for i in range(len(my_ids))]

@@ -98,6 +98,10 @@ class Engine:
                                               float(n_fraction), int(telomere_n), _ptr(self._hdr), _ptr(self._hoff),
                                               _ptr(self._nam), _ptr(self._noff)))
 
+    def reserve_foreign(self, nbytes: int):
+        """Staging space behind the genome for partner contigs owned by another GPU (call before upload)."""
+        self._check(self._lib.ms_genome_reserve(self._h, int(nbytes)))
+
     def download_genome(self) -> np.ndarray:
         out = np.empty(self.total_bases, dtype=np.uint8)
         self._check(self._lib.ms_genome_download(self._h, _ptr(out), out.size))
@@ -171,6 +175,23 @@ class Engine:
         out = np.empty(self.n_contigs, dtype=np.int64)
         self._check(self._lib.ms_contig_out_len(self._h, _ptr(out)))
         return out
+
+    def contig_layout(self):
+        """-> (fasta_off[n+1], vcf_off[n+1], sep[n], partial[n]) of the last apply()."""
+        n = self.n_contigs
+        fo = np.empty(n + 1, np.int64); vo = np.empty(n + 1, np.int64)
+        sep = np.empty(n, np.uint8); par = np.empty(n, np.uint8)
+        self._check(self._lib.ms_contig_layout(self._h, _ptr(fo), _ptr(vo), _ptr(sep), _ptr(par)))
+        return fo, vo, sep, par
+
+    def sample_positions(self, seed: int, gid, start, stop, k, min_dist: int):
+        """util.sample_with_minimum_distance for many ranges; returns the concatenated sorted positions."""
+        gid = np.ascontiguousarray(gid, np.uint32); start = np.ascontiguousarray(start, np.uint32)
+        stop = np.ascontiguousarray(stop, np.uint32); k = np.ascontiguousarray(k, np.uint32)
+        out = np.empty(max(1, int(k.sum())), np.uint32)
+        self._check(self._lib.ms_sample_positions(self._h, C.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), len(gid), _ptr(gid), _ptr(start),
+                                                  _ptr(stop), _ptr(k), int(min_dist), _ptr(out)))
+        return out[:int(k.sum())]
 
     # -- IT ----------------------------------------------------------------
     def it_breakpoints(self, seed: int, contig_a, contig_b, n):

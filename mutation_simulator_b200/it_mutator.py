@@ -12,6 +12,7 @@ import random
 
 import numpy as np
 
+from . import distributed as D
 from .bedpe_writer import BedpeWriter, rows
 from .engine import BUF_FASTA, Engine
 from .fasta_writer import FastaWriter
@@ -23,9 +24,13 @@ from .util import print_warning
 class ITMutator:
     def __init__(self, args, fasta, sim):
         self._args, self._fasta, self._sim = args, fasta, sim
-        self._fasta_writer = FastaWriter(args.outfastait)
-        self._bedpe_writer = BedpeWriter(args.outbedpe)
-        self._seed = run_seed(args)
+        self._rank, self._world = D.init()
+        if self._world == 1:
+            self._fasta_writer = FastaWriter(args.outfastait)
+            self._bedpe_writer = BedpeWriter(args.outbedpe)
+        else:
+            self._fasta_writer = self._bedpe_writer = None
+        self._seed = D.broadcast_object(run_seed(args))
         self._rng = random.Random(self._seed)
         # it_mutator.py:51-70: eligible contigs, then random disjoint pairs
         avail = [c.number for c in sim.chromosomes if c.it_rate is not None and len(fasta[c.number]) > 2]
@@ -46,8 +51,9 @@ class ITMutator:
             pass
 
     def close(self):
-        self._fasta_writer.close()
-        self._bedpe_writer.close()
+        if self._fasta_writer is not None:
+            self._fasta_writer.close()
+            self._bedpe_writer.close()
         if self._engine is not None:
             self._engine.close()
             self._engine = None
@@ -80,18 +86,29 @@ class ITMutator:
             counts.append(n)
         bps = {}
         if pairs:
-            bpa, bpb = eng.it_breakpoints(self._seed, [p[0] for p in pairs], [p[1] for p in pairs], counts)
+            # sample_with_minimum_distance(1, len, n, 1) for both members of every pair (it_mutator.py:108-111);
+            # keyed by the global contig index, so every rank computes the same breakpoints
+            gid, stop, k = [], [], []
+            for (a, b), n in zip(pairs, counts):
+                gid += [a, b]; stop += [len(fasta[a]), len(fasta[b])]; k += [n, n]
+            pos = eng.sample_positions(self._seed, gid, [1] * len(gid), stop, k, 1)
             o = 0
             for (a, b), n in zip(pairs, counts):
-                bps[a] = {"self": bpa[o:o + n], "partner": bpb[o:o + n]}
-                bps[b] = {"self": bpb[o:o + n], "partner": bpa[o:o + n]}
-                o += n
+                pa, pb = pos[o:o + n], pos[o + n:o + 2 * n]
+                bps[a] = {"self": pa, "partner": pb}
+                bps[b] = {"self": pb, "partner": pa}
+                o += 2 * n
         return bps
 
-    def _records(self, bps):
+    def _records(self, bps, my_ids=None, src_of=None):
+        """One raw far-copy record per interval taken from the partner.  my_ids: global contigs resident on this
+        engine (local index = position); src_of[p]: genome index of partner p's first base on this engine."""
         fasta = self._fasta
         parts = []
+        local = None if my_ids is None else {g: i for i, g in enumerate(my_ids)}
         for c in sorted(bps):
+            if local is not None and c not in local:
+                continue
             p = self._partners[c]
             a = np.concatenate(([0], bps[c]["self"].astype(np.int64), [len(fasta[c])]))
             b = np.concatenate(([0], bps[c]["partner"].astype(np.int64), [len(fasta[p])]))
@@ -100,16 +117,18 @@ class ITMutator:
             r["pos"] = a[odd]
             r["cons"] = a[odd + 1] - a[odd]
             r["prod"] = b[odd + 1] - b[odd]
-            r["src"] = fasta.goff[p] + b[odd]
+            r["src"] = (fasta.goff[p] if src_of is None else src_of[p]) + b[odd]
             r["kind"] = K_RAW
             r["type"] = T_IT
-            r["contig"] = c
+            r["contig"] = c if local is None else local[c]
             parts.append(r)
         return np.concatenate(parts) if parts else np.zeros(0, dtype=REC_DTYPE)
 
     def mutate(self):
         """Creates interchromosomal translocations and writes them to a Fasta and BEDPE file."""
         fasta = self._fasta
+        if self._world > 1:
+            return self._mutate_partitioned()
         eng = self._engine = Engine(getattr(self._args, "device", 0))
         fasta.upload(eng)
         bps = self.breakpoints = self._generate_all_breakpoints(eng)
@@ -122,3 +141,53 @@ class ITMutator:
                 p = self._partners[c]
                 self._bedpe_writer._f.write(rows(fasta[c].name, bps[c]["self"], len(fasta[c]), fasta[p].name,
                                                  bps[c]["partner"], len(fasta[p])))
+
+    def _mutate_partitioned(self):
+        """One process per GPU: contigs are partitioned; a pair that straddles two GPUs swaps its members over
+        NCCL P2P into the staging region behind each receiver's genome."""
+        fasta, rank, world = self._fasta, self._rank, self._world
+        n_contigs = len(fasta.names)
+        parts = D.lpt_partition(fasta.lengths, world)
+        own = D.owners(parts, n_contigs)
+        my_ids = parts[rank]
+        device = D.local_device()
+        eng = self._engine = Engine(device)
+        # breakpoints need no resident genome (keyed by global contig id): identical on every rank
+        bps = self.breakpoints = self._generate_all_breakpoints(eng)
+        # which partner contigs must be fetched from a peer
+        foreign = sorted(self._partners[c] for c in my_ids if c in bps and own[self._partners[c]] != rank)
+        stage_off, acc = {}, 0
+        for p in foreign:
+            stage_off[p] = acc
+            acc += int(fasta.lengths[p]) + 64
+        eng.reserve_foreign(acc)
+        fasta.upload(eng, my_ids)
+        total = int(sum(int(fasta.lengths[g]) for g in my_ids))
+        local_goff, o = {}, 0
+        for g in my_ids:
+            local_goff[g] = o
+            o += int(fasta.lengths[g])
+        src_of = {p: local_goff[p] for p in my_ids}
+        src_of.update({p: total + 64 + off for p, off in stage_off.items()})
+        # globally agreed order: ascending (min, max) of each straddling pair
+        sends, recvs = [], []
+        for a in sorted(bps):
+            b = self._partners[a]
+            if a < b and own[a] != own[b]:
+                for mine, theirs in ((a, b), (b, a)):
+                    if own[mine] == rank:
+                        sends.append((int(own[theirs]), local_goff[mine], int(fasta.lengths[mine])))
+                        recvs.append((int(own[theirs]), src_of[theirs], int(fasta.lengths[theirs])))
+        D.exchange_contigs(eng, device, sends, recvs)
+        eng.load_records(self._records(bps, my_ids, src_of))
+        eng.apply()
+        chunks, _ = D.fasta_chunks(eng, my_ids, n_contigs)
+        D.write_partitioned(self._args.outfastait, my_ids, chunks, n_contigs)
+        bed = []
+        for g in my_ids:
+            if g in bps:
+                p = self._partners[g]
+                bed.append(rows(fasta[g].name, bps[g]["self"], len(fasta[g]), fasta[p].name, bps[g]["partner"], len(fasta[p])))
+            else:
+                bed.append(b"")
+        D.write_partitioned(self._args.outbedpe, my_ids, bed, n_contigs)

@@ -1,0 +1,70 @@
+"""N-GPU output == 1-GPU output, byte for byte (needs >= 2 GPUs; run with `gpurun --gpus 2`).
+ARGS mode shards contigs with no collective; IT mode swaps partner contigs over NCCL P2P."""
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from tests.helpers import GOLDEN
+
+pytestmark = pytest.mark.gpu
+REPO = Path(__file__).resolve().parent.parent
+
+
+def _ngpu():
+    import torch
+    return torch.cuda.device_count()
+
+
+def cli(argv, nproc, port):
+    env = dict(os.environ, PYTHONPATH=str(REPO))
+    if nproc == 1:
+        cmd = [sys.executable, "-m", "mutation_simulator_b200"] + argv
+    else:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
+               f"--master-port={port}", "-m", "mutation_simulator_b200"] + argv
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def make_genome(path, lens, seed, bpl=60):
+    rng = np.random.default_rng(seed)
+    with open(path, "w") as fh:
+        for i, n in enumerate(lens):
+            s = rng.choice(np.frombuffer(b"ACGT", np.uint8), n).tobytes().decode()
+            fh.write(f">ctg{i+1} len={n}\n")
+            for j in range(0, n, bpl):
+                fh.write(s[j:j + bpl] + "\n")
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
+def test_partitioned_runs_equal_single_gpu(tmp_path):
+    n = min(_ngpu(), 4)
+    lens = [90_000, 70_011, 65_000, 40_000, 33_333, 20_000, 7, 1_000]
+    make_genome(tmp_path / "g.fa", lens, 1)
+    common = ["-q", "--seed", "77", "args", "-sn", "0.01", "-in", "0.002", "-inmax", "9", "-de", "0.002", "-demax", "9", "-du", "0.001",
+              "-dumax", "30", "-iv", "0.001", "-ivmax", "30", "-tl", "0.002", "-tlmax", "20"]
+    (tmp_path / "a").mkdir(); (tmp_path / "b").mkdir()
+    cli([str(tmp_path / "g.fa"), "-o", str(tmp_path / "a" / "g")] + common, 1, 0)
+    cli([str(tmp_path / "g.fa"), "-o", str(tmp_path / "b" / "g")] + common, n, 29541)
+    for f in ("g_ms.fa", "g_ms.vcf"):
+        a, b = (tmp_path / "a" / f).read_bytes(), (tmp_path / "b" / f).read_bytes()
+        if f.endswith(".vcf"):
+            a = b"".join(l for l in a.splitlines(keepends=True) if not l.startswith(b"##filedate"))
+            b = b"".join(l for l in b.splitlines(keepends=True) if not l.startswith(b"##filedate"))
+        assert a == b, f
+    # IT: several seeds so that at least one pairing straddles the GPUs
+    for seed in (1, 2, 3):
+        for d in ("a", "b"):
+            for f in (tmp_path / d).glob("*_it*"):
+                f.unlink()
+        it = ["-q", "--seed", str(seed), "it", "0.001"]
+        cli([str(tmp_path / "g.fa"), "-o", str(tmp_path / "a" / "g")] + it, 1, 0)
+        cli([str(tmp_path / "g.fa"), "-o", str(tmp_path / "b" / "g")] + it, n, 29542 + seed)
+        for f in ("g_ms_it.fa", "g_ms_it.bedpe"):
+            assert (tmp_path / "a" / f).read_bytes() == (tmp_path / "b" / f).read_bytes(), (seed, f)
+        assert (tmp_path / "a" / "g_ms_it.bedpe").stat().st_size > 0
