@@ -566,14 +566,14 @@ int ms_sample_positions(ms_ctx* c, uint64_t seed, int32_t n, const uint32_t* gid
         c->h_ranges.push_back(g);
     }
     int rc = upload_ranges(c, min_dist, ctg);
-    c->n_ranges = -1;  // the range table now holds position-only ranges: ms_sample needs ms_set_ranges again
-    if (rc) return rc;
+    if (rc) { c->n_ranges = -1; return rc; }
     const int64_t K = c->n_candidates;
-    if (K == 0) return MS_OK;
+    if (K == 0) { c->n_ranges = -1; return MS_OK; }
     MS_CUDA(c, c->tmp_contigs.ensure(sizeof(Contig) * (size_t)n));
     MS_CUDA(c, cudaMemcpyAsync(c->tmp_contigs.p, ctg.data(), sizeof(Contig) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     MS_CUDA(c, cudaMemsetAsync(c->totals.p, 0, sizeof(Totals), c->stream));
     rc = draw_and_sort(c, make_seed(seed), P_IT_PRP, min_dist, 1, c->tmp_contigs.as<Contig>());
+    c->n_ranges = -1;  // the range table now holds position-only ranges: ms_sample needs ms_set_ranges again
     if (rc) return rc;
     std::vector<int64_t> gpos((size_t)K);
     MS_CUDA(c, cudaMemcpyAsync(gpos.data(), c->svec.p, (size_t)K * 8, cudaMemcpyDeviceToHost, c->stream));
