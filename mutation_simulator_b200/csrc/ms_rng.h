@@ -95,11 +95,15 @@ MS_HD uint64_t bounded(uint64_t r, uint64_t n) { return mulhi64(r, n); }
 // network over ceil(log2 n) bits with cycle walking (values >= n are re-encrypted
 // until they fall inside the range; expected < 2 walks since 2^bits < 2n).
 // ---------------------------------------------------------------------------
-constexpr int PRP_ROUNDS = 12;
+// Rounds: 8 on domains of >= 12 bits (statistically flat for k-subsets of genome-sized ranges);
+// 16 on tiny domains, where each round function has only a few output bits (tests/test_emu.py checks
+// that all arrangements of small domains are equally likely over keys).
+constexpr int PRP_MAX_ROUNDS = 16;
 
 struct Prp {
-    uint32_t key[PRP_ROUNDS];
+    uint32_t key[PRP_MAX_ROUNDS];
     uint32_t n;        // domain size
+    uint32_t rounds;
     uint32_t abits;    // high half width
     uint32_t bbits;    // low half width
 };
@@ -117,13 +121,15 @@ MS_HD uint32_t mix32(uint32_t x, uint32_t k) {
 
 MS_HD Prp make_prp(Seed s, uint32_t contig, uint32_t purpose, uint64_t idx, uint32_t n) {
     Prp p;
-    for (int b = 0; b < PRP_ROUNDS / 4; ++b) {
-        U4 r = draw(s, contig, purpose | ((uint32_t)(b + 1) << 8), idx);
-        p.key[4 * b + 0] = r.x; p.key[4 * b + 1] = r.y; p.key[4 * b + 2] = r.z; p.key[4 * b + 3] = r.w;
-    }
     p.n = n;
     uint32_t bits = 2;
     while (bits < 32 && (1ull << bits) < (uint64_t)n) ++bits;
+    p.rounds = bits >= 12 ? 8u : 16u;
+    for (uint32_t b = 0; b < PRP_MAX_ROUNDS / 4; ++b) {
+        U4 r{0, 0, 0, 0};
+        if (4 * b < p.rounds) r = draw(s, contig, purpose | ((uint32_t)(b + 1) << 8), idx);
+        p.key[4 * b + 0] = r.x; p.key[4 * b + 1] = r.y; p.key[4 * b + 2] = r.z; p.key[4 * b + 3] = r.w;
+    }
     p.abits = bits / 2;
     p.bbits = bits - p.abits;
     return p;
@@ -138,9 +144,18 @@ MS_HD uint32_t prp_apply(const Prp& p, uint32_t j) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-        for (int r = 0; r < PRP_ROUNDS; r += 2) {
+        for (int r = 0; r < 8; r += 2) {
             a ^= mix32(b, p.key[r]) & amask;
             b ^= mix32(a, p.key[r + 1]) & bmask;
+        }
+        if (p.rounds > 8u) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int r = 8; r < PRP_MAX_ROUNDS; r += 2) {
+                a ^= mix32(b, p.key[r]) & amask;
+                b ^= mix32(a, p.key[r + 1]) & bmask;
+            }
         }
         x = (a << p.bbits) | b;
     } while (x >= p.n);

@@ -21,7 +21,7 @@ struct Range {
     uint32_t contig;    // local contig index
     uint32_t bucket_lo; // first sort bucket
     uint32_t nb;        // number of sort buckets
-    uint32_t pad;
+    uint32_t bscale;    // floor(2^32 * nb / n): bucket of value v = mulhi32(v, bscale) (monotone, < nb)
     double cdf[7];      // cumulative mut_chances in canonical type order (numpy.random.choice, mutator.py:170-174)
     int32_t minlen[7];
     int32_t maxlen[7];
