@@ -513,7 +513,7 @@ __global__ void k_headers(const Contig* contigs, int32_t n_contigs, const uint8_
 // copy jobs and moved by whole warps afterwards (profiles/r1b: the per-byte REF/ALT
 // loops ran on 1.5 lanes and were half of all instructions).
 constexpr int VCF_THREADS = 256;
-constexpr int VCF_SMEM = 32 * 1024;
+constexpr int VCF_SMEM = 22 * 1024;
 constexpr int VCF_MAX_JOBS = 2 * VCF_THREADS;
 enum SegMode : uint32_t { SM_IMM = 0, SM_RAW = 1, SM_CONV = 2, SM_RC = 3, SM_LIT = 4 };
 struct Seg { int64_t src; uint32_t len; uint32_t mode; };
@@ -533,7 +533,14 @@ __device__ __forceinline__ uint8_t* put_u32(uint8_t* p, uint32_t v) {
     const uint32_t n = ndigits(v);
     uint8_t* e = p + n;
     uint8_t* q = e;
-    do { const uint32_t d = v / 10u; *--q = (uint8_t)('0' + (v - d * 10u)); v = d; } while (v);
+    while (v >= 100u) {   // two digits per division
+        const uint32_t d = v / 100u, r = v - d * 100u, t = (r * 205u) >> 11;   // t = r / 10 for r < 100
+        *--q = (uint8_t)('0' + (r - t * 10u));
+        *--q = (uint8_t)('0' + t);
+        v = d;
+    }
+    if (v >= 10u) { const uint32_t t = (v * 205u) >> 11; *--q = (uint8_t)('0' + (v - t * 10u)); *--q = (uint8_t)('0' + t); }
+    else *--q = (uint8_t)('0' + v);
     return e;
 }
 
@@ -699,7 +706,16 @@ k_vcf_write(VcfView v, const Rec* recs, int64_t n_recs, const Contig* contigs, c
         const uint32_t len = job.len_mode & 0x1FFFFFFFu, mode = job.len_mode >> 29;
         if (len > 2048u) { any_big = true; continue; }
         uint8_t* d = line0 + job.dst;
-        for (uint32_t x = lane; x < len; x += 32u) d[x] = seg_byte(v, mode, job.src, len, x);
+        if (mode == SM_RC) {
+            const uint8_t* g = v.genome + job.src + (len - 1u);
+            for (uint32_t x = lane; x < len; x += 32u) d[x] = s_comp[s_conv[g[-(int)x]]];
+        } else if (mode == SM_CONV) {
+            const uint8_t* g = v.genome + job.src;
+            for (uint32_t x = lane; x < len; x += 32u) d[x] = s_conv[g[x]];
+        } else {
+            const uint8_t* g = (mode == SM_RAW ? v.genome : v.lit) + job.src;
+            for (uint32_t x = lane; x < len; x += 32u) d[x] = g[x];
+        }
     }
     if (__syncthreads_or(any_big)) {
         for (int jb = 0; jb < nj; ++jb) {
