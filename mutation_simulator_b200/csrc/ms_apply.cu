@@ -177,8 +177,10 @@ struct LoadWinGlobal {
 // per-group record lookups (profiles/r1b); here lookups are per run.
 constexpr int SP_TILE_MAX = 16384;
 constexpr int SP_RUN_CAP = 512;
-constexpr int SP_SEG_CAP = 640;
+constexpr int SP_SEG_CAP = 320;
 constexpr int SP_JOB_CAP = 192;
+constexpr uint32_t SP_STAGE_CAP = 18 * 1024;       // TMA staging of the runs' input spans (tile + alignment slack)
+constexpr uint32_t SP_DIRECT = 0xFFFFFFFFu;        // segment did not fit the staging buffer: copied straight from global
 constexpr uint32_t SP_SEG_SPLIT = 2048;
 struct SegC { int64_t src; uint32_t dst; uint32_t n; };   // copy n bytes genome[src..] -> tile[dst..]; jobs: n | kind << 24
 
@@ -191,6 +193,53 @@ __device__ __forceinline__ uint4 shift16(const uint4 a, const uint4 b, uint32_t 
     const uint32_t bs = (o & 3u) * 8u;
     return make_uint4(__funnelshift_r(u0, u1, bs), __funnelshift_r(u1, u2, bs), __funnelshift_r(u2, u3, bs),
                       __funnelshift_r(u3, u4, bs));
+}
+
+// ---- TMA (bulk async copy) + mbarrier, raw PTX -----------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completion is signalled on `bar`
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_global, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst_smem)),
+                 "l"(src_global), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+
+// shifted copy shared -> shared: n bytes from stage[so..] (any alignment) to tile[d0..]
+__device__ __forceinline__ void warp_copy_stage_to_tile(uint8_t* tile, const uint8_t* stage, uint32_t so, uint32_t d0, uint32_t n, int lane) {
+    const uint32_t d1 = d0 + n;
+    const uint32_t a0 = (d0 + 15u) & ~15u, a1 = d1 & ~15u;
+    if (a0 >= a1) {
+        const uint32_t x = d0 + lane;
+        if (x < d1) tile[x] = stage[so + lane];
+        return;
+    }
+    {
+        const uint32_t x = lane < 16 ? d0 + lane : a1 + (lane - 16);
+        if (x < (lane < 16 ? a0 : d1)) tile[x] = stage[so + (x - d0)];
+    }
+    for (uint32_t c = a0 + 16u * lane; c < a1; c += 512u) {
+        const uint32_t s = so + (c - d0);
+        const uint4* w = reinterpret_cast<const uint4*>(stage + (s & ~15u));
+        *reinterpret_cast<uint4*>(tile + c) = shift16(w[0], w[1], s & 15u);
+    }
 }
 
 __device__ __forceinline__ void warp_copy_to_tile(uint8_t* tile, const uint8_t* __restrict__ genome, const SegC sg, int lane) {
@@ -229,14 +278,20 @@ __device__ __forceinline__ int64_t warp_last_le(const Rec* recs, const Contig& k
     }
 }
 
-__global__ void __launch_bounds__(SPLICE_THREADS, 6)
+__global__ void __launch_bounds__(SPLICE_THREADS, 5)
 k_splice(SpliceView v, const Contig* contigs, int32_t n_contigs, const int64_t* piece_lo, const Tables* tables,
          uint8_t* fasta, int64_t tile_bytes) {
     __shared__ Contig sc;
-    __shared__ __align__(16) uint8_t tile[SP_TILE_MAX + 64];
+    extern __shared__ __align__(16) uint8_t sp_dyn[];      // [tile | stage]
+    uint8_t* const tile = sp_dyn;
+    uint8_t* const stage = sp_dyn + SP_TILE_MAX + 64;
     __shared__ SegC segs[SP_SEG_CAP];
-    __shared__ SegC jobs[SP_JOB_CAP];
-    __shared__ uint32_t nout[SP_RUN_CAP + 1], nidx[SP_RUN_CAP];
+    __shared__ uint32_t seg_stage[SP_SEG_CAP];     // offset of the segment's 16-byte aligned input span in `stage`, or SP_DIRECT
+    SegC* const jobs = reinterpret_cast<SegC*>(stage);   // payload jobs are queued after S1, when the staging buffer is dead
+    __shared__ uint32_t nout[SP_RUN_CAP + 1];
+    __shared__ uint16_t nidx[SP_RUN_CAP];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t stage_used;
     __shared__ uint32_t warp_tot[SPLICE_THREADS / 32];
     __shared__ int n_segs, n_jobs, fallback;
     __shared__ long long s_first, s_last;
@@ -259,7 +314,7 @@ k_splice(SpliceView v, const Contig* contigs, int32_t n_contigs, const int64_t* 
         const uint32_t* src = reinterpret_cast<const uint32_t*>(contigs + lo);
         uint32_t* dst = reinterpret_cast<uint32_t*>(&sc);
         if (lane < (int)(sizeof(Contig) / 4)) dst[lane] = __ldg(src + lane);
-        if (lane == 0) { n_segs = 0; n_jobs = 0; fallback = 0; }
+        if (lane == 0) { n_segs = 0; n_jobs = 0; fallback = 0; stage_used = 0u; mbar_init(&bar, SPLICE_THREADS / 32); }
     }
     s_conv[tid] = tables->conv[tid];
     s_comp[tid] = tables->comp[tid];
@@ -267,8 +322,9 @@ k_splice(SpliceView v, const Contig* contigs, int32_t n_contigs, const int64_t* 
     const Contig& k = sc;
     v.conv = s_conv;
     v.comp = s_comp;
-    const int64_t tile_i = k.body_off / tile_bytes + (p - k.piece_lo);
-    int64_t f_lo = tile_i * tile_bytes, f_hi = f_lo + tile_bytes;
+    // tile_bytes == SP_TILE_MAX (checked by the host): shifts instead of 64-bit divisions
+    const int64_t tile_i = (k.body_off >> 14) + (p - k.piece_lo);
+    int64_t f_lo = tile_i << 14, f_hi = f_lo + SP_TILE_MAX;
     if (f_lo < k.body_off) f_lo = k.body_off;
     if (f_hi > k.body_off + k.body_bytes) f_hi = k.body_off + k.body_bytes;
     const int64_t g0 = f_lo & ~(int64_t)15;
@@ -317,7 +373,7 @@ k_splice(SpliceView v, const Contig* contigs, int32_t n_contigs, const int64_t* 
         for (int w = 0; w < SPLICE_THREADS / 32; ++w) { const int c = (int)warp_tot[w]; if (w < warp) before += c; total += c; }
         if (flag) {
             const int pos = n_runs + before + __popc(m & ((1u << lane) - 1u));
-            if (pos < SP_RUN_CAP) { nout[pos] = o; nidx[pos] = (uint32_t)t; }
+            if (pos < SP_RUN_CAP) { nout[pos] = o; nidx[pos] = (uint16_t)t; }
         }
         n_runs += total;
         __syncthreads();
@@ -357,7 +413,14 @@ k_splice(SpliceView v, const Contig* contigs, int32_t n_contigs, const int64_t* 
             while (lo < hi) {
                 const uint32_t n = hi - lo < SP_SEG_SPLIT ? hi - lo : SP_SEG_SPLIT;
                 const int slot = atomicAdd(&n_segs, 1);
-                if (slot < SP_SEG_CAP) segs[slot] = SegC{src, lo - b_lo, n}; else fallback = 1;
+                if (slot < SP_SEG_CAP) {
+                    segs[slot] = SegC{src, lo - b_lo, n};
+                    const uint32_t span = (uint32_t)(((src + n + 15) & ~(int64_t)15) - (src & ~(int64_t)15));
+                    const uint32_t off = atomicAdd(&stage_used, span);
+                    seg_stage[slot] = off + span <= SP_STAGE_CAP ? off : SP_DIRECT;
+                } else {
+                    fallback = 1;
+                }
                 lo += n; src += n;
             }
         }
@@ -365,23 +428,47 @@ k_splice(SpliceView v, const Contig* contigs, int32_t n_contigs, const int64_t* 
     __syncthreads();
 
     if (!fallback) {
-        // ---- S1: shifted copies, one warp per segment
+        // ---- S0: one TMA bulk copy per segment brings its 16-byte aligned input span into `stage`; all of the
+        //      tile's DRAM reads are in flight at once instead of one dependent round trip per segment and warp
+        //      (UBLKCP is a per-warp uniform instruction: every warp issues its own segments from one elected lane)
         const int ns = n_segs;
-        for (int sidx = warp; sidx < ns; sidx += SPLICE_THREADS / 32) warp_copy_to_tile(tile, v.genome, segs[sidx], lane);
+        if (lane == 0) {
+            uint32_t bytes = 0u;
+            for (int sidx = warp; sidx < ns; sidx += SPLICE_THREADS / 32) {
+                const uint32_t off = seg_stage[sidx];
+                if (off == SP_DIRECT) continue;
+                const SegC sg = segs[sidx];
+                const int64_t al = sg.src & ~(int64_t)15;
+                const uint32_t span = (uint32_t)(((sg.src + sg.n + 15) & ~(int64_t)15) - al);
+                tma_load_1d(stage + off, v.genome + al, span, &bar);
+                bytes += span;
+            }
+            mbar_arrive_expect_tx(&bar, bytes);
+        }
+        mbar_wait(&bar, 0u);
+        // ---- S1: shifted copies shared -> shared, one warp per segment
+        for (int sidx = warp; sidx < ns; sidx += SPLICE_THREADS / 32) {
+            const SegC sg = segs[sidx];
+            const uint32_t off = seg_stage[sidx];
+            if (off == SP_DIRECT) warp_copy_to_tile(tile, v.genome, sg, lane);
+            else warp_copy_stage_to_tile(tile, stage, off + (uint32_t)(sg.src & 15), sg.dst, sg.n, lane);
+        }
         __syncthreads();
         // ---- S2: SNP bases and non-raw payloads
         for (int t = tid; t < n_rec; t += SPLICE_THREADS) {
             const int64_t j = i_first + t;
             if (j < k.rec_lo) continue;
-            const uint4 a = __ldg(reinterpret_cast<const uint4*>(recs + j));
-            const uint4 b = __ldg(reinterpret_cast<const uint4*>(recs + j) + 1);
-            const uint32_t o = a.w, pr = a.z, kind = b.z & 0xffu;
+            const uint32_t* rw = reinterpret_cast<const uint32_t*>(recs + j);
+            const uint32_t o = __ldg(rw + 3), kw = __ldg(rw + 6), kind = kw & 0xffu;
             if (kind == K_SNP) {
-                if (o >= b_lo && o < b_hi) tile[o - b_lo] = (uint8_t)(b.z >> 24);
-            } else if (pr > 0u && kind != K_RAW) {
+                if (o >= b_lo && o < b_hi) tile[o - b_lo] = (uint8_t)(kw >> 24);
+                continue;
+            }
+            const uint32_t pr = __ldg(rw + 2);
+            if (pr > 0u && kind != K_RAW) {
                 const uint32_t lo = o > b_lo ? o : b_lo, hi = o + pr < b_hi ? o + pr : b_hi;
                 if (lo < hi) {
-                    const int64_t src = (int64_t)(((uint64_t)b.y << 32) | b.x);
+                    const int64_t src = (int64_t)(((uint64_t)__ldg(rw + 5) << 32) | __ldg(rw + 4));
                     const uint32_t rel = lo - o, n = hi - lo;
                     const int64_t s0 = kind == K_RC ? src + (int64_t)(pr - 1u - rel) : src + rel;   // RC walks backwards
                     if (n <= 3u) {
@@ -409,10 +496,16 @@ k_splice(SpliceView v, const Contig* contigs, int32_t n_contigs, const int64_t* 
         for (int jb = warp; jb < nj; jb += SPLICE_THREADS / 32) {
             const SegC job = jobs[jb];
             const uint32_t n = job.n & 0xFFFFFFu, kind = job.n >> 24;
-            for (uint32_t x = lane; x < n; x += 32u) {
-                const uint8_t ch = kind == K_LIT ? v.lit[job.src + x]
-                                 : kind == K_CONV ? s_conv[v.genome[job.src + x]] : s_comp[s_conv[v.genome[job.src - (int64_t)x]]];
-                tile[job.dst + x] = ch;
+            uint8_t* d = tile + job.dst;
+            if (kind == K_RC) {
+                const uint8_t* g = v.genome + job.src;
+                for (uint32_t x = lane; x < n; x += 32u) d[x] = s_comp[s_conv[g[-(int)x]]];
+            } else if (kind == K_CONV) {
+                const uint8_t* g = v.genome + job.src;
+                for (uint32_t x = lane; x < n; x += 32u) d[x] = s_conv[g[x]];
+            } else {
+                const uint8_t* g = v.lit + job.src;
+                for (uint32_t x = lane; x < n; x += 32u) d[x] = g[x];
             }
         }
         __syncthreads();
@@ -436,20 +529,17 @@ k_splice(SpliceView v, const Contig* contigs, int32_t n_contigs, const int64_t* 
                 uint4 y = make_uint4(__funnelshift_r(u0, u1, bs), __funnelshift_r(u1, u2, bs), __funnelshift_r(u2, u3, bs),
                                      __funnelshift_r(u3, u4, bs));
                 if (j < 16u) {
-                    // word q of the result: untouched below the break, shifted up by one byte above it,
-                    // and a 4-way byte permute (with '\n') in the word that holds the break
-                    const uint32_t jw = j >> 2;
-                    const uint32_t t = j & 3u;
-                    // selectors for prmt(cur, '\n' word): byte t becomes '\n' (index 4), bytes above take cur[t..]
-                    const uint32_t selnl = t == 0u ? 0x2104u : t == 1u ? 0x2140u : t == 2u ? 0x2410u : 0x4210u;
-                    const uint32_t NL = 0x0Au;
+                    // one PRMT per word: word w = prmt(x_w, other, sel) with
+                    //   w <  jw : sel 0x3210 (untouched)
+                    //   w == jw : other = '\n', byte t becomes '\n', bytes above it take x_w[t..]
+                    //   w >  jw : other = x_{w-1}, sel 0x2107 (shifted up by one byte)
+                    const uint32_t jw = j >> 2, t = j & 3u;
+                    const uint32_t selnl = (uint32_t)(0x4210241021402104ull >> (16u * t)) & 0xFFFFu;
                     const uint32_t x0 = y.x, x1 = y.y, x2 = y.z, x3 = y.w;
-                    // bytes that fall off the top of the break word when '\n' is inserted
-                    const uint32_t sh1 = __byte_perm(x0, x1, 0x6543u), sh2 = __byte_perm(x1, x2, 0x6543u), sh3 = __byte_perm(x2, x3, 0x6543u);
-                    y.x = jw == 0u ? __byte_perm(x0, NL, selnl) : x0;
-                    y.y = jw > 1u ? x1 : (jw == 1u ? __byte_perm(x1, NL, selnl) : sh1);
-                    y.z = jw > 2u ? x2 : (jw == 2u ? __byte_perm(x2, NL, selnl) : sh2);
-                    y.w = jw == 3u ? __byte_perm(x3, NL, selnl) : sh3;
+                    y.x = __byte_perm(x0, 0x0Au, jw == 0u ? selnl : 0x3210u);
+                    y.y = __byte_perm(x1, jw == 1u ? 0x0Au : x0, jw > 1u ? 0x3210u : (jw == 1u ? selnl : 0x2107u));
+                    y.z = __byte_perm(x2, jw == 2u ? 0x0Au : x1, jw > 2u ? 0x3210u : (jw == 2u ? selnl : 0x2107u));
+                    y.w = __byte_perm(x3, jw == 3u ? 0x0Au : x2, jw == 3u ? selnl : 0x2107u);
                 }
                 __stcs(reinterpret_cast<uint4*>(out), y);
                 out += step_q;
@@ -821,10 +911,14 @@ int apply_pipeline(ms_ctx* c) {
     MS_LAUNCH_CHECK(c);
     stage_end(c, ST_INDEX);
 
+    if (c->tile_bytes != SP_TILE_MAX) MS_FAIL(c, MS_ERR_INTERNAL, "tile_bytes must equal %d", SP_TILE_MAX);
     stage_begin(c, ST_SPLICE);
     SpliceView sv{c->genome.as<uint8_t>(), c->lit.as<uint8_t>(), d_recs, d_blk, d_tab->conv, d_tab->comp};
     if (t.n_pieces > 0) {
-        k_splice<<<(unsigned)t.n_pieces, SPLICE_THREADS, 0, st>>>(sv, d_contigs, c->n_contigs, c->piece_lo.as<int64_t>(), d_tab,
+        constexpr int SP_DYN = SP_TILE_MAX + 64 + (int)SP_STAGE_CAP + 32;
+        static bool sp_attr = false;
+        if (!sp_attr) { MS_CUDA(c, cudaFuncSetAttribute(k_splice, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_DYN)); sp_attr = true; }
+        k_splice<<<(unsigned)t.n_pieces, SPLICE_THREADS, SP_DYN, st>>>(sv, d_contigs, c->n_contigs, c->piece_lo.as<int64_t>(), d_tab,
                                                                  c->fasta.as<uint8_t>(), (int64_t)c->tile_bytes);
         MS_LAUNCH_CHECK(c);
     }
