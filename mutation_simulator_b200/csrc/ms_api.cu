@@ -85,6 +85,25 @@ int ms_synchronize(ms_ctx* c) {
     return MS_OK;
 }
 
+// util.py:87 sequence_always_upper: done on the device, 16 bytes per thread
+__global__ void __launch_bounds__(256) k_upper(uint8_t* g, int64_t n16) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n16) return;
+    uint4 v = reinterpret_cast<uint4*>(g)[i];
+    uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t x = w[k];
+        // bytes in 'a'..'z' get bit 5 cleared: SWAR range test on 7-bit ASCII (bytes >= 0x80 are left alone)
+        const uint32_t lo7 = x & 0x7F7F7F7Fu;
+        const uint32_t ge_a = (lo7 + 0x1F1F1F1Fu) & 0x80808080u;          // byte >= 0x61
+        const uint32_t gt_z = (lo7 + 0x05050505u) & 0x80808080u;          // byte >= 0x7B
+        const uint32_t is_lower = ge_a & ~gt_z & ~(x & 0x80808080u);
+        w[k] = x & ~(is_lower >> 2);
+    }
+    reinterpret_cast<uint4*>(g)[i] = v;
+}
+
 // ---- genome ---------------------------------------------------------------------------
 static int set_contig_table(ms_ctx* c, int64_t total_bases, int32_t n_contigs, const int64_t* contig_len, const int32_t* bpl,
                             const uint32_t* gid, const uint8_t* headers, const int64_t* hdr_off, const uint8_t* names,
@@ -128,6 +147,11 @@ int ms_genome_upload(ms_ctx* c, const uint8_t* bases, int64_t total_bases, int32
     MS_CUDA(c, c->genome.ensure((size_t)total_bases + 64 + (size_t)c->foreign_cap + 64));
     MS_CUDA(c, cudaMemcpyAsync(c->genome.p, bases, (size_t)total_bases, cudaMemcpyHostToDevice, c->stream));
     MS_CUDA(c, cudaMemsetAsync(c->genome.as<uint8_t>() + total_bases, 'N', 64, c->stream));
+    if (total_bases > 0) {
+        const int64_t n16 = (total_bases + 15) / 16;
+        k_upper<<<(unsigned)((n16 + 255) / 256), 256, 0, c->stream>>>(c->genome.as<uint8_t>(), n16);
+        MS_LAUNCH_CHECK(c);
+    }
     stage_end(c, ST_UPLOAD);
     return set_contig_table(c, total_bases, n_contigs, contig_len, bpl, gid, headers, hdr_off, names, name_off);
 }

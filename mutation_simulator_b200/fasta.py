@@ -10,6 +10,8 @@ reads: ``fasta[int|str]``, ``keys()``, ``get_seq(name, start1, end1)``,
 """
 from __future__ import annotations
 
+import mmap
+import os
 from pathlib import Path
 
 import numpy as np
@@ -39,16 +41,24 @@ class _Faidx:
 
 
 class FastaRecord:
-    """One contig; a view into the genome array."""
+    """One contig; a view into the genome array (upper-cased on access when the loader kept the file's case)."""
 
-    def __init__(self, name: str, long_name: str, bases: np.ndarray, lenc: int):
+    def __init__(self, name: str, long_name: str, bases: np.ndarray, lenc: int, is_upper: bool = True):
         self.name = name
         self.long_name = long_name
-        self._b = bases
+        self._raw = bases
         self._lenc = lenc
+        self._is_upper = is_upper
+
+    @property
+    def _b(self) -> np.ndarray:
+        if not self._is_upper:
+            self._raw = _UPPER[self._raw]
+            self._is_upper = True
+        return self._raw
 
     def __len__(self):
-        return int(self._b.size)
+        return int(self._raw.size)
 
     def __getitem__(self, n):
         if isinstance(n, slice):
@@ -87,22 +97,113 @@ class Fasta:
     def __init__(self, filename, one_based_attributes=False, as_raw=True, sequence_always_upper=True,
                  read_ahead=None, build_index=True, **_):
         self.filename = str(filename)
+        self.genome_is_upper = True
         try:
-            data = np.fromfile(self.filename, dtype=np.uint8)
+            if not self._parse_regular():
+                self._parse(np.fromfile(self.filename, dtype=np.uint8), sequence_always_upper)
         except (FileNotFoundError, IsADirectoryError, PermissionError):
             raise FastaNotFoundError(f"Cannot read FASTA from file {self.filename}")
-        self._parse(data, sequence_always_upper)
         self.faidx = _Faidx()
         self._records = {}
         for i, nm in enumerate(self.names):
             if nm in self._records:
                 raise ValueError(f"Duplicate key \"{nm}\"")  # util.py:89-91 maps this to FastaDuplicateHeaderError
-            self._records[nm] = FastaRecord(nm, self.long_names[i], self.genome[self.goff[i]:self.goff[i + 1]], int(self.bpl[i]))
+            self._records[nm] = FastaRecord(nm, self.long_names[i], self.genome[self.goff[i]:self.goff[i + 1]], int(self.bpl[i]),
+                                            self.genome_is_upper)
             self.faidx.index[nm] = IndexEntry(int(self.lengths[i]), int(self._seq_off[i]), int(self.bpl[i]), int(self._lenb[i]))
         if build_index:
             self._write_fai()
 
     # -- parsing -----------------------------------------------------------
+    def _parse_regular(self) -> bool:
+        """Fast path for regularly wrapped files (every line of a record but the last has the same width, LF line
+        ends): contig boundaries by memmem, bases by one strided 2-D copy per contig, no per-byte masking.  The
+        file's case is kept; the GPU upper-cases at upload (ms_genome_upload) and host views upper-case lazily.
+        Returns False when the layout is not regular (the general parser then decides whether it is an error)."""
+        with open(self.filename, "rb") as fh:
+            size = os.fstat(fh.fileno()).st_size
+            if size == 0:
+                return False
+            mm = mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ)
+        try:
+            if mm[0:1] != b">":
+                return False
+            data = np.frombuffer(mm, dtype=np.uint8)
+            spans = []      # (header start, header end, seq_lo, seq_hi)
+            pos = 0
+            while pos < size:
+                he = mm.find(b"\n", pos)
+                if he < 0:
+                    he = size
+                nxt = mm.find(b"\n>", he) if he < size else -1
+                seq_lo = min(he + 1, size)
+                seq_hi = nxt + 1 if nxt >= 0 else size
+                spans.append((pos, he, seq_lo, seq_hi))
+                pos = seq_hi
+            n = len(spans)
+            lengths = np.zeros(n, np.int64); lenc = np.zeros(n, np.int64); lenb = np.zeros(n, np.int64)
+            layout = []
+            for i, (_, _, lo, hi) in enumerate(spans):
+                R = hi - lo
+                if R == 0:
+                    layout.append((0, 0, 0))
+                    continue
+                nl = mm.find(b"\n", lo, hi)
+                if nl < 0:                       # one line, no line break at the end of the file
+                    if mm.find(b"\r", lo, hi) >= 0:
+                        return False
+                    lenb[i] = R; lenc[i] = R; lengths[i] = R
+                    layout.append((0, R, R))
+                    continue
+                if nl > lo and mm[nl - 1] == 13:
+                    return False                 # CRLF files go through the general parser
+                b = nl - lo + 1
+                nfull = R // b
+                tail = R - nfull * b
+                tail_bases = tail
+                # the partial last line may end with line breaks (blank lines at EOF are tolerated)
+                while tail_bases > 0 and mm[lo + nfull * b + tail_bases - 1] == 10:
+                    tail_bases -= 1
+                if tail_bases and mm.find(b"\n", lo + nfull * b, lo + nfull * b + tail_bases) >= 0:
+                    return False
+                lenb[i] = b; lenc[i] = b - 1
+                lengths[i] = nfull * (b - 1) + tail_bases
+                layout.append((nfull, tail_bases, b))
+            goff = np.zeros(n + 1, np.int64)
+            np.cumsum(lengths, out=goff[1:])
+            genome = np.empty(int(goff[-1]), dtype=np.uint8)
+            for i, (_, _, lo, hi) in enumerate(spans):
+                nfull, tail_bases, b = layout[i]
+                o = int(goff[i])
+                if nfull:
+                    block = data[lo:lo + nfull * b].reshape(nfull, b)
+                    if not (block[:, b - 1] == 10).all():
+                        return False             # ragged lines
+                    genome[o:o + nfull * (b - 1)].reshape(nfull, b - 1)[:] = block[:, :b - 1]
+                    o += nfull * (b - 1)
+                if tail_bases:
+                    genome[o:o + tail_bases] = data[lo + nfull * b:lo + nfull * b + tail_bases]
+            self.names, self.long_names = [], []
+            for hs, he, _, _ in spans:
+                line = mm[hs + 1:he].decode("latin-1").rstrip("\r")
+                self.long_names.append(line)
+                tok = line.split()
+                self.names.append(tok[0] if tok else "")
+            self.lengths = lengths
+            self.bpl = lenc.astype(np.int32)
+            self._lenb = lenb
+            self._seq_off = np.array([sp[2] for sp in spans], dtype=np.int64)
+            self.goff = goff
+            self.genome = genome
+            self.genome_is_upper = False
+            del data
+            return True
+        finally:
+            try:
+                mm.close()
+            except BufferError:       # a view is still alive (early return paths): the GC closes it
+                pass
+
     def _parse(self, data: np.ndarray, upper: bool):
         n = data.size
         nl = np.flatnonzero(data == 10)
@@ -215,6 +316,7 @@ class Fasta:
     # -- engine side -------------------------------------------------------
     def upload(self, engine, contig_ids=None):
         """Make this genome (or a subset of its contigs) resident on the engine's GPU."""
+        # (the engine upper-cases on the device, so a mixed-case host array is fine)
         ids = list(range(len(self.names))) if contig_ids is None else list(contig_ids)
         if contig_ids is None:
             bases = self.genome
