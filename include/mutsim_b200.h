@@ -136,6 +136,8 @@ int ms_contig_out_len(ms_ctx* ctx, int64_t* out_len /* n_contigs */);
  * last line (fasta_writer.py:44-45); partial[c] = 1 if the last line is partial.  Arrays have n_contigs+1 /
  * n_contigs entries. */
 int ms_contig_layout(ms_ctx* ctx, int64_t* fasta_off, int64_t* vcf_off, uint8_t* sep, uint8_t* partial);
+/* Number of records (applied mutations) of each contig after ms_sample / ms_load_records + ms_apply. */
+int ms_contig_records(ms_ctx* ctx, int64_t* n_records /* n_contigs */);
 
 /* ---- interchromosomal translocations ------------------------------------
  * Replaces ITMutator.__get_breakpoints (it_mutator.py:94-118): for each pair p,

@@ -50,6 +50,7 @@ PROTOTYPES = {
     "ms_genome_download": (C.c_int, [_P, _P, _I64]),
     "ms_genome_reserve": (C.c_int, [_P, _I64]),
     "ms_contig_layout": (C.c_int, [_P, _P, _P, _P, _P]),
+    "ms_contig_records": (C.c_int, [_P, _P]),
     "ms_sample_positions": (C.c_int, [_P, _U64, _I32, _P, _P, _P, _P, _I32, _P]),
     "ms_set_ranges": (C.c_int, [_P, _P, _I32, _P, _I32, C.c_double]),
     "ms_sample": (C.c_int, [_P, _U64]),

@@ -207,6 +207,7 @@ int ms_load_records(ms_ctx* c, const ms_rec* recs, int64_t n_recs, const uint8_t
     c->n_recs = n_recs;
     c->lit_bytes = lit_bytes;
     c->counts_valid = false;
+    c->sizes_valid = false;
     return MS_OK;
 }
 
@@ -288,6 +289,15 @@ int ms_contig_layout(ms_ctx* c, int64_t* fasta_off, int64_t* vcf_off, uint8_t* s
         }
     }
     vcf_off[c->n_contigs] = c->vcf_bytes;
+    return MS_OK;
+}
+
+int ms_contig_records(ms_ctx* c, int64_t* n_records) {
+    if (!c || !n_records) return MS_ERR_ARG;
+    MS_CUDA(c, cudaSetDevice(c->device));
+    MS_CUDA(c, cudaStreamSynchronize(c->stream));
+    MS_CUDA(c, cudaMemcpy(c->h_contigs.data(), c->contigs.p, sizeof(Contig) * (size_t)c->n_contigs, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < c->n_contigs; ++i) n_records[i] = c->h_contigs[i].rec_hi - c->h_contigs[i].rec_lo;
     return MS_OK;
 }
 

@@ -9,6 +9,12 @@
 
 namespace ms {
 
+// Random-insert bytes are rare (0.5 % of the output); calling Philox out of line keeps it from inflating the
+// register count (and lowering the occupancy) of the kernels that consume them.
+__device__ __noinline__ uint8_t rand_base_ool(Seed seed, uint32_t gid, uint32_t pos, uint32_t j) {
+    return rand_insert_base(seed, gid, pos, j);
+}
+
 struct Gap { int64_t start; uint32_t count; uint32_t value; };
 constexpr uint32_t GAP_INLINE = 32;
 
@@ -242,6 +248,19 @@ __device__ __forceinline__ void warp_copy_stage_to_tile(uint8_t* tile, const uin
     }
 }
 
+// byte x of a clipped non-raw payload; s0 as prepared in S2 (RC: last source index, RAND: the cached 2-bit bases
+// shifted to the first byte, RANDL (insert reaching past its 32 cached bases): pos << 32 | first byte index)
+constexpr uint32_t K_RANDL = 7;
+__device__ __forceinline__ uint8_t payload_at(const SpliceView& v, uint32_t kind, int64_t s0, uint32_t x, uint32_t gid) {
+    switch (kind) {
+        case K_LIT:   return v.lit[s0 + x];
+        case K_CONV:  return v.conv[v.genome[s0 + x]];
+        case K_RAND:  return cached_insert_base(s0, x);
+        case K_RANDL: return rand_base_ool(v.seed, gid, (uint32_t)((uint64_t)s0 >> 32), (uint32_t)s0 + x);
+        default:      return v.comp[v.conv[v.genome[s0 - (int64_t)x]]];
+    }
+}
+
 __device__ __forceinline__ void warp_copy_to_tile(uint8_t* tile, const uint8_t* __restrict__ genome, const SegC sg, int lane) {
     const uint32_t d0 = sg.dst, d1 = sg.dst + sg.n;
     const uint32_t a0 = (d0 + 15u) & ~15u, a1 = d1 & ~15u;
@@ -465,25 +484,29 @@ k_splice(SpliceView v, const Contig* contigs, int32_t n_contigs, const int64_t* 
                 continue;
             }
             const uint32_t pr = __ldg(rw + 2);
+            uint32_t pkind = kind;
             if (pr > 0u && kind != K_RAW) {
                 const uint32_t lo = o > b_lo ? o : b_lo, hi = o + pr < b_hi ? o + pr : b_hi;
                 if (lo < hi) {
                     const int64_t src = (int64_t)(((uint64_t)__ldg(rw + 5) << 32) | __ldg(rw + 4));
                     const uint32_t rel = lo - o, n = hi - lo;
-                    const int64_t s0 = kind == K_RC ? src + (int64_t)(pr - 1u - rel) : src + rel;   // RC walks backwards
+                    // RC walks backwards; a random insert is addressed by (position, first byte index)
+                    int64_t s0;
+                    if (kind == K_RC) s0 = src + (int64_t)(pr - 1u - rel);
+                    else if (kind != K_RAND) s0 = src + rel;
+                    else if (rel + n <= 32u) s0 = (int64_t)((uint64_t)src >> (2u * rel));
+                    else { s0 = (int64_t)(((uint64_t)__ldg(rw) << 32) | rel); pkind = K_RANDL; }
                     if (n <= 3u) {
                         for (uint32_t x = 0; x < n; ++x) {
-                            const uint8_t ch = kind == K_LIT ? v.lit[s0 + x]
-                                             : kind == K_CONV ? s_conv[v.genome[s0 + x]] : s_comp[s_conv[v.genome[s0 - (int64_t)x]]];
+                            const uint8_t ch = payload_at(v, pkind, s0, x, k.gid);
                             tile[lo - b_lo + x] = ch;
                         }
                     } else {
                         const int slot = atomicAdd(&n_jobs, 1);
-                        if (slot < SP_JOB_CAP) jobs[slot] = SegC{s0, lo - b_lo, n | (kind << 24)};
+                        if (slot < SP_JOB_CAP) jobs[slot] = SegC{s0, lo - b_lo, n | (pkind << 24)};
                         else {
                             for (uint32_t x = 0; x < n; ++x) {
-                                const uint8_t ch = kind == K_LIT ? v.lit[s0 + x]
-                                                 : kind == K_CONV ? s_conv[v.genome[s0 + x]] : s_comp[s_conv[v.genome[s0 - (int64_t)x]]];
+                                const uint8_t ch = payload_at(v, pkind, s0, x, k.gid);
                                 tile[lo - b_lo + x] = ch;
                             }
                         }
@@ -503,6 +526,8 @@ k_splice(SpliceView v, const Contig* contigs, int32_t n_contigs, const int64_t* 
             } else if (kind == K_CONV) {
                 const uint8_t* g = v.genome + job.src;
                 for (uint32_t x = lane; x < n; x += 32u) d[x] = s_conv[g[x]];
+            } else if (kind == K_RAND || kind == K_RANDL) {
+                for (uint32_t x = lane; x < n; x += 32u) d[x] = payload_at(v, kind, job.src, x, k.gid);
             } else {
                 const uint8_t* g = v.lit + job.src;
                 for (uint32_t x = lane; x < n; x += 32u) d[x] = g[x];
@@ -605,7 +630,7 @@ __global__ void k_headers(const Contig* contigs, int32_t n_contigs, const uint8_
 constexpr int VCF_THREADS = 256;
 constexpr int VCF_SMEM = 22 * 1024;
 constexpr int VCF_MAX_JOBS = 2 * VCF_THREADS;
-enum SegMode : uint32_t { SM_IMM = 0, SM_RAW = 1, SM_CONV = 2, SM_RC = 3, SM_LIT = 4 };
+enum SegMode : uint32_t { SM_IMM = 0, SM_RAW = 1, SM_CONV = 2, SM_RC = 3, SM_LIT = 4, SM_RAND = 5, SM_RANDL = 6 };   // RAND: src = cached 2-bit bases (<= 32); RANDL: src = gid << 32 | pos
 struct Seg { int64_t src; uint32_t len; uint32_t mode; };
 struct CopyJob { int64_t src; uint32_t dst; uint32_t len_mode; };   // len | mode << 29
 
@@ -615,6 +640,8 @@ __device__ __forceinline__ uint8_t seg_byte(const VcfView& v, uint32_t mode, int
         case SM_RAW:  return v.genome[src + i];
         case SM_CONV: return v.conv[v.genome[src + i]];
         case SM_RC:   return v.comp[v.conv[v.genome[src + (int64_t)(len - 1 - i)]]];
+        case SM_RAND: return cached_insert_base(src, i);
+        case SM_RANDL: return rand_base_ool(v.seed, (uint32_t)((uint64_t)src >> 32), (uint32_t)src, i);
         default:      return v.lit[src + i];
     }
 }
@@ -646,7 +673,8 @@ __device__ __forceinline__ void vcf_segments(const VcfView& v, const Contig& c, 
     const uint32_t p = r.pos;
     const Seg none{0, 0u, SM_IMM};
     sg[0] = sg[1] = sg[2] = sg[3] = none;
-    const uint32_t pmode = r.kind == K_LIT ? SM_LIT : r.kind == K_RAW ? SM_RAW : r.kind == K_CONV ? SM_CONV : SM_RC;
+    const uint32_t pmode = r.kind == K_LIT ? SM_LIT : r.kind == K_RAW ? SM_RAW : r.kind == K_CONV ? SM_CONV
+                         : r.kind == K_RAND ? (r.prod <= 32u ? SM_RAND : SM_RANDL) : SM_RC;
     switch (r.type) {
         case T_SN:
             pos1 = p + 1u; end = 0u; svlen = 0u; svt = 0u;
@@ -655,7 +683,7 @@ __device__ __forceinline__ void vcf_segments(const VcfView& v, const Contig& c, 
         case T_IN: case T_TLI: {
             pos1 = p > 0u ? p : 1u; end = pos1; svlen = r.prod; svt = r.type == T_IN ? 1u : 6u;
             const Seg anchor{g0 + (p > 0u ? (int64_t)p - 1 : 0), 1u, SM_CONV};
-            const Seg pay{r.src, r.prod, pmode};
+            const Seg pay{pmode == SM_RANDL ? (int64_t)(((uint64_t)c.gid << 32) | p) : r.src, r.prod, pmode};
             sg[0] = anchor;
             if (p > 0u) { sg[1] = anchor; sg[2] = pay; } else { sg[1] = pay; sg[2] = anchor; }
         } break;
@@ -802,6 +830,8 @@ k_vcf_write(VcfView v, const Rec* recs, int64_t n_recs, const Contig* contigs, c
         } else if (mode == SM_CONV) {
             const uint8_t* g = v.genome + job.src;
             for (uint32_t x = lane; x < len; x += 32u) d[x] = s_conv[g[x]];
+        } else if (mode == SM_RAND || mode == SM_RANDL) {
+            for (uint32_t x = lane; x < len; x += 32u) d[x] = seg_byte(v, mode, job.src, len, x);
         } else {
             const uint8_t* g = (mode == SM_RAW ? v.genome : v.lit) + job.src;
             for (uint32_t x = lane; x < len; x += 32u) d[x] = g[x];
@@ -865,13 +895,20 @@ int apply_pipeline(ms_ctx* c) {
     k_rec_bounds<<<(unsigned)ceil_div(c->n_contigs + 1, 128), 128, 0, st>>>(d_recs, M, d_contigs, c->n_contigs);
     MS_LAUNCH_CHECK(c);
 
-    VcfView vv{c->genome.as<uint8_t>(), c->lit.as<uint8_t>(), c->names.as<uint8_t>(), d_tab->conv, d_tab->comp};
+    VcfView vv{c->genome.as<uint8_t>(), c->lit.as<uint8_t>(), c->names.as<uint8_t>(), d_tab->conv, d_tab->comp, c->seed_last};
     {
-        MS_CUDA(c, c->lvec.ensure((size_t)(M + 1) * 4));
-        MS_CUDA(c, c->vvec.ensure((size_t)(M + 1) * 4));
-        int32_t* d_delta = c->lvec.as<int32_t>();
-        uint32_t* d_vsize = c->vvec.as<uint32_t>();
-        if (M > 0) {
+        int32_t* d_delta;
+        uint32_t* d_vsize;
+        if (c->sizes_valid) {   // ms_sample already produced them while building the records
+            d_delta = c->keep.as<int32_t>();
+            d_vsize = c->cand_val.as<uint32_t>();
+        } else {
+            MS_CUDA(c, c->lvec.ensure((size_t)(M + 1) * 4));
+            MS_CUDA(c, c->vvec.ensure((size_t)(M + 1) * 4));
+            d_delta = c->lvec.as<int32_t>();
+            d_vsize = c->vvec.as<uint32_t>();
+        }
+        if (M > 0 && !c->sizes_valid) {
             k_rec_sizes<<<(unsigned)ceil_div(M, 256), 256, 0, st>>>(vv, d_recs, M, d_contigs, d_delta, d_vsize);
             MS_LAUNCH_CHECK(c);
         }
@@ -913,7 +950,7 @@ int apply_pipeline(ms_ctx* c) {
 
     if (c->tile_bytes != SP_TILE_MAX) MS_FAIL(c, MS_ERR_INTERNAL, "tile_bytes must equal %d", SP_TILE_MAX);
     stage_begin(c, ST_SPLICE);
-    SpliceView sv{c->genome.as<uint8_t>(), c->lit.as<uint8_t>(), d_recs, d_blk, d_tab->conv, d_tab->comp};
+    SpliceView sv{c->genome.as<uint8_t>(), c->lit.as<uint8_t>(), d_recs, d_blk, d_tab->conv, d_tab->comp, c->seed_last};
     if (t.n_pieces > 0) {
         constexpr int SP_DYN = SP_TILE_MAX + 64 + (int)SP_STAGE_CAP + 32;
         static bool sp_attr = false;

@@ -78,6 +78,8 @@ struct ms_ctx {
     double p_ti = 0.5;
     int32_t min_dist = 1;
     bool counts_valid = false;
+    bool sizes_valid = false;     // keep/cand_val hold (delta, vcf size) of the current records (written by k_build_records)
+    ms::Seed seed_last{0, 0};     // seed of the last ms_sample (K_RAND payloads are a function of it)
 
     // records + outputs
     ms::DevBuf recs, lit, blk, piece_lo, long_gaps, fasta, vcf, vcf_off, totals;

@@ -19,6 +19,10 @@ enum Kind : uint8_t {
     K_RAW  = 3,  // prod raw genome bytes from src          (DU, IT partner interval)
     K_CONV = 4,  // prod IUPAC-converted genome bytes from src (TLI)
     K_RC   = 5,  // reverse complement of the converted bytes [src, src+prod) (IV, reversed TLI)
+    K_RAND = 6,  // prod random bases (mutator.py:466-471), a pure function of (seed, contig id, pos): base j of the
+                 // insert at pos comes from Philox block j/64 — generated where it is consumed, never stored.
+                 // src caches the first 64 bits of block 0 = bases 0..31 (2 bits each), so inserts of up to 32
+                 // bases never touch Philox again
 };
 
 // One applied mutation.  32 bytes, sorted by (contig, pos).
@@ -66,6 +70,21 @@ struct Tables {
     uint8_t comp[256];   // complement
     uint8_t trans[256];  // transitions
 };
+
+// first 32 bases of the random insert at `pos`, 2 bits each (what Rec.src caches for K_RAND)
+MS_HD int64_t rand_insert_cache(Seed seed, uint32_t gid, uint32_t pos) {
+    const U4 blk = draw(seed, gid, P_INSERT, pos);
+    return (int64_t)u64_of(blk.x, blk.y);
+}
+MS_HD uint8_t cached_insert_base(int64_t cache, uint32_t j) { return (uint8_t)("ATGC"[((uint64_t)cache >> (2u * j)) & 3u]); }
+
+// base j of the random insert at contig position `pos` (64 bases per Philox block, 2 bits each, "ATGC")
+MS_HD uint8_t rand_insert_base(Seed seed, uint32_t gid, uint32_t pos, uint32_t j) {
+    const U4 blk = draw(seed, gid, P_INSERT | ((j >> 6) << 8), pos);
+    const uint32_t wsel = (j >> 4) & 3u;
+    const uint32_t wv = wsel == 0 ? blk.x : wsel == 1 ? blk.y : wsel == 2 ? blk.z : blk.w;
+    return (uint8_t)("ATGC"[(wv >> ((j & 15u) * 2u)) & 3u]);
+}
 
 inline void fill_tables(Tables& t) {
     for (int i = 0; i < 256; ++i) t.conv[i] = t.comp[i] = t.trans[i] = (uint8_t)i;

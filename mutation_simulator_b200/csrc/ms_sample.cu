@@ -237,18 +237,24 @@ k_link(const Contig* contigs, const Range* ranges, const uint32_t* cand_range, c
     link[tli_slot] = (int32_t)tl_slot;
 }
 
-// K4b: one 32-byte record per kept mutation.
+// K4b: one 32-byte record per accepted candidate, in place of the accepted list (no second compaction: an
+// unpaired TL / TLI becomes a dead no-op record), together with its length delta and VCF line size so that the
+// plan stage does not have to re-read the records.
+}  // namespace ms
+#include "ms_vcf_core.h"
+namespace ms {
+
 __global__ void __launch_bounds__(256)
-k_build_records(int64_t n_acc, const uint32_t* acc_slot, const int64_t* rec_idx, const int64_t* lit_off, const int64_t* gpos,
-                const uint8_t* type, const uint32_t* len, const uint32_t* cand_range, const int32_t* link, const Range* ranges,
-                const Contig* contigs, const uint8_t* genome, const Tables* tab, Seed seed, double p_ti, Rec* recs, uint8_t* lit) {
+k_build_records(int64_t n_acc, const uint32_t* acc_slot, const int64_t* gpos, const uint8_t* type, const uint32_t* len,
+                const uint32_t* cand_range, const int32_t* link, const Range* ranges, const Contig* contigs, VcfView vv,
+                const Tables* tab, Seed seed, double p_ti, Rec* recs, int32_t* delta, uint32_t* vsize) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_acc) return;
-    if (rec_idx[e + 1] == rec_idx[e]) return;  // dropped TL / TLI
     const uint32_t s = acc_slot[e];
     const uint32_t cidx = ranges[cand_range[s]].contig;
     const Contig& ct = contigs[cidx];
-    const uint32_t pos = (uint32_t)(gpos[s] - ct.goff);
+    const int64_t g = gpos[s];
+    const uint32_t pos = (uint32_t)(g - ct.goff);
     const uint8_t t = type[s];
     const uint32_t l = len[s];
     Rec r;
@@ -256,28 +262,27 @@ k_build_records(int64_t n_acc, const uint32_t* acc_slot, const int64_t* rec_idx,
     switch (t) {
         case T_SN: {
             r.cons = 1; r.prod = 1; r.kind = K_SNP;
-            r.ref = tab->conv[genome[gpos[s]]];
+            r.ref = tab->conv[vv.genome[g]];
             r.alt = draw_snp(seed, ct.gid, pos, r.ref, p_ti, tab->trans);
         } break;
-        case T_IN: {
-            r.cons = 0; r.prod = l; r.kind = K_LIT; r.src = lit_off[e];
-            U4 blk{0, 0, 0, 0};
-            for (uint32_t j = 0; j < l; ++j) {
-                if ((j & 63u) == 0) blk = draw(seed, ct.gid, P_INSERT | ((j >> 6) << 8), pos);
-                lit[r.src + j] = insert_base(blk, j);
+        case T_IN: r.cons = 0; r.prod = l; r.kind = K_RAND; r.src = rand_insert_cache(seed, ct.gid, pos); break;
+        case T_DE: r.cons = l; r.prod = 0; r.kind = K_NONE; break;
+        case T_IV: r.cons = l; r.prod = l; r.kind = K_RC; r.src = g; break;
+        case T_DU: r.cons = 0; r.prod = l; r.kind = K_RAW; r.src = g; break;
+        default: {  // T_TL / T_TLI: kept only when linked (link: -1 unlinked, -2 kept TL, >= 0 slot of the TLI's TL)
+            const int32_t lk = link[s];
+            if (lk == -1) { r.cons = 0; r.prod = 0; r.kind = K_NONE; r.type = T_DEAD; }
+            else if (t == T_TL) { r.cons = l; r.prod = 0; r.kind = K_NONE; }
+            else {
+                const uint32_t tl_len = len[lk];
+                r.cons = 0; r.prod = tl_len; r.src = gpos[lk];
+                r.kind = draw_tl_reverse(seed, ct.gid, pos, tl_len) ? K_RC : K_CONV;
             }
         } break;
-        case T_DE: case T_TL: r.cons = l; r.prod = 0; r.kind = K_NONE; break;
-        case T_IV: r.cons = l; r.prod = l; r.kind = K_RC; r.src = gpos[s]; break;
-        case T_DU: r.cons = 0; r.prod = l; r.kind = K_RAW; r.src = gpos[s]; break;
-        default: {  // T_TLI linked to the TL at candidate slot link[s]
-            const int32_t tl = link[s];
-            const uint32_t tl_len = len[tl];
-            r.cons = 0; r.prod = tl_len; r.src = gpos[tl];
-            r.kind = draw_tl_reverse(seed, ct.gid, pos, tl_len) ? K_RC : K_CONV;
-        } break;
     }
-    recs[rec_idx[e]] = r;
+    recs[e] = r;
+    delta[e] = (int32_t)r.prod - (int32_t)r.cons;
+    vsize[e] = vcf_line_size(vv, ct, r);
 }
 
 __global__ void __launch_bounds__(256) k_count_types(const Rec* recs, int64_t n, Totals* tot) {
@@ -285,7 +290,7 @@ __global__ void __launch_bounds__(256) k_count_types(const Rec* recs, int64_t n,
     if (threadIdx.x < 8) h[threadIdx.x] = 0;
     __syncthreads();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        atomicAdd(&h[recs[i].type & 7], 1u);
+        { const uint8_t t = recs[i].type; if (t < 8) atomicAdd(&h[t], 1u); }
     __syncthreads();
     if (threadIdx.x < 8 && h[threadIdx.x]) atomicAdd((unsigned long long*)&tot->counts[threadIdx.x], (unsigned long long)h[threadIdx.x]);
 }
@@ -433,34 +438,16 @@ int sample_pipeline(ms_ctx* c, uint64_t seed64) {
 
     // ---- K4b: records -----------------------------------------------------------------
     stage_begin(c, ST_SAMPLE_FINAL);
-    MS_CUDA(c, c->vvec.ensure((size_t)(n_acc + 1) * 8));
-    MS_CUDA(c, c->vcf_off.ensure((size_t)(n_acc + 1) * 8));
-    int64_t* d_recidx = c->vvec.as<int64_t>();
-    int64_t* d_litoff = c->vcf_off.as<int64_t>();
-    {
-        auto in = [=] __device__(int64_t e) -> I64x2 {
-            const uint32_t s = d_acc[e];
-            const uint8_t t = d_type[s];
-            const bool keep = (t != T_TL && t != T_TLI) || d_link[s] != -1;
-            return I64x2{keep ? 1 : 0, (keep && t == T_IN) ? (int64_t)d_len[s] : 0};
-        };
-        auto out = [=] __device__(int64_t e, I64x2 ex, I64x2) { d_recidx[e] = ex.a; d_litoff[e] = ex.b; };
-        I64x2* d_total = nullptr;
-        MS_CUDA(c, (device_scan<I64x2>(c, in, out, n_acc, I64x2{0, 0}, SumOp(), c->scan_tmp, &d_total)));
-        k_copy_scalar<int64_t><<<1, 1, 0, st>>>(&d_total->a, d_recidx + n_acc);
-        MS_LAUNCH_CHECK(c);
-        MS_CUDA(c, cudaMemcpyAsync(c->h_totals, d_total, sizeof(I64x2), cudaMemcpyDeviceToHost, st));
-    }
-    MS_CUDA(c, cudaStreamSynchronize(st));
-    const I64x2 fin = *reinterpret_cast<const I64x2*>(c->h_totals);
-    const int64_t n_recs = fin.a, lit_bytes = fin.b;
-    MS_CUDA(c, c->recs.ensure((size_t)(n_recs + 1) * sizeof(Rec)));
-    MS_CUDA(c, c->lit.ensure((size_t)lit_bytes + 64));
+    c->seed_last = seed;
+    MS_CUDA(c, c->recs.ensure((size_t)(n_acc + 1) * sizeof(Rec)));
+    MS_CUDA(c, c->keep.ensure((size_t)(n_acc + 1) * 4));
+    MS_CUDA(c, c->cand_val.ensure((size_t)(n_acc + 1) * 4));
     if (n_acc > 0) {
-        k_build_records<<<(unsigned)ceil_div(n_acc, 256), 256, 0, st>>>(n_acc, d_acc, d_recidx, d_litoff, d_gpos, d_type, d_len, d_crange,
-                                                                        d_link, d_ranges, d_contigs, c->genome.as<uint8_t>(),
-                                                                        c->tables.as<Tables>(), seed, c->p_ti, c->recs.as<Rec>(),
-                                                                        c->lit.as<uint8_t>());
+        const Tables* d_tab = c->tables.as<Tables>();
+        VcfView vv{c->genome.as<uint8_t>(), c->lit.as<uint8_t>(), c->names.as<uint8_t>(), d_tab->conv, d_tab->comp, seed};
+        k_build_records<<<(unsigned)ceil_div(n_acc, 256), 256, 0, st>>>(n_acc, d_acc, d_gpos, d_type, d_len, d_crange, d_link, d_ranges,
+                                                                        d_contigs, vv, d_tab, seed, c->p_ti, c->recs.as<Rec>(),
+                                                                        c->keep.as<int32_t>(), c->cand_val.as<uint32_t>());
         MS_LAUNCH_CHECK(c);
     }
     MS_CUDA(c, cudaMemcpyAsync(c->h_totals, d_tot, sizeof(Totals), cudaMemcpyDeviceToHost, st));
@@ -468,11 +455,12 @@ int sample_pipeline(ms_ctx* c, uint64_t seed64) {
     MS_CUDA(c, cudaStreamSynchronize(st));
     if (c->h_totals->error) MS_FAIL(c, (int)c->h_totals->error, "ms_sample: kernel error %lld (arg %lld)", (long long)c->h_totals->error,
                                     (long long)c->h_totals->error_arg);
-    c->n_recs = n_recs;
-    c->lit_bytes = lit_bytes;
-    c->last_totals.n_recs = n_recs;
-    c->last_totals.lit_bytes = lit_bytes;
+    c->n_recs = n_acc;
+    c->lit_bytes = 0;
+    c->last_totals.n_recs = n_acc;
+    c->last_totals.lit_bytes = 0;
     c->counts_valid = false;
+    c->sizes_valid = true;
     return MS_OK;
 }
 

@@ -20,6 +20,7 @@ struct SpliceView {
     const uint32_t* blk;    // coarse block index
     const uint8_t* conv;    // 256-entry tables (global or shared memory)
     const uint8_t* comp;
+    Seed seed;              // for K_RAND payloads
 };
 
 MS_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {
@@ -32,6 +33,7 @@ MS_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {
 
 // Record cursor: the record governing output base b and its cached fields.
 struct Cursor {
+    uint32_t pos, gid;  // for K_RAND payloads
     int64_t i;        // absolute record index, rec_lo-1 when b precedes every record
     uint32_t out;     // payload start
     uint32_t prod;    // payload length
@@ -43,12 +45,13 @@ struct Cursor {
 
 MS_HD void cursor_load(const SpliceView& v, const Contig& c, int64_t i, Cursor& k) {
     k.i = i;
+    k.gid = c.gid; k.pos = 0;
     if (i < c.rec_lo) {
         k.out = 0; k.prod = 0; k.kind = K_NONE; k.alt = 0; k.src = 0;
         k.run_src = c.goff;
     } else {
         const Rec r = v.recs[i];
-        k.out = r.out; k.prod = r.prod; k.kind = r.kind; k.alt = r.alt; k.src = r.src;
+        k.out = r.out; k.prod = r.prod; k.kind = r.kind; k.alt = r.alt; k.src = r.src; k.pos = r.pos;
         k.run_src = c.goff + (int64_t)r.pos + (int64_t)r.cons;
     }
     k.next = (i + 1 < c.rec_hi) ? v.recs[i + 1].out : (uint32_t)c.out_len;
@@ -75,6 +78,7 @@ MS_HD uint8_t payload_byte(const SpliceView& v, const Cursor& k, uint32_t rel) {
         case K_RAW:  return v.genome[k.src + rel];
         case K_CONV: return v.conv[v.genome[k.src + rel]];
         case K_RC:   return v.comp[v.conv[v.genome[k.src + (int64_t)(k.prod - 1 - rel)]]];
+        case K_RAND: return rel < 32u ? cached_insert_base(k.src, rel) : rand_insert_base(v.seed, k.gid, k.pos, rel);
         default:     return '?';
     }
 }

@@ -15,6 +15,7 @@ struct VcfView {
     const uint8_t* names;   // contig names blob
     const uint8_t* conv;
     const uint8_t* comp;
+    Seed seed;              // for K_RAND payloads
 };
 
 struct CountSink {
@@ -65,9 +66,12 @@ template <class S> MS_HD void put_rc(S& s, const VcfView& v, int64_t g, uint32_t
 }
 
 // payload bytes of a record as the FASTA shows them (insert of IN / TLI)
-template <class S> MS_HD void put_payload(S& s, const VcfView& v, const Rec& r) {
+template <class S> MS_HD void put_payload(S& s, const VcfView& v, const Rec& r, uint32_t gid = 0) {
     if constexpr (S::counting) { s.skip(r.prod); return; }
     else switch (r.kind) {
+        case K_RAND:
+            for (uint32_t i = 0; i < r.prod; ++i) s.put(i < 32u ? cached_insert_base(r.src, i) : rand_insert_base(v.seed, gid, r.pos, i));
+            break;
         case K_LIT:  for (uint32_t i = 0; i < r.prod; ++i) s.put(v.lit[r.src + i]); break;
         case K_RAW:  put_bases(s, v, r.src, r.prod, false); break;
         case K_CONV: put_bases(s, v, r.src, r.prod, true); break;
@@ -88,7 +92,7 @@ MS_HD bool vcf_omitted(const VcfView& v, const Contig& c, const Rec& r) {
         }
         case T_DE: case T_TL:  // only a deletion of a whole 1-base contig degenerates to REF == ALT
             return r.pos == 0 && c.len == 1;
-        case T_IT: return true;
+        case T_IT: case T_DEAD: return true;
         default: return false;
     }
 }
@@ -129,8 +133,8 @@ template <class S> MS_HD void vcf_emit(S& s, const VcfView& v, const Contig& c, 
         case T_IN: case T_TLI: {  // mutator.py:343-358, 401-421
             const uint8_t anchor = v.conv[v.genome[g0 + (p > 0 ? (int64_t)p - 1 : 0)]];
             s.put(anchor); s.put('\t');
-            if (p > 0) { s.put(anchor); put_payload(s, v, r); }
-            else       { put_payload(s, v, r); s.put(anchor); }
+            if (p > 0) { s.put(anchor); put_payload(s, v, r, c.gid); }
+            else       { put_payload(s, v, r, c.gid); s.put(anchor); }
         } break;
         case T_DE: case T_TL: {  // mutator.py:360-377
             if (p > 0) {

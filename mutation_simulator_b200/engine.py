@@ -160,8 +160,11 @@ class Engine:
     def vcf(self) -> bytes:
         return self.download(BUF_VCF).tobytes()
 
-    def records(self) -> np.ndarray:
-        return self.download(BUF_RECS).view(REC_DTYPE)
+    def records(self, include_dead: bool = False) -> np.ndarray:
+        """Applied mutations as splice descriptors.  Unpaired translocation halves stay in the device table as
+        no-op records (type 255); they are filtered here unless asked for."""
+        r = self.download(BUF_RECS).view(REC_DTYPE)
+        return r if include_dead else r[r["type"] != 255]
 
     def literals(self) -> np.ndarray:
         return self.download(BUF_LIT)
@@ -174,6 +177,11 @@ class Engine:
     def contig_out_len(self) -> np.ndarray:
         out = np.empty(self.n_contigs, dtype=np.int64)
         self._check(self._lib.ms_contig_out_len(self._h, _ptr(out)))
+        return out
+
+    def contig_records(self) -> np.ndarray:
+        out = np.empty(self.n_contigs, dtype=np.int64)
+        self._check(self._lib.ms_contig_records(self._h, _ptr(out)))
         return out
 
     def contig_layout(self):

@@ -66,7 +66,7 @@ class Mutator:
         eng.sample(seed)
         eng.apply()
         if not args.ignore_warnings:
-            per = np.bincount(eng.records()["contig"], minlength=len(my_ids))
+            per = eng.contig_records()
             for i in np.flatnonzero(per == 0):
                 print(format_warning(f"No mutations could be generated on sequence {my_ids[int(i)]+1} (mutation rates too low)",
                                      args.no_color), file=sys.stderr)

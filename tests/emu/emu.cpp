@@ -79,7 +79,7 @@ int emu_apply(const uint8_t* genome, int32_t n_contigs, const int64_t* goff, con
             blk[k.blk_lo + b] = (uint32_t)(r - k.rec_lo);
         }
     }
-    SpliceView v{genome, lit, recs, blk.data(), tab.conv, tab.comp};
+    SpliceView v{genome, lit, recs, blk.data(), tab.conv, tab.comp, Seed{0, 0}};
     memset(fasta, 0, (size_t)file);
     int64_t nf = 0, ns = 0;
     for (int c = 0; c < n_contigs; ++c) {
@@ -112,7 +112,7 @@ int emu_apply(const uint8_t* genome, int32_t n_contigs, const int64_t* goff, con
     }
     *n_fast_groups = nf; *n_slow_groups = ns;
     // VCF (K7): sizes -> offsets -> bytes
-    VcfView vv{genome, lit, names, tab.conv, tab.comp};
+    VcfView vv{genome, lit, names, tab.conv, tab.comp, Seed{0, 0}};
     int64_t off = 0;
     std::vector<int64_t> offs(n_recs + 1);
     for (int64_t i = 0; i < n_recs; ++i) { offs[i] = off; off += vcf_line_size(vv, C[recs[i].contig], recs[i]); }
@@ -136,6 +136,11 @@ int emu_type_len(uint64_t seed, uint32_t gid, uint32_t pos, const double cdf[7],
     rp.limit = limit;
     draw_type_len(make_seed(seed), gid, pos, rp, *type, *len);
     return 0;
+}
+
+// bases of the random insert at (gid, pos): what K_RAND payloads expand to
+void emu_rand_insert(uint64_t seed, uint32_t gid, uint32_t pos, uint32_t n, uint8_t* out) {
+    for (uint32_t j = 0; j < n; ++j) out[j] = rand_insert_base(make_seed(seed), gid, pos, j);
 }
 
 int emu_snp(uint64_t seed, uint32_t gid, uint32_t pos, uint8_t ref, double p_ti, uint8_t* alt) {

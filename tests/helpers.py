@@ -76,7 +76,34 @@ def engine_for(contigs, device=0):
     return eng, genome, goff, np.array(lens)
 
 
-def recs_to_muts(recs, lit, goff):
+_EMU = None
+
+
+def emu_lib():
+    """tests/emu/emu.cpp compiled with g++ (host build of the kernels' shared host/device headers)."""
+    global _EMU
+    if _EMU is None:
+        import ctypes as C
+        import subprocess
+        here = Path(__file__).resolve().parent
+        src, lib = here / "emu" / "emu.cpp", here / "emu" / "_build" / "libemu.so"
+        lib.parent.mkdir(exist_ok=True)
+        deps = [src] + list((here.parent / "mutation_simulator_b200" / "csrc").glob("*.h"))
+        if not lib.exists() or lib.stat().st_mtime < max(p.stat().st_mtime for p in deps):
+            subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-o", str(lib), str(src)])
+        _EMU = C.CDLL(str(lib))
+    return _EMU
+
+
+def rand_insert(seed, gid, pos, n) -> bytes:
+    """The random insert a K_RAND record expands to (Philox, keyed by seed / global contig id / position)."""
+    import ctypes as C
+    out = C.create_string_buffer(max(1, n))
+    emu_lib().emu_rand_insert(C.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), C.c_uint32(gid), C.c_uint32(pos), C.c_uint32(n), out)
+    return out.raw[:n]
+
+
+def recs_to_muts(recs, lit, goff, seed=0, gids=None):
     """Decode device records back into per-contig lists of pyref.Mut (for the oracle)."""
     from mutation_simulator_b200 import records as R
     n_contigs = len(goff) - 1
@@ -89,7 +116,10 @@ def recs_to_muts(recs, lit, goff):
         if t == R.T_SN:
             m.alt = bytes([int(r["alt"])])
         elif t == R.T_IN:
-            m.insert = lit[int(r["src"]):int(r["src"]) + int(r["prod"])]
+            if int(r["kind"]) == 6:   # K_RAND: generated where consumed
+                m.insert = rand_insert(seed, c if gids is None else int(gids[c]), pos, int(r["prod"]))
+            else:
+                m.insert = lit[int(r["src"]):int(r["src"]) + int(r["prod"])]
             m.stop = pos + int(r["prod"]) - 1
         elif t in (R.T_DE, R.T_TL, R.T_IV):
             m.stop = pos + int(r["cons"]) - 1

@@ -18,11 +18,8 @@ LIB = HERE / "emu" / "_build" / "libemu.so"
 
 @pytest.fixture(scope="session")
 def emu():
-    LIB.parent.mkdir(exist_ok=True)
-    deps = [SRC] + list((HERE.parent / "mutation_simulator_b200" / "csrc").glob("*.h"))
-    if not LIB.exists() or LIB.stat().st_mtime < max(p.stat().st_mtime for p in deps):
-        subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-o", str(LIB), str(SRC)])
-    return C.CDLL(str(LIB))
+    from tests.helpers import emu_lib
+    return emu_lib()
 
 
 def philox(emu, ctr, key):

@@ -21,7 +21,7 @@ def test_c1_full_size_bit_exact_against_c_oracle():
     assert 119_000 < len(recs) < 120_000                 # reference: 119 473 written (0.44 % lost to greedy rejection)
     check_invariants(recs, [L], [1] * 7)
     fb, vb = eng.apply()
-    want_fa, want_vcf = c_oracle.mutate_genome(contigs, recs_to_muts(recs, lit, goff))
+    want_fa, want_vcf = c_oracle.mutate_genome(contigs, recs_to_muts(recs, lit, goff, seed=42))
     assert eng.fasta() == want_fa
     assert eng.vcf() == want_vcf
     eng.close()
@@ -38,7 +38,7 @@ def test_many_small_contigs_bit_exact_against_c_oracle():
     recs, lit = sample(eng, ranges, [1] * 7, 2.0 / 3.0, seed=7)
     check_invariants(recs, lens, [1] * 7)
     eng.apply()
-    want_fa, want_vcf = c_oracle.mutate_genome(contigs, recs_to_muts(recs, lit, goff))
+    want_fa, want_vcf = c_oracle.mutate_genome(contigs, recs_to_muts(recs, lit, goff, seed=7))
     assert eng.fasta() == want_fa
     assert eng.vcf() == want_vcf
     eng.close()

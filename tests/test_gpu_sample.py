@@ -64,7 +64,7 @@ def test_sampling_invariants_and_apply_matches_oracle():
     assert 0.9 * st["n_candidates"] < len(recs) <= st["n_candidates"]
     check_invariants(recs, lens, block)
     eng.apply()
-    want_fa, want_vcf = c_oracle.mutate_genome(contigs, recs_to_muts(recs, lit, goff))
+    want_fa, want_vcf = c_oracle.mutate_genome(contigs, recs_to_muts(recs, lit, goff, seed=5))
     assert eng.fasta() == want_fa
     assert eng.vcf() == want_vcf
     # determinism: same seed -> identical records; different seed -> different
@@ -255,4 +255,21 @@ def test_it_breakpoints_match_sampler_contract():
         assert (np.diff(arr) >= 2).all()
     a2, b2 = eng.it_breakpoints(3, [0, 1], [2, 3], [120, 80])
     assert np.array_equal(a, a2) and np.array_equal(b, b2)
+    eng.close()
+
+
+def test_long_random_inserts_match_oracle():
+    """Inserts longer than the 32 bases cached in the record (K_RAND beyond its cache -> Philox blocks 0, 1, ...)."""
+    from oracle import c_oracle
+    lens = [150_000, 40_000]
+    contigs = random_contigs(lens, seed=21)
+    eng, genome, goff, _ = engine_for(contigs)
+    ranges = args_ranges(lens, [0.004, 0.004, 0.001, 0, 0, 0], [1, 20, 1, 2, 1, 1, 1], [1, 150, 10, 3, 2, 2, 2])
+    recs, lit = sample(eng, ranges, [1] * 7, 0.5, seed=31)
+    ins = recs[recs["type"] == 1]
+    assert (ins["prod"] > 64).sum() > 50 and (ins["prod"] <= 32).sum() > 10
+    eng.apply()
+    want_fa, want_vcf = c_oracle.mutate_genome(contigs, recs_to_muts(recs, lit, goff, seed=31))
+    assert eng.fasta() == want_fa
+    assert eng.vcf() == want_vcf
     eng.close()
