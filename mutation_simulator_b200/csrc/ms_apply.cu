@@ -181,13 +181,6 @@ struct LoadWinGlobal {
 //       lane (2 x LDS.128 -> 1 x STG.128).
 // The group-centric version it replaces spent ~490 warp-instructions per 512 bytes on
 // per-group record lookups (profiles/r1b); here lookups are per run.
-constexpr int SP_TILE_MAX = 16384;
-constexpr int SP_RUN_CAP = 512;
-constexpr int SP_SEG_CAP = 320;
-constexpr int SP_JOB_CAP = 192;
-constexpr uint32_t SP_STAGE_CAP = 18 * 1024;       // TMA staging of the runs' input spans (tile + alignment slack)
-constexpr uint32_t SP_DIRECT = 0xFFFFFFFFu;        // segment did not fit the staging buffer: copied straight from global
-constexpr uint32_t SP_SEG_SPLIT = 2048;
 struct SegC { int64_t src; uint32_t dst; uint32_t n; };   // copy n bytes genome[src..] -> tile[dst..]; jobs: n | kind << 24
 
 // bytes [o, o+16) of the 32-byte window (a, b)
@@ -199,6 +192,74 @@ __device__ __forceinline__ uint4 shift16(const uint4 a, const uint4 b, uint32_t 
     const uint32_t bs = (o & 3u) * 8u;
     return make_uint4(__funnelshift_r(u0, u1, bs), __funnelshift_r(u1, u2, bs), __funnelshift_r(u2, u3, bs),
                       __funnelshift_r(u3, u4, bs));
+}
+
+constexpr int SP_TILE_MAX = 16384;
+constexpr int SP_RUN_CAP = 512;
+constexpr int SP_SEG_CAP = 320;
+constexpr int SP_JOB_CAP = 192;
+constexpr uint32_t SP_STAGE_CAP = 18 * 1024;       // TMA staging of the runs' input spans (tile + alignment slack)
+constexpr uint32_t SP_DIRECT = 0xFFFFFFFFu;        // segment did not fit the staging buffer: copied straight from global
+constexpr uint32_t SP_SEG_SPLIT = 2048;
+// Everything a splice CTA needs to start, precomputed by a fully parallel kernel so that the CTA's own dependent
+// chain of global round trips (piece -> contig search, contig, block index, record window) collapses into one
+// 96-byte load (profiles/r1h: the kernel is bound by that chain, not by issue slots or bandwidth).
+struct PieceDesc {
+    int64_t f_lo, f_hi;          // file bytes of the piece
+    int64_t i_first, i_last;     // records governing its bases (i_first may be the virtual rec_lo - 1)
+    int64_t body_off, goff, rec_lo;
+    int64_t in_lo;               // 16-byte aligned genome index where the tile's contiguous input span starts
+    uint32_t bpl, gid, cidx, b_lo, b_hi;
+    uint32_t in_bytes;           // staged bytes of that span (multiple of 16, <= SP_STAGE_CAP)
+    uint32_t pad[2];
+};
+static_assert(sizeof(PieceDesc) == 96, "PieceDesc layout");
+
+__global__ void __launch_bounds__(256)
+k_piece_desc(const Contig* contigs, int32_t n_contigs, const int64_t* piece_lo, int64_t n_pieces, const Rec* recs,
+             const uint32_t* blk, PieceDesc* out) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pieces) return;
+    int lo = 0, hi = n_contigs;  // last c with piece_lo[c] <= p
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (piece_lo[mid] <= p) lo = mid; else hi = mid;
+    }
+    const Contig k = contigs[lo];
+    PieceDesc d;
+    const int64_t tile_i = (k.body_off >> 14) + (p - k.piece_lo);
+    d.f_lo = tile_i << 14; d.f_hi = d.f_lo + 16384;
+    if (d.f_lo < k.body_off) d.f_lo = k.body_off;
+    if (d.f_hi > k.body_off + k.body_bytes) d.f_hi = k.body_off + k.body_bytes;
+    const uint32_t w1 = (uint32_t)k.bpl + 1u;
+    const uint32_t q_lo = (uint32_t)(d.f_lo - k.body_off), q_hi = (uint32_t)(d.f_hi - k.body_off);
+    d.b_lo = q_lo - q_lo / w1; d.b_hi = q_hi - q_hi / w1;
+    int64_t r = k.rec_lo + (int64_t)blk[k.blk_lo + (d.b_lo >> BLK_SHIFT)] - 1;
+    while (r + 1 < k.rec_hi && recs[r + 1].out <= d.b_lo) ++r;
+    d.i_first = r;
+    const uint32_t t = d.b_hi > d.b_lo ? d.b_hi - 1u : d.b_lo;
+    r = k.rec_lo + (int64_t)blk[k.blk_lo + (t >> BLK_SHIFT)] - 1;
+    if (r < d.i_first) r = d.i_first;
+    while (r + 1 < k.rec_hi && recs[r + 1].out <= t) ++r;
+    d.i_last = r;
+    d.body_off = k.body_off; d.goff = k.goff; d.rec_lo = k.rec_lo;
+    d.bpl = (uint32_t)k.bpl; d.gid = k.gid; d.cidx = (uint32_t)lo; d.pad[0] = d.pad[1] = 0u;
+    // the copy runs of a tile read one contiguous, monotone stretch of the contig: from the source of its first
+    // base to the source of its last base (payloads come from elsewhere and are not part of it)
+    auto src_of = [&](int64_t ri, uint32_t b) -> int64_t {
+        if (ri < k.rec_lo) return k.goff + (int64_t)b;
+        const Rec q = recs[ri];
+        const uint32_t rel = b - q.out;
+        return k.goff + (int64_t)q.pos + (int64_t)q.cons + (rel >= q.prod ? (int64_t)(rel - q.prod) : 0);
+    };
+    const int64_t s_lo = src_of(d.i_first, d.b_lo);
+    int64_t s_hi = src_of(d.i_last, t) + 1;
+    if (s_hi > k.goff + k.len) s_hi = k.goff + k.len;
+    d.in_lo = s_lo & ~(int64_t)15;
+    int64_t nb = s_hi > d.in_lo ? ((s_hi + 15) & ~(int64_t)15) - d.in_lo : 0;
+    if (nb > (int64_t)SP_STAGE_CAP) nb = SP_STAGE_CAP;
+    d.in_bytes = (uint32_t)nb;
+    out[p] = d;
 }
 
 // ---- TMA (bulk async copy) + mbarrier, raw PTX -----------------------------------------------------------
@@ -261,6 +322,27 @@ __device__ __forceinline__ uint8_t payload_at(const SpliceView& v, uint32_t kind
     }
 }
 
+// Same, with 16 lanes per segment (the average run is ~270 bytes = 17 chunks, so a full warp per segment
+// leaves half of the lanes idle).  hl = lane within the half-warp; n == 0 makes the half idle.
+__device__ __forceinline__ void half_copy_stage_to_tile(uint8_t* tile, const uint8_t* stage, uint32_t so, uint32_t d0, uint32_t n, int hl) {
+    const uint32_t d1 = d0 + n;
+    const uint32_t a0 = (d0 + 15u) & ~15u, a1 = d1 & ~15u;
+    if (a0 >= a1) {                                   // no aligned chunk inside: at most 30 bytes
+        for (uint32_t x = d0 + hl; x < d1; x += 16u) tile[x] = stage[so + (x - d0)];
+        return;
+    }
+#pragma unroll
+    for (int e = hl; e < 30; e += 16) {               // <= 15 head bytes (slots 0..14) and <= 15 tail bytes (slots 15..29)
+        const uint32_t x = e < 15 ? d0 + e : a1 + (e - 15);
+        if (x < (e < 15 ? a0 : d1)) tile[x] = stage[so + (x - d0)];
+    }
+    for (uint32_t c = a0 + 16u * hl; c < a1; c += 256u) {
+        const uint32_t s = so + (c - d0);
+        const uint4* w = reinterpret_cast<const uint4*>(stage + (s & ~15u));
+        *reinterpret_cast<uint4*>(tile + c) = shift16(w[0], w[1], s & 15u);
+    }
+}
+
 __device__ __forceinline__ void warp_copy_to_tile(uint8_t* tile, const uint8_t* __restrict__ genome, const SegC sg, int lane) {
     const uint32_t d0 = sg.dst, d1 = sg.dst + sg.n;
     const uint32_t a0 = (d0 + 15u) & ~15u, a1 = d1 & ~15u;
@@ -298,9 +380,9 @@ __device__ __forceinline__ int64_t warp_last_le(const Rec* recs, const Contig& k
 }
 
 __global__ void __launch_bounds__(SPLICE_THREADS, 5)
-k_splice(SpliceView v, const Contig* contigs, int32_t n_contigs, const int64_t* piece_lo, const Tables* tables,
-         uint8_t* fasta, int64_t tile_bytes) {
+k_splice(SpliceView v, const Contig* contigs, const PieceDesc* pieces, const Tables* tables, uint8_t* fasta) {
     __shared__ Contig sc;
+    __shared__ __align__(16) PieceDesc sd;
     extern __shared__ __align__(16) uint8_t sp_dyn[];      // [tile | stage]
     uint8_t* const tile = sp_dyn;
     uint8_t* const stage = sp_dyn + SP_TILE_MAX + 64;
@@ -310,62 +392,38 @@ k_splice(SpliceView v, const Contig* contigs, int32_t n_contigs, const int64_t* 
     __shared__ uint32_t nout[SP_RUN_CAP + 1];
     __shared__ uint16_t nidx[SP_RUN_CAP];
     __shared__ __align__(8) uint64_t bar;
-    __shared__ uint32_t stage_used;
     __shared__ uint32_t warp_tot[SPLICE_THREADS / 32];
     __shared__ int n_segs, n_jobs, fallback;
-    __shared__ long long s_first, s_last;
     __shared__ uint8_t s_conv[256], s_comp[256];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t p = blockIdx.x;
     if (warp == 0) {
-        // last c with piece_lo[c] <= p, by a 32-ary search (one round for a human-sized contig table)
-        int lo = 0, hi = n_contigs;
-        while (hi - lo > 1) {
-            const int step = (hi - lo + 31) >> 5;
-            const int probe = lo + step * (lane + 1);
-            const bool le = probe < hi && __ldg(piece_lo + probe) <= p;
-            const int cnt = __popc(__ballot_sync(0xffffffffu, le));   // probes are ascending: the first cnt are <= p
-            const int nlo = lo + step * cnt;
-            const int nhi = lo + step * (cnt + 1);
-            lo = nlo; hi = nhi < hi ? nhi : hi;
+        if (lane < (int)(sizeof(PieceDesc) / 4))
+            reinterpret_cast<uint32_t*>(&sd)[lane] = __ldg(reinterpret_cast<const uint32_t*>(pieces + p) + lane);
+        if (lane == 0) { n_segs = 0; n_jobs = 0; fallback = 0; mbar_init(&bar, 1u); }
+        __syncwarp();
+        // the tile's whole input span as ONE TMA bulk copy, issued before anything else so that it overlaps the
+        // record passes below (S1 waits for it)
+        if (lane == 0) {
+            const int64_t in_lo = sd.in_lo;
+            const uint32_t nb = sd.in_bytes;
+            if (nb) tma_load_1d(stage, v.genome + in_lo, nb, &bar);
+            mbar_arrive_expect_tx(&bar, nb);
         }
-        // copy the contig descriptor with the whole warp
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(contigs + lo);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&sc);
-        if (lane < (int)(sizeof(Contig) / 4)) dst[lane] = __ldg(src + lane);
-        if (lane == 0) { n_segs = 0; n_jobs = 0; fallback = 0; stage_used = 0u; mbar_init(&bar, SPLICE_THREADS / 32); }
     }
     s_conv[tid] = tables->conv[tid];
     s_comp[tid] = tables->comp[tid];
     __syncthreads();
-    const Contig& k = sc;
+    const PieceDesc& k = sd;     // (the fields the fast path needs carry the contig's names)
     v.conv = s_conv;
     v.comp = s_comp;
-    // tile_bytes == SP_TILE_MAX (checked by the host): shifts instead of 64-bit divisions
-    const int64_t tile_i = (k.body_off >> 14) + (p - k.piece_lo);
-    int64_t f_lo = tile_i << 14, f_hi = f_lo + SP_TILE_MAX;
-    if (f_lo < k.body_off) f_lo = k.body_off;
-    if (f_hi > k.body_off + k.body_bytes) f_hi = k.body_off + k.body_bytes;
+    const int64_t f_lo = k.f_lo, f_hi = k.f_hi;
     const int64_t g0 = f_lo & ~(int64_t)15;
     const int ngroups = (int)((f_hi - g0 + 15) >> 4);
-    const uint32_t bpl = (uint32_t)k.bpl, w1 = bpl + 1u;
-    const uint32_t q_lo = (uint32_t)(f_lo - k.body_off), q_hi = (uint32_t)(f_hi - k.body_off);
-    const uint32_t b_lo = q_lo - q_lo / w1, b_hi = q_hi - q_hi / w1;   // mutated bases [b_lo, b_hi) live in this tile
+    const uint32_t bpl = k.bpl, w1 = bpl + 1u;
+    const uint32_t b_lo = k.b_lo, b_hi = k.b_hi;   // mutated bases [b_lo, b_hi) live in this tile
     const Rec* recs = v.recs;
-
-    // ---- records of the tile: [i_first, i_last], i_first = governing record of b_lo (may be the virtual rec_lo-1)
-    if (warp == 0) {
-        const int64_t r0 = k.rec_lo + (int64_t)__ldg(v.blk + k.blk_lo + (b_lo >> BLK_SHIFT)) - 1;
-        const int64_t r = warp_last_le(recs, k, r0, b_lo, lane);
-        if (lane == 0) s_first = r;
-    } else if (warp == 1) {
-        const uint32_t t = b_hi > b_lo ? b_hi - 1u : b_lo;
-        const int64_t r0 = k.rec_lo + (int64_t)__ldg(v.blk + k.blk_lo + (t >> BLK_SHIFT)) - 1;
-        const int64_t r = warp_last_le(recs, k, r0, t, lane);
-        if (lane == 0) s_last = r;
-    }
-    __syncthreads();
-    const int64_t i_first = s_first, i_last = s_last;
+    const int64_t i_first = k.i_first, i_last = k.i_last;
     const int n_rec = (int)(i_last - i_first + 1);
 
     // ---- pass 1: ordered list of the run-starting records (the governing one + every non-SNP record)
@@ -434,9 +492,9 @@ k_splice(SpliceView v, const Contig* contigs, int32_t n_contigs, const int64_t* 
                 const int slot = atomicAdd(&n_segs, 1);
                 if (slot < SP_SEG_CAP) {
                     segs[slot] = SegC{src, lo - b_lo, n};
-                    const uint32_t span = (uint32_t)(((src + n + 15) & ~(int64_t)15) - (src & ~(int64_t)15));
-                    const uint32_t off = atomicAdd(&stage_used, span);
-                    seg_stage[slot] = off + span <= SP_STAGE_CAP ? off : SP_DIRECT;
+                    // staged iff the segment's source lies inside the span the prologue's TMA copy brings in
+                    const int64_t rel = src - k.in_lo;
+                    seg_stage[slot] = (rel >= 0 && rel + (int64_t)n <= (int64_t)k.in_bytes) ? (uint32_t)rel : SP_DIRECT;
                 } else {
                     fallback = 1;
                 }
@@ -447,30 +505,30 @@ k_splice(SpliceView v, const Contig* contigs, int32_t n_contigs, const int64_t* 
     __syncthreads();
 
     if (!fallback) {
-        // ---- S0: one TMA bulk copy per segment brings its 16-byte aligned input span into `stage`; all of the
-        //      tile's DRAM reads are in flight at once instead of one dependent round trip per segment and warp
-        //      (UBLKCP is a per-warp uniform instruction: every warp issues its own segments from one elected lane)
         const int ns = n_segs;
-        if (lane == 0) {
-            uint32_t bytes = 0u;
-            for (int sidx = warp; sidx < ns; sidx += SPLICE_THREADS / 32) {
-                const uint32_t off = seg_stage[sidx];
-                if (off == SP_DIRECT) continue;
-                const SegC sg = segs[sidx];
-                const int64_t al = sg.src & ~(int64_t)15;
-                const uint32_t span = (uint32_t)(((sg.src + sg.n + 15) & ~(int64_t)15) - al);
-                tma_load_1d(stage + off, v.genome + al, span, &bar);
-                bytes += span;
+        // one warp waits on the mbarrier; the others park at the CTA barrier instead of spinning on try_wait
+        // (8 spinning warps were 11.6 % of all issued instructions, profiles/r1h)
+        if (warp == 0) mbar_wait(&bar, 0u);
+        __syncthreads();
+        // ---- S1: shifted copies shared -> shared, one half-warp per segment
+        {
+            const int half = lane >> 4, hl = lane & 15;
+            bool any_direct = false;
+            for (int s0 = 2 * warp; s0 < ns; s0 += 2 * (SPLICE_THREADS / 32)) {
+                const int sidx = s0 + half;
+                uint32_t so = 0u, d0 = 0u, n = 0u;
+                if (sidx < ns) {
+                    const uint32_t off = seg_stage[sidx];
+                    if (off == SP_DIRECT) any_direct = true;
+                    else { const SegC sg = segs[sidx]; so = off; d0 = sg.dst; n = sg.n; }
+                }
+                half_copy_stage_to_tile(tile, stage, so, d0, n, hl);
             }
-            mbar_arrive_expect_tx(&bar, bytes);
-        }
-        mbar_wait(&bar, 0u);
-        // ---- S1: shifted copies shared -> shared, one warp per segment
-        for (int sidx = warp; sidx < ns; sidx += SPLICE_THREADS / 32) {
-            const SegC sg = segs[sidx];
-            const uint32_t off = seg_stage[sidx];
-            if (off == SP_DIRECT) warp_copy_to_tile(tile, v.genome, sg, lane);
-            else warp_copy_stage_to_tile(tile, stage, off + (uint32_t)(sg.src & 15), sg.dst, sg.n, lane);
+            if (__any_sync(0xffffffffu, any_direct)) {   // segments that did not fit the staging buffer (rare)
+                for (int s0 = 2 * warp; s0 < ns; s0 += 2 * (SPLICE_THREADS / 32))
+                    for (int h = 0; h < 2; ++h)
+                        if (s0 + h < ns && seg_stage[s0 + h] == SP_DIRECT) warp_copy_to_tile(tile, v.genome, segs[s0 + h], lane);
+            }
         }
         __syncthreads();
         // ---- S2: SNP bases and non-raw payloads
@@ -589,12 +647,14 @@ k_splice(SpliceView v, const Contig* contigs, int32_t n_contigs, const int64_t* 
         }
     } else {
         // ---- fallback for tiles with more runs than the staging lists hold: generic per-byte path
+        if (tid == 0) sc = contigs[k.cidx];
+        __syncthreads();
         for (int gi = tid; gi < ngroups; gi += SPLICE_THREADS) {
             const int64_t g = g0 + ((int64_t)gi << 4);
             const int64_t a = g < f_lo ? f_lo : g;
             const int64_t b = g + 16 > f_hi ? f_hi : g + 16;
             uint32_t w[4] = {0u, 0u, 0u, 0u};
-            group_slow(v, k, (uint32_t)(a - k.body_off), (int)(b - a), (int)(a - g), w);
+            group_slow(v, sc, (uint32_t)(a - k.body_off), (int)(b - a), (int)(a - g), w);
             for (int64_t x = a; x < b; ++x) {
                 const int ln = (int)(x - g);
                 fasta[x] = (uint8_t)(w[ln >> 2] >> (8 * (ln & 3)));
@@ -946,6 +1006,12 @@ int apply_pipeline(ms_ctx* c) {
     MS_LAUNCH_CHECK(c);
     k_fill_gaps<<<NUM_SMS_B200 * 4, 256, 0, st>>>(d_blk, c->long_gaps.as<Gap>(), d_tot);
     MS_LAUNCH_CHECK(c);
+    MS_CUDA(c, c->piece_desc.ensure((size_t)(t.n_pieces + 1) * sizeof(PieceDesc)));
+    if (t.n_pieces > 0) {
+        k_piece_desc<<<(unsigned)ceil_div(t.n_pieces, 256), 256, 0, st>>>(d_contigs, c->n_contigs, c->piece_lo.as<int64_t>(), t.n_pieces,
+                                                                        d_recs, d_blk, c->piece_desc.as<PieceDesc>());
+        MS_LAUNCH_CHECK(c);
+    }
     stage_end(c, ST_INDEX);
 
     if (c->tile_bytes != SP_TILE_MAX) MS_FAIL(c, MS_ERR_INTERNAL, "tile_bytes must equal %d", SP_TILE_MAX);
@@ -955,8 +1021,8 @@ int apply_pipeline(ms_ctx* c) {
         constexpr int SP_DYN = SP_TILE_MAX + 64 + (int)SP_STAGE_CAP + 32;
         static bool sp_attr = false;
         if (!sp_attr) { MS_CUDA(c, cudaFuncSetAttribute(k_splice, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_DYN)); sp_attr = true; }
-        k_splice<<<(unsigned)t.n_pieces, SPLICE_THREADS, SP_DYN, st>>>(sv, d_contigs, c->n_contigs, c->piece_lo.as<int64_t>(), d_tab,
-                                                                 c->fasta.as<uint8_t>(), (int64_t)c->tile_bytes);
+        k_splice<<<(unsigned)t.n_pieces, SPLICE_THREADS, SP_DYN, st>>>(sv, d_contigs, c->piece_desc.as<PieceDesc>(), d_tab,
+                                                                 c->fasta.as<uint8_t>());
         MS_LAUNCH_CHECK(c);
     }
     k_headers<<<(unsigned)ceil_div(c->n_contigs, 128), 128, 0, st>>>(d_contigs, c->n_contigs, c->headers.as<uint8_t>(), c->fasta.as<uint8_t>());

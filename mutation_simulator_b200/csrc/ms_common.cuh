@@ -82,7 +82,7 @@ struct ms_ctx {
     ms::Seed seed_last{0, 0};     // seed of the last ms_sample (K_RAND payloads are a function of it)
 
     // records + outputs
-    ms::DevBuf recs, lit, blk, piece_lo, long_gaps, fasta, vcf, vcf_off, totals;
+    ms::DevBuf recs, lit, blk, piece_lo, piece_desc, long_gaps, fasta, vcf, vcf_off, totals;
     int64_t n_recs = 0, lit_bytes = 0, fasta_bytes = 0, vcf_bytes = 0, n_pieces = 0, n_blk = 0;
     ms::Totals* h_totals = nullptr;  // pinned
     ms::Totals last_totals{};
