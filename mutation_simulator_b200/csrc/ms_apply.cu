@@ -94,6 +94,57 @@ k_contig_layout(Contig* contigs, int32_t n_contigs, const int64_t* S, int64_t* p
     }
 }
 
+// The same layout for large contig tables (many-small-contig genomes): two device-wide scans instead of one CTA
+// walking 200 k contigs (3.6 ms on C5).
+__global__ void k_layout_totals(const I64x2* t1, const int64_t* t2, int64_t* piece_lo, int32_t n_contigs, Totals* tot, int64_t n_recs,
+                                const int64_t* V) {
+    piece_lo[n_contigs] = *t2;
+    tot->fasta_bytes = t1->a; tot->n_blk = t1->b; tot->n_pieces = *t2;
+    tot->vcf_bytes = V[n_recs]; tot->n_recs = n_recs;
+}
+
+static int layout_by_scan(ms_ctx* c, Contig* d_contigs, const int64_t* S, const int64_t* V, int64_t M, Totals* d_tot) {
+    const int32_t n = c->n_contigs;
+    int64_t* d_piece_lo = c->piece_lo.as<int64_t>();
+    const int64_t tile_bytes = c->tile_bytes;
+    MS_CUDA(c, c->scan_tmp2.ensure(64));
+    I64x2* d_t1 = c->scan_tmp2.as<I64x2>();
+    int64_t* d_t2 = reinterpret_cast<int64_t*>(d_t1 + 1);
+    {
+        auto in = [=] __device__(int64_t i) -> I64x2 {
+            Contig& k = d_contigs[i];
+            const int64_t out_len = k.len + (S[k.rec_hi] - S[k.rec_lo]);
+            if (out_len < 0) raise_error(d_tot, MS_ERR_OVERLAP, i);
+            const int64_t bpl = k.bpl;
+            const int64_t body = out_len + out_len / bpl;
+            if (body >= (int64_t)0xFFFFFFF0ll) raise_error(d_tot, MS_ERR_LIMIT, i);
+            const uint32_t sep = (out_len % bpl != 0 && i != n - 1) ? 1u : 0u;
+            k.out_len = out_len; k.body_bytes = body; k.sep = sep;    // idempotent: the scan evaluates `in` twice
+            return I64x2{(int64_t)k.hdr_len + 2 + body + sep, (out_len >> BLK_SHIFT) + 1};
+        };
+        auto out = [=] __device__(int64_t i, I64x2 ex, I64x2) {
+            Contig& k = d_contigs[i];
+            k.hdr_off = ex.a; k.body_off = ex.a + k.hdr_len + 2; k.blk_lo = ex.b;
+        };
+        I64x2* tot1 = nullptr;
+        MS_CUDA(c, (device_scan<I64x2>(c, in, out, (int64_t)n, I64x2{0, 0}, SumOp(), c->scan_tmp, &tot1)));
+        MS_CUDA(c, cudaMemcpyAsync(d_t1, tot1, sizeof(I64x2), cudaMemcpyDeviceToDevice, c->stream));
+    }
+    {
+        auto in = [=] __device__(int64_t i) -> int64_t {
+            const Contig& k = d_contigs[i];
+            return k.body_bytes > 0 ? (k.body_off + k.body_bytes - 1) / tile_bytes - k.body_off / tile_bytes + 1 : 0;
+        };
+        auto out = [=] __device__(int64_t i, int64_t ex, int64_t) { d_contigs[i].piece_lo = ex; d_piece_lo[i] = ex; };
+        int64_t* tot2 = nullptr;
+        MS_CUDA(c, (device_scan<int64_t>(c, in, out, (int64_t)n, (int64_t)0, SumOp(), c->scan_tmp, &tot2)));
+        MS_CUDA(c, cudaMemcpyAsync(d_t2, tot2, sizeof(int64_t), cudaMemcpyDeviceToDevice, c->stream));
+    }
+    k_layout_totals<<<1, 1, 0, c->stream>>>(d_t1, d_t2, d_piece_lo, n, d_tot, M, V);
+    MS_LAUNCH_CHECK(c);
+    return MS_OK;
+}
+
 // ---- out positions, validation and the coarse block index ----------------------------
 // blk[k] of a contig = number of its records with out < k*BLK_BASES.
 __device__ inline void fill_blk(uint32_t* blk, int64_t start, int64_t count, uint32_t value, Gap* gaps, int64_t gap_cap, Totals* tot) {
@@ -982,9 +1033,14 @@ int apply_pipeline(ms_ctx* c) {
     // gap list capacity is bounded by the block count; size it from the input side (exact bound needs out_len)
     const int64_t gap_cap = c->total_bases / (BLK_BASES * GAP_INLINE) + 4 * (int64_t)c->n_contigs + M / GAP_INLINE + 1024;
     MS_CUDA(c, c->long_gaps.ensure((size_t)gap_cap * sizeof(Gap)));
-    k_contig_layout<<<1, SCAN_THREADS, 0, st>>>(d_contigs, c->n_contigs, S, c->piece_lo.as<int64_t>(), (int64_t)c->tile_bytes,
-                                                c->long_gaps.as<Gap>(), gap_cap, d_tot, M, V);
-    MS_LAUNCH_CHECK(c);
+    if (c->n_contigs <= 2048) {
+        k_contig_layout<<<1, SCAN_THREADS, 0, st>>>(d_contigs, c->n_contigs, S, c->piece_lo.as<int64_t>(), (int64_t)c->tile_bytes,
+                                                    c->long_gaps.as<Gap>(), gap_cap, d_tot, M, V);
+        MS_LAUNCH_CHECK(c);
+    } else {
+        int rc = layout_by_scan(c, d_contigs, S, V, M, d_tot);
+        if (rc) return rc;
+    }
     MS_CUDA(c, cudaMemcpyAsync(c->h_totals, d_tot, sizeof(Totals), cudaMemcpyDeviceToHost, st));
     stage_end(c, ST_PLAN);
     MS_CUDA(c, cudaStreamSynchronize(st));

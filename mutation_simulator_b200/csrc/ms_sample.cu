@@ -110,11 +110,59 @@ __device__ __forceinline__ uint32_t bitonic_sorted(uint32_t v, int tid, uint32_t
     return v;
 }
 
+constexpr int SMALL_BUCKET = 128;   // buckets of at most this many keys are sorted four per CTA (k_sort_emit_small)
+
+// position, type, length and blocking reach of the candidate that ends up in `slot` (K2)
+__device__ __forceinline__ void emit_candidate(const Range& g, const Contig& ct, uint32_t r_idx, int64_t slot, uint32_t v, Seed seed,
+                                               int32_t min_dist, const int32_t* blk, int positions_only, int64_t* cand_gpos,
+                                               uint8_t* cand_type, uint32_t* cand_len, int64_t* cand_reach, uint32_t* cand_range) {
+    const uint32_t rank = (uint32_t)(slot - g.cand_lo);
+    const uint32_t pos = g.start + v + (uint32_t)min_dist * rank;   // util.py:106-108
+    cand_gpos[slot] = ct.goff + pos;
+    if (positions_only) return;
+    uint8_t type; uint32_t len;
+    draw_type_len(seed, ct.gid, pos, g, type, len);
+    int64_t reach = block_reach(type, pos, len, blk);
+    if (reach > ct.len) reach = ct.len;
+    cand_type[slot] = type;
+    cand_len[slot] = len;
+    cand_reach[slot] = type == T_DEAD ? 0 : ct.goff + reach;
+    cand_range[slot] = r_idx;
+}
+
+// Small buckets (many-small-contig genomes: a 5 kbp contig has ~67 candidates): four buckets per CTA, 128 threads
+// each, instead of one mostly idle 512-thread CTA per bucket (C5: 4.0 ms -> see profiles).
+__global__ void __launch_bounds__(SORT_THREADS)
+k_sort_emit_small(const Range* ranges, const int64_t* bucket_lo_key, int32_t n_ranges, const Contig* contigs, const int64_t* bucket_off,
+                  int64_t n_buckets, const uint32_t* store, Seed seed, int32_t min_dist, const int32_t* block7, int positions_only,
+                  int64_t* cand_gpos, uint8_t* cand_type, uint32_t* cand_len, int64_t* cand_reach, uint32_t* cand_range) {
+    __shared__ uint32_t sm[SORT_THREADS];
+    __shared__ Range g4[SORT_THREADS / SMALL_BUCKET];
+    __shared__ uint32_t ridx4[SORT_THREADS / SMALL_BUCKET];
+    __shared__ int32_t blk[7];
+    const int tid = threadIdx.x, grp = tid / SMALL_BUCKET, t = tid % SMALL_BUCKET;
+    const int64_t b = (int64_t)blockIdx.x * (SORT_THREADS / SMALL_BUCKET) + grp;
+    int64_t lo = 0;
+    int cnt = 0;
+    if (b < n_buckets) { lo = bucket_off[b]; cnt = (int)(bucket_off[b + 1] - lo); }
+    const bool mine = cnt > 0 && cnt <= SMALL_BUCKET;
+    if (mine && t == 0) { ridx4[grp] = (uint32_t)upper_idx(bucket_lo_key, n_ranges, b); g4[grp] = ranges[ridx4[grp]]; }
+    if (tid < 7) blk[tid] = block7[tid];
+    __syncthreads();
+    uint32_t v = 0xFFFFFFFFu;
+    if (mine && t < cnt) v = store[bucket_store(g4[grp], (uint32_t)b) + t];
+    v = bitonic_sorted<SMALL_BUCKET>(v, t, sm + grp * SMALL_BUCKET);   // CTA-wide barriers inside: every thread takes part
+    if (mine && t < cnt)
+        emit_candidate(g4[grp], contigs[g4[grp].contig], ridx4[grp], lo + t, v, seed, min_dist, blk, positions_only, cand_gpos, cand_type,
+                       cand_len, cand_reach, cand_range);
+}
+
 // K1d + K2: sort one bucket in shared memory, then write position, type, length and reach.
 __global__ void __launch_bounds__(SORT_THREADS)
 k_sort_emit(const Range* ranges, const int64_t* bucket_lo_key, int32_t n_ranges, const Contig* contigs, const int64_t* bucket_off,
             const uint32_t* store, Seed seed, int32_t min_dist, const int32_t* block7, int positions_only,
-            int64_t* cand_gpos, uint8_t* cand_type, uint32_t* cand_len, int64_t* cand_reach, uint32_t* cand_range, Totals* tot) {
+            int64_t* cand_gpos, uint8_t* cand_type, uint32_t* cand_len, int64_t* cand_reach, uint32_t* cand_range, Totals* tot,
+            int skip_small) {
     __shared__ uint32_t sm[SORT_CAP];
     __shared__ Range g;
     __shared__ int32_t blk[7];
@@ -123,7 +171,7 @@ k_sort_emit(const Range* ranges, const int64_t* bucket_lo_key, int32_t n_ranges,
     const int64_t b = blockIdx.x;
     const int64_t lo = bucket_off[b], hi = bucket_off[b + 1];
     const int cnt = (int)(hi - lo);
-    if (cnt <= 0) return;
+    if (cnt <= 0 || (skip_small && cnt <= SMALL_BUCKET)) return;
     if (cnt > SORT_CAP) { if (tid == 0) raise_error_s(tot, MS_ERR_INTERNAL, 100 + b); return; }
     if (tid == 0) { s_ridx = (uint32_t)upper_idx(bucket_lo_key, n_ranges, b); g = ranges[s_ridx]; }
     if (tid < 7) blk[tid] = block7[tid];
@@ -163,22 +211,9 @@ k_sort_emit(const Range* ranges, const int64_t* bucket_lo_key, int32_t n_ranges,
         }
     }
     const Contig& ct = contigs[g.contig];
-    const uint32_t r_idx = s_ridx;
-    for (int i = tid; i < cnt; i += SORT_THREADS) {
-        const int64_t slot = lo + i;
-        const uint32_t rank = (uint32_t)(slot - g.cand_lo);
-        const uint32_t pos = g.start + sm[i] + (uint32_t)min_dist * rank;   // util.py:106-108
-        cand_gpos[slot] = ct.goff + pos;
-        if (positions_only) continue;
-        uint8_t type; uint32_t len;
-        draw_type_len(seed, ct.gid, pos, g, type, len);
-        int64_t reach = block_reach(type, pos, len, blk);
-        if (reach > ct.len) reach = ct.len;
-        cand_type[slot] = type;
-        cand_len[slot] = len;
-        cand_reach[slot] = type == T_DEAD ? 0 : ct.goff + reach;
-        cand_range[slot] = r_idx;
-    }
+    for (int i = tid; i < cnt; i += SORT_THREADS)
+        emit_candidate(g, ct, s_ridx, lo + i, sm[i], seed, min_dist, blk, positions_only, cand_gpos, cand_type, cand_len, cand_reach,
+                       cand_range);
 }
 
 // K3b: walk the chain that starts at each anchor (mutator.py:184-213).
@@ -339,11 +374,22 @@ static int draw_and_sort(ms_ctx* c, Seed seed, uint32_t purpose, int32_t min_dis
     stage_end(c, ST_SAMPLE_POS);
 
     stage_begin(c, ST_SAMPLE_TYPE);
-    k_sort_emit<<<(unsigned)c->n_buckets, SORT_THREADS, 0, st>>>(d_ranges, d_bucket_lo, R, d_ctg, d_boff,
-                                                                 c->cand_sorted.as<uint32_t>(), seed, min_dist, d_block, positions_only,
-                                                                 c->svec.as<int64_t>(), c->cand_type.as<uint8_t>(), c->cand_len.as<uint32_t>(),
-                                                                 c->cand_reach.as<int64_t>(), c->lvec.as<uint32_t>(), d_tot);
-    MS_LAUNCH_CHECK(c);
+    int any_small = 0, any_large = 0;
+    for (const Range& g : c->h_ranges) { if (g.nb == 1u && g.k <= (uint32_t)SMALL_BUCKET) any_small = 1; else any_large = 1; }
+    if (any_small) {
+        k_sort_emit_small<<<(unsigned)ceil_div(c->n_buckets, SORT_THREADS / SMALL_BUCKET), SORT_THREADS, 0, st>>>(
+            d_ranges, d_bucket_lo, R, d_ctg, d_boff, c->n_buckets, c->cand_sorted.as<uint32_t>(), seed, min_dist, d_block, positions_only,
+            c->svec.as<int64_t>(), c->cand_type.as<uint8_t>(), c->cand_len.as<uint32_t>(), c->cand_reach.as<int64_t>(),
+            c->lvec.as<uint32_t>());
+        MS_LAUNCH_CHECK(c);
+    }
+    if (any_large) {
+        k_sort_emit<<<(unsigned)c->n_buckets, SORT_THREADS, 0, st>>>(d_ranges, d_bucket_lo, R, d_ctg, d_boff,
+                                                                     c->cand_sorted.as<uint32_t>(), seed, min_dist, d_block, positions_only,
+                                                                     c->svec.as<int64_t>(), c->cand_type.as<uint8_t>(), c->cand_len.as<uint32_t>(),
+                                                                     c->cand_reach.as<int64_t>(), c->lvec.as<uint32_t>(), d_tot, any_small);
+        MS_LAUNCH_CHECK(c);
+    }
     stage_end(c, ST_SAMPLE_TYPE);
     return MS_OK;
 }
