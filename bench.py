@@ -370,8 +370,13 @@ def main():
     alg_bytes = my_bases + (fasta_bytes - hdr_bytes) + 32 * recs_n + tli_src
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (splice_ms * 1e-3) / 1e9 if splice_ms > 0 else 0.0
+    traffic = None
+    tf = REPO / "profiles" / "k_splice_traffic.json"
+    if tf.exists() and args.workload == "c2" and world == 1:   # ncu --set full capture of this kernel on this workload
+        t_ = json.loads(tf.read_text())
+        traffic = t_["dram_bytes_read"] + t_["dram_bytes_write"]
     roofline = {"bound": "hbm", "kernel": "k_splice", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
                 "alg_bytes_per_launch": alg_bytes, "kernel_ms": splice_ms,
                 "all_kernels_frac": ((my_bases + fasta_bytes + vcf_bytes + 64 * recs_n) / (ms_per_step * 1e-3) / 1e9) / peak}
 
