@@ -13,6 +13,7 @@
 //                   smaller list into the larger one via a keyed permutation.
 //   K4b records     32-byte splice descriptors + SNP ALT (mutator.py:429-463) +
 //                   random insert strings (mutator.py:466-471).
+#include <algorithm>
 #include "ms_common.cuh"
 #include "ms_scan.cuh"
 
@@ -229,6 +230,29 @@ k_resolve(int64_t K, const int64_t* gpos, const int64_t* reach, const uint8_t* t
     }
 }
 
+// The same without the prefix-max scan, for the usual case of short blocking spans: an earlier candidate can only
+// block j if it starts less than `maxspan` before it, so "no earlier candidate reaches past j" is a look-back of
+// 0-1 steps (average spacing is 1/rate, spans are a few dozen bases).
+__device__ __forceinline__ bool is_anchor_local(int64_t j, const int64_t* gpos, const int64_t* reach, const uint8_t* type, int64_t maxspan) {
+    if (type[j] == T_DEAD) return false;
+    const int64_t g = gpos[j];
+    for (int64_t i = j - 1; i >= 0 && g - gpos[i] < maxspan; --i)
+        if (reach[i] > g) return false;
+    return true;
+}
+
+__global__ void __launch_bounds__(256)
+k_resolve_local(int64_t K, const int64_t* gpos, const int64_t* reach, const uint8_t* type, int64_t maxspan, uint8_t* accept) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= K || !is_anchor_local(s, gpos, reach, type, maxspan)) return;
+    accept[s] = 1;
+    int64_t cur = reach[s];
+    for (int64_t t = s + 1; t < K && !is_anchor_local(t, gpos, reach, type, maxspan); ++t) {
+        if (type[t] == T_DEAD) continue;
+        if (gpos[t] >= cur) { accept[t] = 1; cur = reach[t]; }
+    }
+}
+
 __global__ void k_contig_tl_bounds(const Contig* contigs, int32_t n_contigs, const int64_t* gpos, const uint32_t* tl_list, int64_t n_tl,
                                    const uint32_t* tli_list, int64_t n_tli, int64_t* tl_base, int64_t* tli_base) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -427,15 +451,26 @@ int sample_pipeline(ms_ctx* c, uint64_t seed64) {
     uint8_t* d_anchor = c->cand_pm.as<uint8_t>();
     uint8_t* d_accept = c->cand_accept.as<uint8_t>();
     MS_CUDA(c, cudaMemsetAsync(d_accept, 0, (size_t)K, st));
-    {
+    // longest stretch a candidate can block past its own start (reach - pos), over all ranges and types
+    int64_t maxspan = 2;
+    for (const Range& g : c->h_ranges) {
+        for (int t = 0; t < 7; ++t) {
+            const int64_t len = (t == T_SN || t == T_IN || t == T_TLI) ? 1 : g.maxlen[t];
+            maxspan = std::max<int64_t>(maxspan, len + c->block[t] + 1);
+        }
+    }
+    if (maxspan <= 4096) {
+        k_resolve_local<<<(unsigned)ceil_div(K, 256), 256, 0, st>>>(K, d_gpos, d_reach, d_type, maxspan, d_accept);
+        MS_LAUNCH_CHECK(c);
+    } else {
         auto in = [=] __device__(int64_t i) -> int64_t { return d_reach[i]; };
         auto out = [=] __device__(int64_t i, int64_t ex, int64_t) {
             d_anchor[i] = (d_type[i] != T_DEAD && d_gpos[i] >= ex) ? 1 : 0;
         };
         MS_CUDA(c, (device_scan<int64_t>(c, in, out, K, (int64_t)0, MaxOp(), c->scan_tmp, (int64_t**)nullptr)));
+        k_resolve<<<(unsigned)ceil_div(K, 256), 256, 0, st>>>(K, d_gpos, d_reach, d_type, d_anchor, d_accept);
+        MS_LAUNCH_CHECK(c);
     }
-    k_resolve<<<(unsigned)ceil_div(K, 256), 256, 0, st>>>(K, d_gpos, d_reach, d_type, d_anchor, d_accept);
-    MS_LAUNCH_CHECK(c);
     // compaction of accepted candidates + TL / TLI lists in one pass
     MS_CUDA(c, c->acc_idx.ensure((size_t)K * 4 + 16));
     MS_CUDA(c, c->tl_list.ensure((size_t)K * 4 + 16));

@@ -273,3 +273,33 @@ def test_long_random_inserts_match_oracle():
     assert eng.fasta() == want_fa
     assert eng.vcf() == want_vcf
     eng.close()
+
+
+def test_long_blocking_spans_use_the_scan_path_and_agree_with_chain_semantics():
+    """maxlen far above the spacing (span > 4096 -> prefix-max scan path) and huge blocks: acceptance must still be
+    the reference's first-come rule (mutator.py:184-213), checked by replaying the rule on the host."""
+    lens = [600_000]
+    contigs = random_contigs(lens, seed=33)
+    eng, *_ = engine_for(contigs)
+    for maxlen, block in ((6000, [1, 1, 50, 1, 1, 1, 1]), (30, [3, 1, 200, 7, 1, 1, 1])):
+        ranges = args_ranges(lens, [0.002, 0.0005, 0.001, 0.0005, 0.0005, 0.001], [1, 1, 1, 2, 1, 1, 1],
+                             [1, 5, maxlen, maxlen, maxlen, maxlen, maxlen])
+        eng.set_ranges(ranges, block, min(block), 0.5)
+        eng.sample(3)
+        gpos, typ, ln, acc = eng.debug_candidates()
+        last_hi = -1
+        want = np.zeros(len(gpos), np.uint8)
+        for j in range(len(gpos)):
+            t = int(typ[j])
+            if t == 255 or gpos[j] < last_hi:
+                continue
+            want[j] = 1
+            p = int(gpos[j])
+            if t in (0, 1):
+                last_hi = p + 1 + block[t]
+            elif t == 6:
+                last_hi = 1 + block[6]
+            else:
+                last_hi = min(p + int(ln[j]) + block[t], lens[0])
+        assert np.array_equal(acc, want)
+    eng.close()
