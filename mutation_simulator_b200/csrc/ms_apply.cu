@@ -739,7 +739,7 @@ __global__ void k_headers(const Contig* contigs, int32_t n_contigs, const uint8_
 // copy jobs and moved by whole warps afterwards (profiles/r1b: the per-byte REF/ALT
 // loops ran on 1.5 lanes and were half of all instructions).
 constexpr int VCF_THREADS = 256;
-constexpr int VCF_SMEM = 22 * 1024;
+constexpr int VCF_SMEM = 17 * 1024;
 constexpr int VCF_MAX_JOBS = 2 * VCF_THREADS;
 enum SegMode : uint32_t { SM_IMM = 0, SM_RAW = 1, SM_CONV = 2, SM_RC = 3, SM_LIT = 4, SM_RAND = 5, SM_RANDL = 6 };   // RAND: src = cached 2-bit bases (<= 32); RANDL: src = gid << 32 | pos
 struct Seg { int64_t src; uint32_t len; uint32_t mode; };
@@ -869,28 +869,40 @@ k_vcf_write(VcfView v, const Rec* recs, int64_t n_recs, const Contig* contigs, c
     __shared__ uint8_t sv_list[VCF_THREADS];
     __shared__ CopyJob jobs[VCF_MAX_JOBS];
     extern __shared__ __align__(16) uint8_t buf[];
+    __shared__ __align__(16) Rec s_rec[VCF_THREADS];          // this CTA's records and line offsets, brought in by two
+    __shared__ __align__(16) int64_t s_V[VCF_THREADS + 2];    // TMA bulk copies issued before anything else
+    __shared__ __align__(8) uint64_t bar;
     const int tid = threadIdx.x;
-    s_conv[tid] = tables->conv[tid];
-    s_comp[tid] = tables->comp[tid];
-    if (tid == 0) { n_jobs = 0; n_sv = 0; }
-    v.conv = s_conv; v.comp = s_comp;
     const int64_t i0 = (int64_t)blockIdx.x * VCF_THREADS;
     const int64_t i1 = i0 + VCF_THREADS < n_recs ? i0 + VCF_THREADS : n_recs;
-    const int64_t base = V[i0], end = V[i1];
+    if (tid == 0) {
+        n_jobs = 0; n_sv = 0;
+        mbar_init(&bar, 1u);
+        const uint32_t nr = (uint32_t)(i1 - i0) * (uint32_t)sizeof(Rec);
+        const uint32_t nv = ((uint32_t)(i1 - i0 + 1) * 8u + 15u) & ~15u;     // the offsets array has slack behind V[n_recs]
+        tma_load_1d(s_rec, recs + i0, nr, &bar);
+        tma_load_1d(s_V, V + i0, nv, &bar);
+        mbar_arrive_expect_tx(&bar, nr + nv);
+    }
+    s_conv[tid] = tables->conv[tid];
+    s_comp[tid] = tables->comp[tid];
+    v.conv = s_conv; v.comp = s_comp;
+    if (tid < 32) mbar_wait(&bar, 0u);
+    __syncthreads();
+    const int64_t base = s_V[0], end = s_V[i1 - i0];
     const uint32_t shift = (uint32_t)(base & 15);
     const bool staged = (end - base) + shift <= VCF_SMEM;
     uint8_t* line0 = staged ? buf + shift : vcf + base;   // byte 0 of this CTA's lines
-    __syncthreads();
     const int64_t i = i0 + tid;
     // pass 1: SNP lines (three quarters of all records) in lock step; everything else is queued
     bool is_sv = false;
     if (i < i1) {
-        const int64_t a = V[i], b = V[i + 1];
+        const int64_t a = s_V[tid], b = s_V[tid + 1];
         if (b > a) {
-            const uint4 hi = __ldg(reinterpret_cast<const uint4*>(recs + i) + 1);   // src, kind/type/ref/alt, contig
+            const uint4 hi = reinterpret_cast<const uint4*>(s_rec + tid)[1];   // src, kind/type/ref/alt, contig
             const uint32_t type = (hi.z >> 8) & 0xffu;
             if (type == T_SN) {
-                const uint32_t pos = __ldg(&recs[i].pos);
+                const uint32_t pos = s_rec[tid].pos;
                 const Contig& c = contigs[hi.w];
                 uint8_t* p = staged ? buf + shift + (a - base) : vcf + a;
                 for (int q = 0; q < c.name_len; ++q) p[q] = v.names[c.name_src + q];
@@ -919,9 +931,8 @@ k_vcf_write(VcfView v, const Rec* recs, int64_t n_recs, const Contig* contigs, c
     __syncthreads();
     // pass 2: the remaining record types, densely packed over the threads
     for (int e = tid; e < n_sv; e += VCF_THREADS) {
-        const int64_t ii = i0 + sv_list[e];
-        const int64_t a = V[ii];
-        const Rec r = recs[ii];
+        const int64_t a = s_V[sv_list[e]];
+        const Rec r = s_rec[sv_list[e]];
         if (staged) vcf_emit_uniform<true>(v, contigs[r.contig], r, line0, buf + shift + (a - base), jobs, &n_jobs);
         else vcf_emit_uniform<false>(v, contigs[r.contig], r, line0, vcf + a, jobs, &n_jobs);
     }
