@@ -43,22 +43,26 @@ class _Faidx:
 class FastaRecord:
     """One contig; a view into the genome array (upper-cased on access when the loader kept the file's case)."""
 
-    def __init__(self, name: str, long_name: str, bases: np.ndarray, lenc: int, is_upper: bool = True):
+    def __init__(self, name: str, long_name: str, bases, lenc: int, is_upper: bool = True, length: int = None):
+        """bases: a uint8 array, or a zero-argument callable that produces it on first use (lazy contigs)."""
         self.name = name
         self.long_name = long_name
         self._raw = bases
         self._lenc = lenc
         self._is_upper = is_upper
+        self._length = int(length) if length is not None else int(bases.size)
 
     @property
     def _b(self) -> np.ndarray:
+        if callable(self._raw):
+            self._raw = self._raw()
         if not self._is_upper:
             self._raw = _UPPER[self._raw]
             self._is_upper = True
         return self._raw
 
     def __len__(self):
-        return int(self._raw.size)
+        return self._length
 
     def __getitem__(self, n):
         if isinstance(n, slice):
@@ -98,6 +102,8 @@ class Fasta:
                  read_ahead=None, build_index=True, **_):
         self.filename = str(filename)
         self.genome_is_upper = True
+        self._lazy = None          # (mmap, uint8 view, spans, layout) of a regularly wrapped file: bases are copied on demand
+        self._genome = None
         try:
             if not self._parse_regular():
                 self._parse(np.fromfile(self.filename, dtype=np.uint8), sequence_always_upper)
@@ -108,8 +114,11 @@ class Fasta:
         for i, nm in enumerate(self.names):
             if nm in self._records:
                 raise ValueError(f"Duplicate key \"{nm}\"")  # util.py:89-91 maps this to FastaDuplicateHeaderError
-            self._records[nm] = FastaRecord(nm, self.long_names[i], self.genome[self.goff[i]:self.goff[i + 1]], int(self.bpl[i]),
-                                            self.genome_is_upper)
+            if self._lazy is not None:
+                src = (lambda k=i: self.gather([k]))
+            else:
+                src = self._genome[self.goff[i]:self.goff[i + 1]]
+            self._records[nm] = FastaRecord(nm, self.long_names[i], src, int(self.bpl[i]), self.genome_is_upper, int(self.lengths[i]))
             self.faidx.index[nm] = IndexEntry(int(self.lengths[i]), int(self._seq_off[i]), int(self.bpl[i]), int(self._lenb[i]))
         if build_index:
             self._write_fai()
@@ -125,10 +134,12 @@ class Fasta:
             if size == 0:
                 return False
             mm = mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ)
+        keep_open = False
         try:
             if mm[0:1] != b">":
                 return False
             data = np.frombuffer(mm, dtype=np.uint8)
+            keep_open = False
             spans = []      # (header start, header end, seq_lo, seq_hi)
             pos = 0
             while pos < size:
@@ -171,18 +182,11 @@ class Fasta:
                 layout.append((nfull, tail_bases, b))
             goff = np.zeros(n + 1, np.int64)
             np.cumsum(lengths, out=goff[1:])
-            genome = np.empty(int(goff[-1]), dtype=np.uint8)
+            # validate the line structure now (cheap: one strided compare per contig), copy bases lazily
             for i, (_, _, lo, hi) in enumerate(spans):
                 nfull, tail_bases, b = layout[i]
-                o = int(goff[i])
-                if nfull:
-                    block = data[lo:lo + nfull * b].reshape(nfull, b)
-                    if not (block[:, b - 1] == 10).all():
-                        return False             # ragged lines
-                    genome[o:o + nfull * (b - 1)].reshape(nfull, b - 1)[:] = block[:, :b - 1]
-                    o += nfull * (b - 1)
-                if tail_bases:
-                    genome[o:o + tail_bases] = data[lo + nfull * b:lo + nfull * b + tail_bases]
+                if nfull and not (data[lo + b - 1:lo + nfull * b:b] == 10).all():
+                    return False             # ragged lines
             self.names, self.long_names = [], []
             for hs, he, _, _ in spans:
                 line = mm[hs + 1:he].decode("latin-1").rstrip("\r")
@@ -194,15 +198,64 @@ class Fasta:
             self._lenb = lenb
             self._seq_off = np.array([sp[2] for sp in spans], dtype=np.int64)
             self.goff = goff
-            self.genome = genome
             self.genome_is_upper = False
-            del data
+            self._lazy = (mm, data, spans, layout)
+            keep_open = True
             return True
         finally:
-            try:
-                mm.close()
-            except BufferError:       # a view is still alive (early return paths): the GC closes it
-                pass
+            if not keep_open:
+                try:
+                    del data
+                except NameError:
+                    pass
+                try:
+                    mm.close()
+                except BufferError:       # a view is still alive (early return paths): the GC closes it
+                    pass
+
+    def _copy_contig(self, i: int, dest: np.ndarray):
+        """Bases of contig i (file case) into dest: one strided 2-D copy for the full lines + the partial last line."""
+        _, data, spans, layout = self._lazy
+        lo = spans[i][2]
+        nfull, tail_bases, b = layout[i]
+        o = 0
+        if nfull:
+            dest[:nfull * (b - 1)].reshape(nfull, b - 1)[:] = data[lo:lo + nfull * b].reshape(nfull, b)[:, :b - 1]
+            o = nfull * (b - 1)
+        if tail_bases:
+            dest[o:o + tail_bases] = data[lo + nfull * b:lo + nfull * b + tail_bases]
+
+    def gather(self, ids) -> np.ndarray:
+        """Concatenated bases of the given contigs (file case for lazily loaded files; the GPU upper-cases)."""
+        ids = list(ids)
+        if self._lazy is None:
+            if len(ids) == len(self.names) and ids == list(range(len(self.names))):
+                return self._genome
+            return np.concatenate([self._genome[self.goff[i]:self.goff[i + 1]] for i in ids]) if ids else np.zeros(0, np.uint8)
+        off = np.zeros(len(ids) + 1, np.int64)
+        np.cumsum([int(self.lengths[i]) for i in ids], out=off[1:])
+        out = np.empty(int(off[-1]), dtype=np.uint8)
+        jobs = [(i, out[off[k]:off[k + 1]]) for k, i in enumerate(ids) if self.lengths[i] > 0]
+        big = sum(int(self.lengths[i]) for i in ids) > (64 << 20)
+        if big and len(jobs) > 1:
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(min(len(jobs), os.cpu_count() or 1, 16)) as ex:   # numpy copies release the GIL
+                list(ex.map(lambda j: self._copy_contig(*j), jobs))
+        else:
+            for j in jobs:
+                self._copy_contig(*j)
+        return out
+
+    @property
+    def genome(self) -> np.ndarray:
+        """All contigs concatenated (materialised on first use for lazily loaded files)."""
+        if self._genome is None:
+            self._genome = self.gather(range(len(self.names)))
+        return self._genome
+
+    @genome.setter
+    def genome(self, value):
+        self._genome = value
 
     def _parse(self, data: np.ndarray, upper: bool):
         n = data.size
@@ -311,17 +364,20 @@ class Fasta:
         return self._records[name]._b[start - 1:end].tobytes().decode("latin-1")
 
     def close(self):
-        pass
+        if self._lazy is not None:
+            mm = self._lazy[0]
+            self._lazy = None
+            try:
+                mm.close()
+            except BufferError:
+                pass
 
     # -- engine side -------------------------------------------------------
     def upload(self, engine, contig_ids=None):
         """Make this genome (or a subset of its contigs) resident on the engine's GPU."""
         # (the engine upper-cases on the device, so a mixed-case host array is fine)
         ids = list(range(len(self.names))) if contig_ids is None else list(contig_ids)
-        if contig_ids is None:
-            bases = self.genome
-        else:
-            bases = np.concatenate([self.genome[self.goff[i]:self.goff[i + 1]] for i in ids]) if ids else np.zeros(0, np.uint8)
+        bases = self.gather(ids)
         engine.upload_genome(bases, [int(self.lengths[i]) for i in ids], [int(self.bpl[i]) for i in ids],
                              [self.long_names[i].encode("latin-1") for i in ids],
                              [self.names[i].encode("latin-1") for i in ids], gid=ids)
