@@ -129,6 +129,11 @@ int ms_apply(ms_ctx* ctx, int64_t* fasta_bytes, int64_t* vcf_bytes);
 /* which: 0 FASTA image, 1 VCF body, 2 records (ms_rec[]), 3 literal pool */
 int ms_download(ms_ctx* ctx, int which, void* dst, int64_t cap, int64_t* nbytes);
 int ms_device_ptr(ms_ctx* ctx, int which, void** dptr, int64_t* nbytes);
+/* Stream bytes [src_off, src_off+nbytes) of an output buffer into an open file at file_off: D2H through two pinned
+ * staging buffers with the pwrite of one chunk overlapping the copy of the next.  Replaces the per-base
+ * file.write() calls of FastaWriter.write (fasta_writer.py:49-58) / VcfWriter.write (vcf_writer.py:118-126) for a whole
+ * file (or, with several GPUs, one contig's slice of it). */
+int ms_download_to_fd(ms_ctx* ctx, int which, int64_t src_off, int64_t nbytes, int fd, int64_t file_off);
 int ms_contig_out_len(ms_ctx* ctx, int64_t* out_len /* n_contigs */);
 /* Per-contig slices of the last ms_apply outputs, for assembling one file from several GPUs:
  * fasta_off[c]..fasta_off[c+1] = header + body (+ separator) bytes of contig c in the FASTA image,

@@ -58,6 +58,7 @@ PROTOTYPES = {
     "ms_apply": (C.c_int, [_P, C.POINTER(_I64), C.POINTER(_I64)]),
     "ms_download": (C.c_int, [_P, C.c_int, _P, _I64, C.POINTER(_I64)]),
     "ms_device_ptr": (C.c_int, [_P, C.c_int, C.POINTER(_P), C.POINTER(_I64)]),
+    "ms_download_to_fd": (C.c_int, [_P, C.c_int, _I64, _I64, C.c_int, _I64]),
     "ms_contig_out_len": (C.c_int, [_P, _P]),
     "ms_it_breakpoints": (C.c_int, [_P, _U64, _I32, _P, _P, _P, _P, _P]),
     "ms_get_stats": (C.c_int, [_P, C.POINTER(MsStats)]),

@@ -1,6 +1,8 @@
 // ms_api.cu — extern "C" entry points of libmutsim_b200.so (include/mutsim_b200.h):
 // lifecycle, genome residency, record loading, downloads and introspection.
+#include <errno.h>
 #include <string.h>
+#include <unistd.h>
 #include "ms_common.cuh"
 
 using namespace ms;
@@ -65,6 +67,10 @@ int ms_destroy(ms_ctx* c) {
     for (DevBuf* b : bufs) b->release();
     for (int s = 0; s < ST_COUNT; ++s) { cudaEventDestroy(c->ev[s][0]); cudaEventDestroy(c->ev[s][1]); }
     if (c->h_totals) cudaFreeHost(c->h_totals);
+    for (int i = 0; i < 2; ++i) {
+        if (c->h_stage[i]) cudaFreeHost(c->h_stage[i]);
+        if (c->h_stage_ev[i]) cudaEventDestroy(c->h_stage_ev[i]);
+    }
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return MS_OK;
@@ -246,6 +252,52 @@ int ms_download(ms_ctx* c, int which, void* dst, int64_t cap, int64_t* nbytes) {
     if (n) MS_CUDA(c, cudaMemcpyAsync(dst, p, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
     stage_end(c, ST_DOWNLOAD);
     MS_CUDA(c, cudaStreamSynchronize(c->stream));
+    return MS_OK;
+}
+
+static int pwrite_all(ms_ctx* c, int fd, const uint8_t* p, int64_t n, int64_t off) {
+    while (n > 0) {
+        const ssize_t w = pwrite(fd, p, (size_t)n, (off_t)off);
+        if (w < 0) {
+            if (errno == EINTR) continue;
+            MS_FAIL(c, MS_ERR_ARG, "pwrite failed: %s", strerror(errno));
+        }
+        p += w; n -= w; off += w;
+    }
+    return MS_OK;
+}
+
+int ms_download_to_fd(ms_ctx* c, int which, int64_t src_off, int64_t nbytes, int fd, int64_t file_off) {
+    if (!c || fd < 0 || src_off < 0 || nbytes < 0 || file_off < 0) return MS_ERR_ARG;
+    void* p; int64_t total;
+    int rc = which_buffer(c, which, &p, &total);
+    if (rc) return rc;
+    if (src_off + nbytes > total) MS_FAIL(c, MS_ERR_ARG, "ms_download_to_fd: range outside the buffer");
+    if (nbytes == 0) return MS_OK;
+    MS_CUDA(c, cudaSetDevice(c->device));
+    constexpr int64_t CH = 16 << 20;
+    for (int i = 0; i < 2; ++i) {
+        if (!c->h_stage[i]) MS_CUDA(c, cudaMallocHost((void**)&c->h_stage[i], (size_t)CH));
+        if (!c->h_stage_ev[i]) MS_CUDA(c, cudaEventCreateWithFlags(&c->h_stage_ev[i], cudaEventDisableTiming));
+    }
+    const uint8_t* src = static_cast<const uint8_t*>(p) + src_off;
+    const int64_t nch = (nbytes + CH - 1) / CH;
+    stage_begin(c, ST_DOWNLOAD);
+    for (int64_t i = 0; i <= nch; ++i) {
+        if (i < nch) {   // start the copy of chunk i ...
+            const int64_t n = (i + 1) * CH <= nbytes ? CH : nbytes - i * CH;
+            MS_CUDA(c, cudaMemcpyAsync(c->h_stage[i & 1], src + i * CH, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+            MS_CUDA(c, cudaEventRecord(c->h_stage_ev[i & 1], c->stream));
+        }
+        if (i > 0) {     // ... and write chunk i-1 while it is in flight
+            const int64_t j = i - 1;
+            const int64_t n = (j + 1) * CH <= nbytes ? CH : nbytes - j * CH;
+            MS_CUDA(c, cudaEventSynchronize(c->h_stage_ev[j & 1]));
+            rc = pwrite_all(c, fd, c->h_stage[j & 1], n, file_off + j * CH);
+            if (rc) return rc;
+        }
+    }
+    stage_end(c, ST_DOWNLOAD);
     return MS_OK;
 }
 

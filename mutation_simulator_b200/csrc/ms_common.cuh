@@ -85,6 +85,8 @@ struct ms_ctx {
     ms::DevBuf recs, lit, blk, piece_lo, piece_desc, long_gaps, fasta, vcf, vcf_off, totals;
     int64_t n_recs = 0, lit_bytes = 0, fasta_bytes = 0, vcf_bytes = 0, n_pieces = 0, n_blk = 0;
     ms::Totals* h_totals = nullptr;  // pinned
+    uint8_t* h_stage[2] = {nullptr, nullptr};   // pinned staging of ms_download_to_fd
+    cudaEvent_t h_stage_ev[2] = {nullptr, nullptr};
     ms::Totals last_totals{};
 
     // timing

@@ -164,3 +164,65 @@ def vcf_chunks(engine, my_ids, vcf_off):
     from .engine import BUF_VCF
     body = engine.download(BUF_VCF)
     return [body[int(vcf_off[i]):int(vcf_off[i + 1])].tobytes() for i in range(len(my_ids))]
+
+
+def _global_offsets(my_ids, my_sizes, n_contigs, prefix_len):
+    sizes = np.zeros(n_contigs, dtype=np.int64)
+    for r_ids, r_sizes in all_gather_object((list(my_ids), [int(x) for x in my_sizes])):
+        sizes[r_ids] = r_sizes
+    off = np.zeros(n_contigs + 1, dtype=np.int64)
+    np.cumsum(sizes, out=off[1:])
+    return off + prefix_len
+
+
+def _create(path, prefix: bytes, total: int):
+    if rank_world()[0] == 0:
+        with open(path, "wb") as fh:
+            fh.write(prefix)
+            fh.truncate(int(total))
+    barrier()
+
+
+def write_slices_partitioned(path, engine, which, my_ids, slice_off, n_contigs, prefix: bytes = b""):
+    """Contig i of this rank owns bytes [slice_off[i], slice_off[i+1]) of device buffer `which`; all ranks stream
+    their slices into one file, contigs in global order, without passing through Python."""
+    sizes = [int(slice_off[i + 1] - slice_off[i]) for i in range(len(my_ids))]
+    off = _global_offsets(my_ids, sizes, n_contigs, len(prefix))
+    _create(path, prefix, off[-1])
+    fd = os.open(path, os.O_WRONLY)
+    try:
+        # consecutive local contigs that are also consecutive in the file go out as one transfer
+        i = 0
+        while i < len(my_ids):
+            j = i
+            while j + 1 < len(my_ids) and my_ids[j + 1] == my_ids[j] + 1:
+                j += 1
+            n = int(slice_off[j + 1] - slice_off[i])
+            if n:
+                engine.download_to_fd(which, fd, int(off[my_ids[i]]), int(slice_off[i]), n)
+            i = j + 1
+    finally:
+        os.close(fd)
+    barrier()
+
+
+def write_fasta_partitioned(path, engine, my_ids, n_contigs_global):
+    """FASTA image slices with the separator fixed up for the global file order (a '\\n' follows a partial last
+    line unless the contig is the last one of the whole file).  Returns the per-contig VCF offsets of the layout."""
+    fo, vo, sep, partial = engine.contig_layout()
+    body = [int(fo[i + 1] - fo[i]) - int(sep[i]) for i in range(len(my_ids))]
+    extra = [1 if (partial[i] and g != n_contigs_global - 1) else 0 for i, g in enumerate(my_ids)]
+    off = _global_offsets(my_ids, [b + e for b, e in zip(body, extra)], n_contigs_global, 0)
+    _create(path, b"", off[-1])
+    from .engine import BUF_FASTA
+    fd = os.open(path, os.O_WRONLY)
+    try:
+        for i, g in enumerate(my_ids):
+            if body[i]:
+                engine.download_to_fd(BUF_FASTA, fd, int(off[g]), int(fo[i]), body[i])
+            if extra[i]:
+                os.pwrite(fd, b"\n", int(off[g]) + body[i])
+    finally:
+        os.close(fd)
+    barrier()
+    return vo

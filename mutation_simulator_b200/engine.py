@@ -154,6 +154,18 @@ class Engine:
         self._check(self._lib.ms_download(self._h, which, _ptr(out), out.nbytes, C.byref(n)))
         return out[:n.value] if out.dtype == np.uint8 else out
 
+    def size_of(self, which: int) -> int:
+        n = C.c_int64()
+        self._check(self._lib.ms_download(self._h, which, None, 0, C.byref(n)))
+        return n.value
+
+    def download_to_fd(self, which: int, fd: int, file_off: int = 0, src_off: int = 0, nbytes: Optional[int] = None) -> int:
+        """Stream (a slice of) an output buffer into an open file descriptor at file_off; returns the bytes written."""
+        if nbytes is None:
+            nbytes = self.size_of(which) - src_off
+        self._check(self._lib.ms_download_to_fd(self._h, which, int(src_off), int(nbytes), int(fd), int(file_off)))
+        return int(nbytes)
+
     def fasta(self) -> bytes:
         return self.download(BUF_FASTA).tobytes()
 

@@ -29,6 +29,13 @@ class FastaWriter:
         """Write a complete device-built file image (bytes / memoryview / numpy uint8)."""
         self._f.write(memoryview(image))
 
+    def write_from_engine(self, engine, which: int):
+        """Stream a device buffer straight into the file (pinned double buffering inside libmutsim_b200)."""
+        self._f.flush()
+        off = self._f.tell()
+        n = engine.download_to_fd(which, self._f.fileno(), off)
+        self._f.seek(off + n)
+
     # reference-compatible streaming API
     def set_bpl(self, bpl: int):
         self._bpl = bpl

@@ -134,7 +134,7 @@ class ITMutator:
         bps = self.breakpoints = self._generate_all_breakpoints(eng)
         eng.load_records(self._records(bps))
         eng.apply()
-        self._fasta_writer.write_image(eng.download(BUF_FASTA))
+        self._fasta_writer.write_from_engine(eng, BUF_FASTA)
         for chrom in self._sim.chromosomes:            # FASTA order, one block of rows per paired contig
             c = chrom.number
             if c in bps:
@@ -181,8 +181,7 @@ class ITMutator:
         D.exchange_contigs(eng, device, sends, recvs)
         eng.load_records(self._records(bps, my_ids, src_of))
         eng.apply()
-        chunks, _ = D.fasta_chunks(eng, my_ids, n_contigs)
-        D.write_partitioned(self._args.outfastait, my_ids, chunks, n_contigs)
+        D.write_fasta_partitioned(self._args.outfastait, eng, my_ids, n_contigs)
         bed = []
         for g in my_ids:
             if g in bps:

@@ -6,8 +6,10 @@ formats FASTA + VCF — all on the GPU through libmutsim_b200 — then writes th
 Nothing here touches a base on the host."""
 from __future__ import annotations
 
+import os
 import secrets
 import sys
+import time
 
 import numpy as np
 
@@ -56,28 +58,36 @@ class Mutator:
         """Creates random mutations and writes them to a Fasta and VCF file."""
         args, fasta, sim = self._args, self._fasta, self._sim
         world = self._world
+        marks = [("start", time.perf_counter())]
+        lap = lambda name: marks.append((name, time.perf_counter()))
         n_contigs = len(fasta.names)
         my_ids = D.lpt_partition(fasta.lengths, world)[self._rank] if world > 1 else list(range(n_contigs))
         seed = D.broadcast_object(run_seed(args))
         eng = self._engine = Engine(D.local_device(getattr(args, "device", 0)) if world > 1 else getattr(args, "device", 0))
+        lap("engine")
         fasta.upload(eng, my_ids if world > 1 else None)
+        lap("gather+upload")
         ranges, n = build_ranges(sim, fasta.lengths, my_ids)
         eng.set_ranges_array(ranges, n, block_list(sim), min(sim.mut_block.values()), p_transition(sim.titv))
         eng.sample(seed)
         eng.apply()
+        lap("sample+apply")
         if not args.ignore_warnings:
             per = eng.contig_records()
             for i in np.flatnonzero(per == 0):
                 print(format_warning(f"No mutations could be generated on sequence {my_ids[int(i)]+1} (mutation rates too low)",
                                      args.no_color), file=sys.stderr)
         if world == 1:
-            self._fasta_writer.write_image(eng.download(BUF_FASTA))
-            self._vcf_writer.write_body(eng.download(BUF_VCF))
+            self._fasta_writer.write_from_engine(eng, BUF_FASTA)
+            self._vcf_writer.write_from_engine(eng, BUF_VCF)
         else:
             from .vcf_writer import header_text
-            chunks, vcf_off = D.fasta_chunks(eng, my_ids, n_contigs)
-            D.write_partitioned(args.outfasta, my_ids, chunks, n_contigs)
+            vcf_off = D.write_fasta_partitioned(args.outfasta, eng, my_ids, n_contigs)
             head = header_text(args.infile.name, [(fasta[k].name, len(fasta[k])) for k in fasta.keys()], sim.assembly_name,
                                sim.species_name, sim.sample_name).encode("latin-1")
-            D.write_partitioned(args.outvcf, my_ids, D.vcf_chunks(eng, my_ids, vcf_off), n_contigs, prefix=head)
+            D.write_slices_partitioned(args.outvcf, eng, BUF_VCF, my_ids, vcf_off, n_contigs, prefix=head)
+        lap("download+write")
         self.stats = eng.stats()
+        self.host_seconds = {b[0]: b[1] - a[1] for a, b in zip(marks, marks[1:])}
+        if os.environ.get("MS_TIMING"):
+            print(f"[rank {self._rank}] " + " ".join(f"{k}={v:.3f}s" for k, v in self.host_seconds.items()), file=sys.stderr)

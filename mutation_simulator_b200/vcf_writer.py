@@ -67,6 +67,12 @@ class VcfWriter:
     def write_body(self, body):
         self._f.write(memoryview(body))
 
+    def write_from_engine(self, engine, which: int):
+        self._f.flush()
+        off = self._f.tell()
+        n = engine.download_to_fd(which, self._f.fileno(), off)
+        self._f.seek(off + n)
+
     def write(self, record: VcfRecord, seq_name: str):
         if record.ref != record.alt:
             self._f.write(f"{seq_name}\t{record.start}\t.\t{record.ref}\t{record.alt}\t.\t.\t{record.info}\tGT\t1\n".encode("latin-1"))
