@@ -80,3 +80,72 @@ def test_chromosome_sized_contig_properties():
     st = eng.stats()
     assert st["counts"][5] == st["counts"][6] > 0
     eng.close()
+
+
+def test_c3_shaped_rmt_hot_cold_ranges_and_blocked_centromeres(tmp_path):
+    """BASELINE config 3 shape, scaled: 3 contigs / 60 Mbp, ~1 200 alternating hot/cold ranges and a blocked (None)
+    centromere per contig, through the real RMT parser and range planner.  Checks per-range rates, zero starts and
+    zero extents in blocked ranges, and the length bookkeeping."""
+    from mutation_simulator_b200 import plan
+    from mutation_simulator_b200.engine import Engine
+    from mutation_simulator_b200.rmt import SimulationSettings
+    lens = [30_000_000, 20_000_000, 10_000_000]
+    rng = np.random.default_rng(8)
+    lines = ["titv=2.0", "std", "it None", "sn 0.001", ""]
+    blocked, hot = [], []
+    for ci, L in enumerate(lens):
+        lines.append(f"chr {ci+1}")
+        cen_lo, cen_hi = int(L * 0.4), int(L * 0.43)
+        pos = 10_000
+        k = 0
+        while pos + 120_000 < L:
+            n = int(rng.integers(10_000, 100_000))
+            if pos < cen_hi and pos + n > cen_lo:          # the centromere: one None range
+                lines.append(f"{cen_lo+1}-{cen_hi} None")
+                blocked.append((ci, cen_lo, cen_hi - 1))
+                pos = cen_hi + int(rng.integers(1, 5000))
+                continue
+            if k % 2 == 0:
+                lines.append(f"{pos+1}-{pos+n} sn 0.05 in 0.005 inmin 1 inmax 10 de 0.005 demin 1 demax 60 tl 0.004 tlmin 5 tlmax 40")
+                hot.append((ci, pos, pos + n - 1))
+            else:
+                lines.append(f"{pos+1}-{pos+n} sn 0.0001")
+            pos += n + int(rng.integers(0, 3000))
+            k += 1
+    p = tmp_path / "c3.rmt"
+    p.write_text("\n".join(lines) + "\n")
+
+    class FakeFasta:                                   # the settings model only needs names and lengths
+        def keys(self):
+            return [f"c{i}" for i in range(len(lens))]
+
+        def __getitem__(self, i):
+            n = lens[i if isinstance(i, int) else int(i[1:])]
+            return type("R", (), {"__len__": lambda s: n})()
+    sim = SimulationSettings.from_rmt(p, FakeFasta(), True)
+    arr, n_ranges = plan.build_ranges(sim, lens)
+    assert n_ranges > 1000
+    eng = Engine(0)
+    names = [b"c0", b"c1", b"c2"]
+    eng.synth_genome(11, lens, [60] * 3, names, names)
+    eng.set_ranges_array(arr, n_ranges, plan.block_list(sim), min(sim.mut_block.values()), plan.p_transition(sim.titv))
+    eng.sample(4)
+    eng.apply()
+    recs = eng.records()
+    check_invariants(recs, lens, [1] * 7)
+    pos = recs["pos"].astype(np.int64)
+    ext = pos + np.maximum(recs["cons"].astype(np.int64), 1)
+    for ci, lo, hi in blocked:
+        m = recs["contig"] == ci
+        assert not ((pos[m] >= lo) & (pos[m] <= hi)).any(), "start inside a blocked range"
+        assert not ((pos[m] < lo) & (ext[m] > lo)).any(), "extent reaches into a blocked range"
+    # hot ranges carry ~0.064 candidates per base, a few percent of them lost to first-come rejection
+    got = exp = 0
+    for ci, lo, hi in hot[::7]:
+        m = (recs["contig"] == ci) & (pos >= lo) & (pos <= hi)
+        got += int(m.sum()); exp += int((hi - lo + 1) * 0.064)
+    assert 0.80 * exp < got <= exp, (got, exp)
+    d = recs["prod"].astype(np.int64) - recs["cons"].astype(np.int64)
+    for ci, L in enumerate(lens):
+        assert int(eng.contig_out_len()[ci]) == L + int(d[recs["contig"] == ci].sum())
+    eng.close()
