@@ -100,6 +100,11 @@ int ms_genome_synth(ms_ctx* ctx, uint64_t seed, int32_t n_contigs, const int64_t
                     const uint8_t* headers, const int64_t* hdr_off,
                     const uint8_t* names, const int64_t* name_off);
 int ms_genome_download(ms_ctx* ctx, uint8_t* bases, int64_t cap);
+/* Make the mutated genome of the last ms_apply the resident genome (headers / line breaks stripped on the device):
+ * what __main__.py:88-95 does by re-loading the just-written *_ms.fa before ITMutator runs.  Contig lengths become
+ * the mutated lengths; bpl follows pyfaidx's rule for the re-loaded file (a contig shorter than one line gets
+ * bpl = its length).  Records and ranges are cleared. */
+int ms_genome_adopt_output(ms_ctx* ctx);
 /* Reserve `extra_bytes` of staging space behind the genome for bases of contigs that live on another GPU
  * (interchromosomal partners, it_mutator.py:133-137).  Call before ms_genome_upload.  The region starts at
  * genome index total_bases + 64 (ms_device_ptr(4) gives the base pointer); K_RAW records may point into it,

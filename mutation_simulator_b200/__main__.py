@@ -2,6 +2,7 @@
 entry point (__main__.py:34-107) — same modes, messages and exit codes."""
 from __future__ import annotations
 
+import os
 from timeit import default_timer as timer
 
 from . import (BedpeWriterError, ChromNotExistError, FastaDuplicateHeaderError, FastaIndexingError, FastaNotFoundError,
@@ -44,17 +45,25 @@ def warn_user(args, sim):
 def main():
     start = timer()
     args, fasta, sim = initialize()
+    from . import distributed
+    resident = None
     if sim.has_mutations:
         try:
             mutator = Mutator(args, fasta, sim)
             mutator.mutate()
+            # one GPU: the mutated genome stays in HBM for the IT step (MS_NO_CHAIN=1 forces the reference's reload)
+            if sim.has_it and distributed.rank_world()[1] == 1 and not os.environ.get("MS_NO_CHAIN") \
+                    and int(mutator._engine.contig_out_len().min()) > 0:
+                from .fasta import ResidentFasta
+                resident = ResidentFasta(mutator.detach_engine(), fasta)
             mutator.close()
             fasta.close()
         except (FastaWriterError, VcfWriterError, MutSimError, RangeOverlapError) as e:
             exit_with_error(e, args.no_color)
     if sim.has_it:
-        if sim.has_mutations:   # IT runs on the mutated genome (__main__.py:88-95)
-            from . import distributed
+        if resident is not None:
+            fasta = resident
+        elif sim.has_mutations:   # IT runs on the mutated genome (__main__.py:88-95)
             distributed.barrier()   # all ranks have written their slices of *_ms.fa
             try:
                 fasta = load_fasta(args.outfasta)
@@ -68,7 +77,6 @@ def main():
         except (FastaWriterError, BedpeWriterError, MutSimError) as e:
             exit_with_error(e, args.no_color)
     runtime = round(timer() - start, 4)
-    from . import distributed
     if distributed.rank_world()[0] != 0:
         return
     if not args.quiet:

@@ -181,6 +181,12 @@ int ms_genome_reserve(ms_ctx* c, int64_t extra_bytes) {
     return MS_OK;
 }
 
+int ms_genome_adopt_output(ms_ctx* c) {
+    if (!c) return MS_ERR_ARG;
+    MS_CUDA(c, cudaSetDevice(c->device));
+    return adopt_output(c);
+}
+
 int ms_genome_download(ms_ctx* c, uint8_t* bases, int64_t cap) {
     if (!c || !bases) return MS_ERR_ARG;
     if (cap < c->total_bases) MS_FAIL(c, MS_ERR_ARG, "buffer too small");

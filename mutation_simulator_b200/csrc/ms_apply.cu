@@ -994,6 +994,65 @@ __global__ void k_store_total2(const I64x2* total, int64_t* S_end, int64_t* V_en
     *V_end = total->b;
 }
 
+// ---- image -> bases (chained RMT -> IT without the file round trip) ---------------------------------------------
+// new_off[c] = index of contig c's first base in the new genome; 16 bases per thread.
+__global__ void __launch_bounds__(256)
+k_strip_image(const uint8_t* image, const Contig* contigs, int32_t n_contigs, const int64_t* new_off, int64_t total, uint8_t* out) {
+    const int64_t g0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (g0 >= total) return;
+    int lo = 0, hi = n_contigs;   // last c with new_off[c] <= g0
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (new_off[mid] <= g0) lo = mid; else hi = mid; }
+    int c = lo;
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+    for (int t = 0; t < 16 && g0 + t < total; ++t) {
+        const int64_t g = g0 + t;
+        while (c + 1 < n_contigs && new_off[c + 1] <= g) ++c;
+        const Contig& k = contigs[c];
+        const int64_t b = g - new_off[c];
+        const uint8_t ch = image[k.body_off + b + b / k.bpl];
+        w[t >> 2] |= (uint32_t)ch << (8 * (t & 3));
+    }
+    if (g0 + 16 <= total) *reinterpret_cast<uint4*>(out + g0) = make_uint4(w[0], w[1], w[2], w[3]);
+    else for (int t = 0; g0 + t < total; ++t) out[g0 + t] = (uint8_t)(w[t >> 2] >> (8 * (t & 3)));
+}
+
+int adopt_output(ms_ctx* c) {
+    if (c->n_contigs <= 0 || !c->fasta.p || c->fasta_bytes <= 0) MS_FAIL(c, MS_ERR_STATE, "ms_genome_adopt_output: no applied output");
+    cudaStream_t st = c->stream;
+    MS_CUDA(c, cudaMemcpyAsync(c->h_contigs.data(), c->contigs.p, sizeof(Contig) * (size_t)c->n_contigs, cudaMemcpyDeviceToHost, st));
+    MS_CUDA(c, cudaStreamSynchronize(st));
+    std::vector<int64_t> off((size_t)c->n_contigs + 1);
+    int64_t total = 0;
+    for (int i = 0; i < c->n_contigs; ++i) { off[i] = total; total += c->h_contigs[i].out_len; }
+    off[c->n_contigs] = total;
+    MS_CUDA(c, c->scan_tmp2.ensure((size_t)(c->n_contigs + 1) * 8));
+    MS_CUDA(c, cudaMemcpyAsync(c->scan_tmp2.p, off.data(), (size_t)(c->n_contigs + 1) * 8, cudaMemcpyHostToDevice, st));
+    DevBuf fresh;
+    MS_CUDA(c, fresh.ensure((size_t)total + 64 + (size_t)c->foreign_cap + 64));
+    if (total > 0) {
+        k_strip_image<<<(unsigned)ceil_div(ceil_div(total, 16), 256), 256, 0, st>>>(c->fasta.as<uint8_t>(), c->contigs.as<Contig>(), c->n_contigs,
+                                                                                    c->scan_tmp2.as<int64_t>(), total, fresh.as<uint8_t>());
+        MS_LAUNCH_CHECK(c);
+    }
+    MS_CUDA(c, cudaMemsetAsync(fresh.as<uint8_t>() + total, 'N', 64, st));
+    MS_CUDA(c, cudaStreamSynchronize(st));
+    c->genome.release();
+    c->genome = fresh;
+    for (int i = 0; i < c->n_contigs; ++i) {
+        Contig& k = c->h_contigs[i];
+        const int64_t L = k.out_len;
+        if (L > 0 && L < k.bpl) k.bpl = (int32_t)L;        // pyfaidx lenc of a record shorter than one line
+        k.goff = off[i]; k.len = L; k.out_len = L;
+        k.rec_lo = k.rec_hi = 0;
+    }
+    c->total_bases = total;
+    MS_CUDA(c, cudaMemcpyAsync(c->contigs.p, c->h_contigs.data(), sizeof(Contig) * (size_t)c->n_contigs, cudaMemcpyHostToDevice, st));
+    MS_CUDA(c, cudaStreamSynchronize(st));
+    c->n_recs = 0; c->lit_bytes = 0; c->n_ranges = 0; c->sizes_valid = false; c->counts_valid = false;
+    c->fasta_bytes = 0; c->vcf_bytes = 0;
+    return MS_OK;
+}
+
 // ---- host orchestration --------------------------------------------------------------
 int apply_pipeline(ms_ctx* c) {
     if (c->n_contigs <= 0 || !c->genome.p) MS_FAIL(c, MS_ERR_STATE, "ms_apply: no genome resident");

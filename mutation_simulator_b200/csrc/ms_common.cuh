@@ -129,6 +129,7 @@ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // pipeline entry points implemented in the .cu files
 int apply_pipeline(ms_ctx* c);
+int adopt_output(ms_ctx* c);
 int sample_pipeline(ms_ctx* c, uint64_t seed);
 int count_types(ms_ctx* c);
 }  // namespace ms

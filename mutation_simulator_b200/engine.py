@@ -102,6 +102,14 @@ class Engine:
         """Staging space behind the genome for partner contigs owned by another GPU (call before upload)."""
         self._check(self._lib.ms_genome_reserve(self._h, int(nbytes)))
 
+    def adopt_output(self) -> np.ndarray:
+        """The mutated genome of the last apply() becomes the resident genome; returns the new contig lengths."""
+        self._check(self._lib.ms_genome_adopt_output(self._h))
+        lens = self.contig_out_len()
+        self._len = lens.copy()
+        self.total_bases = int(lens.sum())
+        return lens
+
     def download_genome(self) -> np.ndarray:
         out = np.empty(self.total_bases, dtype=np.uint8)
         self._check(self._lib.ms_genome_download(self._h, _ptr(out), out.size))

@@ -382,3 +382,38 @@ class Fasta:
                              [self.long_names[i].encode("latin-1") for i in ids],
                              [self.names[i].encode("latin-1") for i in ids], gid=ids)
         return ids
+
+
+class ResidentFasta:
+    """The mutated genome of a finished Mutator run, still resident on its engine: what the reference obtains by
+    load_fasta(args.outfasta) between Mutator and ITMutator (__main__.py:88-95), without the trip through the file.
+    Exposes the part of the Fasta surface ITMutator uses (names, lengths, records with len()/name)."""
+
+    def __init__(self, engine, source: "Fasta"):
+        lens = engine.adopt_output()
+        self.engine = engine
+        self.names = list(source.names)
+        self.long_names = list(source.long_names)
+        self.lengths = np.asarray(lens, dtype=np.int64)
+        self.goff = np.concatenate(([0], np.cumsum(self.lengths)[:-1])).astype(np.int64)
+        self._records = {nm: FastaRecord(nm, ln, None, 0, length=int(n))
+                         for nm, ln, n in zip(self.names, self.long_names, self.lengths)}
+
+    def keys(self):
+        return list(self.names)
+
+    def __len__(self):
+        return len(self.names)
+
+    def __getitem__(self, key):
+        if isinstance(key, (int, np.integer)):
+            return self._records[self.names[key]]
+        return self._records[key]
+
+    def close(self):
+        pass
+
+    def upload(self, engine, contig_ids=None):
+        if engine is not self.engine or contig_ids is not None:
+            raise ValueError("a resident genome lives on the engine that produced it")
+        return list(range(len(self.names)))

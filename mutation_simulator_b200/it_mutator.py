@@ -129,7 +129,7 @@ class ITMutator:
         fasta = self._fasta
         if self._world > 1:
             return self._mutate_partitioned()
-        eng = self._engine = Engine(getattr(self._args, "device", 0))
+        eng = self._engine = getattr(fasta, "engine", None) or Engine(getattr(self._args, "device", 0))
         fasta.upload(eng)
         bps = self.breakpoints = self._generate_all_breakpoints(eng)
         eng.load_records(self._records(bps))

@@ -40,6 +40,12 @@ class Mutator:
         self._vcf_writer = VcfWriter(args.outvcf)
         self._vcf_writer.write_header(args.infile.name, fasta, sim.assembly_name, sim.species_name, sim.sample_name)
 
+    def detach_engine(self):
+        """Hand the engine (with the mutated genome's FASTA image still in HBM) to the caller; close() then
+        leaves it alone."""
+        eng, self._engine = self._engine, None
+        return eng
+
     def close(self):
         if self._fasta_writer is not None:
             self._fasta_writer.close()

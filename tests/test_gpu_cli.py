@@ -139,3 +139,32 @@ def test_cli_it_mode_and_rmt_with_it(tmp_path):
     it = read_fasta_simple(tmp_path / "k_ms_it.fa")
     assert sum(len(c[2]) for c in it) == sum(len(c[2]) for c in ms)
     assert (tmp_path / "k_ms_it.bedpe").stat().st_size > 0
+
+
+def test_chained_rmt_then_it_in_hbm_equals_reload_of_the_written_file(tmp_path, monkeypatch):
+    """__main__.py:88-95 re-loads *_ms.fa before ITMutator; the chained path strips the FASTA image on the device
+    instead.  Both must give the same IT FASTA and BEDPE, including pyfaidx's line width rule for a re-loaded
+    contig shorter than one line."""
+    rng = np.random.default_rng(11)
+    seqs = [rng.choice(list(b"ACGT"), size=n).astype(np.uint8).tobytes() for n in (5000, 41, 7300, 3, 6100, 2500)]
+    with open(tmp_path / "g.fa", "wb") as f:
+        for i, s in enumerate(seqs):
+            f.write(b">c%d some text\n" % i)
+            for o in range(0, len(s), 50):
+                f.write(s[o:o + 50] + b"\n")
+    rmt = ["std", "it 0.002",
+           "sn 0.01 in 0.004 inmin 1 inmax 9 de 0.004 demin 1 demax 30 du 0.002 dumin 2 dumax 12",
+           "chr 2", "it 0.05", "1-41 de 0.1 demin 1 demax 3"]
+    (tmp_path / "g.rmt").write_text("\n".join(rmt) + "\n")
+    outs = {}
+    for mode in ("chain", "reload"):
+        if mode == "reload":
+            monkeypatch.setenv("MS_NO_CHAIN", "1")
+        run_main([tmp_path / "g.fa", "-o", tmp_path / mode, "-q", "-w", "--seed", "21", "rmt", tmp_path / "g.rmt"])
+        outs[mode] = [(tmp_path / f"{mode}{suffix}").read_bytes() for suffix in ("_ms.fa", "_ms.vcf", "_ms_it.fa", "_ms_it.bedpe")]
+    assert outs["chain"] == outs["reload"]
+    assert len(outs["chain"][3].splitlines()) >= 2
+    ms = read_fasta_simple(tmp_path / "chain_ms.fa")
+    it = read_fasta_simple(tmp_path / "chain_ms_it.fa")
+    assert sum(len(c[2]) for c in it) == sum(len(c[2]) for c in ms)
+    assert len(ms[1][2]) < 41   # the short contig lost bases, so its re-loaded line width shrank
