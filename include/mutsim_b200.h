@@ -105,6 +105,10 @@ int ms_genome_download(ms_ctx* ctx, uint8_t* bases, int64_t cap);
  * the mutated lengths; bpl follows pyfaidx's rule for the re-loaded file (a contig shorter than one line gets
  * bpl = its length).  Records and ranges are cleared. */
 int ms_genome_adopt_output(ms_ctx* ctx);
+/* Contig table only: the bases follow with ms_mutate_streamed. */
+int ms_genome_declare(ms_ctx* ctx, int64_t total_bases, int32_t n_contigs, const int64_t* contig_len,
+                      const int32_t* bpl, const uint32_t* gid, const uint8_t* headers, const int64_t* hdr_off,
+                      const uint8_t* names, const int64_t* name_off);
 /* Reserve `extra_bytes` of staging space behind the genome for bases of contigs that live on another GPU
  * (interchromosomal partners, it_mutator.py:133-137).  Call before ms_genome_upload.  The region starts at
  * genome index total_bases + 64 (ms_device_ptr(4) gives the base pointer); K_RAW records may point into it,
@@ -131,6 +135,16 @@ int ms_load_records(ms_ctx* ctx, const ms_rec* recs, int64_t n_recs, const uint8
  * (fasta_writer.py:40-65) and VcfWriter.write (vcf_writer.py:118-126): builds the
  * complete output FASTA image and the VCF body (no header) in device memory. */
 int ms_apply(ms_ctx* ctx, int64_t* fasta_bytes, int64_t* vcf_bytes);
+/* Mutator.mutate() (mutator.py:105-142) for a genome in HOST memory in one call: = ms_genome_upload + ms_sample +
+ * ms_apply + ms_download of both outputs, with the copies overlapped with the kernels.  Contigs are grouped
+ * (>= group_min_bases per group, 0 = 48 Mbp); the upload of group g+1, the splice of group g and the download of group g-1 run
+ * concurrently on three streams (PCIe is full duplex).  Everything that does not need bases — positions, types,
+ * lengths, conflict resolution, TL links, the output layout — runs while the first group is still in flight.
+ * Needs ms_genome_declare + ms_set_ranges first; `bases` as for ms_genome_upload (any case); pinned host buffers
+ * give the overlap, pageable ones still work.  Results are byte-identical to the unstreamed calls. */
+int ms_mutate_streamed(ms_ctx* ctx, uint64_t seed, const uint8_t* bases, uint8_t* fasta, int64_t fasta_cap,
+                       uint8_t* vcf, int64_t vcf_cap, int64_t* fasta_bytes, int64_t* vcf_bytes,
+                       int64_t group_min_bases);
 /* which: 0 FASTA image, 1 VCF body, 2 records (ms_rec[]), 3 literal pool */
 int ms_download(ms_ctx* ctx, int which, void* dst, int64_t cap, int64_t* nbytes);
 int ms_device_ptr(ms_ctx* ctx, int which, void** dptr, int64_t* nbytes);

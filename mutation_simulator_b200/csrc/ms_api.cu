@@ -175,6 +175,23 @@ int ms_genome_adopt(ms_ctx* c, const uint8_t* d_bases, int64_t total_bases, int3
     return set_contig_table(c, total_bases, n_contigs, contig_len, bpl, gid, headers, hdr_off, names, name_off);
 }
 
+int ms_genome_declare(ms_ctx* c, int64_t total_bases, int32_t n_contigs, const int64_t* contig_len, const int32_t* bpl,
+                      const uint32_t* gid, const uint8_t* headers, const int64_t* hdr_off, const uint8_t* names,
+                      const int64_t* name_off) {
+    if (!c || total_bases < 0) return MS_ERR_ARG;
+    MS_CUDA(c, cudaSetDevice(c->device));
+    MS_CUDA(c, c->genome.ensure((size_t)total_bases + 64 + (size_t)c->foreign_cap + 64));
+    MS_CUDA(c, cudaMemsetAsync(c->genome.as<uint8_t>() + total_bases, 'N', 64, c->stream));
+    return set_contig_table(c, total_bases, n_contigs, contig_len, bpl, gid, headers, hdr_off, names, name_off);
+}
+
+int ms_mutate_streamed(ms_ctx* c, uint64_t seed, const uint8_t* bases, uint8_t* fasta, int64_t fasta_cap, uint8_t* vcf,
+                       int64_t vcf_cap, int64_t* fasta_bytes, int64_t* vcf_bytes, int64_t group_min_bases) {
+    if (!c || !bases || !fasta || !vcf) return MS_ERR_ARG;
+    MS_CUDA(c, cudaSetDevice(c->device));
+    return mutate_streamed(c, seed, bases, fasta, fasta_cap, vcf, vcf_cap, fasta_bytes, vcf_bytes, group_min_bases);
+}
+
 int ms_genome_reserve(ms_ctx* c, int64_t extra_bytes) {
     if (!c || extra_bytes < 0) return MS_ERR_ARG;
     c->foreign_cap = extra_bytes;

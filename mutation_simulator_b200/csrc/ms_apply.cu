@@ -6,6 +6,7 @@
 #include "ms_scan.cuh"
 #include "ms_splice_core.h"
 #include "ms_vcf_core.h"
+#include "ms_sample_core.h"
 
 namespace ms {
 
@@ -1054,12 +1055,11 @@ int adopt_output(ms_ctx* c) {
 }
 
 // ---- host orchestration --------------------------------------------------------------
-int apply_pipeline(ms_ctx* c) {
-    if (c->n_contigs <= 0 || !c->genome.p) MS_FAIL(c, MS_ERR_STATE, "ms_apply: no genome resident");
+// plan: per-record output offsets (S) and VCF offsets (V), contig layout, output buffers.
+// vcf_sizes = false (streamed run: bases not resident yet) plans the FASTA only; vcf_stage() sizes the VCF later.
+static int plan_stage(ms_ctx* c, bool vcf_sizes) {
     const int64_t M = c->n_recs;
     Contig* d_contigs = c->contigs.as<Contig>();
-    Rec* d_recs = c->recs.as<Rec>();
-    const Tables* d_tab = c->tables.as<Tables>();
     Totals* d_tot = c->totals.as<Totals>();
     cudaStream_t st = c->stream;
 
@@ -1069,13 +1069,14 @@ int apply_pipeline(ms_ctx* c) {
     MS_CUDA(c, c->vcf_off.ensure((size_t)(M + 1) * sizeof(int64_t)));
     MS_CUDA(c, c->piece_lo.ensure((size_t)(c->n_contigs + 1) * sizeof(int64_t)));
     MS_CUDA(c, c->recs.ensure(32));  // M == 0: keep pointers valid
-    d_recs = c->recs.as<Rec>();
+    Rec* d_recs = c->recs.as<Rec>();
     int64_t* S = c->svec.as<int64_t>();
     int64_t* V = c->vcf_off.as<int64_t>();
 
     k_rec_bounds<<<(unsigned)ceil_div(c->n_contigs + 1, 128), 128, 0, st>>>(d_recs, M, d_contigs, c->n_contigs);
     MS_LAUNCH_CHECK(c);
 
+    const Tables* d_tab = c->tables.as<Tables>();
     VcfView vv{c->genome.as<uint8_t>(), c->lit.as<uint8_t>(), c->names.as<uint8_t>(), d_tab->conv, d_tab->comp, c->seed_last};
     {
         int32_t* d_delta;
@@ -1090,6 +1091,7 @@ int apply_pipeline(ms_ctx* c) {
             d_vsize = c->vvec.as<uint32_t>();
         }
         if (M > 0 && !c->sizes_valid) {
+            if (!vcf_sizes) MS_FAIL(c, MS_ERR_INTERNAL, "plan without bases needs sizes from the sampler");
             k_rec_sizes<<<(unsigned)ceil_div(M, 256), 256, 0, st>>>(vv, d_recs, M, d_contigs, d_delta, d_vsize);
             MS_LAUNCH_CHECK(c);
         }
@@ -1121,8 +1123,20 @@ int apply_pipeline(ms_ctx* c) {
     MS_CUDA(c, c->blk.ensure((size_t)(t.n_blk + 1) * sizeof(uint32_t)));
     MS_CUDA(c, c->fasta.ensure((size_t)t.fasta_bytes + 64));
     MS_CUDA(c, c->vcf.ensure((size_t)t.vcf_bytes + 64));
-    uint32_t* d_blk = c->blk.as<uint32_t>();
+    MS_CUDA(c, c->piece_desc.ensure((size_t)(t.n_pieces + 1) * sizeof(PieceDesc)));
+    return MS_OK;
+}
 
+// index: record output positions, coarse block index, per-tile descriptors
+static int index_stage(ms_ctx* c) {
+    const int64_t M = c->n_recs;
+    Contig* d_contigs = c->contigs.as<Contig>();
+    Rec* d_recs = c->recs.as<Rec>();
+    Totals* d_tot = c->totals.as<Totals>();
+    uint32_t* d_blk = c->blk.as<uint32_t>();
+    const int64_t* S = c->svec.as<int64_t>();
+    const int64_t gap_cap = (int64_t)(c->long_gaps.cap / sizeof(Gap));
+    cudaStream_t st = c->stream;
     stage_begin(c, ST_INDEX);
     if (M > 0) {
         k_rec_out<<<(unsigned)ceil_div(M, 256), 256, 0, st>>>(d_recs, M, d_contigs, S, d_blk, c->long_gaps.as<Gap>(), gap_cap, d_tot);
@@ -1132,45 +1146,226 @@ int apply_pipeline(ms_ctx* c) {
     MS_LAUNCH_CHECK(c);
     k_fill_gaps<<<NUM_SMS_B200 * 4, 256, 0, st>>>(d_blk, c->long_gaps.as<Gap>(), d_tot);
     MS_LAUNCH_CHECK(c);
-    MS_CUDA(c, c->piece_desc.ensure((size_t)(t.n_pieces + 1) * sizeof(PieceDesc)));
-    if (t.n_pieces > 0) {
-        k_piece_desc<<<(unsigned)ceil_div(t.n_pieces, 256), 256, 0, st>>>(d_contigs, c->n_contigs, c->piece_lo.as<int64_t>(), t.n_pieces,
-                                                                        d_recs, d_blk, c->piece_desc.as<PieceDesc>());
+    if (c->n_pieces > 0) {
+        k_piece_desc<<<(unsigned)ceil_div(c->n_pieces, 256), 256, 0, st>>>(d_contigs, c->n_contigs, c->piece_lo.as<int64_t>(), c->n_pieces,
+                                                                          d_recs, d_blk, c->piece_desc.as<PieceDesc>());
         MS_LAUNCH_CHECK(c);
     }
     stage_end(c, ST_INDEX);
+    return MS_OK;
+}
 
+// splice: tiles [piece_lo, piece_lo + n_pieces) and the headers of contigs [ctg_lo, ctg_lo + n_ctg)
+static int splice_launch(ms_ctx* c, int64_t piece_lo, int64_t n_pieces, int32_t ctg_lo, int32_t n_ctg) {
     if (c->tile_bytes != SP_TILE_MAX) MS_FAIL(c, MS_ERR_INTERNAL, "tile_bytes must equal %d", SP_TILE_MAX);
-    stage_begin(c, ST_SPLICE);
-    SpliceView sv{c->genome.as<uint8_t>(), c->lit.as<uint8_t>(), d_recs, d_blk, d_tab->conv, d_tab->comp, c->seed_last};
-    if (t.n_pieces > 0) {
+    const Tables* d_tab = c->tables.as<Tables>();
+    Contig* d_contigs = c->contigs.as<Contig>();
+    cudaStream_t st = c->stream;
+    SpliceView sv{c->genome.as<uint8_t>(), c->lit.as<uint8_t>(), c->recs.as<Rec>(), c->blk.as<uint32_t>(), d_tab->conv, d_tab->comp, c->seed_last};
+    if (n_pieces > 0) {
         constexpr int SP_DYN = SP_TILE_MAX + 64 + (int)SP_STAGE_CAP + 32;
         static bool sp_attr = false;
         if (!sp_attr) { MS_CUDA(c, cudaFuncSetAttribute(k_splice, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_DYN)); sp_attr = true; }
-        k_splice<<<(unsigned)t.n_pieces, SPLICE_THREADS, SP_DYN, st>>>(sv, d_contigs, c->piece_desc.as<PieceDesc>(), d_tab,
-                                                                 c->fasta.as<uint8_t>());
+        k_splice<<<(unsigned)n_pieces, SPLICE_THREADS, SP_DYN, st>>>(sv, d_contigs, c->piece_desc.as<PieceDesc>() + piece_lo, d_tab,
+                                                                   c->fasta.as<uint8_t>());
         MS_LAUNCH_CHECK(c);
     }
-    k_headers<<<(unsigned)ceil_div(c->n_contigs, 128), 128, 0, st>>>(d_contigs, c->n_contigs, c->headers.as<uint8_t>(), c->fasta.as<uint8_t>());
-    MS_LAUNCH_CHECK(c);
-    stage_end(c, ST_SPLICE);
+    if (n_ctg > 0) {
+        k_headers<<<(unsigned)ceil_div(n_ctg, 128), 128, 0, st>>>(d_contigs + ctg_lo, n_ctg, c->headers.as<uint8_t>(), c->fasta.as<uint8_t>());
+        MS_LAUNCH_CHECK(c);
+    }
+    return MS_OK;
+}
 
-    stage_begin(c, ST_VCF);
+// VCF lines of all records (V already holds their offsets)
+static int vcf_launch(ms_ctx* c) {
+    const int64_t M = c->n_recs;
+    const Tables* d_tab = c->tables.as<Tables>();
+    VcfView vv{c->genome.as<uint8_t>(), c->lit.as<uint8_t>(), c->names.as<uint8_t>(), d_tab->conv, d_tab->comp, c->seed_last};
     if (M > 0) {
         static bool attr_set = false;
         if (!attr_set) { MS_CUDA(c, cudaFuncSetAttribute(k_vcf_write, cudaFuncAttributeMaxDynamicSharedMemorySize, VCF_SMEM + 32)); attr_set = true; }
-        k_vcf_write<<<(unsigned)ceil_div(M, VCF_THREADS), VCF_THREADS, VCF_SMEM + 32, st>>>(vv, d_recs, M, d_contigs, d_tab, V, c->vcf.as<uint8_t>());
+        k_vcf_write<<<(unsigned)ceil_div(M, VCF_THREADS), VCF_THREADS, VCF_SMEM + 32, c->stream>>>(
+            vv, c->recs.as<Rec>(), M, c->contigs.as<Contig>(), d_tab, c->vcf_off.as<int64_t>(), c->vcf.as<uint8_t>());
         MS_LAUNCH_CHECK(c);
     }
-    MS_CUDA(c, cudaMemcpyAsync(c->h_totals, d_tot, sizeof(Totals), cudaMemcpyDeviceToHost, st));
-    stage_end(c, ST_VCF);
-    MS_CUDA(c, cudaStreamSynchronize(st));
-    t = *c->h_totals;
+    return MS_OK;
+}
+
+static int finish_apply(ms_ctx* c) {
+    MS_CUDA(c, cudaMemcpyAsync(c->h_totals, c->totals.p, sizeof(Totals), cudaMemcpyDeviceToHost, c->stream));
+    MS_CUDA(c, cudaStreamSynchronize(c->stream));
+    const Totals t = *c->h_totals;
     if (t.error) MS_FAIL(c, (int)t.error, "ms_apply: records invalid (code %lld at record %lld): overlapping or out of bounds",
                          (long long)t.error, (long long)t.error_arg);
-    c->last_totals.fasta_bytes = t.fasta_bytes;
-    c->last_totals.vcf_bytes = t.vcf_bytes;
-    c->last_totals.n_recs = M;
+    c->last_totals.fasta_bytes = c->fasta_bytes;
+    c->last_totals.vcf_bytes = c->vcf_bytes;
+    c->last_totals.n_recs = c->n_recs;
+    return MS_OK;
+}
+
+int apply_pipeline(ms_ctx* c) {
+    if (c->n_contigs <= 0 || !c->genome.p) MS_FAIL(c, MS_ERR_STATE, "ms_apply: no genome resident");
+    int rc = plan_stage(c, true);
+    if (rc) return rc;
+    if ((rc = index_stage(c))) return rc;
+    stage_begin(c, ST_SPLICE);
+    if ((rc = splice_launch(c, 0, c->n_pieces, 0, c->n_contigs))) return rc;
+    stage_end(c, ST_SPLICE);
+    stage_begin(c, ST_VCF);
+    if ((rc = vcf_launch(c))) return rc;
+    stage_end(c, ST_VCF);
+    return finish_apply(c);
+}
+
+// ---- streamed run: host genome in, host FASTA + VCF out, copies overlapped with the kernels --------------------
+// upper-case genome bytes [lo, hi) (util.py:87 sequence_always_upper); byte-exact at both ends so that neighbouring
+// groups never touch each other's bytes
+__global__ void __launch_bounds__(256) k_upper_range(uint8_t* g, int64_t lo, int64_t hi) {
+    const int64_t w = (lo >> 4) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t b0 = w << 4;
+    if (b0 >= hi) return;
+    if (b0 >= lo && b0 + 16 <= hi) {
+        uint4 v = *reinterpret_cast<uint4*>(g + b0);
+        uint32_t* x = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t lo7 = x[k] & 0x7F7F7F7Fu;
+            const uint32_t is_lower = ((lo7 + 0x1F1F1F1Fu) & ~(lo7 + 0x05050505u) & ~x[k]) & 0x80808080u;
+            x[k] &= ~(is_lower >> 2);
+        }
+        *reinterpret_cast<uint4*>(g + b0) = v;
+    } else {
+        for (int64_t b = b0 > lo ? b0 : lo; b < b0 + 16 && b < hi; ++b) {
+            const uint8_t ch = g[b];
+            if (ch >= 'a' && ch <= 'z') g[b] = ch - 32;
+        }
+    }
+}
+
+// ref/alt of the SNP records [lo, hi): the part of record building that needs the bases (mutator.py:429-455)
+__global__ void __launch_bounds__(256)
+k_snp_fill(Rec* recs, int64_t lo, int64_t hi, const Contig* contigs, const uint8_t* genome, const Tables* tab, Seed seed, double p_ti) {
+    const int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= hi) return;
+    const uint32_t kind_type = reinterpret_cast<const uint32_t*>(recs + i)[6];   // kind | type<<8 | ref<<16 | alt<<24
+    if ((kind_type & 0xFFu) != K_SNP) return;
+    const uint32_t pos = recs[i].pos;
+    const Contig& ct = contigs[recs[i].contig];
+    const uint8_t ref = tab->conv[genome[ct.goff + pos]];
+    const uint8_t alt = draw_snp(seed, ct.gid, pos, ref, p_ti, tab->trans);
+    reinterpret_cast<uint32_t*>(recs + i)[6] = (kind_type & 0xFFFFu) | ((uint32_t)ref << 16) | ((uint32_t)alt << 24);
+}
+
+__global__ void k_store_total1(const I64x2* total, int64_t* V_end, Totals* tot) { *V_end = total->b; tot->vcf_bytes = total->b; }
+
+int mutate_streamed(ms_ctx* c, uint64_t seed, const uint8_t* h_bases, uint8_t* h_fasta, int64_t fasta_cap, uint8_t* h_vcf,
+                    int64_t vcf_cap, int64_t* fasta_bytes, int64_t* vcf_bytes, int64_t group_min) {
+    if (c->n_contigs <= 0 || !c->genome.p) MS_FAIL(c, MS_ERR_STATE, "ms_mutate_streamed: declare a genome first");
+    if (c->n_ranges < 0) MS_FAIL(c, MS_ERR_STATE, "ms_mutate_streamed: set ranges first");
+    if (!c->s_up) {
+        MS_CUDA(c, cudaStreamCreateWithFlags(&c->s_up, cudaStreamNonBlocking));
+        MS_CUDA(c, cudaStreamCreateWithFlags(&c->s_down, cudaStreamNonBlocking));
+    }
+    // contig groups of >= GROUP_MIN bases: the unit of upload / splice / download
+    const int64_t GROUP_MIN = group_min > 0 ? group_min : (48ll << 20);
+    std::vector<int32_t> g_lo;   // first contig of each group (+ sentinel)
+    {
+        int64_t acc = 0;
+        for (int i = 0; i < c->n_contigs; ++i) {
+            if (acc == 0) g_lo.push_back(i);
+            acc += c->h_contigs[i].len;
+            if (acc >= GROUP_MIN) acc = 0;
+        }
+        g_lo.push_back(c->n_contigs);
+    }
+    const int G = (int)g_lo.size() - 1;
+    while ((int)c->ev_up.size() < G) {
+        cudaEvent_t a, b;
+        MS_CUDA(c, cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        MS_CUDA(c, cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        c->ev_up.push_back(a); c->ev_done.push_back(b);
+    }
+    uint8_t* d_genome = c->genome.as<uint8_t>();
+    auto goff_of = [&](int32_t ctg) { return ctg < c->n_contigs ? c->h_contigs[ctg].goff : c->total_bases; };
+
+    // uploads: queued now, run while the sampler works on the compute stream
+    MS_CUDA(c, cudaEventRecord(c->ev_done[0], c->stream));          // the previous call's readers of the genome are done
+    MS_CUDA(c, cudaStreamWaitEvent(c->s_up, c->ev_done[0], 0));
+    for (int g = 0; g < G; ++g) {
+        const int64_t lo = goff_of(g_lo[g]), hi = goff_of(g_lo[g + 1]);
+        if (hi > lo) {
+            MS_CUDA(c, cudaMemcpyAsync(d_genome + lo, h_bases + lo, (size_t)(hi - lo), cudaMemcpyHostToDevice, c->s_up));
+            const int64_t words = ((hi + 15) >> 4) - (lo >> 4);
+            k_upper_range<<<(unsigned)ceil_div(words, 256), 256, 0, c->s_up>>>(d_genome, lo, hi);
+            MS_LAUNCH_CHECK(c);
+        }
+        MS_CUDA(c, cudaEventRecord(c->ev_up[g], c->s_up));
+    }
+
+    int rc = sample_pipeline(c, seed, true);      // positions, types, lengths, conflicts, TL links: no bases needed
+    if (rc) return rc;
+    if ((rc = plan_stage(c, false))) return rc;   // FASTA layout only (VCF sizes depend on bases)
+    if (c->fasta_bytes > fasta_cap) MS_FAIL(c, MS_ERR_ARG, "FASTA buffer too small: need %lld bytes", (long long)c->fasta_bytes);
+    if ((rc = index_stage(c))) return rc;
+    // contig table with rec / piece / file offsets for the per-group launches
+    MS_CUDA(c, cudaMemcpyAsync(c->h_contigs.data(), c->contigs.p, sizeof(Contig) * (size_t)c->n_contigs, cudaMemcpyDeviceToHost, c->stream));
+    MS_CUDA(c, cudaStreamSynchronize(c->stream));
+    std::vector<int64_t> h_piece_lo((size_t)c->n_contigs + 1);
+    MS_CUDA(c, cudaMemcpy(h_piece_lo.data(), c->piece_lo.p, (size_t)(c->n_contigs + 1) * 8, cudaMemcpyDeviceToHost));
+
+    const Tables* d_tab = c->tables.as<Tables>();
+    stage_begin(c, ST_SPLICE);
+    for (int g = 0; g < G; ++g) {
+        const int32_t c0 = g_lo[g], c1 = g_lo[g + 1];
+        const int64_t r0 = c->h_contigs[c0].rec_lo, r1 = c->h_contigs[c1 - 1].rec_hi;
+        MS_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_up[g], 0));
+        if (r1 > r0) {
+            k_snp_fill<<<(unsigned)ceil_div(r1 - r0, 256), 256, 0, c->stream>>>(c->recs.as<Rec>(), r0, r1, c->contigs.as<Contig>(), d_genome, d_tab,
+                                                                             c->seed_last, c->p_ti);
+            MS_LAUNCH_CHECK(c);
+        }
+        if ((rc = splice_launch(c, h_piece_lo[c0], h_piece_lo[c1] - h_piece_lo[c0], c0, c1 - c0))) return rc;
+        MS_CUDA(c, cudaEventRecord(c->ev_done[g], c->stream));
+        const int64_t f0 = c->h_contigs[c0].hdr_off, f1 = c1 < c->n_contigs ? c->h_contigs[c1].hdr_off : c->fasta_bytes;
+        MS_CUDA(c, cudaStreamWaitEvent(c->s_down, c->ev_done[g], 0));
+        MS_CUDA(c, cudaMemcpyAsync(h_fasta + f0, c->fasta.as<uint8_t>() + f0, (size_t)(f1 - f0), cudaMemcpyDeviceToHost, c->s_down));
+    }
+    stage_end(c, ST_SPLICE);
+
+    // VCF: sizes need the bases (a SNP or inversion with REF == ALT is not written, vcf_writer.py:123)
+    stage_begin(c, ST_VCF);
+    const int64_t M = c->n_recs;
+    if (M > 0) {
+        VcfView vv{d_genome, c->lit.as<uint8_t>(), c->names.as<uint8_t>(), d_tab->conv, d_tab->comp, c->seed_last};
+        int32_t* d_delta = c->keep.as<int32_t>();
+        uint32_t* d_vsize = c->cand_val.as<uint32_t>();
+        k_rec_sizes<<<(unsigned)ceil_div(M, 256), 256, 0, c->stream>>>(vv, c->recs.as<Rec>(), M, c->contigs.as<Contig>(), d_delta, d_vsize);
+        MS_LAUNCH_CHECK(c);
+        int64_t* V = c->vcf_off.as<int64_t>();
+        auto in = [=] __device__(int64_t i) -> I64x2 { return I64x2{0, (int64_t)d_vsize[i]}; };
+        auto out = [=] __device__(int64_t i, I64x2 ex, I64x2) { V[i] = ex.b; };
+        I64x2* d_total = nullptr;
+        MS_CUDA(c, (device_scan<I64x2>(c, in, out, M, I64x2{0, 0}, SumOp(), c->scan_tmp, &d_total)));
+        k_store_total1<<<1, 1, 0, c->stream>>>(d_total, V + M, c->totals.as<Totals>());
+        MS_LAUNCH_CHECK(c);
+        MS_CUDA(c, cudaMemcpyAsync(c->h_totals, c->totals.p, sizeof(Totals), cudaMemcpyDeviceToHost, c->stream));
+        MS_CUDA(c, cudaStreamSynchronize(c->stream));
+        c->vcf_bytes = c->h_totals->vcf_bytes;
+        if (c->vcf_bytes > vcf_cap) MS_FAIL(c, MS_ERR_ARG, "VCF buffer too small: need %lld bytes", (long long)c->vcf_bytes);
+        MS_CUDA(c, c->vcf.ensure((size_t)c->vcf_bytes + 64));
+        if ((rc = vcf_launch(c))) return rc;
+        MS_CUDA(c, cudaMemcpyAsync(h_vcf, c->vcf.p, (size_t)c->vcf_bytes, cudaMemcpyDeviceToHost, c->stream));
+    } else {
+        c->vcf_bytes = 0;
+    }
+    stage_end(c, ST_VCF);
+    rc = finish_apply(c);
+    MS_CUDA(c, cudaStreamSynchronize(c->s_down));
+    if (rc) return rc;
+    c->sizes_valid = false;
+    if (fasta_bytes) *fasta_bytes = c->fasta_bytes;
+    if (vcf_bytes) *vcf_bytes = c->vcf_bytes;
     return MS_OK;
 }
 

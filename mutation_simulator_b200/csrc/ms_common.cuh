@@ -95,6 +95,10 @@ struct ms_ctx {
     float stage_ms[ms::ST_COUNT];
     int64_t kernel_launches = 0;
     int tile_bytes = 16384;
+
+    // streamed run (ms_mutate_streamed): copy streams and per-group events
+    cudaStream_t s_up = nullptr, s_down = nullptr;
+    std::vector<cudaEvent_t> ev_up, ev_done;
 };
 
 #define MS_CUDA(ctx, call)                                                                        \
@@ -130,6 +134,8 @@ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 // pipeline entry points implemented in the .cu files
 int apply_pipeline(ms_ctx* c);
 int adopt_output(ms_ctx* c);
-int sample_pipeline(ms_ctx* c, uint64_t seed);
+int sample_pipeline(ms_ctx* c, uint64_t seed, bool defer_bases = false);
+int mutate_streamed(ms_ctx* c, uint64_t seed, const uint8_t* h_bases, uint8_t* h_fasta, int64_t fasta_cap, uint8_t* h_vcf,
+                    int64_t vcf_cap, int64_t* fasta_bytes, int64_t* vcf_bytes, int64_t group_min);
 int count_types(ms_ctx* c);
 }  // namespace ms

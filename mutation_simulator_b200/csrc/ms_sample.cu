@@ -306,7 +306,7 @@ namespace ms {
 __global__ void __launch_bounds__(256)
 k_build_records(int64_t n_acc, const uint32_t* acc_slot, const int64_t* gpos, const uint8_t* type, const uint32_t* len,
                 const uint32_t* cand_range, const int32_t* link, const Range* ranges, const Contig* contigs, VcfView vv,
-                const Tables* tab, Seed seed, double p_ti, Rec* recs, int32_t* delta, uint32_t* vsize) {
+                const Tables* tab, Seed seed, double p_ti, Rec* recs, int32_t* delta, uint32_t* vsize, bool defer_bases) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_acc) return;
     const uint32_t s = acc_slot[e];
@@ -321,8 +321,10 @@ k_build_records(int64_t n_acc, const uint32_t* acc_slot, const int64_t* gpos, co
     switch (t) {
         case T_SN: {
             r.cons = 1; r.prod = 1; r.kind = K_SNP;
-            r.ref = tab->conv[vv.genome[g]];
-            r.alt = draw_snp(seed, ct.gid, pos, r.ref, p_ti, tab->trans);
+            if (!defer_bases) {   // streamed runs fill these per contig group once its bases have arrived (k_snp_fill)
+                r.ref = tab->conv[vv.genome[g]];
+                r.alt = draw_snp(seed, ct.gid, pos, r.ref, p_ti, tab->trans);
+            }
         } break;
         case T_IN: r.cons = 0; r.prod = l; r.kind = K_RAND; r.src = rand_insert_cache(seed, ct.gid, pos); break;
         case T_DE: r.cons = l; r.prod = 0; r.kind = K_NONE; break;
@@ -341,7 +343,7 @@ k_build_records(int64_t n_acc, const uint32_t* acc_slot, const int64_t* gpos, co
     }
     recs[e] = r;
     delta[e] = (int32_t)r.prod - (int32_t)r.cons;
-    vsize[e] = vcf_line_size(vv, ct, r);
+    vsize[e] = defer_bases ? 0u : vcf_line_size(vv, ct, r);
 }
 
 __global__ void __launch_bounds__(256) k_count_types(const Rec* recs, int64_t n, Totals* tot) {
@@ -418,7 +420,7 @@ static int draw_and_sort(ms_ctx* c, Seed seed, uint32_t purpose, int32_t min_dis
     return MS_OK;
 }
 
-int sample_pipeline(ms_ctx* c, uint64_t seed64) {
+int sample_pipeline(ms_ctx* c, uint64_t seed64, bool defer_bases) {
     if (c->n_contigs <= 0 || !c->genome.p) MS_FAIL(c, MS_ERR_STATE, "ms_sample: no genome resident");
     if (c->n_ranges < 0) MS_FAIL(c, MS_ERR_STATE, "ms_sample: call ms_set_ranges first");
     cudaStream_t st = c->stream;
@@ -528,7 +530,7 @@ int sample_pipeline(ms_ctx* c, uint64_t seed64) {
         VcfView vv{c->genome.as<uint8_t>(), c->lit.as<uint8_t>(), c->names.as<uint8_t>(), d_tab->conv, d_tab->comp, seed};
         k_build_records<<<(unsigned)ceil_div(n_acc, 256), 256, 0, st>>>(n_acc, d_acc, d_gpos, d_type, d_len, d_crange, d_link, d_ranges,
                                                                         d_contigs, vv, d_tab, seed, c->p_ti, c->recs.as<Rec>(),
-                                                                        c->keep.as<int32_t>(), c->cand_val.as<uint32_t>());
+                                                                        c->keep.as<int32_t>(), c->cand_val.as<uint32_t>(), defer_bases);
         MS_LAUNCH_CHECK(c);
     }
     MS_CUDA(c, cudaMemcpyAsync(c->h_totals, d_tot, sizeof(Totals), cudaMemcpyDeviceToHost, st));

@@ -98,6 +98,24 @@ class Engine:
                                               float(n_fraction), int(telomere_n), _ptr(self._hdr), _ptr(self._hoff),
                                               _ptr(self._nam), _ptr(self._noff)))
 
+    def declare_genome(self, lengths, bpl, headers: Sequence[bytes], names: Sequence[bytes], gid=None):
+        """Contig table without bases (they arrive with mutate_streamed)."""
+        self._contig_args(lengths, bpl, headers, names, gid)
+        self._check(self._lib.ms_genome_declare(self._h, self.total_bases, self.n_contigs, _ptr(self._len), _ptr(self._bpl),
+                                                _ptr(self._gid), _ptr(self._hdr), _ptr(self._hoff), _ptr(self._nam),
+                                                _ptr(self._noff)))
+
+    def mutate_streamed(self, seed: int, bases: np.ndarray, fasta_out: np.ndarray, vcf_out: np.ndarray, group_min_bases: int = 0):
+        """Host genome in, host FASTA image + VCF body out, copies overlapped with the kernels (ms_mutate_streamed).
+        Returns (fasta_bytes, vcf_bytes).  Pass pinned arrays for the overlap."""
+        if bases.dtype != np.uint8 or not bases.flags.c_contiguous or bases.size != self.total_bases:
+            raise ValueError("bases must be a contiguous uint8 array of total_bases elements")
+        fb, vb = C.c_int64(0), C.c_int64(0)
+        self._check(self._lib.ms_mutate_streamed(self._h, C.c_uint64(seed & (2**64 - 1)), _ptr(bases), _ptr(fasta_out),
+                                                 fasta_out.nbytes, _ptr(vcf_out), vcf_out.nbytes, C.byref(fb), C.byref(vb),
+                                                 int(group_min_bases)))
+        return fb.value, vb.value
+
     def reserve_foreign(self, nbytes: int):
         """Staging space behind the genome for partner contigs owned by another GPU (call before upload)."""
         self._check(self._lib.ms_genome_reserve(self._h, int(nbytes)))

@@ -303,3 +303,41 @@ def test_long_blocking_spans_use_the_scan_path_and_agree_with_chain_semantics():
                 last_hi = min(p + int(ln[j]) + block[t], lens[0])
         assert np.array_equal(acc, want)
     eng.close()
+
+
+@pytest.mark.parametrize("group_min", [0, 1, 120_000])
+def test_streamed_run_is_byte_identical_to_upload_sample_apply_download(group_min):
+    """ms_mutate_streamed = ms_genome_upload + ms_sample + ms_apply + ms_download with the copies overlapped: same
+    bytes for every contig grouping, lower-case input, palindromic inversions and N SNPs (records the VCF omits)."""
+    from mutation_simulator_b200.engine import BUF_FASTA, BUF_VCF, Engine
+    lens = [300_000, 70_001, 50_000, 3, 90_017, 1, 15, 220_000]
+    contigs = random_contigs(lens, seed=5, alphabet=b"ACGTNacgtnRY", bpl=70)
+    # a stretch of AT repeats makes reverse-complement palindromes (REF == ALT inversions are not written)
+    c0 = bytearray(contigs[0][2]); c0[1000:9000] = b"AT" * 4000
+    contigs[0] = (contigs[0][0], contigs[0][1], bytes(c0), 70)
+    ranges = args_ranges(lens, [0.02, 0.004, 0.004, 0.006, 0.002, 0.004], [1, 1, 1, 2, 1, 1, 1], [1, 40, 10, 4, 30, 20, 20])
+    block = [1, 1, 1, 1, 1, 1, 1]
+    eng, genome, goff, _ = engine_for(contigs)
+    eng.set_ranges(ranges, block, 1, 2 / 3)
+    eng.sample(77)
+    fb, vb = eng.apply()
+    want_fa, want_vcf = eng.download(BUF_FASTA).tobytes(), eng.download(BUF_VCF).tobytes()
+    recs_want = eng.records(include_dead=True)
+    eng.close()
+
+    eng = Engine(0)
+    eng.declare_genome(lens, [70] * len(lens), [c[1] for c in contigs], [c[0] for c in contigs])
+    eng.set_ranges(ranges, block, 1, 2 / 3)
+    raw = np.frombuffer(b"".join(c[2] for c in contigs), dtype=np.uint8).copy()
+    fa = np.zeros(fb + 100, np.uint8)
+    vcf = np.zeros(vb + 100, np.uint8)
+    for _ in range(2):   # second run reuses every buffer and event
+        got = eng.mutate_streamed(77, raw, fa, vcf, group_min)
+        assert got == (fb, vb)
+        assert fa[:fb].tobytes() == want_fa
+        assert vcf[:vb].tobytes() == want_vcf
+    assert (eng.records(include_dead=True) == recs_want).all()
+    assert eng.download(BUF_FASTA).tobytes() == want_fa       # the device copies are complete as well
+    with pytest.raises(Exception):
+        eng.mutate_streamed(77, raw, fa[:1000], vcf, group_min)
+    eng.close()
