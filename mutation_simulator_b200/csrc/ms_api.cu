@@ -189,7 +189,12 @@ int ms_mutate_streamed(ms_ctx* c, uint64_t seed, const uint8_t* bases, uint8_t* 
                        int64_t vcf_cap, int64_t* fasta_bytes, int64_t* vcf_bytes, int64_t group_min_bases) {
     if (!c || !bases || !fasta || !vcf) return MS_ERR_ARG;
     MS_CUDA(c, cudaSetDevice(c->device));
-    return mutate_streamed(c, seed, bases, fasta, fasta_cap, vcf, vcf_cap, fasta_bytes, vcf_bytes, group_min_bases);
+    const int rc = mutate_streamed(c, seed, bases, fasta, fasta_cap, vcf, vcf_cap, fasta_bytes, vcf_bytes, group_min_bases);
+    if (rc != MS_OK) {   // nothing may still be copying from / into the caller's buffers when the error is reported
+        cudaStreamSynchronize(c->stream);
+        if (c->s_up) { cudaStreamSynchronize(c->s_up); cudaStreamSynchronize(c->s_down); cudaStreamSynchronize(c->s_vcf); }
+    }
+    return rc;
 }
 
 int ms_genome_reserve(ms_ctx* c, int64_t extra_bytes) {

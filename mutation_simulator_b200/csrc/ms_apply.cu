@@ -864,7 +864,8 @@ __device__ __forceinline__ void vcf_emit_uniform(const VcfView& v, const Contig&
 }
 
 __global__ void __launch_bounds__(VCF_THREADS)
-k_vcf_write(VcfView v, const Rec* recs, int64_t n_recs, const Contig* contigs, const Tables* tables, const int64_t* V, uint8_t* vcf) {
+k_vcf_write(VcfView v, const Rec* recs, int64_t rec_lo, int64_t n_recs, const Contig* contigs, const Tables* tables, const int64_t* V,
+            uint8_t* vcf) {
     __shared__ uint8_t s_conv[256], s_comp[256];
     __shared__ int n_jobs, n_sv;
     __shared__ uint8_t sv_list[VCF_THREADS];
@@ -874,8 +875,10 @@ k_vcf_write(VcfView v, const Rec* recs, int64_t n_recs, const Contig* contigs, c
     __shared__ __align__(16) int64_t s_V[VCF_THREADS + 2];    // TMA bulk copies issued before anything else
     __shared__ __align__(8) uint64_t bar;
     const int tid = threadIdx.x;
-    const int64_t i0 = (int64_t)blockIdx.x * VCF_THREADS;
+    // records [rec_lo, n_recs); CTAs start at an even record so that the TMA source of the offsets is 16-byte aligned
+    const int64_t i0 = (rec_lo & ~(int64_t)1) + (int64_t)blockIdx.x * VCF_THREADS;
     const int64_t i1 = i0 + VCF_THREADS < n_recs ? i0 + VCF_THREADS : n_recs;
+    const int skip = i0 < rec_lo ? 1 : 0;     // record i0 belongs to an earlier launch
     if (tid == 0) {
         n_jobs = 0; n_sv = 0;
         mbar_init(&bar, 1u);
@@ -890,14 +893,14 @@ k_vcf_write(VcfView v, const Rec* recs, int64_t n_recs, const Contig* contigs, c
     v.conv = s_conv; v.comp = s_comp;
     if (tid < 32) mbar_wait(&bar, 0u);
     __syncthreads();
-    const int64_t base = s_V[0], end = s_V[i1 - i0];
+    const int64_t base = s_V[skip], end = s_V[i1 - i0];
     const uint32_t shift = (uint32_t)(base & 15);
     const bool staged = (end - base) + shift <= VCF_SMEM;
     uint8_t* line0 = staged ? buf + shift : vcf + base;   // byte 0 of this CTA's lines
     const int64_t i = i0 + tid;
     // pass 1: SNP lines (three quarters of all records) in lock step; everything else is queued
     bool is_sv = false;
-    if (i < i1) {
+    if (i < i1 && tid >= skip) {
         const int64_t a = s_V[tid], b = s_V[tid + 1];
         if (b > a) {
             const uint4 hi = reinterpret_cast<const uint4*>(s_rec + tid)[1];   // src, kind/type/ref/alt, contig
@@ -1177,16 +1180,15 @@ static int splice_launch(ms_ctx* c, int64_t piece_lo, int64_t n_pieces, int32_t 
     return MS_OK;
 }
 
-// VCF lines of all records (V already holds their offsets)
-static int vcf_launch(ms_ctx* c) {
-    const int64_t M = c->n_recs;
+// VCF lines of records [r0, r1) (V already holds their offsets)
+static int vcf_launch(ms_ctx* c, int64_t r0, int64_t r1, cudaStream_t st) {
     const Tables* d_tab = c->tables.as<Tables>();
     VcfView vv{c->genome.as<uint8_t>(), c->lit.as<uint8_t>(), c->names.as<uint8_t>(), d_tab->conv, d_tab->comp, c->seed_last};
-    if (M > 0) {
+    if (r1 > r0) {
         static bool attr_set = false;
         if (!attr_set) { MS_CUDA(c, cudaFuncSetAttribute(k_vcf_write, cudaFuncAttributeMaxDynamicSharedMemorySize, VCF_SMEM + 32)); attr_set = true; }
-        k_vcf_write<<<(unsigned)ceil_div(M, VCF_THREADS), VCF_THREADS, VCF_SMEM + 32, c->stream>>>(
-            vv, c->recs.as<Rec>(), M, c->contigs.as<Contig>(), d_tab, c->vcf_off.as<int64_t>(), c->vcf.as<uint8_t>());
+        k_vcf_write<<<(unsigned)ceil_div(r1 - (r0 & ~(int64_t)1), VCF_THREADS), VCF_THREADS, VCF_SMEM + 32, st>>>(
+            vv, c->recs.as<Rec>(), r0, r1, c->contigs.as<Contig>(), d_tab, c->vcf_off.as<int64_t>(), c->vcf.as<uint8_t>());
         MS_LAUNCH_CHECK(c);
     }
     return MS_OK;
@@ -1213,7 +1215,7 @@ int apply_pipeline(ms_ctx* c) {
     if ((rc = splice_launch(c, 0, c->n_pieces, 0, c->n_contigs))) return rc;
     stage_end(c, ST_SPLICE);
     stage_begin(c, ST_VCF);
-    if ((rc = vcf_launch(c))) return rc;
+    if ((rc = vcf_launch(c, 0, c->n_recs, c->stream))) return rc;
     stage_end(c, ST_VCF);
     return finish_apply(c);
 }
@@ -1257,7 +1259,11 @@ k_snp_fill(Rec* recs, int64_t lo, int64_t hi, const Contig* contigs, const uint8
     reinterpret_cast<uint32_t*>(recs + i)[6] = (kind_type & 0xFFFFu) | ((uint32_t)ref << 16) | ((uint32_t)alt << 24);
 }
 
-__global__ void k_store_total1(const I64x2* total, int64_t* V_end, Totals* tot) { *V_end = total->b; tot->vcf_bytes = total->b; }
+// VCF bytes written up to the end of a contig group: vend[1] = vend[0] + this group's bytes
+__global__ void k_store_vend(const I64x2* total, int64_t* vend, int64_t* V_end, Totals* tot) {
+    const int64_t e = vend[0] + (total ? total->b : 0);
+    vend[1] = e; *V_end = e; tot->vcf_bytes = e;
+}
 
 int mutate_streamed(ms_ctx* c, uint64_t seed, const uint8_t* h_bases, uint8_t* h_fasta, int64_t fasta_cap, uint8_t* h_vcf,
                     int64_t vcf_cap, int64_t* fasta_bytes, int64_t* vcf_bytes, int64_t group_min) {
@@ -1266,6 +1272,7 @@ int mutate_streamed(ms_ctx* c, uint64_t seed, const uint8_t* h_bases, uint8_t* h
     if (!c->s_up) {
         MS_CUDA(c, cudaStreamCreateWithFlags(&c->s_up, cudaStreamNonBlocking));
         MS_CUDA(c, cudaStreamCreateWithFlags(&c->s_down, cudaStreamNonBlocking));
+        MS_CUDA(c, cudaStreamCreateWithFlags(&c->s_vcf, cudaStreamNonBlocking));
     }
     // contig groups of >= GROUP_MIN bases: the unit of upload / splice / download
     const int64_t GROUP_MIN = group_min > 0 ? group_min : (48ll << 20);
@@ -1281,10 +1288,11 @@ int mutate_streamed(ms_ctx* c, uint64_t seed, const uint8_t* h_bases, uint8_t* h
     }
     const int G = (int)g_lo.size() - 1;
     while ((int)c->ev_up.size() < G) {
-        cudaEvent_t a, b;
+        cudaEvent_t a, b, d;
         MS_CUDA(c, cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
         MS_CUDA(c, cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
-        c->ev_up.push_back(a); c->ev_done.push_back(b);
+        MS_CUDA(c, cudaEventCreateWithFlags(&d, cudaEventDisableTiming));
+        c->ev_up.push_back(a); c->ev_done.push_back(b); c->ev_sized.push_back(d);
     }
     uint8_t* d_genome = c->genome.as<uint8_t>();
     auto goff_of = [&](int32_t ctg) { return ctg < c->n_contigs ? c->h_contigs[ctg].goff : c->total_bases; };
@@ -1315,10 +1323,42 @@ int mutate_streamed(ms_ctx* c, uint64_t seed, const uint8_t* h_bases, uint8_t* h
     MS_CUDA(c, cudaMemcpy(h_piece_lo.data(), c->piece_lo.p, (size_t)(c->n_contigs + 1) * 8, cudaMemcpyDeviceToHost));
 
     const Tables* d_tab = c->tables.as<Tables>();
+    // c->vcf was sized by the plan from base-independent line sizes (an upper bound); the real offsets are computed
+    // group by group as the bases arrive (a SNP or inversion with REF == ALT is not written, vcf_writer.py:123)
+    const int64_t M = c->n_recs;
+    MS_CUDA(c, c->vend.ensure((size_t)(G + 1) * 8));
+    if ((int)c->h_vend_cap < G + 1) {
+        if (c->h_vend) cudaFreeHost(c->h_vend);
+        MS_CUDA(c, cudaHostAlloc(&c->h_vend, (size_t)(G + 1) * 8 * 2, cudaHostAllocDefault));
+        c->h_vend_cap = 2 * (G + 1);
+    }
+    int64_t* d_vend = c->vend.as<int64_t>();
+    MS_CUDA(c, cudaMemsetAsync(d_vend, 0, 8, c->stream));
+    c->h_vend[0] = 0;
+    int32_t* d_delta = c->keep.as<int32_t>();
+    uint32_t* d_vsize = c->cand_val.as<uint32_t>();
+    int64_t* V = c->vcf_off.as<int64_t>();
+    VcfView vv{d_genome, c->lit.as<uint8_t>(), c->names.as<uint8_t>(), d_tab->conv, d_tab->comp, c->seed_last};
+    std::vector<int64_t> g_r0(G), g_r1(G);
+
+    // VCF lines of group g: wait for its sizes, then write and download its byte range
+    auto flush_vcf = [&](int g) -> int {
+        MS_CUDA(c, cudaEventSynchronize(c->ev_sized[g]));
+        const int64_t lo = c->h_vend[g], hi = c->h_vend[g + 1];
+        if (hi > vcf_cap) MS_FAIL(c, MS_ERR_ARG, "VCF buffer too small: need more than %lld bytes", (long long)vcf_cap);
+        if (hi == lo) return MS_OK;
+        MS_CUDA(c, cudaStreamWaitEvent(c->s_vcf, c->ev_sized[g], 0));
+        int r = vcf_launch(c, g_r0[g], g_r1[g], c->s_vcf);
+        if (r) return r;
+        MS_CUDA(c, cudaMemcpyAsync(h_vcf + lo, c->vcf.as<uint8_t>() + lo, (size_t)(hi - lo), cudaMemcpyDeviceToHost, c->s_vcf));
+        return MS_OK;
+    };
+
     stage_begin(c, ST_SPLICE);
     for (int g = 0; g < G; ++g) {
         const int32_t c0 = g_lo[g], c1 = g_lo[g + 1];
         const int64_t r0 = c->h_contigs[c0].rec_lo, r1 = c->h_contigs[c1 - 1].rec_hi;
+        g_r0[g] = r0; g_r1[g] = r1;
         MS_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_up[g], 0));
         if (r1 > r0) {
             k_snp_fill<<<(unsigned)ceil_div(r1 - r0, 256), 256, 0, c->stream>>>(c->recs.as<Rec>(), r0, r1, c->contigs.as<Contig>(), d_genome, d_tab,
@@ -1330,37 +1370,29 @@ int mutate_streamed(ms_ctx* c, uint64_t seed, const uint8_t* h_bases, uint8_t* h
         const int64_t f0 = c->h_contigs[c0].hdr_off, f1 = c1 < c->n_contigs ? c->h_contigs[c1].hdr_off : c->fasta_bytes;
         MS_CUDA(c, cudaStreamWaitEvent(c->s_down, c->ev_done[g], 0));
         MS_CUDA(c, cudaMemcpyAsync(h_fasta + f0, c->fasta.as<uint8_t>() + f0, (size_t)(f1 - f0), cudaMemcpyDeviceToHost, c->s_down));
-    }
-    stage_end(c, ST_SPLICE);
-
-    // VCF: sizes need the bases (a SNP or inversion with REF == ALT is not written, vcf_writer.py:123)
-    stage_begin(c, ST_VCF);
-    const int64_t M = c->n_recs;
-    if (M > 0) {
-        VcfView vv{d_genome, c->lit.as<uint8_t>(), c->names.as<uint8_t>(), d_tab->conv, d_tab->comp, c->seed_last};
-        int32_t* d_delta = c->keep.as<int32_t>();
-        uint32_t* d_vsize = c->cand_val.as<uint32_t>();
-        k_rec_sizes<<<(unsigned)ceil_div(M, 256), 256, 0, c->stream>>>(vv, c->recs.as<Rec>(), M, c->contigs.as<Contig>(), d_delta, d_vsize);
-        MS_LAUNCH_CHECK(c);
-        int64_t* V = c->vcf_off.as<int64_t>();
-        auto in = [=] __device__(int64_t i) -> I64x2 { return I64x2{0, (int64_t)d_vsize[i]}; };
-        auto out = [=] __device__(int64_t i, I64x2 ex, I64x2) { V[i] = ex.b; };
+        // sizes and offsets of this group's VCF lines
         I64x2* d_total = nullptr;
-        MS_CUDA(c, (device_scan<I64x2>(c, in, out, M, I64x2{0, 0}, SumOp(), c->scan_tmp, &d_total)));
-        k_store_total1<<<1, 1, 0, c->stream>>>(d_total, V + M, c->totals.as<Totals>());
+        if (r1 > r0) {
+            k_rec_sizes<<<(unsigned)ceil_div(r1 - r0, 256), 256, 0, c->stream>>>(vv, c->recs.as<Rec>() + r0, r1 - r0, c->contigs.as<Contig>(),
+                                                                              d_delta + r0, d_vsize + r0);
+            MS_LAUNCH_CHECK(c);
+            const int64_t* carry = d_vend + g;
+            auto in = [=] __device__(int64_t i) -> I64x2 { return I64x2{0, (int64_t)d_vsize[r0 + i]}; };
+            auto out = [=] __device__(int64_t i, I64x2 ex, I64x2) { V[r0 + i] = ex.b + *carry; };
+            MS_CUDA(c, (device_scan<I64x2>(c, in, out, r1 - r0, I64x2{0, 0}, SumOp(), c->scan_tmp, &d_total)));
+        }
+        k_store_vend<<<1, 1, 0, c->stream>>>(d_total, d_vend + g, V + r1, c->totals.as<Totals>());
         MS_LAUNCH_CHECK(c);
-        MS_CUDA(c, cudaMemcpyAsync(c->h_totals, c->totals.p, sizeof(Totals), cudaMemcpyDeviceToHost, c->stream));
-        MS_CUDA(c, cudaStreamSynchronize(c->stream));
-        c->vcf_bytes = c->h_totals->vcf_bytes;
-        if (c->vcf_bytes > vcf_cap) MS_FAIL(c, MS_ERR_ARG, "VCF buffer too small: need %lld bytes", (long long)c->vcf_bytes);
-        MS_CUDA(c, c->vcf.ensure((size_t)c->vcf_bytes + 64));
-        if ((rc = vcf_launch(c))) return rc;
-        MS_CUDA(c, cudaMemcpyAsync(h_vcf, c->vcf.p, (size_t)c->vcf_bytes, cudaMemcpyDeviceToHost, c->stream));
-    } else {
-        c->vcf_bytes = 0;
+        MS_CUDA(c, cudaMemcpyAsync(c->h_vend + g + 1, d_vend + g + 1, 8, cudaMemcpyDeviceToHost, c->stream));
+        MS_CUDA(c, cudaEventRecord(c->ev_sized[g], c->stream));
+        if (g >= 1 && (rc = flush_vcf(g - 1))) return rc;
     }
-    stage_end(c, ST_VCF);
+    if ((rc = flush_vcf(G - 1))) return rc;
+    stage_end(c, ST_SPLICE);
+    c->vcf_bytes = c->h_vend[G];
+    (void)M;
     rc = finish_apply(c);
+    MS_CUDA(c, cudaStreamSynchronize(c->s_vcf));
     MS_CUDA(c, cudaStreamSynchronize(c->s_down));
     if (rc) return rc;
     c->sizes_valid = false;

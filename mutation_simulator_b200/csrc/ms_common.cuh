@@ -97,8 +97,11 @@ struct ms_ctx {
     int tile_bytes = 16384;
 
     // streamed run (ms_mutate_streamed): copy streams and per-group events
-    cudaStream_t s_up = nullptr, s_down = nullptr;
-    std::vector<cudaEvent_t> ev_up, ev_done;
+    cudaStream_t s_up = nullptr, s_down = nullptr, s_vcf = nullptr;
+    std::vector<cudaEvent_t> ev_up, ev_done, ev_sized;
+    ms::DevBuf vend;                 // VCF bytes up to the end of each contig group
+    int64_t* h_vend = nullptr;       // pinned copy
+    size_t h_vend_cap = 0;
 };
 
 #define MS_CUDA(ctx, call)                                                                        \

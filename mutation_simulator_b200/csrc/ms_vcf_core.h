@@ -169,4 +169,14 @@ MS_HD uint32_t vcf_line_size(const VcfView& v, const Contig& c, const Rec& r) {
     return s.n;
 }
 
+// Line size if the record is written: an upper bound that does not look at the bases (the streamed run lays out
+// the VCF buffer before the genome has arrived; whether a SNP / inversion has REF == ALT is decided later).
+MS_HD uint32_t vcf_line_bound(const VcfView& v, const Contig& c, const Rec& r) {
+    if (r.type == T_IT || r.type == T_DEAD) return 0;
+    if ((r.type == T_DE || r.type == T_TL) && r.pos == 0 && c.len == 1) return 0;
+    CountSink s;
+    vcf_emit(s, v, c, r);
+    return s.n;
+}
+
 }  // namespace ms
