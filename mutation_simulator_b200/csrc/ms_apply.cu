@@ -432,7 +432,8 @@ __device__ __forceinline__ int64_t warp_last_le(const Rec* recs, const Contig& k
 }
 
 __global__ void __launch_bounds__(SPLICE_THREADS, 5)
-k_splice(SpliceView v, const Contig* contigs, const PieceDesc* pieces, const Tables* tables, uint8_t* fasta) {
+k_splice(SpliceView v, const Contig* contigs, const PieceDesc* pieces, const Tables* tables, const Totals* tot, uint8_t* fasta) {
+    if (tot->error) return;   // the index stage rejected the records (overlap / out of bounds): nothing here can be trusted
     __shared__ Contig sc;
     __shared__ __align__(16) PieceDesc sd;
     extern __shared__ __align__(16) uint8_t sp_dyn[];      // [tile | stage]
@@ -1170,7 +1171,7 @@ static int splice_launch(ms_ctx* c, int64_t piece_lo, int64_t n_pieces, int32_t 
         static bool sp_attr = false;
         if (!sp_attr) { MS_CUDA(c, cudaFuncSetAttribute(k_splice, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_DYN)); sp_attr = true; }
         k_splice<<<(unsigned)n_pieces, SPLICE_THREADS, SP_DYN, st>>>(sv, d_contigs, c->piece_desc.as<PieceDesc>() + piece_lo, d_tab,
-                                                                   c->fasta.as<uint8_t>());
+                                                                   c->totals.as<Totals>(), c->fasta.as<uint8_t>());
         MS_LAUNCH_CHECK(c);
     }
     if (n_ctg > 0) {
