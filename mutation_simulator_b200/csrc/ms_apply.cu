@@ -269,9 +269,15 @@ static_assert(sizeof(PieceDesc) == 96, "PieceDesc layout");
 
 __global__ void __launch_bounds__(256)
 k_piece_desc(const Contig* contigs, int32_t n_contigs, const int64_t* piece_lo, int64_t n_pieces, const Rec* recs,
-             const uint32_t* blk, PieceDesc* out) {
+             const uint32_t* blk, const Totals* tot, PieceDesc* out) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_pieces) return;
+    if (tot->error) {   // k_rec_out rejected the records (overlap / out of bounds): every piece becomes empty, the
+        PieceDesc z{};  // splice kernel then touches nothing and ms_apply reports the error
+        z.i_last = -1; z.bpl = 60u;
+        out[p] = z;
+        return;
+    }
     int lo = 0, hi = n_contigs;  // last c with piece_lo[c] <= p
     while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
@@ -432,8 +438,7 @@ __device__ __forceinline__ int64_t warp_last_le(const Rec* recs, const Contig& k
 }
 
 __global__ void __launch_bounds__(SPLICE_THREADS, 5)
-k_splice(SpliceView v, const Contig* contigs, const PieceDesc* pieces, const Tables* tables, const Totals* tot, uint8_t* fasta) {
-    if (tot->error) return;   // the index stage rejected the records (overlap / out of bounds): nothing here can be trusted
+k_splice(SpliceView v, const Contig* contigs, const PieceDesc* pieces, const Tables* tables, uint8_t* fasta) {
     __shared__ Contig sc;
     __shared__ __align__(16) PieceDesc sd;
     extern __shared__ __align__(16) uint8_t sp_dyn[];      // [tile | stage]
@@ -1152,7 +1157,7 @@ static int index_stage(ms_ctx* c) {
     MS_LAUNCH_CHECK(c);
     if (c->n_pieces > 0) {
         k_piece_desc<<<(unsigned)ceil_div(c->n_pieces, 256), 256, 0, st>>>(d_contigs, c->n_contigs, c->piece_lo.as<int64_t>(), c->n_pieces,
-                                                                          d_recs, d_blk, c->piece_desc.as<PieceDesc>());
+                                                                          d_recs, d_blk, d_tot, c->piece_desc.as<PieceDesc>());
         MS_LAUNCH_CHECK(c);
     }
     stage_end(c, ST_INDEX);
@@ -1171,7 +1176,7 @@ static int splice_launch(ms_ctx* c, int64_t piece_lo, int64_t n_pieces, int32_t 
         static bool sp_attr = false;
         if (!sp_attr) { MS_CUDA(c, cudaFuncSetAttribute(k_splice, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_DYN)); sp_attr = true; }
         k_splice<<<(unsigned)n_pieces, SPLICE_THREADS, SP_DYN, st>>>(sv, d_contigs, c->piece_desc.as<PieceDesc>() + piece_lo, d_tab,
-                                                                   c->totals.as<Totals>(), c->fasta.as<uint8_t>());
+                                                                   c->fasta.as<uint8_t>());
         MS_LAUNCH_CHECK(c);
     }
     if (n_ctg > 0) {

@@ -68,7 +68,7 @@ struct ms_ctx {
 
     // ranges / sampling
     ms::DevBuf ranges, cand_val, cand_sorted, bucket_cnt, bucket_off, cand_type, cand_len, cand_reach, cand_pm,
-               cand_accept, acc_idx, tl_list, tli_list, link, keep, contig_tl, scan_tmp, scan_tmp2, svec, vvec, lvec;
+               cand_accept, acc_idx, tl_list, tli_list, link, keep, contig_tl, scan_tmp, scan_tmp2, svec, vvec, lvec, bucket_range;
     std::vector<ms::Range> h_ranges;
     int32_t n_ranges = 0;
     int64_t n_candidates = 0;

@@ -57,25 +57,41 @@ __device__ inline int64_t bucket_store(const Range& g, uint32_t b) {
     return g.store_lo + (int64_t)(b - g.bucket_lo) * cap;
 }
 
-__global__ void __launch_bounds__(256)
+// A CTA draws DRAW_TILE consecutive candidate slots: the range lookup (a chain of dependent loads) is paid once
+// per 2048 candidates, and a thread's successive candidates are independent chains the scheduler can overlap
+// (profiles/r1k: with one candidate per thread the kernel sat at 48 % issue utilisation behind that prologue and
+// the bucket atomics).
+constexpr int DRAW_THREADS = 256, DRAW_PER_THREAD = 8, DRAW_TILE = DRAW_THREADS * DRAW_PER_THREAD;
+__global__ void __launch_bounds__(DRAW_THREADS)
 k_draw(const Range* ranges, const int64_t* cand_lo, int32_t n_ranges, const Prp* prps, int64_t K, uint32_t* store, uint32_t* bucket_cnt,
        Totals* tot) {
     __shared__ int r0;
-    const int64_t s0 = (int64_t)blockIdx.x * blockDim.x;
+    const int64_t s0 = (int64_t)blockIdx.x * DRAW_TILE;
     if (threadIdx.x == 0) r0 = upper_idx(cand_lo, n_ranges, s0);
     __syncthreads();
-    const int64_t s = s0 + threadIdx.x;
-    if (s >= K) return;
-    int r = r0;
-    while (s >= cand_lo[r + 1]) ++r;
-    const Range& g = ranges[r];
-    const Prp p = prps[r];
-    const uint32_t v = prp_apply(p, (uint32_t)(s - g.cand_lo));
-    const uint32_t b = bucket_of(g, v);
-    const uint32_t slot = atomicAdd(&bucket_cnt[b], 1u);
-    const uint32_t cap = g.nb == 1u ? g.k : (uint32_t)BUCKET_CAP;
-    if (slot < cap) store[bucket_store(g, b) + slot] = v;
-    else raise_error_s(tot, MS_ERR_INTERNAL, 200 + b);
+    int r = r0, r_have = -1;
+    Prp p;
+    int64_t g_cand_lo = 0, g_store_lo = 0;
+    uint32_t g_nb = 1u, g_bscale = 0u, g_bucket_lo = 0u, g_k = 0u;
+#pragma unroll 2
+    for (int it = 0; it < DRAW_PER_THREAD; ++it) {
+        const int64_t s = s0 + (int64_t)it * DRAW_THREADS + threadIdx.x;
+        if (s >= K) break;
+        while (s >= cand_lo[r + 1]) ++r;
+        if (r != r_have) {
+            const Range& g = ranges[r];
+            p = prps[r];
+            g_cand_lo = g.cand_lo; g_store_lo = g.store_lo; g_nb = g.nb; g_bscale = g.bscale; g_bucket_lo = g.bucket_lo; g_k = g.k;
+            r_have = r;
+        }
+        const uint32_t v = prp_apply(p, (uint32_t)(s - g_cand_lo));
+        uint32_t bl = mulhi32(v, g_bscale);   // nb == 1: bscale = 0
+        if (bl >= g_nb) bl = g_nb - 1u;
+        const uint32_t cap = g_nb == 1u ? g_k : (uint32_t)BUCKET_CAP;
+        const uint32_t slot = atomicAdd(&bucket_cnt[g_bucket_lo + bl], 1u);
+        if (slot < cap) store[g_store_lo + (int64_t)bl * cap + slot] = v;
+        else raise_error_s(tot, MS_ERR_INTERNAL, 200 + (int64_t)(g_bucket_lo + bl));
+    }
 }
 
 template <int K, int J>
@@ -134,7 +150,7 @@ __device__ __forceinline__ void emit_candidate(const Range& g, const Contig& ct,
 // Small buckets (many-small-contig genomes: a 5 kbp contig has ~67 candidates): four buckets per CTA, 128 threads
 // each, instead of one mostly idle 512-thread CTA per bucket (C5: 4.0 ms -> see profiles).
 __global__ void __launch_bounds__(SORT_THREADS)
-k_sort_emit_small(const Range* ranges, const int64_t* bucket_lo_key, int32_t n_ranges, const Contig* contigs, const int64_t* bucket_off,
+k_sort_emit_small(const Range* ranges, const uint32_t* bucket_range, const Contig* contigs, const int64_t* bucket_off,
                   int64_t n_buckets, const uint32_t* store, Seed seed, int32_t min_dist, const int32_t* block7, int positions_only,
                   int64_t* cand_gpos, uint8_t* cand_type, uint32_t* cand_len, int64_t* cand_reach, uint32_t* cand_range) {
     __shared__ uint32_t sm[SORT_THREADS];
@@ -147,7 +163,7 @@ k_sort_emit_small(const Range* ranges, const int64_t* bucket_lo_key, int32_t n_r
     int cnt = 0;
     if (b < n_buckets) { lo = bucket_off[b]; cnt = (int)(bucket_off[b + 1] - lo); }
     const bool mine = cnt > 0 && cnt <= SMALL_BUCKET;
-    if (mine && t == 0) { ridx4[grp] = (uint32_t)upper_idx(bucket_lo_key, n_ranges, b); g4[grp] = ranges[ridx4[grp]]; }
+    if (mine && t == 0) { ridx4[grp] = bucket_range[b]; g4[grp] = ranges[ridx4[grp]]; }
     if (tid < 7) blk[tid] = block7[tid];
     __syncthreads();
     uint32_t v = 0xFFFFFFFFu;
@@ -159,28 +175,65 @@ k_sort_emit_small(const Range* ranges, const int64_t* bucket_lo_key, int32_t n_r
 }
 
 // K1d + K2: sort one bucket in shared memory, then write position, type, length and reach.
-__global__ void __launch_bounds__(SORT_THREADS)
-k_sort_emit(const Range* ranges, const int64_t* bucket_lo_key, int32_t n_ranges, const Contig* contigs, const int64_t* bucket_off,
+__global__ void __launch_bounds__(SORT_THREADS, 3)
+k_sort_emit(const Range* ranges, const uint32_t* bucket_range, const Contig* contigs, const int64_t* bucket_off,
             const uint32_t* store, Seed seed, int32_t min_dist, const int32_t* block7, int positions_only,
             int64_t* cand_gpos, uint8_t* cand_type, uint32_t* cand_len, int64_t* cand_reach, uint32_t* cand_range, Totals* tot,
             int skip_small) {
     __shared__ uint32_t sm[SORT_CAP];
     __shared__ Range g;
     __shared__ int32_t blk[7];
-    __shared__ uint32_t s_ridx;
+    __shared__ uint32_t s_ridx, s_vlo, s_nw;
+    __shared__ uint32_t warp_tot[SORT_THREADS / 32];
     const int tid = threadIdx.x;
     const int64_t b = blockIdx.x;
     const int64_t lo = bucket_off[b], hi = bucket_off[b + 1];
     const int cnt = (int)(hi - lo);
     if (cnt <= 0 || (skip_small && cnt <= SMALL_BUCKET)) return;
     if (cnt > SORT_CAP) { if (tid == 0) raise_error_s(tot, MS_ERR_INTERNAL, 100 + b); return; }
-    if (tid == 0) { s_ridx = (uint32_t)upper_idx(bucket_lo_key, n_ranges, b); g = ranges[s_ridx]; }
+    if (tid == 0) {
+        s_ridx = bucket_range[b];   // (a host-built map: the binary search it replaces was five dependent loads per CTA)
+        g = ranges[s_ridx];
+        // values of this bucket: mulhi32(v, bscale) == bl  <=>  ceil(bl * 2^32 / bscale) <= v < ceil((bl + 1) * 2^32 / bscale)
+        const uint64_t bl = (uint64_t)(b - g.bucket_lo), sc = g.bscale;
+        const uint64_t vlo = (g.nb == 1u || bl == 0) ? 0ull : ((bl << 32) + sc - 1) / sc;
+        const uint64_t vhi = (g.nb == 1u || bl + 1 == g.nb) ? (uint64_t)g.n : (((bl + 1) << 32) + sc - 1) / sc;
+        s_vlo = (uint32_t)vlo;
+        s_nw = (uint32_t)((vhi - vlo + 31) >> 5);
+    }
     if (tid < 7) blk[tid] = block7[tid];
     int n2 = 32;
     while (n2 < cnt) n2 <<= 1;
     __syncthreads();
     const uint32_t* src = store + bucket_store(g, (uint32_t)b);
-    if (n2 <= SORT_THREADS) {
+    if (cnt >= 64 && s_nw <= (uint32_t)SORT_CAP) {
+        // Dense bucket: the keys are distinct (a permutation's values) and span at most 32 Ki positions, so the
+        // sorted order is read off a bitmap — set one bit per key, prefix-sum the popcounts, write each key to
+        // its rank.  ~100 instructions per thread instead of the ~360 of the 512-key bitonic network.
+        const uint32_t vlo = s_vlo, nw = s_nw;
+        for (uint32_t i = tid; i < nw; i += SORT_THREADS) sm[i] = 0u;
+        __syncthreads();
+        for (int i = tid; i < cnt; i += SORT_THREADS) {
+            const uint32_t d = src[i] - vlo;
+            atomicOr(&sm[d >> 5], 1u << (d & 31u));
+        }
+        __syncthreads();
+        const uint32_t i0 = 2u * (uint32_t)tid;
+        uint32_t w0 = i0 < nw ? sm[i0] : 0u, w1 = i0 + 1u < nw ? sm[i0 + 1u] : 0u;
+        const uint32_t mine = (uint32_t)(__popc(w0) + __popc(w1));
+        uint32_t incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d); if ((tid & 31) >= d) incl += y; }
+        if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
+        __syncthreads();                                   // every thread holds its bitmap words: sm can be overwritten
+        uint32_t rank = incl - mine;
+        for (int w = 0; w < (tid >> 5); ++w) rank += warp_tot[w];
+        uint32_t vb = vlo + (i0 << 5);
+        while (w0) { const int bit = __ffs(w0) - 1; w0 &= w0 - 1u; sm[rank++] = vb + (uint32_t)bit; }
+        vb += 32u;
+        while (w1) { const int bit = __ffs(w1) - 1; w1 &= w1 - 1u; sm[rank++] = vb + (uint32_t)bit; }
+        __syncthreads();
+    } else if (n2 <= SORT_THREADS) {
         // one key per thread: strides below 32 are exchanged with shuffles, only the
         // 10 cross-warp phases of a 512-key bitonic network go through shared memory;
         // the network is unrolled at compile time (loop control was 22 % of the kernel, profiles/r1e)
@@ -386,7 +439,7 @@ static int draw_and_sort(ms_ctx* c, Seed seed, uint32_t purpose, int32_t min_dis
     k_make_prps<<<(unsigned)ceil_div(R, 128), 128, 0, st>>>(d_ranges, R, d_ctg, seed, purpose, d_prps);
     MS_LAUNCH_CHECK(c);
     MS_CUDA(c, cudaMemsetAsync(d_cnt, 0, (size_t)(c->n_buckets + 1) * 4, st));
-    k_draw<<<(unsigned)ceil_div(K, 256), 256, 0, st>>>(d_ranges, d_cand_lo, R, d_prps, K, c->cand_sorted.as<uint32_t>(), d_cnt, d_tot);
+    k_draw<<<(unsigned)ceil_div(K, DRAW_TILE), DRAW_THREADS, 0, st>>>(d_ranges, d_cand_lo, R, d_prps, K, c->cand_sorted.as<uint32_t>(), d_cnt, d_tot);
     MS_LAUNCH_CHECK(c);
     {
         const uint32_t* cnt = d_cnt;
@@ -404,13 +457,13 @@ static int draw_and_sort(ms_ctx* c, Seed seed, uint32_t purpose, int32_t min_dis
     for (const Range& g : c->h_ranges) { if (g.nb == 1u && g.k <= (uint32_t)SMALL_BUCKET) any_small = 1; else any_large = 1; }
     if (any_small) {
         k_sort_emit_small<<<(unsigned)ceil_div(c->n_buckets, SORT_THREADS / SMALL_BUCKET), SORT_THREADS, 0, st>>>(
-            d_ranges, d_bucket_lo, R, d_ctg, d_boff, c->n_buckets, c->cand_sorted.as<uint32_t>(), seed, min_dist, d_block, positions_only,
+            d_ranges, c->bucket_range.as<uint32_t>(), d_ctg, d_boff, c->n_buckets, c->cand_sorted.as<uint32_t>(), seed, min_dist, d_block, positions_only,
             c->svec.as<int64_t>(), c->cand_type.as<uint8_t>(), c->cand_len.as<uint32_t>(), c->cand_reach.as<int64_t>(),
             c->lvec.as<uint32_t>());
         MS_LAUNCH_CHECK(c);
     }
     if (any_large) {
-        k_sort_emit<<<(unsigned)c->n_buckets, SORT_THREADS, 0, st>>>(d_ranges, d_bucket_lo, R, d_ctg, d_boff,
+        k_sort_emit<<<(unsigned)c->n_buckets, SORT_THREADS, 0, st>>>(d_ranges, c->bucket_range.as<uint32_t>(), d_ctg, d_boff,
                                                                      c->cand_sorted.as<uint32_t>(), seed, min_dist, d_block, positions_only,
                                                                      c->svec.as<int64_t>(), c->cand_type.as<uint8_t>(), c->cand_len.as<uint32_t>(),
                                                                      c->cand_reach.as<int64_t>(), c->lvec.as<uint32_t>(), d_tot, any_small);
@@ -597,6 +650,11 @@ static int upload_ranges(ms_ctx* c, int32_t min_dist, const std::vector<Contig>&
     MS_CUDA(c, cudaMemcpyAsync(d_cand_lo + (R + 1), bucket_lo.data(), sizeof(int64_t) * (size_t)(R + 1), cudaMemcpyHostToDevice, st));
     int32_t* d_block = reinterpret_cast<int32_t*>(reinterpret_cast<Prp*>(d_cand_lo + 2 * (R + 1)) + R);
     MS_CUDA(c, cudaMemcpyAsync(d_block, c->block, sizeof(int32_t) * 7, cudaMemcpyHostToDevice, st));
+    std::vector<uint32_t> br((size_t)NB + 1, 0u);   // sort bucket -> range
+    for (int32_t r = 0; r < R; ++r)
+        for (int64_t b = bucket_lo[r]; b < bucket_lo[r + 1]; ++b) br[(size_t)b] = (uint32_t)r;
+    MS_CUDA(c, c->bucket_range.ensure(br.size() * 4));
+    MS_CUDA(c, cudaMemcpyAsync(c->bucket_range.p, br.data(), br.size() * 4, cudaMemcpyHostToDevice, st));
     MS_CUDA(c, cudaStreamSynchronize(st));
     return MS_OK;
 }
