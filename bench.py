@@ -248,12 +248,13 @@ def file_to_file(args, wl, eng, rank, world, lengths_all, names_all, total_bases
         a.device = int(os.environ.get("LOCAL_RANK", "0"))
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        fasta = load_fasta(a.infile)
+        fasta = load_fasta(a.infile, device=a.device if world == 1 else None)   # one GPU: FASTA ingest on the device
         t1 = time.perf_counter()
         sim = SimulationSettings.from_args(a, fasta, True)
         m = Mutator(a, fasta, sim)
         m.mutate()
         m.close()
+        fasta.close()
         torch.cuda.synchronize()
         t2 = time.perf_counter()
         dt, parse = reduce_over_ranks([t2 - t0, t1 - t0], "max", world)

@@ -105,6 +105,23 @@ int ms_genome_download(ms_ctx* ctx, uint8_t* bases, int64_t cap);
  * the mutated lengths; bpl follows pyfaidx's rule for the re-loaded file (a contig shorter than one line gets
  * bpl = its length).  Records and ranges are cleared. */
 int ms_genome_adopt_output(ms_ctx* ctx);
+/* ---- FASTA ingest on the device ------------------------------------------
+ * Replaces util.py:77-91 (load_fasta -> pyfaidx.Fasta: build the index, serve upper-cased bases) for regularly wrapped
+ * files.  ms_fasta_ingest_fd reads the open file through two pinned staging buffers into device memory (pread of one
+ * chunk overlapping the H2D copy of the previous) and finds records and their line layout there; *regular = 0 means the
+ * file needs the host parser (CRLF, text before the first record, lines or deflines over 1 MiB).  ms_fasta_index
+ * returns what pyfaidx stores per record (.fai: length, offset of the first base, bases and bytes per line) and the
+ * deflines (without '>'), packed, hdr_off having n_records + 1 entries; hdr_blob may be NULL to query sizes.
+ * ms_fasta_commit strips line breaks, upper-cases (util.py:87) and verifies every line against the index in one pass,
+ * making the bases the resident genome (headers / names / gid as for ms_genome_upload); *regular = 0 if the bytes do
+ * not fit the index (ragged or blank lines) — nothing is resident then.  ms_genome_read copies a slice of the resident
+ * bases to the host (the lazy per-record views of the Python Fasta object). */
+int ms_fasta_ingest_fd(ms_ctx* ctx, int fd, int64_t nbytes, int32_t* n_records, int32_t* regular);
+int ms_fasta_index(ms_ctx* ctx, int64_t* hdr_off, int64_t* seq_off, int64_t* length, int32_t* lenc, int32_t* lenb,
+                   uint8_t* hdr_blob, int64_t blob_cap);
+int ms_fasta_commit(ms_ctx* ctx, const uint32_t* gid, const uint8_t* headers, const int64_t* hdr_off,
+                    const uint8_t* names, const int64_t* name_off, int32_t* regular);
+int ms_genome_read(ms_ctx* ctx, int64_t off, int64_t n, uint8_t* dst);
 /* Contig table only: the bases follow with ms_mutate_streamed. */
 int ms_genome_declare(ms_ctx* ctx, int64_t total_bases, int32_t n_contigs, const int64_t* contig_len,
                       const int32_t* bpl, const uint32_t* gid, const uint8_t* headers, const int64_t* hdr_off,

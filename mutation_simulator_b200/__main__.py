@@ -21,7 +21,9 @@ _SETUP_ERRORS = (FileNotFoundError, ITNotEnoughAvailChromsError, RatesTooHighErr
 def initialize():
     args = get_args()
     try:
-        fasta = load_fasta(args.infile)
+        from . import distributed
+        # one GPU: the file is parsed on the device and stays there for the engines
+        fasta = load_fasta(args.infile, device=getattr(args, "device", 0) if distributed.rank_world()[1] == 1 else None)
         if args.mode == "args":
             sim = SimulationSettings.from_args(args, fasta, args.ignore_warnings)
         elif args.mode == "it":
@@ -56,6 +58,7 @@ def main():
                     and int(mutator._engine.contig_out_len().min()) > 0:
                 from .fasta import ResidentFasta
                 resident = ResidentFasta(mutator.detach_engine(), fasta)
+                fasta.detach_engine()
             mutator.close()
             fasta.close()
         except (FastaWriterError, VcfWriterError, MutSimError, RangeOverlapError) as e:

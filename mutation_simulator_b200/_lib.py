@@ -50,6 +50,10 @@ PROTOTYPES = {
     "ms_genome_download": (C.c_int, [_P, _P, _I64]),
     "ms_genome_reserve": (C.c_int, [_P, _I64]),
     "ms_genome_adopt_output": (C.c_int, [_P]),
+    "ms_fasta_ingest_fd": (C.c_int, [_P, C.c_int, _I64, _P, _P]),
+    "ms_fasta_index": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64]),
+    "ms_fasta_commit": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
+    "ms_genome_read": (C.c_int, [_P, _I64, _I64, _P]),
     "ms_genome_declare": (C.c_int, [_P, _I64, C.c_int32, _P, _P, _P, _P, _P, _P, _P]),
     "ms_mutate_streamed": (C.c_int, [_P, C.c_uint64, _P, _P, _I64, _P, _I64, _P, _P, _I64]),
     "ms_contig_layout": (C.c_int, [_P, _P, _P, _P, _P]),

@@ -1173,8 +1173,10 @@ static int splice_launch(ms_ctx* c, int64_t piece_lo, int64_t n_pieces, int32_t 
     SpliceView sv{c->genome.as<uint8_t>(), c->lit.as<uint8_t>(), c->recs.as<Rec>(), c->blk.as<uint32_t>(), d_tab->conv, d_tab->comp, c->seed_last};
     if (n_pieces > 0) {
         constexpr int SP_DYN = SP_TILE_MAX + 64 + (int)SP_STAGE_CAP + 32;
-        static bool sp_attr = false;
-        if (!sp_attr) { MS_CUDA(c, cudaFuncSetAttribute(k_splice, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_DYN)); sp_attr = true; }
+        if (!c->splice_attr_set) {   // per context: the attribute is per device, and a process may hold contexts on several
+            MS_CUDA(c, cudaFuncSetAttribute(k_splice, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_DYN));
+            c->splice_attr_set = true;
+        }
         k_splice<<<(unsigned)n_pieces, SPLICE_THREADS, SP_DYN, st>>>(sv, d_contigs, c->piece_desc.as<PieceDesc>() + piece_lo, d_tab,
                                                                    c->fasta.as<uint8_t>());
         MS_LAUNCH_CHECK(c);
@@ -1191,8 +1193,10 @@ static int vcf_launch(ms_ctx* c, int64_t r0, int64_t r1, cudaStream_t st) {
     const Tables* d_tab = c->tables.as<Tables>();
     VcfView vv{c->genome.as<uint8_t>(), c->lit.as<uint8_t>(), c->names.as<uint8_t>(), d_tab->conv, d_tab->comp, c->seed_last};
     if (r1 > r0) {
-        static bool attr_set = false;
-        if (!attr_set) { MS_CUDA(c, cudaFuncSetAttribute(k_vcf_write, cudaFuncAttributeMaxDynamicSharedMemorySize, VCF_SMEM + 32)); attr_set = true; }
+        if (!c->vcf_attr_set) {
+            MS_CUDA(c, cudaFuncSetAttribute(k_vcf_write, cudaFuncAttributeMaxDynamicSharedMemorySize, VCF_SMEM + 32));
+            c->vcf_attr_set = true;
+        }
         k_vcf_write<<<(unsigned)ceil_div(r1 - (r0 & ~(int64_t)1), VCF_THREADS), VCF_THREADS, VCF_SMEM + 32, st>>>(
             vv, c->recs.as<Rec>(), r0, r1, c->contigs.as<Contig>(), d_tab, c->vcf_off.as<int64_t>(), c->vcf.as<uint8_t>());
         MS_LAUNCH_CHECK(c);

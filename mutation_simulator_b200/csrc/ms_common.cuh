@@ -52,6 +52,18 @@ enum Stage { ST_UPLOAD = 0, ST_SAMPLE_POS, ST_SAMPLE_TYPE, ST_SAMPLE_RESOLVE, ST
 
 }  // namespace ms
 
+namespace ms {
+// One FASTA record as the device indexer sees it (ms_ingest.cu): what pyfaidx keeps per .fai line, plus the defline.
+struct FaRec {
+    int64_t hdr_lo, hdr_hi;   // '>' and the line break that ends the defline
+    int64_t seq_lo;           // file offset of the first base
+    int64_t goff;             // index of the first base in the stripped genome
+    int64_t len;              // bases
+    int64_t nfull;            // lines of exactly lenc bases followed by a line break
+    int32_t lenc, lenb;       // bases / bytes per line
+};
+}  // namespace ms
+
 struct ms_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -85,8 +97,10 @@ struct ms_ctx {
     ms::DevBuf recs, lit, blk, piece_lo, piece_desc, long_gaps, fasta, vcf, vcf_off, totals;
     int64_t n_recs = 0, lit_bytes = 0, fasta_bytes = 0, vcf_bytes = 0, n_pieces = 0, n_blk = 0;
     ms::Totals* h_totals = nullptr;  // pinned
-    uint8_t* h_stage[2] = {nullptr, nullptr};   // pinned staging of ms_download_to_fd
-    cudaEvent_t h_stage_ev[2] = {nullptr, nullptr};
+    static constexpr int N_STAGE = 6;            // pinned staging buffers of ms_download_to_fd / ms_fasta_ingest_fd:
+    static constexpr int64_t STAGE_BYTES = 16 << 20;   // one file read / write per buffer in flight, each on its own thread
+    uint8_t* h_stage[N_STAGE] = {};
+    cudaEvent_t h_stage_ev[N_STAGE] = {};
     ms::Totals last_totals{};
 
     // timing
@@ -95,6 +109,12 @@ struct ms_ctx {
     float stage_ms[ms::ST_COUNT];
     int64_t kernel_launches = 0;
     int tile_bytes = 16384;
+    bool splice_attr_set = false, vcf_attr_set = false;   // cudaFuncSetAttribute done on this context's device
+
+    // device FASTA ingest (ms_fasta_ingest_fd .. ms_fasta_commit)
+    std::vector<ms::FaRec> fa_recs;
+    ms::DevBuf fa_index;
+    int64_t fa_bytes = 0;
 
     // streamed run (ms_mutate_streamed): copy streams and per-group events
     cudaStream_t s_up = nullptr, s_down = nullptr, s_vcf = nullptr;
@@ -137,6 +157,11 @@ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 // pipeline entry points implemented in the .cu files
 int apply_pipeline(ms_ctx* c);
 int adopt_output(ms_ctx* c);
+int ensure_stage_buffers(ms_ctx* c);
+int fasta_ingest(ms_ctx* c, int fd, int64_t nbytes, int32_t* n_records, int32_t* regular);
+int fasta_index(ms_ctx* c, int64_t* hdr_off, int64_t* seq_off, int64_t* length, int32_t* lenc, int32_t* lenb, uint8_t* hdr_blob,
+                int64_t blob_cap);
+int fasta_strip(ms_ctx* c, int64_t total, int32_t* regular);
 int sample_pipeline(ms_ctx* c, uint64_t seed, bool defer_bases = false);
 int mutate_streamed(ms_ctx* c, uint64_t seed, const uint8_t* h_bases, uint8_t* h_fasta, int64_t fasta_cap, uint8_t* h_vcf,
                     int64_t vcf_cap, int64_t* fasta_bytes, int64_t* vcf_bytes, int64_t group_min);

@@ -132,7 +132,7 @@ def write_partitioned(path, my_ids, chunks, n_contigs, prefix: bytes = b""):
             fh.write(prefix)
             fh.truncate(int(off[-1]))
     barrier()
-    fd = os.open(path, os.O_WRONLY)
+    fd = os.open(path, os.O_RDWR)
     try:
         for g, c in zip(my_ids, chunks):
             if len(c):
@@ -189,7 +189,7 @@ def write_slices_partitioned(path, engine, which, my_ids, slice_off, n_contigs, 
     sizes = [int(slice_off[i + 1] - slice_off[i]) for i in range(len(my_ids))]
     off = _global_offsets(my_ids, sizes, n_contigs, len(prefix))
     _create(path, prefix, off[-1])
-    fd = os.open(path, os.O_WRONLY)
+    fd = os.open(path, os.O_RDWR)
     try:
         # consecutive local contigs that are also consecutive in the file go out as one transfer
         i = 0
@@ -215,7 +215,7 @@ def write_fasta_partitioned(path, engine, my_ids, n_contigs_global):
     off = _global_offsets(my_ids, [b + e for b, e in zip(body, extra)], n_contigs_global, 0)
     _create(path, b"", off[-1])
     from .engine import BUF_FASTA
-    fd = os.open(path, os.O_WRONLY)
+    fd = os.open(path, os.O_RDWR)
     try:
         for i, g in enumerate(my_ids):
             if body[i]:

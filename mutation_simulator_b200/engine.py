@@ -98,6 +98,38 @@ class Engine:
                                               float(n_fraction), int(telomere_n), _ptr(self._hdr), _ptr(self._hoff),
                                               _ptr(self._nam), _ptr(self._noff)))
 
+    def ingest_fasta(self, fd: int, nbytes: int):
+        """Raw FASTA file -> device image + record index (ms_fasta_ingest_fd / ms_fasta_index).  Returns None when the
+        file is not regularly wrapped (the host parser then takes over), else a dict with length, seq_off, lenc, lenb
+        (numpy arrays) and long_names (deflines without '>')."""
+        n, reg = C.c_int32(0), C.c_int32(0)
+        self._check(self._lib.ms_fasta_ingest_fd(self._h, int(fd), int(nbytes), C.byref(n), C.byref(reg)))
+        if not reg.value:
+            return None
+        n = n.value
+        hoff = np.zeros(n + 1, np.int64)
+        seq_off, length = np.zeros(n, np.int64), np.zeros(n, np.int64)
+        lenc, lenb = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        self._check(self._lib.ms_fasta_index(self._h, _ptr(hoff), _ptr(seq_off), _ptr(length), _ptr(lenc), _ptr(lenb), None, 0))
+        blob = np.zeros(int(hoff[-1]) + 1, np.uint8)
+        self._check(self._lib.ms_fasta_index(self._h, _ptr(hoff), None, None, None, None, _ptr(blob), blob.size))
+        raw = blob.tobytes()
+        long_names = [raw[hoff[i]:hoff[i + 1]].decode("latin-1") for i in range(n)]
+        return dict(length=length, seq_off=seq_off, lenc=lenc, lenb=lenb, long_names=long_names)
+
+    def commit_fasta(self, lengths, bpl, headers: Sequence[bytes], names: Sequence[bytes], gid=None) -> bool:
+        """Strip + upper-case + verify the ingested image into the resident genome (ms_fasta_commit)."""
+        self._contig_args(lengths, bpl, headers, names, gid)
+        reg = C.c_int32(0)
+        self._check(self._lib.ms_fasta_commit(self._h, _ptr(self._gid), _ptr(self._hdr), _ptr(self._hoff), _ptr(self._nam),
+                                              _ptr(self._noff), C.byref(reg)))
+        return bool(reg.value)
+
+    def read_genome(self, off: int, n: int) -> np.ndarray:
+        out = np.empty(int(n), dtype=np.uint8)
+        self._check(self._lib.ms_genome_read(self._h, int(off), int(n), _ptr(out)))
+        return out
+
     def declare_genome(self, lengths, bpl, headers: Sequence[bytes], names: Sequence[bytes], gid=None):
         """Contig table without bases (they arrive with mutate_streamed)."""
         self._contig_args(lengths, bpl, headers, names, gid)

@@ -99,13 +99,20 @@ class Fasta:
     """All contigs of one FASTA file, upper-cased, resident in host memory."""
 
     def __init__(self, filename, one_based_attributes=False, as_raw=True, sequence_always_upper=True,
-                 read_ahead=None, build_index=True, **_):
+                 read_ahead=None, build_index=True, device=None, **_):
+        """device: CUDA device index — the file is then ingested on that GPU (ms_fasta_ingest_fd: raw bytes to HBM,
+        records / line layout / stripping / upper-casing there) and `self.engine` holds the resident genome for the
+        Mutator / ITMutator that follows; host views of the bases are fetched from the device on demand.  Files that
+        are not regularly wrapped, and device=None, go through the host parsers."""
         self.filename = str(filename)
         self.genome_is_upper = True
         self._lazy = None          # (mmap, uint8 view, spans, layout) of a regularly wrapped file: bases are copied on demand
         self._genome = None
+        self.engine = None
         try:
-            if not self._parse_regular():
+            if device is not None and self._ingest_device(int(device)):
+                pass
+            elif not self._parse_regular():
                 self._parse(np.fromfile(self.filename, dtype=np.uint8), sequence_always_upper)
         except (FileNotFoundError, IsADirectoryError, PermissionError):
             raise FastaNotFoundError(f"Cannot read FASTA from file {self.filename}")
@@ -114,7 +121,7 @@ class Fasta:
         for i, nm in enumerate(self.names):
             if nm in self._records:
                 raise ValueError(f"Duplicate key \"{nm}\"")  # util.py:89-91 maps this to FastaDuplicateHeaderError
-            if self._lazy is not None:
+            if self._lazy is not None or self.engine is not None:
                 src = (lambda k=i: self.gather([k]))
             else:
                 src = self._genome[self.goff[i]:self.goff[i + 1]]
@@ -124,6 +131,41 @@ class Fasta:
             self._write_fai()
 
     # -- parsing -----------------------------------------------------------
+    def _ingest_device(self, device: int) -> bool:
+        from .engine import Engine
+        with open(self.filename, "rb") as fh:
+            size = os.fstat(fh.fileno()).st_size
+            if size == 0:
+                return False
+            eng = Engine(device)
+            try:
+                info = eng.ingest_fasta(fh.fileno(), size)
+                if info is None:
+                    eng.close()
+                    return False
+                long_names = info["long_names"]
+                names = [(ln.split() or [""])[0] for ln in long_names]
+                if len(set(names)) != len(names):        # (raised as a duplicate-key error by the caller's loop)
+                    eng.close()
+                    return False
+                ok = eng.commit_fasta(info["length"], info["lenc"], [ln.encode("latin-1") for ln in long_names],
+                                      [nm.encode("latin-1") for nm in names])
+            except Exception:
+                eng.close()
+                raise
+            if not ok:
+                eng.close()
+                return False
+        self.engine = eng
+        self.names, self.long_names = names, long_names
+        self.lengths = info["length"].astype(np.int64)
+        self.bpl = info["lenc"].astype(np.int32)
+        self._lenb = info["lenb"].astype(np.int64)
+        self._seq_off = info["seq_off"].astype(np.int64)
+        self.goff = np.zeros(len(names) + 1, np.int64)
+        np.cumsum(self.lengths, out=self.goff[1:])
+        return True
+
     def _parse_regular(self) -> bool:
         """Fast path for regularly wrapped files (every line of a record but the last has the same width, LF line
         ends): contig boundaries by memmem, bases by one strided 2-D copy per contig, no per-byte masking.  The
@@ -228,6 +270,9 @@ class Fasta:
     def gather(self, ids) -> np.ndarray:
         """Concatenated bases of the given contigs (file case for lazily loaded files; the GPU upper-cases)."""
         ids = list(ids)
+        if self.engine is not None and self._genome is None:      # resident on the GPU: fetch the slices
+            parts = [self.engine.read_genome(int(self.goff[i]), int(self.lengths[i])) for i in ids]
+            return np.concatenate(parts) if parts else np.zeros(0, np.uint8)
         if self._lazy is None:
             if len(ids) == len(self.names) and ids == list(range(len(self.names))):
                 return self._genome
@@ -363,7 +408,15 @@ class Fasta:
     def get_seq(self, name, start, end, rc=False):
         return self._records[name]._b[start - 1:end].tobytes().decode("latin-1")
 
+    def detach_engine(self):
+        """Hand the engine that holds the ingested genome to the caller (who then owns and closes it)."""
+        eng, self.engine = self.engine, None
+        return eng
+
     def close(self):
+        if self.engine is not None:
+            self.engine.close()
+            self.engine = None
         if self._lazy is not None:
             mm = self._lazy[0]
             self._lazy = None
@@ -377,6 +430,8 @@ class Fasta:
         """Make this genome (or a subset of its contigs) resident on the engine's GPU."""
         # (the engine upper-cases on the device, so a mixed-case host array is fine)
         ids = list(range(len(self.names))) if contig_ids is None else list(contig_ids)
+        if engine is self.engine and self.engine is not None and contig_ids is None:
+            return ids                                            # ingested on this engine: already resident
         bases = self.gather(ids)
         engine.upload_genome(bases, [int(self.lengths[i]) for i in ids], [int(self.bpl[i]) for i in ids],
                              [self.long_names[i].encode("latin-1") for i in ids],

@@ -12,7 +12,7 @@ class FastaWriterError(Exception):
 class FastaWriter:
     def __init__(self, fname):
         try:
-            self._f = open(fname, "wb")
+            self._f = open(fname, "w+b")   # read-write: libmutsim_b200 maps the file for its parallel writers
         except OSError as e:
             raise FastaWriterError(f"Cannot write to Fasta file {fname} {e}")
         self._written = 0

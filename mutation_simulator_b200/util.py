@@ -45,10 +45,11 @@ def get_md5(fname) -> str:
     return h.hexdigest()
 
 
-def load_fasta(fname) -> Fasta:
-    """Loads a FASTA file (upper-cased) into host memory; the GPU copy is made by the engines."""
+def load_fasta(fname, device=None) -> Fasta:
+    """Loads a FASTA file (util.py:77-91).  With a CUDA device index the file is ingested on that GPU and the returned
+    object carries the engine holding the resident genome; without, it is parsed on the host and the engines upload."""
     path = Path(fname)
     try:
-        return Fasta(str(path.resolve()))
+        return Fasta(str(path.resolve()), device=device)
     except ValueError:
         raise FastaDuplicateHeaderError(f"Fasta {fname} contains duplicate header")

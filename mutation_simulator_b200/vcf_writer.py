@@ -48,7 +48,7 @@ def header_text(input_fasta, contigs, assembly_name, species_name, sample_name, 
 class VcfWriter:
     def __init__(self, fname):
         try:
-            self._f = open(fname, "wb")
+            self._f = open(fname, "w+b")   # read-write: libmutsim_b200 maps the file for its parallel writers
         except OSError as e:
             raise VcfWriterError(f"Cannot write to VCF file {fname} {e}")
 

@@ -168,3 +168,55 @@ def test_chained_rmt_then_it_in_hbm_equals_reload_of_the_written_file(tmp_path, 
     it = read_fasta_simple(tmp_path / "chain_ms_it.fa")
     assert sum(len(c[2]) for c in it) == sum(len(c[2]) for c in ms)
     assert len(ms[1][2]) < 41   # the short contig lost bases, so its re-loaded line width shrank
+
+
+def _write_fasta(path, recs, width, tail=b"\n"):
+    with open(path, "wb") as f:
+        for i, (hdr, seq) in enumerate(recs):
+            f.write(b">" + hdr + b"\n")
+            for o in range(0, len(seq), width[i]):
+                f.write(seq[o:o + width[i]] + b"\n")
+        if tail != b"\n":
+            f.seek(-1, 2); f.truncate(); f.write(tail)
+
+
+def test_device_fasta_ingest_matches_the_host_loader(tmp_path):
+    """ms_fasta_ingest_fd/_index/_commit (util.py:77-91 on the GPU): same index, names, deflines and upper-cased bases
+    as the host parser; irregular files are handed back to it."""
+    from mutation_simulator_b200 import load_fasta
+    rng = np.random.default_rng(3)
+    alpha = np.frombuffer(b"ACGTNacgtnRYKM", np.uint8)
+    lens = [100_003, 60, 1, 0, 7_000, 61, 120]
+    recs = [(b"c%d desc %d" % (i, i) if i % 2 else b"c%d" % i, bytes(rng.choice(alpha, n))) for i, n in enumerate(lens)]
+    widths = [60, 60, 60, 60, 70, 61, 40]
+    for name, tail in (("lf.fa", b"\n"), ("noeol.fa", b""), ("blank_end.fa", b"\n\n\n")):
+        p = tmp_path / name
+        _write_fasta(p, recs, widths, tail)
+        host = load_fasta(p)
+        dev = load_fasta(p, device=0)
+        assert dev.engine is not None, name
+        assert dev.names == host.names and dev.long_names == host.long_names
+        assert (dev.lengths == host.lengths).all() and (dev.bpl == host.bpl).all()
+        for nm in host.names:
+            a, b = dev.faidx.index[nm], host.faidx.index[nm]
+            assert (a.rlen, a.offset, a.lenc, a.lenb) == (b.rlen, b.offset, b.lenc, b.lenb), (name, nm)
+        want = np.concatenate([host.gather([i]) for i in range(len(lens))])
+        want = np.where((want >= 97) & (want <= 122), want - 32, want).astype(np.uint8)
+        assert (dev.engine.download_genome() == want).all()
+        assert str(dev[0][5:15]) == str(host[0][5:15]) and len(dev[4]) == 7_000
+        dev.close(); host.close()
+    # irregular layouts: the device path declines, the host parser decides (and raises what pyfaidx would)
+    ragged = tmp_path / "ragged.fa"
+    ragged.write_bytes(b">a\nACGTACGT\nACG\nACGTACGT\n")
+    from mutation_simulator_b200.fasta import FastaIndexingError
+    with pytest.raises(FastaIndexingError):
+        load_fasta(ragged, device=0)
+    crlf = tmp_path / "crlf.fa"
+    crlf.write_bytes(b">a x\r\nACGT\r\nAC\r\n>b\r\nGG\r\n")
+    f = load_fasta(crlf, device=0)
+    assert f.engine is None and f.names == ["a", "b"] and list(f.lengths) == [6, 2]
+    dup = tmp_path / "dup.fa"
+    dup.write_bytes(b">a\nACGT\n>a\nAC\n")
+    from mutation_simulator_b200 import FastaDuplicateHeaderError
+    with pytest.raises(FastaDuplicateHeaderError):
+        load_fasta(dup, device=0)
