@@ -45,19 +45,27 @@ def build_ranges(sim, lengths, contig_ids=None):
             if not rds[i].mutation_settings.has_mutations and rds[i].stop >= rds[i].start:
                 nxt = rds[i].start
         prev_stop = -1
+        blocked_until = -1     # last base covered by a blocked (None) range seen so far (ranges are sorted by start)
         for rd, limit in zip(rds, limits):
             ms = rd.mutation_settings
             if not ms.has_mutations:
+                blocked_until = max(blocked_until, int(rd.stop))
+                continue
+            # Overlapping explicit ranges (gene annotations overlap; every RMT shipped with the reference has them)
+            # make the reference's gap filler produce negative-length ranges and die in random.sample.  Here blocked
+            # ranges win: a range with mutations is cut back to the part no None range covers; nothing is left of a
+            # negative-length filler.
+            start = max(int(rd.start), blocked_until + 1)
+            stop = min(int(rd.stop), int(limit) - 1)
+            if stop < start:
                 continue
             total = sum(ms.mut_rates.values())
-            k = int(((rd.stop - rd.start) + 1) * total)
-            if k < 0:
-                raise ValueError("Sample larger than population or is negative")   # what random.sample raises (util.py:104)
-            if k == 0:
+            k = int(((stop - start) + 1) * total)
+            if k <= 0:
                 continue
-            if rd.start <= prev_stop:
+            if start <= prev_stop:
                 raise RangeOverlapError(f"Range {rd.start+1}-{rd.stop+1} of chromosome {chrom.number+1} overlaps the previous range")
-            prev_stop = rd.stop
+            prev_stop = stop
             p = np.zeros(7)
             for t, c in ms.mut_chances.items():
                 p[DEVICE_CODE[t]] = c
@@ -70,7 +78,7 @@ def build_ranges(sim, lengths, contig_ids=None):
                 if ms.mut_lengs and src in ms.mut_lengs["min"] and src in ms.mut_lengs["max"]:
                     lo[DEVICE_CODE[t]] = int(ms.mut_lengs["min"][src])
                     hi[DEVICE_CODE[t]] = int(ms.mut_lengs["max"][src])
-            rows.append((local[chrom.number], int(rd.start), int(rd.stop), k, int(limit), cdf, lo, hi))
+            rows.append((local[chrom.number], start, stop, k, int(limit), cdf, lo, hi))
     rows.sort(key=lambda r: (r[0], r[1]))
     arr = (MsRange * max(1, len(rows)))()
     for a, (c, start, stop, k, limit, cdf, lo, hi) in zip(arr, rows):
