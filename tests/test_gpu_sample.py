@@ -341,3 +341,23 @@ def test_streamed_run_is_byte_identical_to_upload_sample_apply_download(group_mi
     with pytest.raises(Exception):
         eng.mutate_streamed(77, raw, fa[:1000], vcf, group_min)
     eng.close()
+
+
+def test_streamed_run_with_nothing_to_mutate():
+    """Rates too low for a single candidate (and no ranges at all): the streamed call still returns the wrapped,
+    upper-cased genome and an empty VCF body."""
+    from mutation_simulator_b200.engine import Engine
+    lens = [1000, 37]
+    contigs = random_contigs(lens, seed=2, alphabet=b"ACGTacgt", bpl=50)
+    raw = np.frombuffer(b"".join(c[2] for c in contigs), dtype=np.uint8).copy()
+    want = b"".join(b">" + c[1] + b"\n" + b"\n".join(c[2].upper()[o:o + 50] for o in range(0, len(c[2]), 50)) + b"\n" for c in contigs)
+    want = want[:-1]    # no line break after a partial last line at the end of the file (fasta_writer.py:44-47)
+    for ranges in ([], args_ranges(lens, [1e-5, 0, 0, 0, 0, 0], [1] * 7, [1] * 7)):
+        ranges = [r for r in ranges if r["k"] > 0]
+        eng = Engine(0)
+        eng.declare_genome(lens, [50, 50], [c[1] for c in contigs], [c[0] for c in contigs])
+        eng.set_ranges(ranges, [1] * 7, 1, 0.5)
+        fa, vcf = np.zeros(4096, np.uint8), np.zeros(64, np.uint8)
+        fb, vb = eng.mutate_streamed(5, raw, fa, vcf)
+        assert vb == 0 and fa[:fb].tobytes() == want
+        eng.close()
