@@ -204,23 +204,8 @@ __global__ void __launch_bounds__(256) k_fill_gaps(uint32_t* blk, const Gap* gap
 }
 
 // ---- K6: splice + SNP + line wrap -----------------------------------------------------
-// One CTA per piece (= 16 KiB tile of the output file image intersected with one
-// contig body).  Pass A: every thread tries the vector path for its 16-byte groups
-// (shifted copy + SNP patches + one line break, 2 x LDG.128 -> 1 x STG.128) and
-// queues the rest; pass B: the queued groups are drained densely through the
-// generic per-byte path.
+// One CTA per piece (= 16 KiB tile of the output file image intersected with one contig body).
 constexpr int SPLICE_THREADS = 256;
-constexpr int MAX_TILE_GROUPS = 2048;
-
-struct LoadWinGlobal {
-    const uint8_t* genome;
-    __device__ __forceinline__ void operator()(int64_t idx, uint32_t win[8]) const {
-        const uint4 a = __ldg(reinterpret_cast<const uint4*>(genome + idx));
-        const uint4 b = __ldg(reinterpret_cast<const uint4*>(genome + idx + 16));
-        win[0] = a.x; win[1] = a.y; win[2] = a.z; win[3] = a.w;
-        win[4] = b.x; win[5] = b.y; win[6] = b.z; win[7] = b.w;
-    }
-};
 
 // Run-centric splice.  SNPs do not move anything, so between two consecutive non-SNP
 // records the output is one shifted copy of the input ("run", ~290 bases at human-like
@@ -347,26 +332,6 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_glob
                  : "memory");
 }
 
-// shifted copy shared -> shared: n bytes from stage[so..] (any alignment) to tile[d0..]
-__device__ __forceinline__ void warp_copy_stage_to_tile(uint8_t* tile, const uint8_t* stage, uint32_t so, uint32_t d0, uint32_t n, int lane) {
-    const uint32_t d1 = d0 + n;
-    const uint32_t a0 = (d0 + 15u) & ~15u, a1 = d1 & ~15u;
-    if (a0 >= a1) {
-        const uint32_t x = d0 + lane;
-        if (x < d1) tile[x] = stage[so + lane];
-        return;
-    }
-    {
-        const uint32_t x = lane < 16 ? d0 + lane : a1 + (lane - 16);
-        if (x < (lane < 16 ? a0 : d1)) tile[x] = stage[so + (x - d0)];
-    }
-    for (uint32_t c = a0 + 16u * lane; c < a1; c += 512u) {
-        const uint32_t s = so + (c - d0);
-        const uint4* w = reinterpret_cast<const uint4*>(stage + (s & ~15u));
-        *reinterpret_cast<uint4*>(tile + c) = shift16(w[0], w[1], s & 15u);
-    }
-}
-
 // byte x of a clipped non-raw payload; s0 as prepared in S2 (RC: last source index, RAND: the cached 2-bit bases
 // shifted to the first byte, RANDL (insert reaching past its 32 cached bases): pos << 32 | first byte index)
 constexpr uint32_t K_RANDL = 7;
@@ -418,22 +383,6 @@ __device__ __forceinline__ void warp_copy_to_tile(uint8_t* tile, const uint8_t* 
         const uint4* w = reinterpret_cast<const uint4*>(genome + (s & ~(int64_t)15));
         const uint4 wa = __ldg(w), wb = __ldg(w + 1);
         *reinterpret_cast<uint4*>(tile + c) = shift16(wa, wb, (uint32_t)(s & 15));
-    }
-}
-
-// number of records among recs[r0 .. ) (r0 may be rec_lo-1 = the virtual record with out 0) whose out <= target,
-// minus one, as an absolute index: the last record with out <= target.
-__device__ __forceinline__ int64_t warp_last_le(const Rec* recs, const Contig& k, int64_t r0, uint32_t target, int lane) {
-    int64_t r = r0;
-    for (;;) {
-        const int64_t my = r + lane;
-        uint32_t o;
-        if (my < k.rec_lo) o = 0u;
-        else if (my < k.rec_hi) o = __ldg(&recs[my].out);
-        else o = 0xffffffffu;
-        const int cnt = __popc(__ballot_sync(0xffffffffu, o <= target && my < k.rec_hi));
-        if (cnt < 32) return r + cnt - 1;
-        r += 32;
     }
 }
 
