@@ -89,6 +89,8 @@ struct ms_ctx {
     int32_t block[7] = {1, 1, 1, 1, 1, 1, 1};
     double p_ti = 0.5;
     int32_t min_dist = 1;
+    int64_t maxspan = 2;          // longest blocking span of any candidate (set with the ranges)
+    int any_small = 0, any_large = 0;
     bool counts_valid = false;
     bool sizes_valid = false;     // keep/cand_val hold (delta, vcf size) of the current records (written by k_build_records)
     ms::Seed seed_last{0, 0};     // seed of the last ms_sample (K_RAND payloads are a function of it)

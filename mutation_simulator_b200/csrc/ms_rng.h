@@ -10,6 +10,7 @@
 //    a uniform k-subset.
 #pragma once
 #include <stdint.h>
+#include <math.h>
 
 #if defined(__CUDACC__)
 #define MS_HD __host__ __device__ __forceinline__
@@ -91,12 +92,17 @@ MS_HD double unit_double(uint32_t lo, uint32_t hi) {
 MS_HD uint64_t bounded(uint64_t r, uint64_t n) { return mulhi64(r, n); }
 
 // ---------------------------------------------------------------------------
-// Pseudo-random permutation of range(n), n < 2^32, by an alternating Feistel
-// network over ceil(log2 n) bits with cycle walking (values >= n are re-encrypted
-// until they fall inside the range; expected < 2 walks since 2^bits < 2n).
+// Pseudo-random permutation of range(n), n < 2^32: a Feistel network over the
+// mixed-radix domain [0,a) x [0,b) with a = ceil(sqrt n), b = ceil(n / a) and
+// modular addition as the combiner, plus cycle walking for the a*b - n < a + b
+// values that fall outside the range (re-encrypted until they land inside).
+// Because a*b exceeds n by at most ~2 sqrt(n), a walk is needed with probability
+// ~2/sqrt(n): on a GPU every lane of a warp finishes in the same pass (the
+// power-of-two Feistel this replaces walked with probability up to 1/2 and ran
+// at 16-18 active lanes, profiles/r1e, r1m).
 // ---------------------------------------------------------------------------
-// Rounds: 8 on domains of >= 12 bits (statistically flat for k-subsets of genome-sized ranges);
-// 16 on tiny domains, where each round function has only a few output bits (tests/test_emu.py checks
+// Rounds: 8 on domains of >= 2^12 values (statistically flat for k-subsets of genome-sized ranges);
+// 16 on tiny domains, where each round function has only a few output values (tests/test_emu.py checks
 // that all arrangements of small domains are equally likely over keys).
 constexpr int PRP_MAX_ROUNDS = 16;
 
@@ -104,8 +110,8 @@ struct Prp {
     uint32_t key[PRP_MAX_ROUNDS];
     uint32_t n;        // domain size
     uint32_t rounds;
-    uint32_t abits;    // high half width
-    uint32_t bbits;    // low half width
+    uint32_t a;        // radix of the high digit
+    uint32_t b;        // radix of the low digit (a * b >= n)
 };
 
 MS_HD uint32_t mix32(uint32_t x, uint32_t k) {
@@ -122,42 +128,44 @@ MS_HD uint32_t mix32(uint32_t x, uint32_t k) {
 MS_HD Prp make_prp(Seed s, uint32_t contig, uint32_t purpose, uint64_t idx, uint32_t n) {
     Prp p;
     p.n = n;
-    uint32_t bits = 2;
-    while (bits < 32 && (1ull << bits) < (uint64_t)n) ++bits;
-    p.rounds = bits >= 12 ? 8u : 16u;
+    p.rounds = n >= 4096u ? 8u : 16u;
     for (uint32_t b = 0; b < PRP_MAX_ROUNDS / 4; ++b) {
         U4 r{0, 0, 0, 0};
         if (4 * b < p.rounds) r = draw(s, contig, purpose | ((uint32_t)(b + 1) << 8), idx);
         p.key[4 * b + 0] = r.x; p.key[4 * b + 1] = r.y; p.key[4 * b + 2] = r.z; p.key[4 * b + 3] = r.w;
     }
-    p.abits = bits / 2;
-    p.bbits = bits - p.abits;
+    // a = ceil(sqrt(n)) by integer correction of the floating-point root (n < 2^32: a <= 65536)
+    uint32_t a = (uint32_t)sqrt((double)n);
+    while ((uint64_t)a * a < (uint64_t)n) ++a;
+    while (a > 1u && (uint64_t)(a - 1u) * (a - 1u) >= (uint64_t)n) --a;
+    if (a == 0u) a = 1u;
+    p.a = a;
+    p.b = n == 0u ? 1u : (uint32_t)(((uint64_t)n + a - 1u) / a);
     return p;
 }
 
 MS_HD uint32_t prp_apply(const Prp& p, uint32_t j) {
-    const uint32_t amask = (p.abits >= 32) ? 0xFFFFFFFFu : ((1u << p.abits) - 1u);
-    const uint32_t bmask = (p.bbits >= 32) ? 0xFFFFFFFFu : ((1u << p.bbits) - 1u);
+    const uint32_t a = p.a, b = p.b;
     uint32_t x = j;
     do {
-        uint32_t a = (x >> p.bbits) & amask, b = x & bmask;
+        uint32_t hi = x / b, lo = x - hi * b;          // hi < a because x < n <= a * b
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
         for (int r = 0; r < 8; r += 2) {
-            a ^= mix32(b, p.key[r]) & amask;
-            b ^= mix32(a, p.key[r + 1]) & bmask;
+            hi += mulhi32(mix32(lo, p.key[r]), a);      if (hi >= a) hi -= a;
+            lo += mulhi32(mix32(hi, p.key[r + 1]), b);  if (lo >= b) lo -= b;
         }
         if (p.rounds > 8u) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
             for (int r = 8; r < PRP_MAX_ROUNDS; r += 2) {
-                a ^= mix32(b, p.key[r]) & amask;
-                b ^= mix32(a, p.key[r + 1]) & bmask;
+                hi += mulhi32(mix32(lo, p.key[r]), a);      if (hi >= a) hi -= a;
+                lo += mulhi32(mix32(hi, p.key[r + 1]), b);  if (lo >= b) lo -= b;
             }
         }
-        x = (a << p.bbits) | b;
+        x = hi * b + lo;
     } while (x >= p.n);
     return x;
 }

@@ -73,6 +73,7 @@ k_draw(const Range* ranges, const int64_t* cand_lo, int32_t n_ranges, const Prp*
     Prp p;
     int64_t g_cand_lo = 0, g_store_lo = 0;
     uint32_t g_nb = 1u, g_bscale = 0u, g_bucket_lo = 0u, g_k = 0u;
+    // (issuing a thread's eight bucket atomics back to back before the stores was measured: slower, 0.99 -> 1.11 ms)
 #pragma unroll 2
     for (int it = 0; it < DRAW_PER_THREAD; ++it) {
         const int64_t s = s0 + (int64_t)it * DRAW_THREADS + threadIdx.x;
@@ -127,6 +128,16 @@ __device__ __forceinline__ uint32_t bitonic_sorted(uint32_t v, int tid, uint32_t
     return v;
 }
 
+// Everything a sort CTA needs to start, built on the host with the range table (the lookups it replaces were a
+// chain of dependent loads and two 64-bit divisions on one thread at the head of every CTA, profiles/r1m).
+struct BucketInfo {
+    int64_t store_base;   // first slot of the bucket in the bucket store
+    uint32_t ridx;        // its range
+    uint32_t vlo;         // smallest value that falls into it
+    uint32_t nw;          // 32-bit bitmap words its value span needs
+    uint32_t pad;
+};
+
 constexpr int SMALL_BUCKET = 128;   // buckets of at most this many keys are sorted four per CTA (k_sort_emit_small)
 
 // position, type, length and blocking reach of the candidate that ends up in `slot` (K2)
@@ -150,7 +161,7 @@ __device__ __forceinline__ void emit_candidate(const Range& g, const Contig& ct,
 // Small buckets (many-small-contig genomes: a 5 kbp contig has ~67 candidates): four buckets per CTA, 128 threads
 // each, instead of one mostly idle 512-thread CTA per bucket (C5: 4.0 ms -> see profiles).
 __global__ void __launch_bounds__(SORT_THREADS)
-k_sort_emit_small(const Range* ranges, const uint32_t* bucket_range, const Contig* contigs, const int64_t* bucket_off,
+k_sort_emit_small(const Range* ranges, const BucketInfo* binfo, const Contig* contigs, const int64_t* bucket_off,
                   int64_t n_buckets, const uint32_t* store, Seed seed, int32_t min_dist, const int32_t* block7, int positions_only,
                   int64_t* cand_gpos, uint8_t* cand_type, uint32_t* cand_len, int64_t* cand_reach, uint32_t* cand_range) {
     __shared__ uint32_t sm[SORT_THREADS];
@@ -163,7 +174,7 @@ k_sort_emit_small(const Range* ranges, const uint32_t* bucket_range, const Conti
     int cnt = 0;
     if (b < n_buckets) { lo = bucket_off[b]; cnt = (int)(bucket_off[b + 1] - lo); }
     const bool mine = cnt > 0 && cnt <= SMALL_BUCKET;
-    if (mine && t == 0) { ridx4[grp] = bucket_range[b]; g4[grp] = ranges[ridx4[grp]]; }
+    if (mine && t == 0) { ridx4[grp] = binfo[b].ridx; g4[grp] = ranges[ridx4[grp]]; }
     if (tid < 7) blk[tid] = block7[tid];
     __syncthreads();
     uint32_t v = 0xFFFFFFFFu;
@@ -176,14 +187,12 @@ k_sort_emit_small(const Range* ranges, const uint32_t* bucket_range, const Conti
 
 // K1d + K2: sort one bucket in shared memory, then write position, type, length and reach.
 __global__ void __launch_bounds__(SORT_THREADS, 3)
-k_sort_emit(const Range* ranges, const uint32_t* bucket_range, const Contig* contigs, const int64_t* bucket_off,
+k_sort_emit(const Range* ranges, const BucketInfo* binfo, const Contig* contigs, const int64_t* bucket_off,
             const uint32_t* store, Seed seed, int32_t min_dist, const int32_t* block7, int positions_only,
             int64_t* cand_gpos, uint8_t* cand_type, uint32_t* cand_len, int64_t* cand_reach, uint32_t* cand_range, Totals* tot,
             int skip_small) {
     __shared__ uint32_t sm[SORT_CAP];
-    __shared__ Range g;
     __shared__ int32_t blk[7];
-    __shared__ uint32_t s_ridx, s_vlo, s_nw;
     __shared__ uint32_t warp_tot[SORT_THREADS / 32];
     const int tid = threadIdx.x;
     const int64_t b = blockIdx.x;
@@ -191,21 +200,13 @@ k_sort_emit(const Range* ranges, const uint32_t* bucket_range, const Contig* con
     const int cnt = (int)(hi - lo);
     if (cnt <= 0 || (skip_small && cnt <= SMALL_BUCKET)) return;
     if (cnt > SORT_CAP) { if (tid == 0) raise_error_s(tot, MS_ERR_INTERNAL, 100 + b); return; }
-    if (tid == 0) {
-        s_ridx = bucket_range[b];   // (a host-built map: the binary search it replaces was five dependent loads per CTA)
-        g = ranges[s_ridx];
-        // values of this bucket: mulhi32(v, bscale) == bl  <=>  ceil(bl * 2^32 / bscale) <= v < ceil((bl + 1) * 2^32 / bscale)
-        const uint64_t bl = (uint64_t)(b - g.bucket_lo), sc = g.bscale;
-        const uint64_t vlo = (g.nb == 1u || bl == 0) ? 0ull : ((bl << 32) + sc - 1) / sc;
-        const uint64_t vhi = (g.nb == 1u || bl + 1 == g.nb) ? (uint64_t)g.n : (((bl + 1) << 32) + sc - 1) / sc;
-        s_vlo = (uint32_t)vlo;
-        s_nw = (uint32_t)((vhi - vlo + 31) >> 5);
-    }
+    const BucketInfo bi = binfo[b];                 // one 24-byte broadcast load; no per-CTA lookups, no barrier
+    const Range& g = ranges[bi.ridx];               // fields are read where they are needed (L1 broadcast)
+    const uint32_t s_ridx = bi.ridx, s_nw = bi.nw, s_vlo = bi.vlo;
     if (tid < 7) blk[tid] = block7[tid];
     int n2 = 32;
     while (n2 < cnt) n2 <<= 1;
-    __syncthreads();
-    const uint32_t* src = store + bucket_store(g, (uint32_t)b);
+    const uint32_t* src = store + bi.store_base;
     if (cnt >= 64 && s_nw <= (uint32_t)SORT_CAP) {
         // Dense bucket: the keys are distinct (a permutation's values) and span at most 32 Ki positions, so the
         // sorted order is read off a bitmap — set one bit per key, prefix-sum the popcounts, write each key to
@@ -453,17 +454,16 @@ static int draw_and_sort(ms_ctx* c, Seed seed, uint32_t purpose, int32_t min_dis
     stage_end(c, ST_SAMPLE_POS);
 
     stage_begin(c, ST_SAMPLE_TYPE);
-    int any_small = 0, any_large = 0;
-    for (const Range& g : c->h_ranges) { if (g.nb == 1u && g.k <= (uint32_t)SMALL_BUCKET) any_small = 1; else any_large = 1; }
+    const int any_small = c->any_small, any_large = c->any_large;
     if (any_small) {
         k_sort_emit_small<<<(unsigned)ceil_div(c->n_buckets, SORT_THREADS / SMALL_BUCKET), SORT_THREADS, 0, st>>>(
-            d_ranges, c->bucket_range.as<uint32_t>(), d_ctg, d_boff, c->n_buckets, c->cand_sorted.as<uint32_t>(), seed, min_dist, d_block, positions_only,
+            d_ranges, c->bucket_range.as<BucketInfo>(), d_ctg, d_boff, c->n_buckets, c->cand_sorted.as<uint32_t>(), seed, min_dist, d_block, positions_only,
             c->svec.as<int64_t>(), c->cand_type.as<uint8_t>(), c->cand_len.as<uint32_t>(), c->cand_reach.as<int64_t>(),
             c->lvec.as<uint32_t>());
         MS_LAUNCH_CHECK(c);
     }
     if (any_large) {
-        k_sort_emit<<<(unsigned)c->n_buckets, SORT_THREADS, 0, st>>>(d_ranges, c->bucket_range.as<uint32_t>(), d_ctg, d_boff,
+        k_sort_emit<<<(unsigned)c->n_buckets, SORT_THREADS, 0, st>>>(d_ranges, c->bucket_range.as<BucketInfo>(), d_ctg, d_boff,
                                                                      c->cand_sorted.as<uint32_t>(), seed, min_dist, d_block, positions_only,
                                                                      c->svec.as<int64_t>(), c->cand_type.as<uint8_t>(), c->cand_len.as<uint32_t>(),
                                                                      c->cand_reach.as<int64_t>(), c->lvec.as<uint32_t>(), d_tot, any_small);
@@ -506,14 +506,7 @@ int sample_pipeline(ms_ctx* c, uint64_t seed64, bool defer_bases) {
     uint8_t* d_anchor = c->cand_pm.as<uint8_t>();
     uint8_t* d_accept = c->cand_accept.as<uint8_t>();
     MS_CUDA(c, cudaMemsetAsync(d_accept, 0, (size_t)K, st));
-    // longest stretch a candidate can block past its own start (reach - pos), over all ranges and types
-    int64_t maxspan = 2;
-    for (const Range& g : c->h_ranges) {
-        for (int t = 0; t < 7; ++t) {
-            const int64_t len = (t == T_SN || t == T_IN || t == T_TLI) ? 1 : g.maxlen[t];
-            maxspan = std::max<int64_t>(maxspan, len + c->block[t] + 1);
-        }
-    }
+    const int64_t maxspan = c->maxspan;   // (per-range host loops live in upload_ranges: C5 has 200 k ranges)
     if (maxspan <= 4096) {
         k_resolve_local<<<(unsigned)ceil_div(K, 256), 256, 0, st>>>(K, d_gpos, d_reach, d_type, maxspan, d_accept);
         MS_LAUNCH_CHECK(c);
@@ -638,6 +631,15 @@ static int upload_ranges(ms_ctx* c, int32_t min_dist, const std::vector<Contig>&
         K += g.k; NB += g.nb;
     }
     cand_lo[R] = K; bucket_lo[R] = NB;
+    // longest stretch a candidate can block past its own start (reach - pos), over all ranges and types; bucket classes
+    c->maxspan = 2; c->any_small = 0; c->any_large = 0;
+    for (const Range& g : c->h_ranges) {
+        for (int t = 0; t < 7; ++t) {
+            const int64_t len = (t == T_SN || t == T_IN || t == T_TLI) ? 1 : g.maxlen[t];
+            c->maxspan = std::max<int64_t>(c->maxspan, len + c->block[t] + 1);
+        }
+        if (g.nb == 1u && g.k <= (uint32_t)SMALL_BUCKET) c->any_small = 1; else c->any_large = 1;
+    }
     if (K >= (int64_t)0x7FFFFFF0) MS_FAIL(c, MS_ERR_LIMIT, "more than 2^31 candidates in one call");
     c->n_ranges = R; c->n_candidates = K; c->n_buckets = NB; c->min_dist = min_dist; c->store_entries = STORE;
     const size_t bytes = sizeof(Range) * (size_t)R + 2 * sizeof(int64_t) * (size_t)(R + 1) + sizeof(Prp) * (size_t)R + 64;
@@ -650,11 +652,22 @@ static int upload_ranges(ms_ctx* c, int32_t min_dist, const std::vector<Contig>&
     MS_CUDA(c, cudaMemcpyAsync(d_cand_lo + (R + 1), bucket_lo.data(), sizeof(int64_t) * (size_t)(R + 1), cudaMemcpyHostToDevice, st));
     int32_t* d_block = reinterpret_cast<int32_t*>(reinterpret_cast<Prp*>(d_cand_lo + 2 * (R + 1)) + R);
     MS_CUDA(c, cudaMemcpyAsync(d_block, c->block, sizeof(int32_t) * 7, cudaMemcpyHostToDevice, st));
-    std::vector<uint32_t> br((size_t)NB + 1, 0u);   // sort bucket -> range
-    for (int32_t r = 0; r < R; ++r)
-        for (int64_t b = bucket_lo[r]; b < bucket_lo[r + 1]; ++b) br[(size_t)b] = (uint32_t)r;
-    MS_CUDA(c, c->bucket_range.ensure(br.size() * 4));
-    MS_CUDA(c, cudaMemcpyAsync(c->bucket_range.p, br.data(), br.size() * 4, cudaMemcpyHostToDevice, st));
+    std::vector<BucketInfo> br((size_t)NB + 1, BucketInfo{});   // per sort bucket: range, storage, value span
+    for (int32_t r = 0; r < R; ++r) {
+        const Range& g = c->h_ranges[r];
+        const uint64_t sc = g.bscale;
+        const uint32_t cap = g.nb == 1u ? g.k : (uint32_t)BUCKET_CAP;
+        for (uint64_t bl = 0; bl < g.nb; ++bl) {
+            // values of bucket bl: mulhi32(v, bscale) == bl  <=>  ceil(bl * 2^32 / bscale) <= v < ceil((bl + 1) * 2^32 / bscale)
+            const uint64_t vlo = (g.nb == 1u || bl == 0) ? 0ull : ((bl << 32) + sc - 1) / sc;
+            const uint64_t vhi = (g.nb == 1u || bl + 1 == g.nb) ? (uint64_t)g.n : (((bl + 1) << 32) + sc - 1) / sc;
+            BucketInfo& bi = br[(size_t)(bucket_lo[r] + (int64_t)bl)];
+            bi.store_base = g.store_lo + (int64_t)bl * cap;
+            bi.ridx = (uint32_t)r; bi.vlo = (uint32_t)vlo; bi.nw = (uint32_t)((vhi - vlo + 31) >> 5); bi.pad = 0u;
+        }
+    }
+    MS_CUDA(c, c->bucket_range.ensure(br.size() * sizeof(BucketInfo)));
+    MS_CUDA(c, cudaMemcpyAsync(c->bucket_range.p, br.data(), br.size() * sizeof(BucketInfo), cudaMemcpyHostToDevice, st));
     MS_CUDA(c, cudaStreamSynchronize(st));
     return MS_OK;
 }
