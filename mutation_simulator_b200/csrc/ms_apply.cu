@@ -695,8 +695,8 @@ __global__ void k_headers(const Contig* contigs, int32_t n_contigs, const uint8_
 // copy jobs and moved by whole warps afterwards (profiles/r1b: the per-byte REF/ALT
 // loops ran on 1.5 lanes and were half of all instructions).
 constexpr int VCF_THREADS = 256;
-constexpr int VCF_SMEM = 17 * 1024;
-constexpr int VCF_MAX_JOBS = 2 * VCF_THREADS;
+constexpr int VCF_SMEM = 13 * 1024;
+constexpr int VCF_MAX_JOBS = 192;
 enum SegMode : uint32_t { SM_IMM = 0, SM_RAW = 1, SM_CONV = 2, SM_RC = 3, SM_LIT = 4, SM_RAND = 5, SM_RANDL = 6 };   // RAND: src = cached 2-bit bases (<= 32); RANDL: src = gid << 32 | pos
 struct Seg { int64_t src; uint32_t len; uint32_t mode; };
 struct CopyJob { int64_t src; uint32_t dst; uint32_t len_mode; };   // len | mode << 29
@@ -818,7 +818,7 @@ __device__ __forceinline__ void vcf_emit_uniform(const VcfView& v, const Contig&
     put_lit(p, "\tGT\t1\n", 6);
 }
 
-__global__ void __launch_bounds__(VCF_THREADS)
+__global__ void __launch_bounds__(VCF_THREADS, 8)
 k_vcf_write(VcfView v, const Rec* recs, int64_t rec_lo, int64_t n_recs, const Contig* contigs, const Tables* tables, const int64_t* V,
             uint8_t* vcf) {
     __shared__ uint8_t s_conv[256], s_comp[256];
