@@ -186,7 +186,7 @@ k_sort_emit_small(const Range* ranges, const BucketInfo* binfo, const Contig* co
 }
 
 // K1d + K2: sort one bucket in shared memory, then write position, type, length and reach.
-__global__ void __launch_bounds__(SORT_THREADS, 3)
+__global__ void __launch_bounds__(SORT_THREADS, 4)
 k_sort_emit(const Range* ranges, const BucketInfo* binfo, const Contig* contigs, const int64_t* bucket_off,
             const uint32_t* store, Seed seed, int32_t min_dist, const int32_t* block7, int positions_only,
             int64_t* cand_gpos, uint8_t* cand_type, uint32_t* cand_len, int64_t* cand_reach, uint32_t* cand_range, Totals* tot,
