@@ -460,7 +460,7 @@ k_splice(SpliceView v, const Contig* contigs, const PieceDesc* pieces, const Tab
             if (pos < SP_RUN_CAP) { nout[pos] = o; nidx[pos] = (uint16_t)t; }
         }
         n_runs += total;
-        __syncthreads();
+        if (base + SPLICE_THREADS < n_rec) __syncthreads();   // warp_tot is reused by the next round (the barrier below covers the last one)
     }
     if (n_runs > SP_RUN_CAP) { if (tid == 0) fallback = 1; n_runs = 0; }
     if (tid == 0 && n_runs <= SP_RUN_CAP) nout[n_runs] = b_hi;
@@ -509,14 +509,14 @@ k_splice(SpliceView v, const Contig* contigs, const PieceDesc* pieces, const Tab
             }
         }
     }
+    // one warp waits on the mbarrier (the TMA copy of the input span); the others park at the CTA barrier instead of
+    // spinning on try_wait (8 spinning warps were 11.6 % of all issued instructions, profiles/r1h).  The same barrier
+    // publishes the segment list.
+    if (warp == 0) mbar_wait(&bar, 0u);
     __syncthreads();
 
     if (!fallback) {
         const int ns = n_segs;
-        // one warp waits on the mbarrier; the others park at the CTA barrier instead of spinning on try_wait
-        // (8 spinning warps were 11.6 % of all issued instructions, profiles/r1h)
-        if (warp == 0) mbar_wait(&bar, 0u);
-        __syncthreads();
         // ---- S1: shifted copies shared -> shared, one half-warp per segment
         {
             const int half = lane >> 4, hl = lane & 15;
