@@ -248,7 +248,7 @@ def file_to_file(args, wl, eng, rank, world, lengths_all, names_all, total_bases
         a.device = int(os.environ.get("LOCAL_RANK", "0"))
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        fasta = load_fasta(a.infile, device=a.device if world == 1 else None)   # one GPU: FASTA ingest on the device
+        fasta = load_fasta(a.infile, device=a.device)   # FASTA ingest on the device (every rank; each keeps its contigs)
         t1 = time.perf_counter()
         sim = SimulationSettings.from_args(a, fasta, True)
         m = Mutator(a, fasta, sim)

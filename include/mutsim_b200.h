@@ -122,6 +122,9 @@ int ms_fasta_index(ms_ctx* ctx, int64_t* hdr_off, int64_t* seq_off, int64_t* len
 int ms_fasta_commit(ms_ctx* ctx, const uint32_t* gid, const uint8_t* headers, const int64_t* hdr_off,
                     const uint8_t* names, const int64_t* name_off, int32_t* regular);
 int ms_genome_read(ms_ctx* ctx, int64_t off, int64_t n, uint8_t* dst);
+/* Keep only the listed contigs of the resident genome (in the given order; their gid — the RNG key — is unchanged).
+ * With several GPUs every rank ingests the file and keeps its share (mutator.py:111 iterates contigs independently). */
+int ms_genome_subset(ms_ctx* ctx, const int32_t* ids, int32_t n);
 /* Contig table only: the bases follow with ms_mutate_streamed. */
 int ms_genome_declare(ms_ctx* ctx, int64_t total_bases, int32_t n_contigs, const int64_t* contig_len,
                       const int32_t* bpl, const uint32_t* gid, const uint8_t* headers, const int64_t* hdr_off,

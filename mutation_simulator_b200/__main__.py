@@ -22,8 +22,11 @@ def initialize():
     args = get_args()
     try:
         from . import distributed
-        # one GPU: the file is parsed on the device and stays there for the engines
-        fasta = load_fasta(args.infile, device=getattr(args, "device", 0) if distributed.rank_world()[1] == 1 else None)
+        # the file is parsed on the GPU and stays there for the engines; with several GPUs every
+        # rank ingests it and later keeps its share of the contigs
+        multi = distributed.rank_world()[1] > 1
+        fasta = load_fasta(args.infile, device=distributed.local_device(getattr(args, "device", 0)) if multi
+                           else getattr(args, "device", 0))
         if args.mode == "args":
             sim = SimulationSettings.from_args(args, fasta, args.ignore_warnings)
         elif args.mode == "it":

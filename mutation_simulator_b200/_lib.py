@@ -54,6 +54,7 @@ PROTOTYPES = {
     "ms_fasta_index": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64]),
     "ms_fasta_commit": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     "ms_genome_read": (C.c_int, [_P, _I64, _I64, _P]),
+    "ms_genome_subset": (C.c_int, [_P, _P, C.c_int32]),
     "ms_genome_declare": (C.c_int, [_P, _I64, C.c_int32, _P, _P, _P, _P, _P, _P, _P]),
     "ms_mutate_streamed": (C.c_int, [_P, C.c_uint64, _P, _P, _I64, _P, _I64, _P, _P, _I64]),
     "ms_contig_layout": (C.c_int, [_P, _P, _P, _P, _P]),

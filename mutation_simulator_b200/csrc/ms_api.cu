@@ -237,6 +237,41 @@ int ms_fasta_commit(ms_ctx* c, const uint32_t* gid, const uint8_t* headers, cons
     return set_contig_table(c, total, n, len.data(), bpl.data(), gid, headers, hdr_off, names, name_off);
 }
 
+int ms_genome_subset(ms_ctx* c, const int32_t* ids, int32_t n) {
+    if (!c || !ids || n <= 0) return MS_ERR_ARG;
+    if (c->n_contigs <= 0 || !c->genome.p) MS_FAIL(c, MS_ERR_STATE, "ms_genome_subset: no genome resident");
+    MS_CUDA(c, cudaSetDevice(c->device));
+    std::vector<Contig> keep((size_t)n);
+    int64_t total = 0;
+    for (int i = 0; i < n; ++i) {
+        if (ids[i] < 0 || ids[i] >= c->n_contigs) MS_FAIL(c, MS_ERR_ARG, "ms_genome_subset: contig %d out of range", ids[i]);
+        keep[i] = c->h_contigs[ids[i]];
+        total += keep[i].len;
+    }
+    DevBuf fresh;
+    MS_CUDA(c, fresh.ensure((size_t)total + 64 + (size_t)c->foreign_cap + 64));
+    int64_t off = 0;
+    for (int i = 0; i < n; ++i) {
+        if (keep[i].len > 0)
+            MS_CUDA(c, cudaMemcpyAsync(fresh.as<uint8_t>() + off, c->genome.as<uint8_t>() + keep[i].goff, (size_t)keep[i].len,
+                                       cudaMemcpyDeviceToDevice, c->stream));
+        keep[i].goff = off; keep[i].out_len = keep[i].len; keep[i].rec_lo = keep[i].rec_hi = 0;
+        off += keep[i].len;
+    }
+    MS_CUDA(c, cudaMemsetAsync(fresh.as<uint8_t>() + total, 'N', 64, c->stream));
+    MS_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->genome.release();
+    c->genome = fresh;
+    c->h_contigs = keep;              // header / name blobs stay as they are: the kept entries still point into them
+    c->n_contigs = n;
+    c->total_bases = total;
+    MS_CUDA(c, cudaMemcpyAsync(c->contigs.p, c->h_contigs.data(), sizeof(Contig) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    MS_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->n_recs = 0; c->lit_bytes = 0; c->n_ranges = 0; c->sizes_valid = false; c->counts_valid = false;
+    c->fasta_bytes = 0; c->vcf_bytes = 0;
+    return MS_OK;
+}
+
 int ms_genome_read(ms_ctx* c, int64_t off, int64_t n, uint8_t* dst) {
     if (!c || off < 0 || n < 0 || (n > 0 && !dst)) return MS_ERR_ARG;
     if (off + n > c->total_bases) MS_FAIL(c, MS_ERR_ARG, "ms_genome_read: range outside the genome");

@@ -125,6 +125,16 @@ class Engine:
                                               _ptr(self._noff), C.byref(reg)))
         return bool(reg.value)
 
+    def subset_genome(self, ids):
+        """Keep only contigs `ids` (local indices) of the resident genome, in that order (ms_genome_subset)."""
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        self._check(self._lib.ms_genome_subset(self._h, _ptr(ids), int(ids.size)))
+        self._len = self._len[ids].copy()
+        self._bpl = self._bpl[ids].copy()
+        self.names = [self.names[int(i)] for i in ids]
+        self.n_contigs = int(ids.size)
+        self.total_bases = int(self._len.sum())
+
     def read_genome(self, off: int, n: int) -> np.ndarray:
         out = np.empty(int(n), dtype=np.uint8)
         self._check(self._lib.ms_genome_read(self._h, int(off), int(n), _ptr(out)))

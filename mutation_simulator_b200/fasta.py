@@ -271,6 +271,12 @@ class Fasta:
         """Concatenated bases of the given contigs (file case for lazily loaded files; the GPU upper-cases)."""
         ids = list(ids)
         if self.engine is not None and self._genome is None:      # resident on the GPU: fetch the slices
+            res = getattr(self, "_resident_ids", None)
+            if res is not None:                                   # reduced to a rank's share (ms_genome_subset)
+                loc = {g: k for k, g in enumerate(res)}
+                off = np.concatenate(([0], np.cumsum([int(self.lengths[g]) for g in res])))
+                parts = [self.engine.read_genome(int(off[loc[i]]), int(self.lengths[i])) for i in ids]
+                return np.concatenate(parts) if parts else np.zeros(0, np.uint8)
             parts = [self.engine.read_genome(int(self.goff[i]), int(self.lengths[i])) for i in ids]
             return np.concatenate(parts) if parts else np.zeros(0, np.uint8)
         if self._lazy is None:
@@ -430,8 +436,14 @@ class Fasta:
         """Make this genome (or a subset of its contigs) resident on the engine's GPU."""
         # (the engine upper-cases on the device, so a mixed-case host array is fine)
         ids = list(range(len(self.names))) if contig_ids is None else list(contig_ids)
-        if engine is self.engine and self.engine is not None and contig_ids is None:
-            return ids                                            # ingested on this engine: already resident
+        if engine is self.engine and self.engine is not None:     # ingested on this engine: already resident
+            if ids != list(range(len(self.names))):
+                if self._genome is None and getattr(self, "_resident_ids", None) is None:
+                    self._resident_ids = ids                      # host views of the other contigs are gone from now on
+                    engine.subset_genome(ids)
+                elif getattr(self, "_resident_ids", None) != ids:
+                    raise ValueError("the resident genome was already reduced to a different set of contigs")
+            return ids
         bases = self.gather(ids)
         engine.upload_genome(bases, [int(self.lengths[i]) for i in ids], [int(self.bpl[i]) for i in ids],
                              [self.long_names[i].encode("latin-1") for i in ids],

@@ -151,7 +151,7 @@ class ITMutator:
         own = D.owners(parts, n_contigs)
         my_ids = parts[rank]
         device = D.local_device()
-        eng = self._engine = Engine(device)
+        eng = self._engine = getattr(fasta, "engine", None) or Engine(device)
         # breakpoints need no resident genome (keyed by global contig id): identical on every rank
         bps = self.breakpoints = self._generate_all_breakpoints(eng)
         # which partner contigs must be fetched from a peer

@@ -69,7 +69,7 @@ class Mutator:
         n_contigs = len(fasta.names)
         my_ids = D.lpt_partition(fasta.lengths, world)[self._rank] if world > 1 else list(range(n_contigs))
         seed = D.broadcast_object(run_seed(args))
-        eng = self._engine = (getattr(fasta, "engine", None) if world == 1 else None) or \
+        eng = self._engine = getattr(fasta, "engine", None) or \
             Engine(D.local_device(getattr(args, "device", 0)) if world > 1 else getattr(args, "device", 0))
         lap("engine")
         fasta.upload(eng, my_ids if world > 1 else None)
