@@ -6,6 +6,7 @@
 #include <future>
 #include <sys/mman.h>
 #include <sys/stat.h>
+#include <sys/statvfs.h>
 #include "ms_common.cuh"
 
 using namespace ms;
@@ -403,7 +404,12 @@ int ms_download_to_fd(ms_ctx* c, int which, int64_t src_off, int64_t nbytes, int
     {
         struct stat sb;
         const int64_t end = file_off + nbytes;
-        if (fstat(fd, &sb) == 0 && S_ISREG(sb.st_mode) && (sb.st_size >= end || ftruncate(fd, (off_t)end) == 0)) {
+        // (a store into a mapping of a full file system raises SIGBUS where pwrite returns ENOSPC: the mapping is
+        // only used when the file system reports room for the whole range with a margin)
+        struct statvfs vfs;
+        const bool room = fstatvfs(fd, &vfs) == 0 &&
+                          (uint64_t)vfs.f_bavail * (uint64_t)vfs.f_frsize >= (uint64_t)nbytes + (uint64_t)nbytes / 8 + (64ull << 20);
+        if (room && fstat(fd, &sb) == 0 && S_ISREG(sb.st_mode) && (sb.st_size >= end || ftruncate(fd, (off_t)end) == 0)) {
             const int64_t page = sysconf(_SC_PAGESIZE);
             map_lo = file_off & ~(page - 1);
             map_len = end - map_lo;
