@@ -33,7 +33,7 @@ def initialize():
             sim = SimulationSettings.from_it(args.interchromosomalrate, fasta, args.ignore_warnings)
         else:
             sim = SimulationSettings.from_rmt(args.rmtfile, fasta, args.ignore_warnings)
-    except _SETUP_ERRORS as e:
+    except _SETUP_ERRORS + (MutSimError,) as e:   # MutSimError: no usable CUDA device / library (there is no CPU fallback)
         exit_with_error(e, args.no_color)
     if not args.ignore_warnings:
         warn_user(args, sim)

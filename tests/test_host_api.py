@@ -135,3 +135,21 @@ def test_fasta_loader_errors(tmp_path):
     assert f.keys() == ["a", "b"] and str(f["a"]) == "ACGTNAC" and f[1].long_name == "b"
     assert f.faidx.index["a"].lenc == 5 and (tmp_path / "ok.fa.fai").exists()
     assert f["a"][1:3] == "CG" and f["a"][0:0] == "ACGTNAC" and list(f["a"]) == ["ACGTN", "AC"]
+
+
+def test_cli_without_a_gpu_fails_loudly_with_the_reference_error_convention(tmp_path):
+    """No CPU fallback: on a box without a CUDA device the CLI prints `ERROR: ...` and exits 1 (util.py:21-31)."""
+    import subprocess
+    import sys
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    (tmp_path / "a.fa").write_text(">a\nACGTACGTAC\n")
+    r = subprocess.run([sys.executable, "-m", "mutation_simulator_b200", str(tmp_path / "a.fa"), "-o", str(tmp_path / "o"),
+                        "args", "-sn", "0.1"], capture_output=True, text=True, cwd=str(Path(__file__).resolve().parent.parent))
+    assert r.returncode == 1
+    assert r.stderr.startswith("ERROR: ") and "no CPU fallback" in r.stderr
+    assert not (tmp_path / "o_ms.fa").exists() or (tmp_path / "o_ms.fa").stat().st_size == 0
