@@ -153,3 +153,29 @@ def test_cli_without_a_gpu_fails_loudly_with_the_reference_error_convention(tmp_
     assert r.returncode == 1
     assert r.stderr.startswith("ERROR: ") and "no CPU fallback" in r.stderr
     assert not (tmp_path / "o_ms.fa").exists() or (tmp_path / "o_ms.fa").stat().st_size == 0
+
+
+def test_plan_column_wise_path_equals_the_general_loop(monkeypatch):
+    """Many single-range contigs (C5) take a vectorised path through plan.build_ranges; it must build the same table."""
+    from mutation_simulator_b200.fasta import FastaRecord
+
+    class LengthsOnly:
+        def __init__(self, lens):
+            self.names = [f"c{i}" for i in range(len(lens))]
+            self.lengths = np.array(lens, np.int64)
+            self._r = [FastaRecord(n, n, None, 60, length=int(l)) for n, l in zip(self.names, lens)]
+        def __getitem__(self, k): return self._r[k] if isinstance(k, (int, np.integer)) else self._r[self.names.index(k)]
+        def keys(self): return self.names
+        def __len__(self): return len(self.names)
+
+    rng = np.random.default_rng(1)
+    lens = rng.integers(30, 9000, size=3000).tolist()
+    fa = LengthsOnly(lens)
+    a = get_args(["x.fa", "args", "-sn", "0.013", "-in", "0.001", "-inmax", "10", "-de", "0.0007", "-demax", "9", "-tl", "0.0005", "-tlmax", "50"])
+    sim = SimulationSettings.from_args(a, fa, True)
+    ids = [i for i in range(len(lens)) if i % 3]          # a rank's share
+    fast, nf = plan.build_ranges(sim, fa.lengths, ids)
+    monkeypatch.setattr(plan, "_build_single_range", lambda *a, **k: None)
+    slow, ns = plan.build_ranges(sim, fa.lengths, ids)
+    assert nf == ns > 1000
+    assert bytes(memoryview(fast))[:nf * C.sizeof(_lib.MsRange)] == bytes(memoryview(slow))[:ns * C.sizeof(_lib.MsRange)]
