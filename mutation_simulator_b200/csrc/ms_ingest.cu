@@ -145,6 +145,7 @@ int fasta_ingest(ms_ctx* c, int fd, int64_t nbytes, int32_t* n_records, int32_t*
     cudaStream_t st = c->stream;
     *n_records = 0; *regular = 0;
     c->fa_recs.clear(); c->fa_bytes = 0;
+    c->fasta_bytes = 0; c->vcf_bytes = 0;      // the image takes over the FASTA output buffer: earlier outputs are gone
     if (nbytes <= 0) return MS_OK;
     constexpr int64_t CH = ms_ctx::STAGE_BYTES;
     constexpr int NS = ms_ctx::N_STAGE;
