@@ -155,6 +155,16 @@ int ms_load_records(ms_ctx* ctx, const ms_rec* recs, int64_t n_recs, const uint8
  * (fasta_writer.py:40-65) and VcfWriter.write (vcf_writer.py:118-126): builds the
  * complete output FASTA image and the VCF body (no header) in device memory. */
 int ms_apply(ms_ctx* ctx, int64_t* fasta_bytes, int64_t* vcf_bytes);
+/* ms_apply for ONE PART of the output when several GPUs hold the same genome and the same record table (sampling is
+ * keyed by (seed, contig id, position), so every GPU that runs ms_sample with the same seed draws the same table):
+ * part `part` of `n_parts` produces the 16 KiB tiles [T*part/n, T*(part+1)/n) of the FASTA image (T = all tiles) and the
+ * VCF lines of records [M*part/n, M*(part+1)/n).  This is the chunking of a contig that is larger than one GPU's share
+ * — mutator.py:332 walks a contig serially and README.md:441 benchmarks a single 1 Gbp contig; here the cut points are
+ * tile boundaries of the OUTPUT, and the rejection carry (mutator.py:184-213), the running length delta and the TLI
+ * sources (mutator.py:401-406) that cross a cut need no exchange because only the byte-moving stages are sharded.
+ * window[6] = { fasta_bytes, vcf_bytes (whole outputs), fasta_lo, fasta_hi, vcf_lo, vcf_hi (byte ranges this part
+ * wrote; the buffers returned by ms_download / ms_download_to_fd are valid inside them only) }. */
+int ms_apply_window(ms_ctx* ctx, int32_t part, int32_t n_parts, int64_t* window);
 /* Mutator.mutate() (mutator.py:105-142) for a genome in HOST memory in one call: = ms_genome_upload + ms_sample +
  * ms_apply + ms_download of both outputs, with the copies overlapped with the kernels.  Contigs are grouped
  * (>= group_min_bases per group, 0 = 48 Mbp); the upload of group g+1, the splice of group g and the download of group g-1 run

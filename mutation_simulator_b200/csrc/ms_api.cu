@@ -341,6 +341,12 @@ int ms_apply(ms_ctx* c, int64_t* fasta_bytes, int64_t* vcf_bytes) {
     return MS_OK;
 }
 
+int ms_apply_window(ms_ctx* c, int32_t part, int32_t n_parts, int64_t* window) {
+    if (!c || !window) return MS_ERR_ARG;
+    MS_CUDA(c, cudaSetDevice(c->device));
+    return apply_window(c, part, n_parts, window);
+}
+
 static int which_buffer(ms_ctx* c, int which, void** p, int64_t* n) {
     switch (which) {
         case 0: *p = c->fasta.p; *n = c->fasta_bytes; return MS_OK;

@@ -2,6 +2,8 @@
 // line wrap -> FASTA image), K7 (VCF lines).  Replaces Mutator.__mutate_sequence
 // (mutator.py:318-426), FastaWriter (fasta_writer.py:40-65) and VcfWriter.write
 // (vcf_writer.py:118-126).
+#include <algorithm>
+#include <climits>
 #include "ms_common.cuh"
 #include "ms_scan.cuh"
 #include "ms_splice_core.h"
@@ -672,15 +674,20 @@ k_splice(SpliceView v, const Contig* contigs, const PieceDesc* pieces, const Tab
 
 // ">header\n" of every contig and the "\n" that closes a partial last line
 // (fasta_writer.py:40-47).
-__global__ void k_headers(const Contig* contigs, int32_t n_contigs, const uint8_t* headers, uint8_t* fasta) {
+// Only bytes inside the file window [w_lo, w_hi) are written (ms_apply_window: another GPU owns the rest).
+__global__ void k_headers(const Contig* contigs, int32_t n_contigs, const uint8_t* headers, uint8_t* fasta, int64_t w_lo, int64_t w_hi) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_contigs) return;
     const Contig& k = contigs[c];
-    uint8_t* d = fasta + k.hdr_off;
-    d[0] = '>';
-    for (int i = 0; i < k.hdr_len; ++i) d[1 + i] = headers[k.hdr_src + i];
-    d[1 + k.hdr_len] = '\n';
-    if (k.sep) fasta[k.body_off + k.body_bytes] = '\n';
+    const int64_t h0 = k.hdr_off;
+    if (h0 + k.hdr_len + 2 > w_lo && h0 < w_hi) {
+        auto put = [&](int64_t x, uint8_t ch) { if (x >= w_lo && x < w_hi) fasta[x] = ch; };
+        put(h0, '>');
+        for (int i = 0; i < k.hdr_len; ++i) put(h0 + 1 + i, headers[k.hdr_src + i]);
+        put(h0 + 1 + k.hdr_len, '\n');
+    }
+    const int64_t s = k.body_off + k.body_bytes;
+    if (k.sep && s >= w_lo && s < w_hi) fasta[s] = '\n';
 }
 
 // ---- K7: VCF lines -----------------------------------------------------------------
@@ -1114,7 +1121,8 @@ static int index_stage(ms_ctx* c) {
 }
 
 // splice: tiles [piece_lo, piece_lo + n_pieces) and the headers of contigs [ctg_lo, ctg_lo + n_ctg)
-static int splice_launch(ms_ctx* c, int64_t piece_lo, int64_t n_pieces, int32_t ctg_lo, int32_t n_ctg) {
+static int splice_launch(ms_ctx* c, int64_t piece_lo, int64_t n_pieces, int32_t ctg_lo, int32_t n_ctg, int64_t w_lo = 0,
+                         int64_t w_hi = INT64_MAX) {
     if (c->tile_bytes != SP_TILE_MAX) MS_FAIL(c, MS_ERR_INTERNAL, "tile_bytes must equal %d", SP_TILE_MAX);
     const Tables* d_tab = c->tables.as<Tables>();
     Contig* d_contigs = c->contigs.as<Contig>();
@@ -1131,7 +1139,8 @@ static int splice_launch(ms_ctx* c, int64_t piece_lo, int64_t n_pieces, int32_t 
         MS_LAUNCH_CHECK(c);
     }
     if (n_ctg > 0) {
-        k_headers<<<(unsigned)ceil_div(n_ctg, 128), 128, 0, st>>>(d_contigs + ctg_lo, n_ctg, c->headers.as<uint8_t>(), c->fasta.as<uint8_t>());
+        k_headers<<<(unsigned)ceil_div(n_ctg, 128), 128, 0, st>>>(d_contigs + ctg_lo, n_ctg, c->headers.as<uint8_t>(), c->fasta.as<uint8_t>(),
+                                                                   w_lo, w_hi);
         MS_LAUNCH_CHECK(c);
     }
     return MS_OK;
@@ -1177,6 +1186,55 @@ int apply_pipeline(ms_ctx* c) {
     if ((rc = vcf_launch(c, 0, c->n_recs, c->stream))) return rc;
     stage_end(c, ST_VCF);
     return finish_apply(c);
+}
+
+// ---- tile-sharded apply: one genome, several GPUs ------------------------------------------------------------------
+// Every rank holds the whole genome and the whole record table (sampling is keyed by position, so all ranks draw the
+// same table); the layout of the output is therefore identical everywhere and the work of producing it can be cut at
+// ANY tile / record boundary: part p of n writes tiles [T*p/n, T*(p+1)/n) of the FASTA image and the VCF lines of
+// records [M*p/n, M*(p+1)/n).  This is how a contig larger than one GPU's share (the reference's own benchmark is
+// one 1 Gbp contig, README.md:441) is spread over the box: chunks are cut at 16 KiB tile boundaries of the output;
+// the rejection carry, the delta prefix and TLI sources that cross a cut need no exchange because the (cheap)
+// candidate table is replicated and only the byte-moving stages are sharded.
+int apply_window(ms_ctx* c, int part, int n_parts, int64_t* win) {
+    if (c->n_contigs <= 0 || !c->genome.p) MS_FAIL(c, MS_ERR_STATE, "ms_apply_window: no genome resident");
+    if (n_parts < 1 || part < 0 || part >= n_parts) MS_FAIL(c, MS_ERR_ARG, "ms_apply_window: part %d of %d", part, n_parts);
+    int rc = plan_stage(c, true);
+    if (rc) return rc;
+    if ((rc = index_stage(c))) return rc;
+    MS_CUDA(c, cudaMemcpyAsync(c->h_contigs.data(), c->contigs.p, sizeof(Contig) * (size_t)c->n_contigs, cudaMemcpyDeviceToHost, c->stream));
+    MS_CUDA(c, cudaStreamSynchronize(c->stream));
+    const int64_t tile = c->tile_bytes;
+    const int64_t n_tiles = ceil_div(c->fasta_bytes, tile);
+    const int64_t t_lo = n_tiles * part / n_parts, t_hi = n_tiles * (part + 1) / n_parts;
+    const int64_t w_lo = t_lo * tile, w_hi = std::min(t_hi * tile, c->fasta_bytes);
+    // pieces are ordered by (contig, tile) = by file offset: first piece whose tile is >= T
+    auto first_piece = [&](int64_t T) -> int64_t {
+        for (int i = 0; i < c->n_contigs; ++i) {
+            const Contig& k = c->h_contigs[i];
+            if (k.body_bytes <= 0) continue;
+            const int64_t ft = k.body_off / tile, lt = (k.body_off + k.body_bytes - 1) / tile;
+            if (lt >= T) return k.piece_lo + std::max<int64_t>(0, T - ft);
+        }
+        return c->n_pieces;
+    };
+    const int64_t p_lo = first_piece(t_lo), p_hi = first_piece(t_hi);
+    const int64_t M = c->n_recs;
+    const int64_t r_lo = M * part / n_parts, r_hi = M * (part + 1) / n_parts;
+    stage_begin(c, ST_SPLICE);
+    if ((rc = splice_launch(c, p_lo, p_hi - p_lo, 0, c->n_contigs, w_lo, w_hi))) return rc;
+    stage_end(c, ST_SPLICE);
+    stage_begin(c, ST_VCF);
+    if ((rc = vcf_launch(c, r_lo, r_hi, c->stream))) return rc;
+    stage_end(c, ST_VCF);
+    int64_t v[2] = {0, 0};
+    if (M > 0) {
+        MS_CUDA(c, cudaMemcpyAsync(&v[0], c->vcf_off.as<int64_t>() + r_lo, 8, cudaMemcpyDeviceToHost, c->stream));
+        MS_CUDA(c, cudaMemcpyAsync(&v[1], c->vcf_off.as<int64_t>() + r_hi, 8, cudaMemcpyDeviceToHost, c->stream));
+    }
+    if ((rc = finish_apply(c))) return rc;
+    win[0] = c->fasta_bytes; win[1] = c->vcf_bytes; win[2] = w_lo; win[3] = w_hi; win[4] = v[0]; win[5] = v[1];
+    return MS_OK;
 }
 
 // ---- streamed run: host genome in, host FASTA + VCF out, copies overlapped with the kernels --------------------

@@ -158,6 +158,7 @@ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // pipeline entry points implemented in the .cu files
 int apply_pipeline(ms_ctx* c);
+int apply_window(ms_ctx* c, int part, int n_parts, int64_t* win);
 int adopt_output(ms_ctx* c);
 int ensure_stage_buffers(ms_ctx* c);
 int fasta_ingest(ms_ctx* c, int fd, int64_t nbytes, int32_t* n_records, int32_t* regular);

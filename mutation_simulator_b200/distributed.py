@@ -74,6 +74,25 @@ def lpt_partition(lengths, n):
     return [sorted(b) for b in bins]
 
 
+def shard_mode(lengths, n) -> str:
+    """How n ranks split one run.  'contigs': LPT partition of whole contigs — every stage, sampling included, is
+    sharded and nothing is exchanged.  'tiles': when that would leave a rank idle or overloaded (fewer contigs than
+    ranks, or one contig far larger than a rank's share — the reference's own benchmark is a single 1 Gbp contig,
+    README.md:441) every rank keeps the whole genome, draws the same mutation table, and the byte-moving stages are
+    cut at 16 KiB tile boundaries of the output (ms_apply_window).  MS_SHARD=contigs|tiles overrides."""
+    forced = os.environ.get("MS_SHARD")
+    if forced in ("contigs", "tiles"):
+        return forced
+    if n <= 1:
+        return "contigs"
+    parts = lpt_partition(lengths, n)
+    loads = [sum(int(lengths[i]) for i in p) for p in parts]
+    total = sum(loads)
+    if min(len(p) for p in parts) == 0 or (total > 0 and max(loads) > 1.25 * total / n):
+        return "tiles"
+    return "contigs"
+
+
 def owners(parts, n_contigs):
     own = np.zeros(n_contigs, dtype=np.int64)
     for r, ids in enumerate(parts):
@@ -120,18 +139,8 @@ def exchange_contigs(engine, device, sends, recvs):
 def write_partitioned(path, my_ids, chunks, n_contigs, prefix: bytes = b""):
     """Every rank writes the byte chunks of its contigs (chunks[i] belongs to global contig my_ids[i]) into
     one file, contigs in global order, after `prefix` (written by rank 0)."""
-    rank, world = rank_world()
-    sizes = np.zeros(n_contigs, dtype=np.int64)
-    for r_ids, r_sizes in all_gather_object((list(my_ids), [len(c) for c in chunks])):
-        sizes[r_ids] = r_sizes
-    off = np.zeros(n_contigs + 1, dtype=np.int64)
-    np.cumsum(sizes, out=off[1:])
-    off += len(prefix)
-    if rank == 0:
-        with open(path, "wb") as fh:
-            fh.write(prefix)
-            fh.truncate(int(off[-1]))
-    barrier()
+    off = _global_offsets(my_ids, [len(c) for c in chunks], n_contigs, len(prefix))
+    _create(path, prefix, off[-1])
     fd = os.open(path, os.O_RDWR)
     try:
         for g, c in zip(my_ids, chunks):
@@ -169,17 +178,43 @@ def vcf_chunks(engine, my_ids, vcf_off):
 def _global_offsets(my_ids, my_sizes, n_contigs, prefix_len):
     sizes = np.zeros(n_contigs, dtype=np.int64)
     for r_ids, r_sizes in all_gather_object((list(my_ids), [int(x) for x in my_sizes])):
-        sizes[r_ids] = r_sizes
+        if len(r_ids):
+            sizes[r_ids] = r_sizes
     off = np.zeros(n_contigs + 1, dtype=np.int64)
     np.cumsum(sizes, out=off[1:])
     return off + prefix_len
 
 
+class OutputCreateError(OSError):
+    """Rank 0 could not create an output file; raised on EVERY rank so that all of them leave together."""
+
+
 def _create(path, prefix: bytes, total: int):
+    """Rank 0 creates the file (prefix + room for `total` bytes); the outcome is broadcast, so an unwritable path
+    fails all ranks with the same exception instead of leaving the others at a barrier."""
+    err = None
     if rank_world()[0] == 0:
-        with open(path, "wb") as fh:
-            fh.write(prefix)
-            fh.truncate(int(total))
+        try:
+            with open(path, "wb") as fh:
+                fh.write(prefix)
+                fh.truncate(int(total))
+        except OSError as e:
+            err = str(e)
+    err = broadcast_object(err)
+    if err is not None:
+        raise OutputCreateError(err)
+
+
+def write_window(path, engine, which, lo: int, hi: int, total: int, prefix: bytes = b""):
+    """Tile-sharded runs: this rank produced bytes [lo, hi) of device buffer `which`, whose layout is the same on every
+    rank; all ranks stream their ranges into one file of `total` bytes after `prefix`."""
+    _create(path, prefix, len(prefix) + int(total))
+    if hi > lo:
+        fd = os.open(path, os.O_RDWR)
+        try:
+            engine.download_to_fd(which, fd, len(prefix) + int(lo), int(lo), int(hi - lo))
+        finally:
+            os.close(fd)
     barrier()
 
 
@@ -209,7 +244,10 @@ def write_slices_partitioned(path, engine, which, my_ids, slice_off, n_contigs, 
 def write_fasta_partitioned(path, engine, my_ids, n_contigs_global):
     """FASTA image slices with the separator fixed up for the global file order (a '\\n' follows a partial last
     line unless the contig is the last one of the whole file).  Returns the per-contig VCF offsets of the layout."""
-    fo, vo, sep, partial = engine.contig_layout()
+    if len(my_ids) == 0:      # more ranks than contigs: this rank only takes part in the collectives
+        fo, vo, sep, partial = np.zeros(1, np.int64), np.zeros(1, np.int64), [], []
+    else:
+        fo, vo, sep, partial = engine.contig_layout()
     body = [int(fo[i + 1] - fo[i]) - int(sep[i]) for i in range(len(my_ids))]
     extra = [1 if (partial[i] and g != n_contigs_global - 1) else 0 for i, g in enumerate(my_ids)]
     off = _global_offsets(my_ids, [b + e for b, e in zip(body, extra)], n_contigs_global, 0)

@@ -214,6 +214,14 @@ class Engine:
         self._check(self._lib.ms_apply(self._h, C.byref(fb), C.byref(vb)))
         return fb.value, vb.value
 
+    def apply_window(self, part: int, n_parts: int) -> dict:
+        """ms_apply for one part of the output (tiles / records [part/n_parts, (part+1)/n_parts)); every part must run on
+        a context holding the same genome and record table.  Returns the sizes of the whole outputs and the byte
+        ranges this part produced."""
+        w = np.zeros(6, dtype=np.int64)
+        self._check(self._lib.ms_apply_window(self._h, int(part), int(n_parts), _ptr(w)))
+        return dict(fasta_bytes=int(w[0]), vcf_bytes=int(w[1]), fasta=(int(w[2]), int(w[3])), vcf=(int(w[4]), int(w[5])))
+
     def download(self, which: int, out: Optional[np.ndarray] = None) -> np.ndarray:
         n = C.c_int64()
         self._check(self._lib.ms_download(self._h, which, None, 0, C.byref(n)))

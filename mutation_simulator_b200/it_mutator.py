@@ -21,6 +21,26 @@ from .records import K_RAW, REC_DTYPE, T_IT
 from .util import print_warning
 
 
+def assign_partners(avail, rng) -> dict:
+    """it_mutator.py:59-70 ``__assign_parters``.  The reference iterates ``__avail_chroms`` while removing from the
+    SAME list (``remain_chr`` is an alias): every pass drops the current element and its partner and the iterator's
+    index still advances by one, so the element that slid into the vacated slot is skipped and the loop ends after
+    ceil(n/3) passes.  n eligible contigs therefore give ceil(n/3) pairs (24 -> 8, not 12); the rest stay unpaired
+    and are written unchanged.  Reproduced here step for step (tests/golden/it_pairs.json pins the counts)."""
+    pool = list(avail)
+    rng.shuffle(pool)
+    partners = {}
+    i = 0
+    while i < len(pool):
+        chrom = pool.pop(i)                                 # remain_chr.remove(chrom)
+        if pool:
+            partner = pool.pop(rng.randrange(len(pool)))    # choice(remain_chr); remain_chr.remove(partner)
+            partners[partner] = chrom
+            partners[chrom] = partner
+        i += 1                                              # the list iterator moves on over the shrunken list
+    return partners
+
+
 class ITMutator:
     def __init__(self, args, fasta, sim):
         self._args, self._fasta, self._sim = args, fasta, sim
@@ -32,15 +52,9 @@ class ITMutator:
             self._fasta_writer = self._bedpe_writer = None
         self._seed = D.broadcast_object(run_seed(args))
         self._rng = random.Random(self._seed)
-        # it_mutator.py:51-70: eligible contigs, then random disjoint pairs
+        # it_mutator.py:51-57: eligible contigs
         avail = [c.number for c in sim.chromosomes if c.it_rate is not None and len(fasta[c.number]) > 2]
-        self._rng.shuffle(avail)
-        self._partners = {}
-        while len(avail) >= 2:
-            a = avail.pop(0)
-            b = avail.pop(self._rng.randrange(len(avail)))
-            self._partners[a] = b
-            self._partners[b] = a
+        self._partners = assign_partners(avail, self._rng)
         self._engine = None
         self.breakpoints = {}
 
@@ -142,11 +156,32 @@ class ITMutator:
                 self._bedpe_writer._f.write(rows(fasta[c].name, bps[c]["self"], len(fasta[c]), fasta[p].name,
                                                  bps[c]["partner"], len(fasta[p])))
 
+    def _mutate_tiles(self):
+        """Fewer (or far more uneven) contigs than GPUs: every rank holds the genome and the same breakpoints (they are
+        keyed by the global contig id) and writes its share of the output tiles (ms_apply_window); no exchange."""
+        fasta, rank, world = self._fasta, self._rank, self._world
+        eng = self._engine = getattr(fasta, "engine", None) or Engine(D.local_device())
+        fasta.upload(eng)
+        bps = self.breakpoints = self._generate_all_breakpoints(eng)
+        eng.load_records(self._records(bps))
+        w = eng.apply_window(rank, world)
+        D.write_window(self._args.outfastait, eng, BUF_FASTA, *w["fasta"], w["fasta_bytes"])
+        bed = b""
+        if rank == 0:
+            for chrom in self._sim.chromosomes:
+                c = chrom.number
+                if c in bps:
+                    p = self._partners[c]
+                    bed += rows(fasta[c].name, bps[c]["self"], len(fasta[c]), fasta[p].name, bps[c]["partner"], len(fasta[p]))
+        D.write_partitioned(self._args.outbedpe, [0] if rank == 0 else [], [bed] if rank == 0 else [], 1)
+
     def _mutate_partitioned(self):
         """One process per GPU: contigs are partitioned; a pair that straddles two GPUs swaps its members over
         NCCL P2P into the staging region behind each receiver's genome."""
         fasta, rank, world = self._fasta, self._rank, self._world
         n_contigs = len(fasta.names)
+        if D.shard_mode(fasta.lengths, world) == "tiles":
+            return self._mutate_tiles()
         parts = D.lpt_partition(fasta.lengths, world)
         own = D.owners(parts, n_contigs)
         my_ids = parts[rank]

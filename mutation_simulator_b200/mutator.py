@@ -67,34 +67,56 @@ class Mutator:
         marks = [("start", time.perf_counter())]
         lap = lambda name: marks.append((name, time.perf_counter()))
         n_contigs = len(fasta.names)
-        my_ids = D.lpt_partition(fasta.lengths, world)[self._rank] if world > 1 else list(range(n_contigs))
+        # several GPUs: whole contigs per rank (every stage sharded, no exchange), or — when contigs are too few or too
+        # uneven for that — the same table on every rank and the output cut at tile boundaries (distributed.shard_mode)
+        mode = D.shard_mode(fasta.lengths, world)
+        tiles = world > 1 and mode == "tiles"
+        my_ids = D.lpt_partition(fasta.lengths, world)[self._rank] if world > 1 and not tiles else list(range(n_contigs))
         seed = D.broadcast_object(run_seed(args))
         eng = self._engine = getattr(fasta, "engine", None) or \
             Engine(D.local_device(getattr(args, "device", 0)) if world > 1 else getattr(args, "device", 0))
         lap("engine")
-        fasta.upload(eng, my_ids if world > 1 else None)
-        lap("gather+upload")
-        ranges, n = build_ranges(sim, fasta.lengths, my_ids)
-        eng.set_ranges_array(ranges, n, block_list(sim), min(sim.mut_block.values()), p_transition(sim.titv))
-        eng.sample(seed)
-        eng.apply()
-        lap("sample+apply")
-        if not args.ignore_warnings:
-            per = eng.contig_records()
-            for i in np.flatnonzero(per == 0):
-                print(format_warning(f"No mutations could be generated on sequence {my_ids[int(i)]+1} (mutation rates too low)",
-                                     args.no_color), file=sys.stderr)
+        window = None
+        if my_ids:      # (more ranks than contigs in MS_SHARD=contigs mode: an idle rank only joins the collectives)
+            fasta.upload(eng, my_ids if world > 1 and not tiles else None)
+            lap("gather+upload")
+            ranges, n = build_ranges(sim, fasta.lengths, my_ids)
+            eng.set_ranges_array(ranges, n, block_list(sim), min(sim.mut_block.values()), p_transition(sim.titv))
+            eng.sample(seed)
+            if tiles:
+                window = eng.apply_window(self._rank, world)
+            else:
+                eng.apply()
+            lap("sample+apply")
+            if not args.ignore_warnings and (not tiles or self._rank == 0):
+                per = eng.contig_records()
+                for i in np.flatnonzero(per == 0):
+                    print(format_warning(f"No mutations could be generated on sequence {my_ids[int(i)]+1} (mutation rates too low)",
+                                         args.no_color), file=sys.stderr)
         if world == 1:
             self._fasta_writer.write_from_engine(eng, BUF_FASTA)
             self._vcf_writer.write_from_engine(eng, BUF_VCF)
         else:
-            from .vcf_writer import header_text
-            vcf_off = D.write_fasta_partitioned(args.outfasta, eng, my_ids, n_contigs)
+            from .fasta_writer import FastaWriterError
+            from .vcf_writer import VcfWriterError, header_text
             head = header_text(args.infile.name, [(fasta[k].name, len(fasta[k])) for k in fasta.keys()], sim.assembly_name,
                                sim.species_name, sim.sample_name).encode("latin-1")
-            D.write_slices_partitioned(args.outvcf, eng, BUF_VCF, my_ids, vcf_off, n_contigs, prefix=head)
+            try:
+                if tiles:
+                    D.write_window(args.outfasta, eng, BUF_FASTA, *window["fasta"], window["fasta_bytes"])
+                else:
+                    vcf_off = D.write_fasta_partitioned(args.outfasta, eng, my_ids, n_contigs)
+            except D.OutputCreateError as e:
+                raise FastaWriterError(f"Cannot write to Fasta file {args.outfasta} {e}")
+            try:
+                if tiles:
+                    D.write_window(args.outvcf, eng, BUF_VCF, *window["vcf"], window["vcf_bytes"], prefix=head)
+                else:
+                    D.write_slices_partitioned(args.outvcf, eng, BUF_VCF, my_ids, vcf_off, n_contigs, prefix=head)
+            except D.OutputCreateError as e:
+                raise VcfWriterError(f"Cannot write to VCF file {args.outvcf} {e}")
         lap("download+write")
-        self.stats = eng.stats()
+        self.stats = eng.stats() if my_ids else None
         self.host_seconds = {b[0]: b[1] - a[1] for a, b in zip(marks, marks[1:])}
         if os.environ.get("MS_TIMING"):
             print(f"[rank {self._rank}] " + " ".join(f"{k}={v:.3f}s" for k, v in self.host_seconds.items()), file=sys.stderr)

@@ -32,3 +32,16 @@ def test_two_rank_gloo_reduction(tmp_path):
     assert r0["sum"] == r1["sum"] == [total, 24.0]
     l0 = sum(bench.GRCH38[i] for i in r0["mine"]); l1 = sum(bench.GRCH38[i] for i in r1["mine"])
     assert r0["max"] == r1["max"] == [float(max(l0, l1)), 1.0]
+
+
+def test_shard_mode_switches_to_tiles_when_contigs_cannot_fill_the_ranks(monkeypatch):
+    from mutation_simulator_b200.distributed import shard_mode
+    monkeypatch.delenv("MS_SHARD", raising=False)
+    assert shard_mode(bench.GRCH38, 1) == "contigs"
+    assert shard_mode(bench.GRCH38, 8) == "contigs"
+    assert shard_mode([1_000_000_000], 8) == "tiles"               # README.md:441: one contig, eight GPUs
+    assert shard_mode([5_000_000] * 3, 8) == "tiles"               # fewer contigs than ranks
+    assert shard_mode([900_000_000] + [1_000_000] * 23, 8) == "tiles"
+    assert shard_mode([5000] * 200_000, 8) == "contigs"
+    monkeypatch.setenv("MS_SHARD", "tiles")
+    assert shard_mode(bench.GRCH38, 8) == "tiles"

@@ -20,8 +20,8 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
-def cli(argv, nproc, port):
-    env = dict(os.environ, PYTHONPATH=str(REPO))
+def cli(argv, nproc, port, **extra_env):
+    env = dict(os.environ, PYTHONPATH=str(REPO), **extra_env)
     if nproc == 1:
         cmd = [sys.executable, "-m", "mutation_simulator_b200"] + argv
     else:
@@ -68,3 +68,36 @@ def test_partitioned_runs_equal_single_gpu(tmp_path):
         for f in ("g_ms_it.fa", "g_ms_it.bedpe"):
             assert (tmp_path / "a" / f).read_bytes() == (tmp_path / "b" / f).read_bytes(), (seed, f)
         assert (tmp_path / "a" / "g_ms_it.bedpe").stat().st_size > 0
+
+
+def _same(a: Path, b: Path, f: str):
+    x, y = (a / f).read_bytes(), (b / f).read_bytes()
+    if f.endswith(".vcf"):
+        x = b"".join(l for l in x.splitlines(keepends=True) if not l.startswith(b"##filedate"))
+        y = b"".join(l for l in y.splitlines(keepends=True) if not l.startswith(b"##filedate"))
+    assert x == y, f
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
+def test_one_contig_is_cut_into_tiles_over_the_gpus(tmp_path):
+    """A genome with fewer contigs than GPUs (README.md:441: one contig) is sharded at tile boundaries of the
+    output (ms_apply_window); the assembled files equal the 1-GPU run.  Also: the same sharding forced on a
+    many-contig genome, and IT mode with too few contigs for a contig partition."""
+    n = min(_ngpu(), 8)
+    common = ["-q", "--seed", "5", "args", "-sn", "0.01", "-in", "0.002", "-inmax", "9", "-de", "0.002", "-demax", "9", "-du", "0.001",
+              "-dumax", "30", "-iv", "0.001", "-ivmax", "30", "-tl", "0.002", "-tlmax", "20"]
+    for name, lens, env in (("one", [1_500_000], {}), ("many", [90_000, 70_011, 65_000, 40_000, 33_333, 20_000, 7, 1_000], {"MS_SHARD": "tiles"})):
+        make_genome(tmp_path / f"{name}.fa", lens, 3, bpl=70)
+        (tmp_path / f"{name}_a").mkdir(); (tmp_path / f"{name}_b").mkdir()
+        cli([str(tmp_path / f"{name}.fa"), "-o", str(tmp_path / f"{name}_a" / "g")] + common, 1, 0)
+        cli([str(tmp_path / f"{name}.fa"), "-o", str(tmp_path / f"{name}_b" / "g")] + common, n, 29561, **env)
+        for f in ("g_ms.fa", "g_ms.vcf"):
+            _same(tmp_path / f"{name}_a", tmp_path / f"{name}_b", f)
+    make_genome(tmp_path / "three.fa", [300_000, 200_000, 100_000], 4)
+    (tmp_path / "it_a").mkdir(); (tmp_path / "it_b").mkdir()
+    it = ["-q", "--seed", "11", "it", "0.0005"]
+    cli([str(tmp_path / "three.fa"), "-o", str(tmp_path / "it_a" / "g")] + it, 1, 0)
+    cli([str(tmp_path / "three.fa"), "-o", str(tmp_path / "it_b" / "g")] + it, n, 29562, MS_SHARD="tiles")
+    for f in ("g_ms_it.fa", "g_ms_it.bedpe"):
+        _same(tmp_path / "it_a", tmp_path / "it_b", f)
+    assert (tmp_path / "it_a" / "g_ms_it.bedpe").stat().st_size > 0

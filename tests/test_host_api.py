@@ -179,3 +179,24 @@ def test_plan_column_wise_path_equals_the_general_loop(monkeypatch):
     slow, ns = plan.build_ranges(sim, fa.lengths, ids)
     assert nf == ns > 1000
     assert bytes(memoryview(fast))[:nf * C.sizeof(_lib.MsRange)] == bytes(memoryview(slow))[:ns * C.sizeof(_lib.MsRange)]
+
+
+def test_it_pairing_reproduces_the_reference_pair_count():
+    """it_mutator.py:59-70 iterates a list it is shrinking: ceil(n/3) pairs, not floor(n/2).
+    tests/golden/it_pairs.json = the unmodified reference's counts (tests/golden/make_it_pairs.py)."""
+    import random
+    from mutation_simulator_b200.it_mutator import assign_partners
+    want = json.loads((GOLDEN / "it_pairs.json").read_text())
+    for n in range(2, 41):
+        for seed in range(25):
+            p = assign_partners(list(range(100, 100 + n)), random.Random(seed))
+            assert all(p[p[a]] == a and p[a] != a for a in p)
+            assert set(p) <= set(range(100, 100 + n))
+            assert len(p) // 2 == want[str(n)]["pairs"], (n, seed)
+    # every contig is equally likely to end up paired (the list is shuffled first)
+    hits = np.zeros(24)
+    for seed in range(3000):
+        for a in assign_partners(list(range(24)), random.Random(seed)):
+            hits[a] += 1
+    from scipy import stats
+    assert stats.chisquare(hits).pvalue > 0.01
