@@ -57,6 +57,13 @@ class ITMutator:
         self._partners = assign_partners(avail, self._rng)
         self._engine = None
         self.breakpoints = {}
+        self._replay = None
+
+    def load_bedpe(self, text):
+        """Replay instead of sampling: take the pairing and the breakpoints from a BEDPE file written by the reference
+        (bedpe_writer.py:36-55) or by this package; mutate() then reproduces that run's *_it.fa and .bedpe."""
+        from .bedpe_writer import breakpoints_from_rows
+        self._partners, self._replay = breakpoints_from_rows(text, self._fasta.names, self._fasta.lengths)
 
     def __del__(self):
         try:
@@ -81,6 +88,8 @@ class ITMutator:
         return out
 
     def _generate_all_breakpoints(self, eng):
+        if self._replay is not None:
+            return self._replay
         fasta, sim, args = self._fasta, self._sim, self._args
         pairs, counts = [], []
         for a, b in self._pairs_once():

@@ -33,12 +33,18 @@ class Mutator:
         self._rank, self._world = D.init()
         self._engine = None
         self.stats = None
+        self._replay = None
         if self._world > 1:      # one process per GPU: files are assembled by write_partitioned()
             self._fasta_writer = self._vcf_writer = None
             return
         self._fasta_writer = FastaWriter(args.outfasta)
         self._vcf_writer = VcfWriter(args.outvcf)
         self._vcf_writer.write_header(args.infile.name, fasta, sim.assembly_name, sim.species_name, sim.sample_name)
+
+    def load_vcf(self, text):
+        """Replay instead of sampling: apply the records of a VCF written by the reference (vcf_writer.py:118-126) or by
+        this package to the same FASTA; mutate() then reproduces that run's *_ms.fa and re-emits the VCF."""
+        self._replay = text
 
     def detach_engine(self):
         """Hand the engine (with the mutated genome's FASTA image still in HBM) to the caller; close() then
@@ -80,9 +86,16 @@ class Mutator:
         if my_ids:      # (more ranks than contigs in MS_SHARD=contigs mode: an idle rank only joins the collectives)
             fasta.upload(eng, my_ids if world > 1 and not tiles else None)
             lap("gather+upload")
-            ranges, n = build_ranges(sim, fasta.lengths, my_ids)
-            eng.set_ranges_array(ranges, n, block_list(sim), min(sim.mut_block.values()), p_transition(sim.titv))
-            eng.sample(seed)
+            if self._replay is not None:
+                from .records import genome_offsets, records_from_vcf
+                lens = [int(fasta.lengths[g]) for g in my_ids]
+                recs, lit = records_from_vcf(self._replay, [fasta.names[g] for g in my_ids], genome_offsets(lens), lens,
+                                             skip_unknown=world > 1 and not tiles)
+                eng.load_records(recs, lit)
+            else:
+                ranges, n = build_ranges(sim, fasta.lengths, my_ids)
+                eng.set_ranges_array(ranges, n, block_list(sim), min(sim.mut_block.values()), p_transition(sim.titv))
+                eng.sample(seed)
             if tiles:
                 window = eng.apply_window(self._rank, world)
             else:

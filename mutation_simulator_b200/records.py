@@ -107,3 +107,85 @@ def _get(m, name, default=KeyError):
     if default is KeyError:
         return getattr(m, name)
     return getattr(m, name, default)
+
+
+# ---------------------------------------------------------------------------------------
+# Replay of the reference's FILES: a VCF written by VcfWriter.write (vcf_writer.py:118-126,
+# info string :44-52) back into splice descriptors.  Record wording per type: mutator.py:334-421.
+# ---------------------------------------------------------------------------------------
+_SVTYPE = {"INS": T_IN, "DEL": T_DE, "INV": T_IV, "DUP": T_DU, "DEL:ME": T_TL, "INS:ME": T_TLI}
+
+
+def records_from_vcf(text, names, goff, lengths, skip_unknown: bool = False) -> tuple[np.ndarray, np.ndarray]:
+    """VCF text (header lines are skipped) -> (recs sorted by (contig, pos), literal pool) for ``ms_load_records``.
+
+    names: contig names (VCF CHROM) in genome order; goff/lengths as in :func:`build_records`.
+    The replay rule is "replace REF by ALT at POS"  expressed without touching the anchor base of
+    INS / INS:ME / DEL / DEL:ME records (their REF shows the IUPAC-converted anchor, the FASTA keeps the raw one):
+      SNP     POS=pos+1                                     -> substitute ALT
+      INS     ALT = REF + insert (pos > 0, POS = pos)       -> insert before base POS   (mutator.py:343-358)
+              ALT = insert + REF (pos = 0, POS = END = 1)   -> insert before base 0
+      INS:ME  same, the inserted (already converted / reverse-complemented) string is literal  (:401-421)
+      DEL / DEL:ME  ALT = REF[0] (pos > 0, POS = pos)       -> drop SVLEN bases from POS       (:360-377)
+                    ALT = REF[-1] (pos = 0, POS = 1)        -> drop SVLEN bases from 0
+      INV     POS=pos+1, SVLEN is 0                          -> reverse complement of len(REF) bases  (:379-387)
+      DUP     POS=pos+1                                      -> the SVLEN bases at POS twice           (:389-399)
+    A record whose ALT both starts and ends with REF (or, for DEL, REF[0] == REF[-1] at POS 1) is read as anchored
+    before; both readings give the same output except for an IUPAC anchor at the very first base of a contig."""
+    if isinstance(text, (bytes, bytearray)):
+        text = bytes(text).decode("latin-1")
+    index = {(n.decode("latin-1") if isinstance(n, (bytes, bytearray)) else str(n)): i for i, n in enumerate(names)}
+    rows, lit = [], bytearray()
+    for ln, line in enumerate(text.splitlines(), 1):
+        if not line or line[0] == "#":
+            continue
+        f = line.split("\t")
+        if len(f) < 8:
+            raise ValueError(f"VCF line {ln}: expected at least 8 tab-separated fields")
+        if f[0] not in index:
+            if skip_unknown:      # several GPUs: the contig belongs to another rank
+                continue
+            raise ValueError(f"VCF line {ln}: unknown contig {f[0]!r}")
+        ci = index[f[0]]
+        g0, L = int(goff[ci]), int(lengths[ci])
+        pos1, ref, alt = int(f[1]), f[3].encode("latin-1"), f[4].encode("latin-1")
+        if f[7] == ".":
+            if len(ref) != 1 or len(alt) != 1:
+                raise ValueError(f"VCF line {ln}: a record without INFO must be a single-base substitution")
+            if not (1 <= pos1 <= L):
+                raise ValueError(f"VCF line {ln}: record outside contig {f[0]!r} (length {L})")
+            rows.append((pos1 - 1, 1, 1, 0, 0, K_SNP, T_SN, ref[0], alt[0], ci))
+            continue
+        info = dict(kv.split("=", 1) for kv in f[7].split(";") if "=" in kv)
+        try:
+            t, svlen = _SVTYPE[info["SVTYPE"]], int(info["SVLEN"])
+        except KeyError:
+            raise ValueError(f"VCF line {ln}: unsupported INFO {f[7]!r}") from None
+        if t in (T_IN, T_TLI):
+            if alt.startswith(ref):
+                pos, ins = pos1, alt[len(ref):]
+            elif alt.endswith(ref) and pos1 == 1:
+                pos, ins = 0, alt[:len(alt) - len(ref)]
+            else:
+                raise ValueError(f"VCF line {ln}: ALT of an insertion must extend REF")
+            rows.append((pos, 0, len(ins), 0, len(lit), K_LIT, t, 0, 0, ci))
+            lit += ins
+        elif t in (T_DE, T_TL):
+            if alt == ref[:1]:
+                pos = pos1
+            elif alt == ref[-1:] and pos1 == 1:
+                pos = 0
+            else:
+                raise ValueError(f"VCF line {ln}: ALT of a deletion must be the first (or, at POS 1, the last) base of REF")
+            cons = min(svlen, L - pos)
+            rows.append((pos, cons, 0, 0, 0, K_NONE, t, 0, 0, ci))
+        elif t == T_IV:
+            rows.append((pos1 - 1, len(ref), len(ref), 0, g0 + pos1 - 1, K_RC, t, 0, 0, ci))
+        else:   # DUP
+            rows.append((pos1 - 1, 0, len(ref), 0, g0 + pos1 - 1, K_RAW, t, 0, 0, ci))
+        p, c = rows[-1][0], rows[-1][1]
+        if not (0 <= p < L) or p + c > L:
+            raise ValueError(f"VCF line {ln}: record outside contig {f[0]!r} (length {L})")
+    rows.sort(key=lambda r: (r[9], r[0]))
+    recs = np.array(rows, dtype=REC_DTYPE) if rows else np.zeros(0, dtype=REC_DTYPE)
+    return recs, np.frombuffer(bytes(lit) + b"\0" * 16, dtype=np.uint8).copy()

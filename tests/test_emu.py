@@ -76,7 +76,7 @@ def test_prp_subset_is_uniform_over_positions(emu):
     assert p > 1e-3
 
 
-def run_emu_apply(emu, contigs, tables, tile_bytes=4096):
+def run_emu_apply(emu, contigs, tables, tile_bytes=4096, vcf_text=None):
     seqs = [c[2] for c in contigs]
     genome, goff = R.pack_genome(seqs)
     lens = np.array([len(s) for s in seqs], dtype=np.int64)
@@ -85,7 +85,10 @@ def run_emu_apply(emu, contigs, tables, tile_bytes=4096):
     hoff = np.cumsum([0] + [len(c[1]) for c in contigs]).astype(np.int64)
     names = b"".join(c[0] for c in contigs)
     noff = np.cumsum([0] + [len(c[0]) for c in contigs]).astype(np.int64)
-    recs, lit = R.build_records(genome, goff, lens, tables)
+    if vcf_text is not None:
+        recs, lit = R.records_from_vcf(vcf_text, [c[0] for c in contigs], goff, lens)
+    else:
+        recs, lit = R.build_records(genome, goff, lens, tables)
     cap_f = int(lens.sum() * 3 + recs["prod"].sum() * 2 + 4096 + len(hdr) * 2)
     cap_v = int(64 * len(recs) + 4 * (recs["prod"].sum() + recs["cons"].sum()) + len(names) * len(recs) + 4096)
     fa = np.zeros(cap_f, dtype=np.uint8)
@@ -116,6 +119,71 @@ def test_emulated_splice_and_vcf_match_reference(emu, case, tile):
     assert vcf == vcf_body((d / "out.vcf").read_bytes())
     if case in ("args_all", "c1_small"):
         assert nf > 2 * ns  # most groups take the vector path
+
+
+def assert_fasta_equal_up_to_silent_gap_snps(got: bytes, want: bytes, case: str):
+    """The reference's VCF determines its FASTA except in one case: a SNP drawn on a gap character '-' substitutes
+    conv('-') = 'N' -> 'N' (mutator.py:75, :449-455), which changes the FASTA ('-' becomes 'N') but is not written
+    to the VCF because REF == ALT (vcf_writer.py:123).  A replay from the VCF file keeps the '-'.  Those bytes — and
+    only those — may differ, and each must be a SNP of the reference's own table (muts.json)."""
+    assert len(got) == len(want)
+    if got == want:
+        return
+    a, b = np.frombuffer(got, np.uint8), np.frombuffer(want, np.uint8)
+    diff = np.flatnonzero(a != b)
+    assert set(a[diff]) == {ord("-")} and set(b[diff]) == {ord("N")}, case
+    n_silent = sum(1 for muts in load_muts(case) for m in muts if m.type == "SN" and m.alt == b"N")
+    assert 0 < len(diff) <= n_silent, (case, len(diff), n_silent)
+
+
+@pytest.mark.parametrize("case", MS_CASES)
+def test_replay_of_the_reference_vcf_file_reproduces_fasta_and_vcf(emu, case):
+    """Gate A from the reference's FILES (north star, part one): in.fa + out.vcf -> out.fa, and the VCF re-emitted
+    from the parsed records is the reference's VCF byte for byte (records.records_from_vcf; CPU emulation of the
+    kernels' cores — tests/test_gpu_replay.py does the same through the C ABI on the GPU)."""
+    d, contigs = load_case(case)
+    text = (d / "out.vcf").read_bytes()
+    fa, vcf, _, _ = run_emu_apply(emu, contigs, None, 1024, vcf_text=text)
+    assert vcf == vcf_body(text)
+    assert_fasta_equal_up_to_silent_gap_snps(fa, (d / "out.fa").read_bytes(), case)
+
+
+def test_vcf_loader_rejects_malformed_records():
+    names, goff, lens = [b"c"], np.array([0, 100]), [100]
+    ok = "c\t5\t.\tA\tAGG\t.\t.\tSVTYPE=INS;END=5;SVLEN=2\tGT\t1\n"
+    recs, lit = R.records_from_vcf(ok, names, goff, lens)
+    assert (int(recs[0]["pos"]), int(recs[0]["prod"]), int(recs[0]["cons"])) == (5, 2, 0) and bytes(lit[:2]) == b"GG"
+    first = "c\t1\t.\tA\tGGA\t.\t.\tSVTYPE=INS;END=1;SVLEN=2\tGT\t1\n"       # pos 0: insert + REF (mutator.py:351-354)
+    recs, lit = R.records_from_vcf(first, names, goff, lens)
+    assert int(recs[0]["pos"]) == 0 and bytes(lit[:2]) == b"GG"
+    for bad in ("x\t5\t.\tA\tC\t.\t.\t.\tGT\t1\n",                                # unknown contig
+                "c\t5\t.\tA\tTGG\t.\t.\tSVTYPE=INS;END=5;SVLEN=2\tGT\t1\n",      # ALT does not extend REF
+                "c\t500\t.\tA\tC\t.\t.\t.\tGT\t1\n",                              # outside the contig
+                "c\t5\t.\tAC\tG\t.\t.\tSVTYPE=DEL;END=6;SVLEN=1\tGT\t1\n",       # ALT is not REF[0]
+                "c\t5\t.\tA\tC\t.\t.\tSVTYPE=CNV;END=6;SVLEN=1\tGT\t1\n"):
+        with pytest.raises(ValueError):
+            R.records_from_vcf(bad, names, goff, lens)
+
+
+def test_bedpe_loader_inverts_the_writer():
+    from mutation_simulator_b200.bedpe_writer import breakpoints_from_rows, rows
+    from tests.helpers import GOLDEN
+    import json
+    for case in ("it_basic", "rmt_it"):
+        d = GOLDEN / case
+        bp = json.loads((d / "bp.json").read_text())
+        from tests.helpers import read_fasta_simple
+        src = d / ("out.fa" if (d / "out.fa").exists() else "in.fa")      # rmt_it: IT runs on the mutated genome
+        contigs = read_fasta_simple(src)
+        names, lens = [c[0] for c in contigs], [len(c[2]) for c in contigs]
+        partners, bps = breakpoints_from_rows((d / "out.bedpe").read_bytes(), names, lens)
+        assert partners == {int(k): v for k, v in bp["partners"].items() if k in bp["breakpoints"]}
+        for k, v in bp["breakpoints"].items():
+            assert list(bps[int(k)]["self"]) == v["self"] and list(bps[int(k)]["partner"]) == v["partner"], (case, k)
+        # and forward again
+        text = b"".join(rows(names[c].decode(), bps[c]["self"], lens[c], names[partners[c]].decode(), bps[c]["partner"],
+                             lens[partners[c]]) for c in sorted(bps))
+        assert sorted(text.splitlines()) == sorted((d / "out.bedpe").read_bytes().splitlines())
 
 
 def oracle_tables(seqs, rates, minlen, maxlen, block, seed, titv=1.0):

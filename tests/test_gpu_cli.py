@@ -220,3 +220,52 @@ def test_device_fasta_ingest_matches_the_host_loader(tmp_path):
     from mutation_simulator_b200 import FastaDuplicateHeaderError
     with pytest.raises(FastaDuplicateHeaderError):
         load_fasta(dup, device=0)
+
+
+# ---- Gate A from the reference's FILES (north star, part one) ------------------------------------------------------
+@pytest.mark.parametrize("case", ["args_all", "iupac", "c1_small", "rmt_ranges", "rmt_it", "edges", "tiny"])
+def test_replay_of_the_reference_vcf_file_through_the_class_api(case, tmp_path):
+    """in.fa + the reference's out.vcf -> Mutator.load_vcf().mutate() must write the reference's out.fa, and the VCF
+    re-emitted from the parsed records must be the reference's VCF body byte for byte."""
+    from mutation_simulator_b200 import Mutator, SimulationSettings, load_fasta
+    from tests.test_emu import assert_fasta_equal_up_to_silent_gap_snps
+    from mutation_simulator_b200 import get_args
+    d = GOLDEN / case
+    shutil.copy(d / "in.fa", tmp_path / "in.fa")
+    if (d / "in.rmt").exists():
+        shutil.copy(d / "in.rmt", tmp_path / "in.rmt")
+    argv = json.loads((d / "cmd.json").read_text())["argv"]
+    if argv == ["crafted"]:      # hand-crafted tables pushed through the reference's walk: no command line
+        argv = ["in.fa", "-o", "in", "-q", "args", "-sn", "0.01"]
+    argv = [str(tmp_path / a) if a in ("in.fa", "in.rmt", "in") else a for a in argv]
+    args = get_args(argv)
+    args.outfasta, args.outvcf, args.device = tmp_path / "o.fa", tmp_path / "o.vcf", 0
+    fasta = load_fasta(args.infile, device=0)
+    sim = SimulationSettings.from_rmt(args.rmtfile, fasta, True) if args.mode == "rmt" else SimulationSettings.from_args(args, fasta, True)
+    m = Mutator(args, fasta, sim)
+    m.load_vcf((d / "out.vcf").read_bytes())
+    m.mutate()
+    m.close()
+    fasta.close()
+    assert vcf_body((tmp_path / "o.vcf").read_bytes()) == vcf_body((d / "out.vcf").read_bytes())
+    assert_fasta_equal_up_to_silent_gap_snps((tmp_path / "o.fa").read_bytes(), (d / "out.fa").read_bytes(), case)
+
+
+@pytest.mark.parametrize("case", ["it_basic", "rmt_it"])
+def test_replay_of_the_reference_bedpe_file_through_the_class_api(case, tmp_path):
+    """(input FASTA, the reference's out.bedpe) -> ITMutator.load_bedpe().mutate() must write the reference's
+    out_it.fa and the same BEDPE rows.  rmt_it: the IT step runs on the mutated genome (__main__.py:88-95)."""
+    from argparse import Namespace
+    from mutation_simulator_b200 import ITMutator, SimulationSettings, load_fasta
+    d = GOLDEN / case
+    shutil.copy(d / ("out.fa" if case == "rmt_it" else "in.fa"), tmp_path / "in.fa")
+    fasta = load_fasta(tmp_path / "in.fa", device=0)
+    sim = SimulationSettings.from_it(0.001, fasta, True)
+    args = Namespace(outfastait=tmp_path / "o.fa", outbedpe=tmp_path / "o.bedpe", ignore_warnings=True, no_color=True, seed=1, device=0)
+    it = ITMutator(args, fasta, sim)
+    it.load_bedpe((d / "out.bedpe").read_bytes())
+    it.mutate()
+    it.close()
+    fasta.close()
+    assert (tmp_path / "o.fa").read_bytes() == (d / "out_it.fa").read_bytes()
+    assert (tmp_path / "o.bedpe").read_bytes() == (d / "out.bedpe").read_bytes()
