@@ -94,9 +94,10 @@ int ms_genome_adopt(ms_ctx* ctx, const uint8_t* d_bases, int64_t total_bases, in
                     const int64_t* contig_len, const int32_t* bpl, const uint32_t* gid,
                     const uint8_t* headers, const int64_t* hdr_off,
                     const uint8_t* names, const int64_t* name_off);
-/* Synthetic iid-ACGT genome with N runs generated on the device (benchmarks). */
+/* Synthetic iid-ACGT genome with N runs generated on the device (benchmarks).  Base j of contig gid is a
+ * function of (seed, gid, j) only, so any partition of the contigs over GPUs synthesises the same genome. */
 int ms_genome_synth(ms_ctx* ctx, uint64_t seed, int32_t n_contigs, const int64_t* contig_len,
-                    const int32_t* bpl, double n_fraction, int64_t telomere_n,
+                    const int32_t* bpl, const uint32_t* gid, double n_fraction, int64_t telomere_n,
                     const uint8_t* headers, const int64_t* hdr_off,
                     const uint8_t* names, const int64_t* name_off);
 int ms_genome_download(ms_ctx* ctx, uint8_t* bases, int64_t cap);
@@ -204,6 +205,12 @@ int ms_it_breakpoints(ms_ctx* ctx, uint64_t seed, int32_t n_pairs, const uint32_
  * The stream is keyed by (seed, gid, start), so any GPU computes the same positions. */
 int ms_sample_positions(ms_ctx* ctx, uint64_t seed, int32_t n, const uint32_t* gid, const uint32_t* start,
                         const uint32_t* stop, const uint32_t* k, int32_t min_dist, uint32_t* out);
+
+/* 64-bit content hash of byte ranges [start[i], end[i]) of an output buffer (`which` as for ms_download), computed on
+ * the device: sum over the range's bytes of mix(byte, offset within the range) mod 2^64 — order-free, so any launch
+ * geometry gives the same value.  bench.py uses it to check that the N-GPU outputs are the 1-GPU outputs without
+ * moving them off the devices (results must not depend on the GPU count). */
+int ms_hash_ranges(ms_ctx* ctx, int which, int32_t n, const int64_t* start, const int64_t* end, uint64_t* out);
 
 /* ---- introspection ------------------------------------------------------ */
 int ms_get_stats(ms_ctx* ctx, ms_stats* out);

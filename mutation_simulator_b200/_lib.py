@@ -46,7 +46,8 @@ PROTOTYPES = {
     "ms_synchronize": (C.c_int, [_P]),
     "ms_genome_upload": (C.c_int, [_P, _P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P]),
     "ms_genome_adopt": (C.c_int, [_P, _P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P]),
-    "ms_genome_synth": (C.c_int, [_P, _U64, _I32, _P, _P, C.c_double, _I64, _P, _P, _P, _P]),
+    "ms_genome_synth": (C.c_int, [_P, _U64, _I32, _P, _P, _P, C.c_double, _I64, _P, _P, _P, _P]),
+    "ms_hash_ranges": (C.c_int, [_P, C.c_int, _I32, _P, _P, _P]),
     "ms_genome_download": (C.c_int, [_P, _P, _I64]),
     "ms_genome_reserve": (C.c_int, [_P, _I64]),
     "ms_genome_adopt_output": (C.c_int, [_P]),

@@ -506,6 +506,19 @@ int ms_contig_records(ms_ctx* c, int64_t* n_records) {
     return MS_OK;
 }
 
+int ms_hash_ranges(ms_ctx* c, int which, int32_t n, const int64_t* start, const int64_t* end, uint64_t* out) {
+    if (!c || n < 0 || (n > 0 && (!start || !end || !out))) return MS_ERR_ARG;
+    if (n == 0) return MS_OK;
+    void* p; int64_t nb;
+    int rc = which_buffer(c, which, &p, &nb);
+    if (rc) return rc;
+    for (int32_t i = 0; i < n; ++i)
+        if (start[i] < 0 || end[i] < start[i] || end[i] > nb || (i && start[i] < end[i - 1]))
+            MS_FAIL(c, MS_ERR_ARG, "ms_hash_ranges: range %d is outside the buffer or not in ascending order", i);
+    MS_CUDA(c, cudaSetDevice(c->device));
+    return hash_ranges(c, static_cast<const uint8_t*>(p), n, start, end, out);
+}
+
 int ms_get_stats(ms_ctx* c, ms_stats* out) {
     if (!c || !out) return MS_ERR_ARG;
     memset(out, 0, sizeof(*out));

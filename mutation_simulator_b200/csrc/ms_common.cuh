@@ -169,4 +169,5 @@ int sample_pipeline(ms_ctx* c, uint64_t seed, bool defer_bases = false);
 int mutate_streamed(ms_ctx* c, uint64_t seed, const uint8_t* h_bases, uint8_t* h_fasta, int64_t fasta_cap, uint8_t* h_vcf,
                     int64_t vcf_cap, int64_t* fasta_bytes, int64_t* vcf_bytes, int64_t group_min);
 int count_types(ms_ctx* c);
+int hash_ranges(ms_ctx* c, const uint8_t* buf, int32_t n, const int64_t* start, const int64_t* end, uint64_t* out);
 }  // namespace ms

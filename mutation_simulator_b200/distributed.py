@@ -114,9 +114,9 @@ def device_view(ptr: int, nbytes: int, device: int):
 
 def exchange_contigs(engine, device, sends, recvs):
     """sends: [(peer, genome_index, nbytes)], recvs: [(peer, genome_index, nbytes)] in a globally agreed order.
-    One grouped NCCL call (ncclGroupStart/End under batch_isend_irecv)."""
+    One grouped NCCL call (ncclGroupStart/End under batch_isend_irecv).  Returns the device time of the exchange in ms."""
     if not sends and not recvs:
-        return
+        return 0.0
     import torch
     import torch.distributed as dist
     from .engine import BUF_GENOME
@@ -131,9 +131,14 @@ def exchange_contigs(engine, device, sends, recvs):
         t = device_view(base + idx, n, device)
         keep.append(t)
         ops.append(dist.P2POp(dist.irecv, t, peer))
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    engine.synchronize()                      # the engine's stream may still be reading the staging region
+    ev0.record()
     for w in dist.batch_isend_irecv(ops):
         w.wait()
+    ev1.record()
     torch.cuda.synchronize()
+    return float(ev0.elapsed_time(ev1))
 
 
 def write_partitioned(path, my_ids, chunks, n_contigs, prefix: bytes = b""):

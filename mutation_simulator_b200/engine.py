@@ -92,11 +92,21 @@ class Engine:
                                               _ptr(self._len), _ptr(self._bpl), _ptr(self._gid), _ptr(self._hdr),
                                               _ptr(self._hoff), _ptr(self._nam), _ptr(self._noff)))
 
-    def synth_genome(self, seed: int, lengths, bpl, headers, names, n_fraction=0.0, telomere_n=0):
-        self._contig_args(lengths, bpl, headers, names, None)
-        self._check(self._lib.ms_genome_synth(self._h, seed, self.n_contigs, _ptr(self._len), _ptr(self._bpl),
+    def synth_genome(self, seed: int, lengths, bpl, headers, names, n_fraction=0.0, telomere_n=0, gid=None):
+        """Synthetic genome on the device; gid = global index of each contig (the bases of a contig depend on
+        (seed, gid) only, so a rank's share equals the same contigs of a single-GPU genome)."""
+        self._contig_args(lengths, bpl, headers, names, gid)
+        self._check(self._lib.ms_genome_synth(self._h, seed, self.n_contigs, _ptr(self._len), _ptr(self._bpl), _ptr(self._gid),
                                               float(n_fraction), int(telomere_n), _ptr(self._hdr), _ptr(self._hoff),
                                               _ptr(self._nam), _ptr(self._noff)))
+
+    def hash_ranges(self, which: int, start, end) -> np.ndarray:
+        """64-bit content hashes of byte ranges of an output buffer, computed on the device (ms_hash_ranges)."""
+        start = np.ascontiguousarray(start, dtype=np.int64); end = np.ascontiguousarray(end, dtype=np.int64)
+        out = np.zeros(len(start), dtype=np.uint64)
+        if len(start):
+            self._check(self._lib.ms_hash_ranges(self._h, which, len(start), _ptr(start), _ptr(end), _ptr(out)))
+        return out
 
     def ingest_fasta(self, fd: int, nbytes: int):
         """Raw FASTA file -> device image + record index (ms_fasta_ingest_fd / ms_fasta_index).  Returns None when the

@@ -185,47 +185,81 @@ class ITMutator:
         D.write_partitioned(self._args.outbedpe, [0] if rank == 0 else [], [bed] if rank == 0 else [], 1)
 
     def _mutate_partitioned(self):
-        """One process per GPU: contigs are partitioned; a pair that straddles two GPUs swaps its members over
-        NCCL P2P into the staging region behind each receiver's genome."""
+        """One process per GPU: contigs are partitioned; a pair that straddles two GPUs swaps the intervals each
+        member takes from the other over NCCL P2P, straight into the staging region behind the receiver's genome
+        (SURVEY.md §8e)."""
+        if D.shard_mode(self._fasta.lengths, self._world) == "tiles":
+            return self._mutate_tiles()
+        self.setup_partitioned()
+        self.step_partitioned()
+        self.write_partitioned()
+
+    # The three phases are separate so that bench.py can time the step (breakpoints -> exchange -> splice) alone.
+    def setup_partitioned(self):
+        """Partition, staging space for foreign partner intervals, upload of this rank's contigs."""
         fasta, rank, world = self._fasta, self._rank, self._world
         n_contigs = len(fasta.names)
-        if D.shard_mode(fasta.lengths, world) == "tiles":
-            return self._mutate_tiles()
         parts = D.lpt_partition(fasta.lengths, world)
-        own = D.owners(parts, n_contigs)
-        my_ids = parts[rank]
-        device = D.local_device()
+        self._own = own = D.owners(parts, n_contigs)
+        self._my_ids = my_ids = parts[rank]
+        self._device = device = D.local_device()
         eng = self._engine = getattr(fasta, "engine", None) or Engine(device)
-        # breakpoints need no resident genome (keyed by global contig id): identical on every rank
-        bps = self.breakpoints = self._generate_all_breakpoints(eng)
-        # which partner contigs must be fetched from a peer
-        foreign = sorted(self._partners[c] for c in my_ids if c in bps and own[self._partners[c]] != rank)
+        # partner contigs owned by a peer get a slot in the staging region (sized for the whole contig: an interval
+        # lands at its own coordinate, so the records' sources need no translation table)
+        foreign = sorted(self._partners[c] for c in my_ids if c in self._partners and own[self._partners[c]] != rank)
         stage_off, acc = {}, 0
         for p in foreign:
             stage_off[p] = acc
             acc += int(fasta.lengths[p]) + 64
         eng.reserve_foreign(acc)
-        fasta.upload(eng, my_ids)
+        if my_ids:
+            fasta.upload(eng, my_ids)
         total = int(sum(int(fasta.lengths[g]) for g in my_ids))
-        local_goff, o = {}, 0
+        self._local_goff, o = {}, 0
         for g in my_ids:
-            local_goff[g] = o
+            self._local_goff[g] = o
             o += int(fasta.lengths[g])
-        src_of = {p: local_goff[p] for p in my_ids}
-        src_of.update({p: total + 64 + off for p, off in stage_off.items()})
-        # globally agreed order: ascending (min, max) of each straddling pair
+        self._src_of = {p: self._local_goff[p] for p in my_ids}
+        self._src_of.update({p: total + 64 + off for p, off in stage_off.items()})
+        self.exchange_bytes = self.exchange_ms = 0
+
+    MAX_INTERVAL_OPS = 512      # beyond this many intervals per direction the whole contig goes as one transfer
+
+    def step_partitioned(self):
+        """Breakpoints (identical on every rank: keyed by the global contig id), exchange, records, splice."""
+        fasta, rank = self._fasta, self._rank
+        own, my_ids, src_of, local_goff = self._own, self._my_ids, self._src_of, self._local_goff
+        eng = self._engine
+        bps = self.breakpoints = self._generate_all_breakpoints(eng)
+        # globally agreed order: ascending (min, max) of each straddling pair; for each member the intervals the
+        # OTHER one takes from it (odd-numbered intervals of its own breakpoint list, it_mutator.py:133-137)
         sends, recvs = [], []
         for a in sorted(bps):
             b = self._partners[a]
             if a < b and own[a] != own[b]:
                 for mine, theirs in ((a, b), (b, a)):
-                    if own[mine] == rank:
-                        sends.append((int(own[theirs]), local_goff[mine], int(fasta.lengths[mine])))
-                        recvs.append((int(own[theirs]), src_of[theirs], int(fasta.lengths[theirs])))
-        D.exchange_contigs(eng, device, sends, recvs)
-        eng.load_records(self._records(bps, my_ids, src_of))
-        eng.apply()
-        D.write_fasta_partitioned(self._args.outfastait, eng, my_ids, n_contigs)
+                    if own[mine] != rank:
+                        continue
+                    peer = int(own[theirs])
+                    cut = np.concatenate(([0], bps[mine]["self"].astype(np.int64), [int(fasta.lengths[mine])]))
+                    cut_t = np.concatenate(([0], bps[theirs]["self"].astype(np.int64), [int(fasta.lengths[theirs])]))
+                    odd = np.arange(1, len(cut) - 1, 2)
+                    if len(odd) <= self.MAX_INTERVAL_OPS:
+                        sends += [(peer, local_goff[mine] + int(cut[i]), int(cut[i + 1] - cut[i])) for i in odd]
+                        recvs += [(peer, src_of[theirs] + int(cut_t[i]), int(cut_t[i + 1] - cut_t[i])) for i in odd]
+                    else:
+                        sends.append((peer, local_goff[mine], int(fasta.lengths[mine])))
+                        recvs.append((peer, src_of[theirs], int(fasta.lengths[theirs])))
+        self.exchange_bytes = sum(n for _, _, n in recvs)
+        self.exchange_ms = D.exchange_contigs(eng, self._device, sends, recvs)
+        if my_ids:
+            eng.load_records(self._records(bps, my_ids, src_of))
+            eng.apply()
+
+    def write_partitioned(self):
+        fasta, my_ids, bps = self._fasta, self._my_ids, self.breakpoints
+        n_contigs = len(fasta.names)
+        D.write_fasta_partitioned(self._args.outfastait, self._engine, my_ids, n_contigs)
         bed = []
         for g in my_ids:
             if g in bps:
