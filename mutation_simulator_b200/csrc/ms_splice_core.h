@@ -17,7 +17,6 @@ struct SpliceView {
     const uint8_t* genome;  // padded base array (>= 32 readable bytes past the last base)
     const uint8_t* lit;     // literal pool
     const Rec* recs;
-    const uint32_t* blk;    // coarse block index
     const uint8_t* conv;    // 256-entry tables (global or shared memory)
     const uint8_t* comp;
     Seed seed;              // for K_RAND payloads
@@ -57,11 +56,19 @@ MS_HD void cursor_load(const SpliceView& v, const Contig& c, int64_t i, Cursor& 
     k.next = (i + 1 < c.rec_hi) ? v.recs[i + 1].out : (uint32_t)c.out_len;
 }
 
+// the record governing output base b: the last one of the contig with out <= b (rec_lo - 1 if none)
+MS_HD int64_t rec_find(const SpliceView& v, const Contig& c, uint32_t b) {
+    int64_t lo = c.rec_lo, hi = c.rec_hi;   // first record with out > b
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (v.recs[mid].out <= b) lo = mid + 1; else hi = mid;
+    }
+    return lo - 1;
+}
+
 // Position the cursor on output base b (b < out_len).
 MS_HD void cursor_seek(const SpliceView& v, const Contig& c, uint32_t b, Cursor& k) {
-    int64_t i = c.rec_lo + (int64_t)v.blk[c.blk_lo + (b >> BLK_SHIFT)] - 1;
-    while (i + 1 < c.rec_hi && v.recs[i + 1].out <= b) ++i;
-    cursor_load(v, c, i, k);
+    cursor_load(v, c, rec_find(v, c, b), k);
 }
 
 MS_HD void cursor_advance(const SpliceView& v, const Contig& c, uint32_t b, Cursor& k) {
@@ -130,8 +137,7 @@ MS_HD bool group_fast(const SpliceView& v, const Contig& c, uint32_t q0, uint32_
     const uint32_t bL = bF + nb - 1u;
 
     // governing record of the first base
-    int64_t i = c.rec_lo + (int64_t)v.blk[c.blk_lo + (bF >> BLK_SHIFT)] - 1;
-    while (i + 1 < c.rec_hi && v.recs[i + 1].out <= bF) ++i;
+    const int64_t i = rec_find(v, c, bF);
     int64_t src0;
     uint32_t patch_pos[4];
     uint8_t patch_val[4];

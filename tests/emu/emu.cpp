@@ -13,6 +13,7 @@
 #include "../../mutation_simulator_b200/csrc/ms_splice_core.h"
 #include "../../mutation_simulator_b200/csrc/ms_vcf_core.h"
 #include "../../mutation_simulator_b200/csrc/ms_sample_core.h"
+#include "../../mutation_simulator_b200/csrc/ms_tile_core.h"
 
 using namespace ms;
 
@@ -40,7 +41,7 @@ int emu_apply(const uint8_t* genome, int32_t n_contigs, const int64_t* goff, con
     Tables tab; fill_tables(tab);
     std::vector<Contig> C(n_contigs);
     // delta scan + per-contig record ranges (K5)
-    int64_t ri = 0, file = 0, blk_total = 0, piece_total = 0;
+    int64_t ri = 0, file = 0, piece_total = 0;
     for (int c = 0; c < n_contigs; ++c) {
         Contig& k = C[c];
         memset(&k, 0, sizeof(k));
@@ -61,25 +62,12 @@ int emu_apply(const uint8_t* genome, int32_t n_contigs, const int64_t* goff, con
         k.hdr_off = file;
         k.body_off = file + 1 + k.hdr_len + 1;
         file = k.body_off + k.body_bytes + k.sep;
-        k.blk_lo = blk_total;
-        blk_total += (k.out_len >> BLK_SHIFT) + 1;
         k.piece_lo = piece_total;
         if (k.body_bytes > 0) piece_total += (k.body_off + k.body_bytes - 1) / tile_bytes - k.body_off / tile_bytes + 1;
     }
     if (file > fasta_cap) return -1;
     *fasta_len = file;
-    // coarse block index
-    std::vector<uint32_t> blk(blk_total);
-    for (int c = 0; c < n_contigs; ++c) {
-        const Contig& k = C[c];
-        int64_t nb = (k.out_len >> BLK_SHIFT) + 1;
-        int64_t r = k.rec_lo;
-        for (int64_t b = 0; b < nb; ++b) {
-            while (r < k.rec_hi && (int64_t)recs[r].out < b * BLK_BASES) ++r;
-            blk[k.blk_lo + b] = (uint32_t)(r - k.rec_lo);
-        }
-    }
-    SpliceView v{genome, lit, recs, blk.data(), tab.conv, tab.comp, Seed{0, 0}};
+    SpliceView v{genome, lit, recs, tab.conv, tab.comp, Seed{0, 0}};
     memset(fasta, 0, (size_t)file);
     int64_t nf = 0, ns = 0;
     for (int c = 0; c < n_contigs; ++c) {
@@ -125,6 +113,132 @@ int emu_apply(const uint8_t* genome, int32_t n_contigs, const int64_t* goff, con
         if (s.p != vcf + offs[i + 1]) return -3;
     }
     *vcf_len = off;
+    return 0;
+}
+
+// The second-generation splice kernel (ms_tile_core.h) emulated one "thread" at a time: per piece the same phases the
+// CTA runs — prep, chunk copy with a dirty queue, dirty bytes, SNP scatter, store — with shared memory on the heap.
+// Pieces flagged PD_FALLBACK take the generic per-group path, as on the device.
+int emu_apply_tiles(const uint8_t* genome, int32_t n_contigs, const int64_t* goff, const int64_t* clen, const int32_t* bpl,
+                    const uint8_t* headers, const int64_t* hdr_off, Rec* recs, int64_t n_recs, const uint8_t* lit,
+                    uint8_t* fasta, int64_t fasta_cap, int64_t* fasta_len, int64_t tile_bytes, int64_t* n_clean, int64_t* n_dirty,
+                    int64_t* n_fallback) {
+    Tables tab; fill_tables(tab);
+    std::vector<Contig> C(n_contigs);
+    std::vector<SvRec> sv;
+    std::vector<Snp8> snp;
+    std::vector<int64_t> sv_c(n_contigs + 1), snp_c(n_contigs + 1);
+    int64_t ri = 0, file = 0;
+    for (int c = 0; c < n_contigs; ++c) {
+        Contig& k = C[c];
+        memset(&k, 0, sizeof(k));
+        k.goff = goff[c]; k.len = clen[c]; k.bpl = bpl[c] > 0 ? bpl[c] : 60; k.gid = c;
+        k.hdr_src = hdr_off[c]; k.hdr_len = (int32_t)(hdr_off[c + 1] - hdr_off[c]);
+        k.rec_lo = ri;
+        sv_c[c] = (int64_t)sv.size(); snp_c[c] = (int64_t)snp.size();
+        int64_t delta = 0;
+        while (ri < n_recs && recs[ri].contig == (uint32_t)c) {
+            Rec& r = recs[ri];
+            r.out = (uint32_t)((int64_t)r.pos + delta);
+            delta += (int64_t)r.prod - (int64_t)r.cons;
+            if (r.kind == K_SNP) snp.push_back(Snp8{r.out, r.alt});
+            else sv.push_back(SvRec{r.out, r.prod, r.pos + r.cons, r.pos, r.src, r.kind, 0u});
+            ++ri;
+        }
+        k.rec_hi = ri;
+        k.out_len = k.len + delta;
+        k.body_bytes = k.out_len + k.out_len / k.bpl;
+        k.sep = (k.out_len % k.bpl != 0 && c != n_contigs - 1) ? 1 : 0;
+        k.hdr_off = file;
+        k.body_off = file + 1 + k.hdr_len + 1;
+        file = k.body_off + k.body_bytes + k.sep;
+    }
+    sv_c[n_contigs] = (int64_t)sv.size(); snp_c[n_contigs] = (int64_t)snp.size();
+    sv.resize(sv.size() + 4); snp.resize(snp.size() + 4);
+    if (file > fasta_cap) return -1;
+    *fasta_len = file;
+    memset(fasta, 0, (size_t)file);
+    SpliceView v{genome, lit, recs, tab.conv, tab.comp, Seed{0, 0}};
+    TileView tv{genome, lit, tab.conv, tab.comp, Seed{0, 0}};
+    int64_t nc = 0, nd = 0, nf = 0;
+    std::vector<uint8_t> stage(TL_STAGE_CAP + 64), image(tile_bytes + 64);
+    std::vector<SvRec> ssv(TL_SV_CAP + 1);
+    std::vector<uint32_t> rs(TL_SV_CAP + 2);
+    std::vector<TileRec> dv(TL_SV_CAP + 1);
+    for (int c = 0; c < n_contigs; ++c) {
+        const Contig& k = C[c];
+        fasta[k.hdr_off] = '>';
+        memcpy(fasta + k.hdr_off + 1, headers + k.hdr_src, (size_t)k.hdr_len);
+        fasta[k.hdr_off + 1 + k.hdr_len] = '\n';
+        if (k.sep) fasta[k.body_off + k.body_bytes] = '\n';
+        if (k.body_bytes == 0) continue;
+        int64_t t0 = k.body_off / tile_bytes, t1 = (k.body_off + k.body_bytes - 1) / tile_bytes;
+        for (int64_t t = t0; t <= t1; ++t) {
+            int64_t f_lo = t * tile_bytes, f_hi = f_lo + tile_bytes;
+            if (f_lo < k.body_off) f_lo = k.body_off;
+            if (f_hi > k.body_off + k.body_bytes) f_hi = k.body_off + k.body_bytes;
+            const PieceDesc d = tile_describe(k, (uint32_t)c, f_lo, f_hi, sv.data(), sv_c[c], sv_c[c + 1], snp.data(), snp_c[c], snp_c[c + 1]);
+            const int64_t g0 = f_lo & ~(int64_t)15;
+            if (d.flags & PD_FALLBACK) {
+                ++nf;
+                for (int64_t g = g0; g < f_hi; g += 16) {
+                    int64_t a = g < f_lo ? f_lo : g, b = g + 16 > f_hi ? f_hi : g + 16;
+                    uint32_t w[4] = {0, 0, 0, 0};
+                    group_slow(v, k, (uint32_t)(a - k.body_off), (int)(b - a), (int)(a - g), w);
+                    for (int64_t x = a; x < b; ++x) fasta[x] = (uint8_t)(w[(x - g) >> 2] >> (8 * ((x - g) & 3)));
+                }
+                continue;
+            }
+            // "TMA": staged span, records
+            memset(stage.data(), 0xEE, stage.size());
+            memcpy(stage.data(), genome + d.in_lo, d.in_bytes);
+            memset(image.data(), 0xDD, image.size());
+            if (d.flags & PD_GOV_VIRTUAL) { ssv[0] = SvRec{0u, 0u, 0u, 0u, 0, K_NONE, 0u}; for (uint32_t j = 1; j < d.n_sv; ++j) ssv[j] = sv[d.sv_lo + j - 1]; }
+            else for (uint32_t j = 0; j < d.n_sv; ++j) ssv[j] = sv[d.sv_lo + j];
+            TileShared sh{stage.data(), image.data(), ssv.data(), snp.data() + d.snp_lo, rs.data(), dv.data()};
+            for (uint32_t j = 0; j < d.n_sv; ++j) tile_prep_rec(d, sh, j);
+            rs[d.n_sv] = d.b_hi - d.b_lo;
+            const uint32_t w1 = d.bpl + 1u;
+            const float rcp_w1 = tl_rcp(w1), rcp_bpl = tl_rcp(d.bpl);
+            const uint32_t e = (uint32_t)(f_lo - g0), img_end = (uint32_t)(f_hi - g0);
+            const uint32_t xa = (e + 15u) & ~15u, xb = img_end & ~15u;
+            std::vector<std::pair<uint32_t, uint32_t>> dirty;
+            for (uint32_t x = 0; x < img_end; x += 16u) {
+                const bool full = x >= e && x + 16u <= img_end;
+                const uint32_t d0 = (x > e ? x : e) - e;                       // offset from f_lo of the chunk's first byte
+                const uint32_t dl = div_small(d.col_lo + d0, w1, rcp_w1);
+                const uint32_t col = d.col_lo + d0 - dl * w1;
+                const uint32_t rF = d0 - dl;
+                const uint32_t j = tile_find(rs.data(), d.n_sv, rF);
+                if (!full) { dirty.push_back({x, j}); continue; }               // piece edge: byte-wise
+                const uint32_t j_nl = d.bpl - col;
+                const uint32_t nb = j_nl < 16u ? 15u : 16u;
+                int32_t s_off; int64_t g_src = 0;
+                if (tile_chunk_source(d, sh, j, rF, nb, &s_off, &g_src)) {
+                    ++nc;
+                    const uint8_t* src = s_off != TL_DIRECT ? stage.data() + s_off : genome + g_src;
+                    uint32_t si = 0;
+                    for (uint32_t t2 = 0; t2 < 16u; ++t2) image[x + t2] = (t2 == j_nl) ? (uint8_t)'\n' : src[si++];
+                } else {
+                    dirty.push_back({x, j});
+                }
+            }
+            for (auto& q : dirty) {
+                ++nd;
+                for (uint32_t t2 = 0; t2 < 16u; ++t2) {
+                    const uint32_t X = q.first + t2;
+                    if (X < e || X >= img_end) continue;
+                    image[X] = tile_byte(d, sh, tv, X - e, q.second, rcp_w1);
+                }
+            }
+            for (uint32_t i = 0; i < d.n_snp; ++i) {
+                const Snp8 sp = sh.snp[i];
+                image[e + tile_snp_offset(d, sp.out, rcp_bpl)] = (uint8_t)sp.alt;
+            }
+            for (uint32_t X = e; X < img_end; ++X) fasta[g0 + X] = image[X];
+        }
+    }
+    *n_clean = nc; *n_dirty = nd; *n_fallback = nf;
     return 0;
 }
 

@@ -102,6 +102,36 @@ def run_emu_apply(emu, contigs, tables, tile_bytes=4096, vcf_text=None):
     return fa[:fl.value].tobytes(), vcf[:vl.value].tobytes(), nf.value, ns.value
 
 
+def run_emu_tiles(emu, contigs, tables, tile_bytes=16384):
+    """FASTA image through the second-generation tile kernel's core (ms_tile_core.h) emulated on the CPU."""
+    seqs = [c[2] for c in contigs]
+    genome, goff = R.pack_genome(seqs)
+    lens = np.array([len(s) for s in seqs], dtype=np.int64)
+    bpl = np.array([c[3] for c in contigs], dtype=np.int32)
+    hdr = b"".join(c[1] for c in contigs)
+    hoff = np.cumsum([0] + [len(c[1]) for c in contigs]).astype(np.int64)
+    recs, lit = R.build_records(genome, goff, lens, tables)
+    cap_f = int(lens.sum() * 3 + recs["prod"].sum() * 2 + 4096 + len(hdr) * 2)
+    fa = np.zeros(cap_f, dtype=np.uint8)
+    fl, nc, nd, nf = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = emu.emu_apply_tiles(P(genome), C.c_int32(len(contigs)), P(goff), P(lens), P(bpl), hdr, P(hoff),
+                             P(recs), C.c_int64(len(recs)), P(lit), P(fa), C.c_int64(cap_f), C.byref(fl), C.c_int64(tile_bytes),
+                             C.byref(nc), C.byref(nd), C.byref(nf))
+    assert rc == 0
+    return fa[:fl.value].tobytes(), nc.value, nd.value, nf.value
+
+
+@pytest.mark.parametrize("case", MS_CASES)
+@pytest.mark.parametrize("tile", [1024, 16384])
+def test_emulated_tile_kernel_matches_reference(emu, case, tile):
+    d, contigs = load_case(case)
+    fa, nc, nd, nf = run_emu_tiles(emu, contigs, tables_from_golden(case), tile)
+    assert fa == (d / "out.fa").read_bytes()
+    if case in ("args_all", "c1_small"):
+        assert nc > 2 * nd and nf == 0     # most chunks are single shifted copies; no tile needs the generic path
+
+
 def tables_from_golden(case):
     out = []
     for muts in load_muts(case):
@@ -222,3 +252,10 @@ def test_emulated_apply_matches_c_oracle_randomized(emu, bpl, alphabet):
     fa, vcf, nf, ns = run_emu_apply(emu, contigs, tables, tile_bytes=1024)
     assert fa == want_fa
     assert vcf == want_vcf
+    for tile in (1024, 16384):
+        fa2, nc, nd, nfb = run_emu_tiles(emu, contigs, tables, tile)
+        assert fa2 == want_fa, (bpl, tile)
+        if bpl < 16:
+            assert nfb > 0 and nc == 0     # lines shorter than a chunk take the generic path
+        elif tile == 1024:
+            assert nfb == 0                # (at 16 KiB these very dense tables exceed the per-tile record pool)
