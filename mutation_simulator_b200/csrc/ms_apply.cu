@@ -7,6 +7,8 @@
 #include "ms_common.cuh"
 #include "ms_scan.cuh"
 #include "ms_splice_core.h"
+#define MS_TILE_RAND_OOL 1
+#include "ms_tile_core.h"
 #include "ms_vcf_core.h"
 #include "ms_sample_core.h"
 
@@ -17,9 +19,6 @@ namespace ms {
 __device__ __noinline__ uint8_t rand_base_ool(Seed seed, uint32_t gid, uint32_t pos, uint32_t j) {
     return rand_insert_base(seed, gid, pos, j);
 }
-
-struct Gap { int64_t start; uint32_t count; uint32_t value; };
-constexpr uint32_t GAP_INLINE = 32;
 
 __device__ inline void raise_error(Totals* t, int64_t code, int64_t arg) {
     if (atomicCAS((unsigned long long*)&t->error, 0ull, (unsigned long long)code) == 0ull) t->error_arg = arg;
@@ -40,16 +39,15 @@ __global__ void k_rec_bounds(const Rec* recs, int64_t n_recs, Contig* contigs, i
 
 // ---- layout of the output file image ---------------------------------------------------
 // One CTA walks the contigs in FASTA order (they are few: 24 .. 200k) carrying the
-// running file offset, block-index offset and piece count.
+// running file offset and piece count.
 __global__ void __launch_bounds__(SCAN_THREADS)
 k_contig_layout(Contig* contigs, int32_t n_contigs, const int64_t* S, int64_t* piece_lo, int64_t tile_bytes,
-                Gap* gaps, int64_t gap_cap, Totals* tot, int64_t n_recs, const int64_t* V) {
-    __shared__ I64x2 sm2[2 * SCAN_THREADS / 32];
+                Totals* tot, int64_t n_recs, const int64_t* V, const uint32_t* N) {
     __shared__ int64_t sm1[2 * SCAN_THREADS / 32];
-    I64x2 carry{0, 0};
+    int64_t carry = 0;
     for (int base = 0; base < n_contigs; base += SCAN_THREADS) {
         const int c = base + threadIdx.x;
-        I64x2 v{0, 0};
+        int64_t v = 0;
         if (c < n_contigs) {
             Contig& k = contigs[c];
             const int64_t delta = S[k.rec_hi] - S[k.rec_lo];
@@ -60,18 +58,16 @@ k_contig_layout(Contig* contigs, int32_t n_contigs, const int64_t* S, int64_t* p
             k.body_bytes = out_len + out_len / bpl;
             if (k.body_bytes >= (int64_t)0xFFFFFFF0ll || out_len >= (int64_t)0xFFFFFFF0ll) raise_error(tot, MS_ERR_LIMIT, c);
             k.sep = (out_len % bpl != 0 && c != n_contigs - 1) ? 1u : 0u;
-            v.a = (int64_t)k.hdr_len + 2 + k.body_bytes + k.sep;
-            v.b = (out_len >> BLK_SHIFT) + 1;
+            v = (int64_t)k.hdr_len + 2 + k.body_bytes + k.sep;
         }
-        I64x2 total;
-        I64x2 ex = block_excl_scan(v, I64x2{0, 0}, SumOp(), total, sm2);
+        int64_t total;
+        const int64_t ex = block_excl_scan(v, (int64_t)0, SumOp(), total, sm1);
         if (c < n_contigs) {
             Contig& k = contigs[c];
-            k.hdr_off = carry.a + ex.a;
+            k.hdr_off = carry + ex;
             k.body_off = k.hdr_off + k.hdr_len + 2;
-            k.blk_lo = carry.b + ex.b;
         }
-        carry = carry + total;
+        carry += total;
     }
     __syncthreads();
     int64_t pcarry = 0;
@@ -89,8 +85,8 @@ k_contig_layout(Contig* contigs, int32_t n_contigs, const int64_t* S, int64_t* p
     }
     if (threadIdx.x == 0) {
         piece_lo[n_contigs] = pcarry;
-        tot->fasta_bytes = carry.a;
-        tot->n_blk = carry.b;
+        tot->fasta_bytes = carry;
+        tot->n_blk = (int64_t)N[n_recs];          // (field reused: number of SvRecs)
         tot->n_pieces = pcarry;
         tot->vcf_bytes = V[n_recs];
         tot->n_recs = n_recs;
@@ -99,22 +95,22 @@ k_contig_layout(Contig* contigs, int32_t n_contigs, const int64_t* S, int64_t* p
 
 // The same layout for large contig tables (many-small-contig genomes): two device-wide scans instead of one CTA
 // walking 200 k contigs (3.6 ms on C5).
-__global__ void k_layout_totals(const I64x2* t1, const int64_t* t2, int64_t* piece_lo, int32_t n_contigs, Totals* tot, int64_t n_recs,
-                                const int64_t* V) {
+__global__ void k_layout_totals(const int64_t* t1, const int64_t* t2, int64_t* piece_lo, int32_t n_contigs, Totals* tot, int64_t n_recs,
+                                const int64_t* V, const uint32_t* N) {
     piece_lo[n_contigs] = *t2;
-    tot->fasta_bytes = t1->a; tot->n_blk = t1->b; tot->n_pieces = *t2;
+    tot->fasta_bytes = *t1; tot->n_blk = (int64_t)N[n_recs]; tot->n_pieces = *t2;
     tot->vcf_bytes = V[n_recs]; tot->n_recs = n_recs;
 }
 
-static int layout_by_scan(ms_ctx* c, Contig* d_contigs, const int64_t* S, const int64_t* V, int64_t M, Totals* d_tot) {
+static int layout_by_scan(ms_ctx* c, Contig* d_contigs, const int64_t* S, const int64_t* V, const uint32_t* N, int64_t M, Totals* d_tot) {
     const int32_t n = c->n_contigs;
     int64_t* d_piece_lo = c->piece_lo.as<int64_t>();
     const int64_t tile_bytes = c->tile_bytes;
     MS_CUDA(c, c->scan_tmp2.ensure(64));
-    I64x2* d_t1 = c->scan_tmp2.as<I64x2>();
-    int64_t* d_t2 = reinterpret_cast<int64_t*>(d_t1 + 1);
+    int64_t* d_t1 = c->scan_tmp2.as<int64_t>();
+    int64_t* d_t2 = d_t1 + 1;
     {
-        auto in = [=] __device__(int64_t i) -> I64x2 {
+        auto in = [=] __device__(int64_t i) -> int64_t {
             Contig& k = d_contigs[i];
             const int64_t out_len = k.len + (S[k.rec_hi] - S[k.rec_lo]);
             if (out_len < 0) raise_error(d_tot, MS_ERR_OVERLAP, i);
@@ -122,16 +118,16 @@ static int layout_by_scan(ms_ctx* c, Contig* d_contigs, const int64_t* S, const 
             const int64_t body = out_len + out_len / bpl;
             if (body >= (int64_t)0xFFFFFFF0ll) raise_error(d_tot, MS_ERR_LIMIT, i);
             const uint32_t sep = (out_len % bpl != 0 && i != n - 1) ? 1u : 0u;
-            k.out_len = out_len; k.body_bytes = body; k.sep = sep;    // idempotent: the scan evaluates `in` twice
-            return I64x2{(int64_t)k.hdr_len + 2 + body + sep, (out_len >> BLK_SHIFT) + 1};
+            k.out_len = out_len; k.body_bytes = body; k.sep = sep;
+            return (int64_t)k.hdr_len + 2 + body + sep;
         };
-        auto out = [=] __device__(int64_t i, I64x2 ex, I64x2) {
+        auto out = [=] __device__(int64_t i, int64_t ex, int64_t) {
             Contig& k = d_contigs[i];
-            k.hdr_off = ex.a; k.body_off = ex.a + k.hdr_len + 2; k.blk_lo = ex.b;
+            k.hdr_off = ex; k.body_off = ex + k.hdr_len + 2;
         };
-        I64x2* tot1 = nullptr;
-        MS_CUDA(c, (device_scan<I64x2>(c, in, out, (int64_t)n, I64x2{0, 0}, SumOp(), c->scan_tmp, &tot1)));
-        MS_CUDA(c, cudaMemcpyAsync(d_t1, tot1, sizeof(I64x2), cudaMemcpyDeviceToDevice, c->stream));
+        int64_t* tot1 = nullptr;
+        MS_CUDA(c, (device_scan<int64_t>(c, in, out, (int64_t)n, (int64_t)0, SumOp(), c->scan_tmp, &tot1)));
+        MS_CUDA(c, cudaMemcpyAsync(d_t1, tot1, sizeof(int64_t), cudaMemcpyDeviceToDevice, c->stream));
     }
     {
         auto in = [=] __device__(int64_t i) -> int64_t {
@@ -143,84 +139,47 @@ static int layout_by_scan(ms_ctx* c, Contig* d_contigs, const int64_t* S, const 
         MS_CUDA(c, (device_scan<int64_t>(c, in, out, (int64_t)n, (int64_t)0, SumOp(), c->scan_tmp, &tot2)));
         MS_CUDA(c, cudaMemcpyAsync(d_t2, tot2, sizeof(int64_t), cudaMemcpyDeviceToDevice, c->stream));
     }
-    k_layout_totals<<<1, 1, 0, c->stream>>>(d_t1, d_t2, d_piece_lo, n, d_tot, M, V);
+    k_layout_totals<<<1, 1, 0, c->stream>>>(d_t1, d_t2, d_piece_lo, n, d_tot, M, V, N);
     MS_LAUNCH_CHECK(c);
     return MS_OK;
 }
 
-// ---- out positions, validation and the coarse block index ----------------------------
-// blk[k] of a contig = number of its records with out < k*BLK_BASES.
-__device__ inline void fill_blk(uint32_t* blk, int64_t start, int64_t count, uint32_t value, Gap* gaps, int64_t gap_cap, Totals* tot) {
-    if (count <= 0) return;
-    if (count <= GAP_INLINE) {
-        for (int64_t k = 0; k < count; ++k) blk[start + k] = value;
-    } else {
-        while (count > 0) {  // split very long gaps so one CTA never fills more than 1M entries
-            const int64_t n = count > (1 << 20) ? (1 << 20) : count;
-            const unsigned long long slot = atomicAdd((unsigned long long*)&tot->n_long_gaps, 1ull);
-            if ((int64_t)slot < gap_cap) gaps[slot] = Gap{start, (uint32_t)n, value};
-            else raise_error(tot, MS_ERR_INTERNAL, 1);
-            start += n; count -= n;
-        }
-    }
-}
-
+// ---- out positions, validation, and the two record streams the splice kernel reads -----------------------------
+// S[i] = sum of length deltas before record i, N[i] = number of non-SNP records before i (both over all contigs).
+// Record i lands in slot N[i] of the SvRec stream or slot i - N[i] of the Snp8 stream; a contig's entries are
+// [N[rec_lo], N[rec_hi]) resp. [rec_lo - N[rec_lo], rec_hi - N[rec_hi]).  A SNP's stream slot is also left in its
+// (otherwise unused) Rec.src so that k_snp_fill can patch the substituted base in later (streamed runs).
 __global__ void __launch_bounds__(256)
-k_rec_out(Rec* recs, int64_t n_recs, const Contig* contigs, const int64_t* S, uint32_t* blk, Gap* gaps, int64_t gap_cap, Totals* tot) {
+k_rec_out(Rec* recs, int64_t n_recs, const Contig* contigs, const int64_t* S, const uint32_t* N, SvRec* sv, Snp8* snp, Totals* tot) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_recs) return;
-    Rec r = recs[i];
+    const Rec r = recs[i];
     const Contig& k = contigs[r.contig];
-    const int64_t s0 = S[k.rec_lo];
-    const int64_t out = (int64_t)r.pos + (S[i] - s0);
+    const int64_t out = (int64_t)r.pos + (S[i] - S[k.rec_lo]);
     if ((int64_t)r.pos + r.cons > k.len) raise_error(tot, MS_ERR_OVERLAP, i);
-    int64_t prev_blk = -1;  // block of the previous record's out
     if (i > k.rec_lo) {
         const Rec p = recs[i - 1];
         if ((int64_t)r.pos < (int64_t)p.pos + p.cons || r.pos == p.pos) raise_error(tot, MS_ERR_OVERLAP, i);
-        prev_blk = ((int64_t)p.pos + (S[i - 1] - s0)) >> BLK_SHIFT;
     }
-    recs[i].out = (uint32_t)out;
-    const uint32_t j = (uint32_t)(i - k.rec_lo);
-    const int64_t my_blk = out >> BLK_SHIFT;
-    fill_blk(blk, k.blk_lo + prev_blk + 1, my_blk - prev_blk, j, gaps, gap_cap, tot);
-    if (i + 1 == k.rec_hi) {
-        const int64_t nblk = (k.out_len >> BLK_SHIFT) + 1;
-        fill_blk(blk, k.blk_lo + my_blk + 1, nblk - (my_blk + 1), j + 1, gaps, gap_cap, tot);
-    }
-}
-
-__global__ void k_empty_contig_gaps(const Contig* contigs, int32_t n_contigs, uint32_t* blk, Gap* gaps, int64_t gap_cap, Totals* tot) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n_contigs) return;
-    const Contig& k = contigs[c];
-    if (k.rec_lo == k.rec_hi) fill_blk(blk, k.blk_lo, (k.out_len >> BLK_SHIFT) + 1, 0u, gaps, gap_cap, tot);
-}
-
-__global__ void __launch_bounds__(256) k_fill_gaps(uint32_t* blk, const Gap* gaps, const Totals* tot) {
-    const int64_t n = tot->n_long_gaps;
-    for (int64_t g = blockIdx.x; g < n; g += gridDim.x) {
-        const Gap gp = gaps[g];
-        for (uint32_t k = threadIdx.x; k < gp.count; k += blockDim.x) blk[gp.start + k] = gp.value;
+    const uint32_t nsv = N[i];
+    if (r.kind == K_SNP) {
+        const int64_t slot = i - (int64_t)nsv;
+        snp[slot] = Snp8{(uint32_t)out, (uint32_t)r.alt};
+        uint4 lo4 = *reinterpret_cast<const uint4*>(&r);
+        lo4.w = (uint32_t)out;
+        uint4* dst = reinterpret_cast<uint4*>(recs + i);
+        dst[0] = lo4;
+        reinterpret_cast<int64_t*>(recs + i)[2] = slot;
+    } else {
+        sv[nsv] = SvRec{(uint32_t)out, r.prod, r.pos + r.cons, r.pos, r.src, (uint32_t)r.kind, 0u};
+        recs[i].out = (uint32_t)out;
     }
 }
 
 // ---- K6: splice + SNP + line wrap -----------------------------------------------------
-// One CTA per piece (= 16 KiB tile of the output file image intersected with one contig body).
+// One CTA per piece (= 16 KiB tile of the output file image intersected with one contig body); the index logic lives in
+// ms_tile_core.h (shared with the CPU emulation in tests/emu), this file supplies the memory operations.
 constexpr int SPLICE_THREADS = 256;
-
-// Run-centric splice.  SNPs do not move anything, so between two consecutive non-SNP
-// records the output is one shifted copy of the input ("run", ~290 bases at human-like
-// rates).  A CTA assembles the mutated bases of its tile in shared memory:
-//   S1  every run (and every raw payload: tandem duplications, interchromosomal
-//       segments) is a warp-level shifted copy global -> shared, 16 bytes per lane;
-//   S2  one thread per record scatters SNP bases and queues the remaining payloads
-//       (random inserts, inversions, translocation inserts) as byte jobs for warps;
-//   S3  line breaks are inserted while the tile is written out, 16 aligned bytes per
-//       lane (2 x LDS.128 -> 1 x STG.128).
-// The group-centric version it replaces spent ~490 warp-instructions per 512 bytes on
-// per-group record lookups (profiles/r1b); here lookups are per run.
-struct SegC { int64_t src; uint32_t dst; uint32_t n; };   // copy n bytes genome[src..] -> tile[dst..]; jobs: n | kind << 24
 
 // bytes [o, o+16) of the 32-byte window (a, b)
 __device__ __forceinline__ uint4 shift16(const uint4 a, const uint4 b, uint32_t o) {
@@ -233,35 +192,29 @@ __device__ __forceinline__ uint4 shift16(const uint4 a, const uint4 b, uint32_t 
                       __funnelshift_r(u3, u4, bs));
 }
 
-constexpr int SP_TILE_MAX = 16384;
-constexpr int SP_RUN_CAP = 512;
-constexpr int SP_SEG_CAP = 320;
-constexpr int SP_JOB_CAP = 192;
-constexpr uint32_t SP_STAGE_CAP = 18 * 1024;       // TMA staging of the runs' input spans (tile + alignment slack)
-constexpr uint32_t SP_DIRECT = 0xFFFFFFFFu;        // segment did not fit the staging buffer: copied straight from global
-constexpr uint32_t SP_SEG_SPLIT = 2048;
-// Everything a splice CTA needs to start, precomputed by a fully parallel kernel so that the CTA's own dependent
-// chain of global round trips (piece -> contig search, contig, block index, record window) collapses into one
-// 96-byte load (profiles/r1h: the kernel is bound by that chain, not by issue slots or bandwidth).
-struct PieceDesc {
-    int64_t f_lo, f_hi;          // file bytes of the piece
-    int64_t i_first, i_last;     // records governing its bases (i_first may be the virtual rec_lo - 1)
-    int64_t body_off, goff, rec_lo;
-    int64_t in_lo;               // 16-byte aligned genome index where the tile's contiguous input span starts
-    uint32_t bpl, gid, cidx, b_lo, b_hi;
-    uint32_t in_bytes;           // staged bytes of that span (multiple of 16, <= SP_STAGE_CAP)
-    uint32_t pad[2];
-};
-static_assert(sizeof(PieceDesc) == 96, "PieceDesc layout");
+// the 16 file bytes made of x's first 15 bases with a line break inserted at byte j (< 16): one PRMT per word
+__device__ __forceinline__ uint4 insert_nl(const uint4 x, uint32_t j) {
+    //   word w <  jw : untouched
+    //   word w == jw : byte t becomes '\n', the bytes above it take x_w[t..]
+    //   word w >  jw : shifted up by one byte, filled from x_{w-1}
+    const uint32_t jw = j >> 2, t = j & 3u;
+    const uint32_t selnl = (uint32_t)(0x4210241021402104ull >> (16u * t)) & 0xFFFFu;
+    uint4 y;
+    y.x = __byte_perm(x.x, 0x0Au, jw == 0u ? selnl : 0x3210u);
+    y.y = __byte_perm(x.y, jw == 1u ? 0x0Au : x.x, jw > 1u ? 0x3210u : (jw == 1u ? selnl : 0x2107u));
+    y.z = __byte_perm(x.z, jw == 2u ? 0x0Au : x.y, jw > 2u ? 0x3210u : (jw == 2u ? selnl : 0x2107u));
+    y.w = __byte_perm(x.w, jw == 3u ? 0x0Au : x.z, jw == 3u ? selnl : 0x2107u);
+    return y;
+}
 
 __global__ void __launch_bounds__(256)
-k_piece_desc(const Contig* contigs, int32_t n_contigs, const int64_t* piece_lo, int64_t n_pieces, const Rec* recs,
-             const uint32_t* blk, const Totals* tot, PieceDesc* out) {
+k_piece_desc(const Contig* contigs, int32_t n_contigs, const int64_t* piece_lo, int64_t n_pieces, const SvRec* sv, const Snp8* snp,
+             const uint32_t* N, const Totals* tot, PieceDesc* out) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_pieces) return;
     if (tot->error) {   // k_rec_out rejected the records (overlap / out of bounds): every piece becomes empty, the
         PieceDesc z{};  // splice kernel then touches nothing and ms_apply reports the error
-        z.i_last = -1; z.bpl = 60u;
+        z.bpl = 60u;
         out[p] = z;
         return;
     }
@@ -271,40 +224,12 @@ k_piece_desc(const Contig* contigs, int32_t n_contigs, const int64_t* piece_lo, 
         if (piece_lo[mid] <= p) lo = mid; else hi = mid;
     }
     const Contig k = contigs[lo];
-    PieceDesc d;
     const int64_t tile_i = (k.body_off >> 14) + (p - k.piece_lo);
-    d.f_lo = tile_i << 14; d.f_hi = d.f_lo + 16384;
-    if (d.f_lo < k.body_off) d.f_lo = k.body_off;
-    if (d.f_hi > k.body_off + k.body_bytes) d.f_hi = k.body_off + k.body_bytes;
-    const uint32_t w1 = (uint32_t)k.bpl + 1u;
-    const uint32_t q_lo = (uint32_t)(d.f_lo - k.body_off), q_hi = (uint32_t)(d.f_hi - k.body_off);
-    d.b_lo = q_lo - q_lo / w1; d.b_hi = q_hi - q_hi / w1;
-    int64_t r = k.rec_lo + (int64_t)blk[k.blk_lo + (d.b_lo >> BLK_SHIFT)] - 1;
-    while (r + 1 < k.rec_hi && recs[r + 1].out <= d.b_lo) ++r;
-    d.i_first = r;
-    const uint32_t t = d.b_hi > d.b_lo ? d.b_hi - 1u : d.b_lo;
-    r = k.rec_lo + (int64_t)blk[k.blk_lo + (t >> BLK_SHIFT)] - 1;
-    if (r < d.i_first) r = d.i_first;
-    while (r + 1 < k.rec_hi && recs[r + 1].out <= t) ++r;
-    d.i_last = r;
-    d.body_off = k.body_off; d.goff = k.goff; d.rec_lo = k.rec_lo;
-    d.bpl = (uint32_t)k.bpl; d.gid = k.gid; d.cidx = (uint32_t)lo; d.pad[0] = d.pad[1] = 0u;
-    // the copy runs of a tile read one contiguous, monotone stretch of the contig: from the source of its first
-    // base to the source of its last base (payloads come from elsewhere and are not part of it)
-    auto src_of = [&](int64_t ri, uint32_t b) -> int64_t {
-        if (ri < k.rec_lo) return k.goff + (int64_t)b;
-        const Rec q = recs[ri];
-        const uint32_t rel = b - q.out;
-        return k.goff + (int64_t)q.pos + (int64_t)q.cons + (rel >= q.prod ? (int64_t)(rel - q.prod) : 0);
-    };
-    const int64_t s_lo = src_of(d.i_first, d.b_lo);
-    int64_t s_hi = src_of(d.i_last, t) + 1;
-    if (s_hi > k.goff + k.len) s_hi = k.goff + k.len;
-    d.in_lo = s_lo & ~(int64_t)15;
-    int64_t nb = s_hi > d.in_lo ? ((s_hi + 15) & ~(int64_t)15) - d.in_lo : 0;
-    if (nb > (int64_t)SP_STAGE_CAP) nb = SP_STAGE_CAP;
-    d.in_bytes = (uint32_t)nb;
-    out[p] = d;
+    int64_t f_lo = tile_i << 14, f_hi = f_lo + TL_TILE;
+    if (f_lo < k.body_off) f_lo = k.body_off;
+    if (f_hi > k.body_off + k.body_bytes) f_hi = k.body_off + k.body_bytes;
+    const int64_t n_lo = (int64_t)N[k.rec_lo], n_hi = (int64_t)N[k.rec_hi];
+    out[p] = tile_describe(k, (uint32_t)lo, f_lo, f_hi, sv, n_lo, n_hi, snp, k.rec_lo - n_lo, k.rec_hi - n_hi);
 }
 
 // ---- TMA (bulk async copy) + mbarrier, raw PTX -----------------------------------------------------------
@@ -333,331 +258,78 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_glob
                  "l"(src_global), "r"(bytes), "r"(smem_addr(bar))
                  : "memory");
 }
-
-// byte x of a clipped non-raw payload; s0 as prepared in S2 (RC: last source index, RAND: the cached 2-bit bases
-// shifted to the first byte, RANDL (insert reaching past its 32 cached bases): pos << 32 | first byte index)
-constexpr uint32_t K_RANDL = 7;
-__device__ __forceinline__ uint8_t payload_at(const SpliceView& v, uint32_t kind, int64_t s0, uint32_t x, uint32_t gid) {
-    switch (kind) {
-        case K_LIT:   return v.lit[s0 + x];
-        case K_CONV:  return v.conv[v.genome[s0 + x]];
-        case K_RAND:  return cached_insert_base(s0, x);
-        case K_RANDL: return rand_base_ool(v.seed, gid, (uint32_t)((uint64_t)s0 >> 32), (uint32_t)s0 + x);
-        default:      return v.comp[v.conv[v.genome[s0 - (int64_t)x]]];
-    }
+// shared -> global bulk store (one thread issues it; everything the CTA wrote to the source with ordinary stores must
+// have been made visible to the async proxy with fence_proxy_async() before the barrier that precedes the store)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_1d(void* dst_global, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_global), "r"(smem_addr(src_smem)), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-// Same, with 16 lanes per segment (the average run is ~270 bytes = 17 chunks, so a full warp per segment
-// leaves half of the lanes idle).  hl = lane within the half-warp; n == 0 makes the half idle.
-__device__ __forceinline__ void half_copy_stage_to_tile(uint8_t* tile, const uint8_t* stage, uint32_t so, uint32_t d0, uint32_t n, int hl) {
-    const uint32_t d1 = d0 + n;
-    const uint32_t a0 = (d0 + 15u) & ~15u, a1 = d1 & ~15u;
-    if (a0 >= a1) {                                   // no aligned chunk inside: at most 30 bytes
-        for (uint32_t x = d0 + hl; x < d1; x += 16u) tile[x] = stage[so + (x - d0)];
-        return;
-    }
-#pragma unroll
-    for (int e = hl; e < 30; e += 16) {               // <= 15 head bytes (slots 0..14) and <= 15 tail bytes (slots 15..29)
-        const uint32_t x = e < 15 ? d0 + e : a1 + (e - 15);
-        if (x < (e < 15 ? a0 : d1)) tile[x] = stage[so + (x - d0)];
-    }
-    for (uint32_t c = a0 + 16u * hl; c < a1; c += 256u) {
-        const uint32_t s = so + (c - d0);
-        const uint4* w = reinterpret_cast<const uint4*>(stage + (s & ~15u));
-        *reinterpret_cast<uint4*>(tile + c) = shift16(w[0], w[1], s & 15u);
-    }
-}
+// dynamic shared memory of k_splice
+constexpr int SP_OFF_STAGE = 0;
+constexpr int SP_OFF_IMAGE = SP_OFF_STAGE + TL_STAGE_CAP + 32;
+constexpr int SP_OFF_POOL = SP_OFF_IMAGE + TL_TILE + 32;
+constexpr int SP_OFF_RS = SP_OFF_POOL + TL_POOL;
+constexpr int SP_OFF_DV = SP_OFF_RS + ((TL_SV_CAP + 1) * 4 + 15) / 16 * 16;
+constexpr int SP_OFF_DIRTY = SP_OFF_DV + TL_SV_CAP * 16;
+constexpr int SP_OFF_TAB = SP_OFF_DIRTY + TL_DIRTY_CAP * 4;
+constexpr int SP_DYN = SP_OFF_TAB + 512;
 
-__device__ __forceinline__ void warp_copy_to_tile(uint8_t* tile, const uint8_t* __restrict__ genome, const SegC sg, int lane) {
-    const uint32_t d0 = sg.dst, d1 = sg.dst + sg.n;
-    const uint32_t a0 = (d0 + 15u) & ~15u, a1 = d1 & ~15u;
-    if (a0 >= a1) {   // no aligned 16-byte chunk inside: at most 30 bytes
-        const uint32_t x = d0 + lane;
-        if (x < d1) tile[x] = __ldg(genome + sg.src + lane);
-        return;
-    }
-    {   // <= 15 head bytes on lanes 0..15, <= 15 tail bytes on lanes 16..31
-        const uint32_t x = lane < 16 ? d0 + lane : a1 + (lane - 16);
-        if (x < (lane < 16 ? a0 : d1)) tile[x] = __ldg(genome + sg.src + (x - d0));
-    }
-    for (uint32_t c = a0 + 16u * lane; c < a1; c += 512u) {
-        const int64_t s = sg.src + (int64_t)(c - d0);
-        const uint4* w = reinterpret_cast<const uint4*>(genome + (s & ~(int64_t)15));
-        const uint4 wa = __ldg(w), wb = __ldg(w + 1);
-        *reinterpret_cast<uint4*>(tile + c) = shift16(wa, wb, (uint32_t)(s & 15));
-    }
-}
-
-__global__ void __launch_bounds__(SPLICE_THREADS, 5)
-k_splice(SpliceView v, const Contig* contigs, const PieceDesc* pieces, const Tables* tables, uint8_t* fasta) {
-    __shared__ Contig sc;
+__global__ void __launch_bounds__(SPLICE_THREADS, 4)
+k_splice(SpliceView v, const Contig* contigs, const PieceDesc* pieces, const SvRec* sv_stream, const Snp8* snp_stream,
+         const Tables* tables, uint8_t* fasta, int64_t n_pieces) {
+    extern __shared__ __align__(128) uint8_t sp_dyn[];
     __shared__ __align__(16) PieceDesc sd;
-    extern __shared__ __align__(16) uint8_t sp_dyn[];      // [tile | stage]
-    uint8_t* const tile = sp_dyn;
-    uint8_t* const stage = sp_dyn + SP_TILE_MAX + 64;
-    __shared__ SegC segs[SP_SEG_CAP];
-    __shared__ uint32_t seg_stage[SP_SEG_CAP];     // offset of the segment's 16-byte aligned input span in `stage`, or SP_DIRECT
-    SegC* const jobs = reinterpret_cast<SegC*>(stage);   // payload jobs are queued after S1, when the staging buffer is dead
-    __shared__ uint32_t nout[SP_RUN_CAP + 1];
-    __shared__ uint16_t nidx[SP_RUN_CAP];
     __shared__ __align__(8) uint64_t bar;
-    __shared__ uint32_t warp_tot[SPLICE_THREADS / 32];
-    __shared__ int n_segs, n_jobs, fallback;
-    __shared__ uint8_t s_conv[256], s_comp[256];
+    __shared__ int n_dirty;
+    __shared__ Contig sc;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t p = blockIdx.x;
+    uint8_t* const stage = sp_dyn + SP_OFF_STAGE;
+    uint8_t* const image = sp_dyn + SP_OFF_IMAGE;
+    uint8_t* const pool = sp_dyn + SP_OFF_POOL;
+    uint32_t* const dirty = reinterpret_cast<uint32_t*>(sp_dyn + SP_OFF_DIRTY);
+    uint8_t* const s_tab = sp_dyn + SP_OFF_TAB;
+
     if (warp == 0) {
-        if (lane < (int)(sizeof(PieceDesc) / 4))
-            reinterpret_cast<uint32_t*>(&sd)[lane] = __ldg(reinterpret_cast<const uint32_t*>(pieces + p) + lane);
-        if (lane == 0) { n_segs = 0; n_jobs = 0; fallback = 0; mbar_init(&bar, 1u); }
+        reinterpret_cast<uint32_t*>(&sd)[lane] = __ldg(reinterpret_cast<const uint32_t*>(pieces + p) + lane);
+        if (lane == 0) { n_dirty = 0; mbar_init(&bar, 1u); }
         __syncwarp();
-        // the tile's whole input span as ONE TMA bulk copy, issued before anything else so that it overlaps the
-        // record passes below (S1 waits for it)
-        if (lane == 0) {
-            const int64_t in_lo = sd.in_lo;
-            const uint32_t nb = sd.in_bytes;
-            if (nb) tma_load_1d(stage, v.genome + in_lo, nb, &bar);
-            mbar_arrive_expect_tx(&bar, nb);
+        if (lane == 0 && !(sd.flags & PD_FALLBACK)) {
+            // everything the tile reads arrives by bulk copies issued before any thread does anything else
+            const uint32_t virt = (sd.flags & PD_GOV_VIRTUAL) ? 1u : 0u;
+            const uint32_t nb_in = sd.in_bytes;
+            const uint32_t nb_sv = 32u * (sd.n_sv - virt);
+            const uint32_t skip = (uint32_t)(sd.snp_lo & 1);
+            const uint32_t nb_snp = sd.n_snp ? 8u * ((sd.n_snp + skip + 1u) & ~1u) : 0u;
+            if (nb_in) tma_load_1d(stage, v.genome + sd.in_lo, nb_in, &bar);
+            if (nb_sv) tma_load_1d(pool + 32u * virt, sv_stream + sd.sv_lo, nb_sv, &bar);
+            if (nb_snp) tma_load_1d(pool + 32u * sd.n_sv, snp_stream + (sd.snp_lo - skip), nb_snp, &bar);
+            tma_load_1d(s_tab, tables, 512u, &bar);
+            mbar_arrive_expect_tx(&bar, nb_in + nb_sv + nb_snp + 512u);
+            if (virt) *reinterpret_cast<SvRec*>(pool) = SvRec{0u, 0u, 0u, 0u, 0, (uint32_t)K_NONE, 0u};
         }
+        if (lane == 1 && p + 592 < n_pieces) prefetch_l2(pieces + p + 592);   // the descriptor of a CTA of the next wave
     }
-    s_conv[tid] = tables->conv[tid];
-    s_comp[tid] = tables->comp[tid];
     __syncthreads();
-    const PieceDesc& k = sd;     // (the fields the fast path needs carry the contig's names)
-    v.conv = s_conv;
-    v.comp = s_comp;
+    const PieceDesc& k = sd;
     const int64_t f_lo = k.f_lo, f_hi = k.f_hi;
+    if (f_hi <= f_lo) return;
     const int64_t g0 = f_lo & ~(int64_t)15;
-    const int ngroups = (int)((f_hi - g0 + 15) >> 4);
-    const uint32_t bpl = k.bpl, w1 = bpl + 1u;
-    const uint32_t b_lo = k.b_lo, b_hi = k.b_hi;   // mutated bases [b_lo, b_hi) live in this tile
-    const Rec* recs = v.recs;
-    const int64_t i_first = k.i_first, i_last = k.i_last;
-    const int n_rec = (int)(i_last - i_first + 1);
+    const uint32_t e = (uint32_t)(f_lo - g0), img_end = (uint32_t)(f_hi - g0);
 
-    // ---- pass 1: ordered list of the run-starting records (the governing one + every non-SNP record)
-    int n_runs = 0;
-    for (int base = 0; base < n_rec; base += SPLICE_THREADS) {
-        const int t = base + tid;
-        const int64_t j = i_first + t;
-        bool flag = false;
-        uint32_t o = 0u;
-        if (t < n_rec) {
-            if (j < k.rec_lo) flag = true;   // virtual record before the first one
-            else {
-                const uint4 lo4 = __ldg(reinterpret_cast<const uint4*>(recs + j));
-                const uint32_t kk = __ldg(reinterpret_cast<const uint32_t*>(recs + j) + 6) & 0xffu;
-                o = lo4.w;
-                flag = (kk != K_SNP) || t == 0;
-            }
-        }
-        const uint32_t m = __ballot_sync(0xffffffffu, flag);
-        if (lane == 0) warp_tot[warp] = __popc(m);
-        __syncthreads();
-        int before = 0, total = 0;
-#pragma unroll
-        for (int w = 0; w < SPLICE_THREADS / 32; ++w) { const int c = (int)warp_tot[w]; if (w < warp) before += c; total += c; }
-        if (flag) {
-            const int pos = n_runs + before + __popc(m & ((1u << lane) - 1u));
-            if (pos < SP_RUN_CAP) { nout[pos] = o; nidx[pos] = (uint16_t)t; }
-        }
-        n_runs += total;
-        if (base + SPLICE_THREADS < n_rec) __syncthreads();   // warp_tot is reused by the next round (the barrier below covers the last one)
-    }
-    if (n_runs > SP_RUN_CAP) { if (tid == 0) fallback = 1; n_runs = 0; }
-    if (tid == 0 && n_runs <= SP_RUN_CAP) nout[n_runs] = b_hi;
-    __syncthreads();
-
-    // ---- pass 2: copy segments of every run (raw payload + trailing shifted copy), clipped to the tile
-    for (int r = tid; r < n_runs; r += SPLICE_THREADS) {
-        const int64_t j = i_first + nidx[r];
-        uint32_t o = 0u, pr = 0u, kind = K_NONE;
-        int64_t run_src = k.goff, psrc = 0;   // source of the base right after the payload
-        if (j >= k.rec_lo) {
-            const uint4 a = __ldg(reinterpret_cast<const uint4*>(recs + j));
-            const uint4 b = __ldg(reinterpret_cast<const uint4*>(recs + j) + 1);
-            o = a.w; pr = a.z; kind = b.z & 0xffu;
-            run_src = k.goff + (int64_t)a.x + (int64_t)a.y;
-            psrc = (int64_t)(((uint64_t)b.y << 32) | b.x);
-        }
-        uint32_t end = nout[r + 1];
-        if (end > b_hi) end = b_hi;
-#pragma unroll
-        for (int part = 0; part < 2; ++part) {
-            uint32_t lo, hi;
-            int64_t src;
-            if (part == 0) {  // raw payload [o, o+pr)
-                if (kind != K_RAW || pr == 0u) continue;
-                lo = o > b_lo ? o : b_lo;
-                hi = o + pr < b_hi ? o + pr : b_hi;
-                src = psrc + (int64_t)(lo - o);
-            } else {          // trailing run [o+pr, end)
-                lo = o + pr > b_lo ? o + pr : b_lo;
-                hi = end;
-                src = run_src + (int64_t)(lo - (o + pr));
-            }
-            while (lo < hi) {
-                const uint32_t n = hi - lo < SP_SEG_SPLIT ? hi - lo : SP_SEG_SPLIT;
-                const int slot = atomicAdd(&n_segs, 1);
-                if (slot < SP_SEG_CAP) {
-                    segs[slot] = SegC{src, lo - b_lo, n};
-                    // staged iff the segment's source lies inside the span the prologue's TMA copy brings in
-                    const int64_t rel = src - k.in_lo;
-                    seg_stage[slot] = (rel >= 0 && rel + (int64_t)n <= (int64_t)k.in_bytes) ? (uint32_t)rel : SP_DIRECT;
-                } else {
-                    fallback = 1;
-                }
-                lo += n; src += n;
-            }
-        }
-    }
-    // one warp waits on the mbarrier (the TMA copy of the input span); the others park at the CTA barrier instead of
-    // spinning on try_wait (8 spinning warps were 11.6 % of all issued instructions, profiles/r1h).  The same barrier
-    // publishes the segment list.
-    if (warp == 0) mbar_wait(&bar, 0u);
-    __syncthreads();
-
-    if (!fallback) {
-        const int ns = n_segs;
-        // ---- S1: shifted copies shared -> shared, one half-warp per segment
-        {
-            const int half = lane >> 4, hl = lane & 15;
-            bool any_direct = false;
-            for (int s0 = 2 * warp; s0 < ns; s0 += 2 * (SPLICE_THREADS / 32)) {
-                const int sidx = s0 + half;
-                uint32_t so = 0u, d0 = 0u, n = 0u;
-                if (sidx < ns) {
-                    const uint32_t off = seg_stage[sidx];
-                    if (off == SP_DIRECT) any_direct = true;
-                    else { const SegC sg = segs[sidx]; so = off; d0 = sg.dst; n = sg.n; }
-                }
-                half_copy_stage_to_tile(tile, stage, so, d0, n, hl);
-            }
-            if (__any_sync(0xffffffffu, any_direct)) {   // segments that did not fit the staging buffer (rare)
-                for (int s0 = 2 * warp; s0 < ns; s0 += 2 * (SPLICE_THREADS / 32))
-                    for (int h = 0; h < 2; ++h)
-                        if (s0 + h < ns && seg_stage[s0 + h] == SP_DIRECT) warp_copy_to_tile(tile, v.genome, segs[s0 + h], lane);
-            }
-        }
-        __syncthreads();
-        // ---- S2: SNP bases and non-raw payloads
-        for (int t = tid; t < n_rec; t += SPLICE_THREADS) {
-            const int64_t j = i_first + t;
-            if (j < k.rec_lo) continue;
-            const uint32_t* rw = reinterpret_cast<const uint32_t*>(recs + j);
-            const uint32_t o = __ldg(rw + 3), kw = __ldg(rw + 6), kind = kw & 0xffu;
-            if (kind == K_SNP) {
-                if (o >= b_lo && o < b_hi) tile[o - b_lo] = (uint8_t)(kw >> 24);
-                continue;
-            }
-            const uint32_t pr = __ldg(rw + 2);
-            uint32_t pkind = kind;
-            if (pr > 0u && kind != K_RAW) {
-                const uint32_t lo = o > b_lo ? o : b_lo, hi = o + pr < b_hi ? o + pr : b_hi;
-                if (lo < hi) {
-                    const int64_t src = (int64_t)(((uint64_t)__ldg(rw + 5) << 32) | __ldg(rw + 4));
-                    const uint32_t rel = lo - o, n = hi - lo;
-                    // RC walks backwards; a random insert is addressed by (position, first byte index)
-                    int64_t s0;
-                    if (kind == K_RC) s0 = src + (int64_t)(pr - 1u - rel);
-                    else if (kind != K_RAND) s0 = src + rel;
-                    else if (rel + n <= 32u) s0 = (int64_t)((uint64_t)src >> (2u * rel));
-                    else { s0 = (int64_t)(((uint64_t)__ldg(rw) << 32) | rel); pkind = K_RANDL; }
-                    if (n <= 3u) {
-                        for (uint32_t x = 0; x < n; ++x) {
-                            const uint8_t ch = payload_at(v, pkind, s0, x, k.gid);
-                            tile[lo - b_lo + x] = ch;
-                        }
-                    } else {
-                        const int slot = atomicAdd(&n_jobs, 1);
-                        if (slot < SP_JOB_CAP) jobs[slot] = SegC{s0, lo - b_lo, n | (pkind << 24)};
-                        else {
-                            for (uint32_t x = 0; x < n; ++x) {
-                                const uint8_t ch = payload_at(v, pkind, s0, x, k.gid);
-                                tile[lo - b_lo + x] = ch;
-                            }
-                        }
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        const int nj = n_jobs < SP_JOB_CAP ? n_jobs : SP_JOB_CAP;
-        for (int jb = warp; jb < nj; jb += SPLICE_THREADS / 32) {
-            const SegC job = jobs[jb];
-            const uint32_t n = job.n & 0xFFFFFFu, kind = job.n >> 24;
-            uint8_t* d = tile + job.dst;
-            if (kind == K_RC) {
-                const uint8_t* g = v.genome + job.src;
-                for (uint32_t x = lane; x < n; x += 32u) d[x] = s_comp[s_conv[g[-(int)x]]];
-            } else if (kind == K_CONV) {
-                const uint8_t* g = v.genome + job.src;
-                for (uint32_t x = lane; x < n; x += 32u) d[x] = s_conv[g[x]];
-            } else if (kind == K_RAND || kind == K_RANDL) {
-                for (uint32_t x = lane; x < n; x += 32u) d[x] = payload_at(v, kind, job.src, x, k.gid);
-            } else {
-                const uint8_t* g = v.lit + job.src;
-                for (uint32_t x = lane; x < n; x += 32u) d[x] = g[x];
-            }
-        }
-        __syncthreads();
-        // ---- S3: insert line breaks, write the file image
-        // line / column of a thread's groups advance by a constant per iteration: one division per thread
-        const int g_first = (int)((f_lo - g0 + 15) >> 4);                 // first full group
-        const int g_end = (int)((f_hi - g0) >> 4);                        // one past the last full group
-        if (bpl >= 16u && g_end > g_first) {
-            const uint32_t step_q = 16u * SPLICE_THREADS;
-            const uint32_t step_line = step_q / w1, step_col = step_q - step_line * w1;
-            int gi = g_first + tid;
-            uint32_t q0 = (uint32_t)(g0 - k.body_off) + ((uint32_t)gi << 4);
-            uint32_t line = q0 / w1, col = q0 - line * w1;
-            uint8_t* out = fasta + g0 + ((int64_t)gi << 4);
-            for (; gi < g_end; gi += SPLICE_THREADS) {
-                const uint32_t j = bpl - col;                             // lane of the line break (if < 16)
-                const uint32_t so = (q0 - line) - b_lo;                   // tile offset of the group's first base
-                const uint32_t* w = reinterpret_cast<const uint32_t*>(tile + (so & ~3u));
-                const uint32_t bs = (so & 3u) * 8u;
-                const uint32_t u0 = w[0], u1 = w[1], u2 = w[2], u3 = w[3], u4 = w[4];
-                uint4 y = make_uint4(__funnelshift_r(u0, u1, bs), __funnelshift_r(u1, u2, bs), __funnelshift_r(u2, u3, bs),
-                                     __funnelshift_r(u3, u4, bs));
-                if (j < 16u) {
-                    // one PRMT per word: word w = prmt(x_w, other, sel) with
-                    //   w <  jw : sel 0x3210 (untouched)
-                    //   w == jw : other = '\n', byte t becomes '\n', bytes above it take x_w[t..]
-                    //   w >  jw : other = x_{w-1}, sel 0x2107 (shifted up by one byte)
-                    const uint32_t jw = j >> 2, t = j & 3u;
-                    const uint32_t selnl = (uint32_t)(0x4210241021402104ull >> (16u * t)) & 0xFFFFu;
-                    const uint32_t x0 = y.x, x1 = y.y, x2 = y.z, x3 = y.w;
-                    y.x = __byte_perm(x0, 0x0Au, jw == 0u ? selnl : 0x3210u);
-                    y.y = __byte_perm(x1, jw == 1u ? 0x0Au : x0, jw > 1u ? 0x3210u : (jw == 1u ? selnl : 0x2107u));
-                    y.z = __byte_perm(x2, jw == 2u ? 0x0Au : x1, jw > 2u ? 0x3210u : (jw == 2u ? selnl : 0x2107u));
-                    y.w = __byte_perm(x3, jw == 3u ? 0x0Au : x2, jw == 3u ? selnl : 0x2107u);
-                }
-                __stcs(reinterpret_cast<uint4*>(out), y);
-                out += step_q;
-                q0 += step_q;
-                line += step_line; col += step_col;
-                if (col >= w1) { col -= w1; ++line; }
-            }
-        }
-        // edge bytes of the piece (and everything when lines are shorter than a group)
-        {
-            const int64_t e0 = bpl >= 16u ? g0 + ((int64_t)g_first << 4) : f_lo;   // [f_lo, e0) and [e1, f_hi) go byte-wise
-            const int64_t e1 = bpl >= 16u ? (g_end > g_first ? g0 + ((int64_t)g_end << 4) : e0) : f_lo;
-            const int64_t n_head = (e0 < f_hi ? e0 : f_hi) - f_lo;
-            const int64_t n_tail = f_hi - (e1 > f_lo ? e1 : f_lo);
-            for (int64_t y = tid; y < n_head + (n_tail > 0 ? n_tail : 0); y += SPLICE_THREADS) {
-                const int64_t x = y < n_head ? f_lo + y : e1 + (y - n_head);
-                if (x >= f_hi) continue;
-                const uint32_t q = (uint32_t)(x - k.body_off);
-                const uint32_t ln = q / w1;
-                fasta[x] = (q - ln * w1 == bpl) ? (uint8_t)'\n' : tile[(q - ln) - b_lo];
-            }
-        }
-    } else {
-        // ---- fallback for tiles with more runs than the staging lists hold: generic per-byte path
+    if (k.flags & PD_FALLBACK) {
+        // ---- generic per-byte path: tiles with more records than the pool holds, lines shorter than a chunk
         if (tid == 0) sc = contigs[k.cidx];
+        s_tab[tid] = tables->conv[tid];
+        s_tab[256 + tid] = tables->comp[tid];
         __syncthreads();
+        v.conv = s_tab; v.comp = s_tab + 256;
+        const int ngroups = (int)((img_end + 15u) >> 4);
         for (int gi = tid; gi < ngroups; gi += SPLICE_THREADS) {
             const int64_t g = g0 + ((int64_t)gi << 4);
             const int64_t a = g < f_lo ? f_lo : g;
@@ -668,6 +340,141 @@ k_splice(SpliceView v, const Contig* contigs, const PieceDesc* pieces, const Tab
                 const int ln = (int)(x - g);
                 fasta[x] = (uint8_t)(w[ln >> 2] >> (8 * (ln & 3)));
             }
+        }
+        return;
+    }
+
+    TileShared sh;
+    sh.stage = stage; sh.image = image;
+    sh.sv = reinterpret_cast<SvRec*>(pool);
+    sh.snp = reinterpret_cast<const Snp8*>(pool + 32u * k.n_sv) + (k.snp_lo & 1);
+    sh.rs = reinterpret_cast<uint32_t*>(sp_dyn + SP_OFF_RS);
+    sh.dv = reinterpret_cast<TileRec*>(sp_dyn + SP_OFF_DV);
+    TileView tv{v.genome, v.lit, s_tab, s_tab + 256, v.seed};
+    const uint32_t n_sv = k.n_sv;
+    const uint32_t bpl = k.bpl, w1 = bpl + 1u;
+    const float rcp_w1 = tl_rcp(w1);
+
+    // one warp waits on the mbarrier (the bulk copies); the others park at the CTA barrier instead of spinning
+    if (warp == 0) mbar_wait(&bar, 0u);
+    __syncthreads();
+
+    // ---- prep: one thread per SvRec
+    for (uint32_t j = tid; j < n_sv; j += SPLICE_THREADS) tile_prep_rec(k, sh, j);
+    if (tid == 0) sh.rs[n_sv] = k.b_hi - k.b_lo;
+    __syncthreads();
+
+    // ---- copy: one thread per full 16-byte chunk of the image; a warp owns a contiguous stretch of chunks
+    const uint32_t xa = (e + 15u) & ~15u, xb = img_end & ~15u;
+    {
+        const uint32_t n_full = xb > xa ? (xb - xa) >> 4 : 0u;
+        const uint32_t per_warp = ((n_full + 8u * 32u - 1u) / (8u * 32u)) * 32u;      // chunks per warp, a multiple of 32
+        const uint32_t c_lo = (uint32_t)warp * per_warp;
+        const uint32_t c_hi = c_lo + per_warp < n_full ? c_lo + per_warp : n_full;
+        const uint32_t step_line = 512u / w1, step_col = 512u - step_line * w1;        // a lane's chunks are 512 bytes apart
+        uint32_t c = c_lo + (uint32_t)lane;
+        uint32_t d0 = 0u, dl = 0u, col = 0u, j = 0u;
+        if (c < c_hi) {
+            d0 = xa + (c << 4) - e;
+            dl = div_small(k.col_lo + d0, w1, rcp_w1);
+            col = k.col_lo + d0 - dl * w1;
+            j = tile_find(sh.rs, n_sv, d0 - dl);
+        }
+        for (; c_lo < c_hi && (c - (uint32_t)lane) < c_hi; c += 32u, d0 += 512u) {   // warp-uniform trip count
+            const bool valid = c < c_hi;
+            bool is_dirty = false;
+            if (valid) {
+                const uint32_t rF = d0 - dl;
+                while (rF >= sh.rs[j + 1u]) ++j;
+                const uint32_t j_nl = bpl - col;
+                const uint32_t nb = j_nl < 16u ? 15u : 16u;
+                int32_t s_off; int64_t g_src = 0;
+                if (tile_chunk_source(k, sh, j, rF, nb, &s_off, &g_src)) {
+                    uint4 x;
+                    if (s_off != TL_DIRECT) {
+                        const uint4* w = reinterpret_cast<const uint4*>(stage + ((uint32_t)s_off & ~15u));
+                        x = shift16(w[0], w[1], (uint32_t)s_off & 15u);
+                    } else {
+                        const uint4* w = reinterpret_cast<const uint4*>(v.genome + (g_src & ~(int64_t)15));
+                        x = shift16(__ldg(w), __ldg(w + 1), (uint32_t)(g_src & 15));
+                    }
+                    if (j_nl < 16u) x = insert_nl(x, j_nl);
+                    *reinterpret_cast<uint4*>(image + xa + ((c) << 4)) = x;
+                } else {
+                    is_dirty = true;
+                }
+                // next chunk of this lane
+                dl += step_line; col += step_col;
+                if (col >= w1) { col -= w1; ++dl; }
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, is_dirty);
+            if (m) {
+                int b0 = 0;
+                const int leader = __ffs(m) - 1;
+                if (lane == leader) b0 = atomicAdd(&n_dirty, __popc(m));
+                b0 = __shfl_sync(0xffffffffu, b0, leader);
+                if (is_dirty) {
+                    const int slot = b0 + __popc(m & ((1u << lane) - 1u));
+                    const uint32_t x0 = xa + (c << 4);
+                    if (slot < TL_DIRTY_CAP) dirty[slot] = (x0 >> 4) | (j << 16);
+                    else {   // queue full (pathologically fragmented tile): the discovering thread does the chunk itself
+                        for (uint32_t t = 0; t < 16u; ++t) image[x0 + t] = tile_byte(k, sh, tv, x0 + t - e, j, rcp_w1);
+                    }
+                }
+            }
+        }
+        // piece edges: the partial chunks at both ends go byte-wise (and are stored byte-wise below)
+        if (tid == 0 && e != 0u) {
+            const int slot = atomicAdd(&n_dirty, 1);
+            if (slot < TL_DIRTY_CAP) dirty[slot] = 0u;               // chunk 0, first base of the piece: SvRec 0
+            else for (uint32_t X = e; X < 16u && X < img_end; ++X) image[X] = tile_byte(k, sh, tv, X - e, 0u, rcp_w1);
+        }
+        if (tid == 32 && (img_end & 15u) != 0u && (xb != 0u || e == 0u) && xb >= xa) {
+            const uint32_t dd = xb - e;
+            const uint32_t dl2 = div_small(k.col_lo + dd, w1, rcp_w1);
+            const uint32_t j2 = tile_find(sh.rs, n_sv, dd - dl2);
+            const int slot = atomicAdd(&n_dirty, 1);
+            if (slot < TL_DIRTY_CAP) dirty[slot] = (xb >> 4) | (j2 << 16);
+            else for (uint32_t X = xb; X < img_end; ++X) image[X] = tile_byte(k, sh, tv, X - e, j2, rcp_w1);
+        }
+    }
+    __syncthreads();
+
+    // ---- dirty: one thread per byte of the queued chunks (run boundaries, generated payloads, piece edges)
+    {
+        const int nd = n_dirty < TL_DIRTY_CAP ? n_dirty : TL_DIRTY_CAP;
+        const int half = tid >> 4;
+        const uint32_t hl = (uint32_t)tid & 15u;
+        for (int i = half; i < nd; i += SPLICE_THREADS / 16) {
+            const uint32_t ent = dirty[i];
+            const uint32_t X = ((ent & 0xFFFFu) << 4) + hl;
+            if (X >= e && X < img_end) image[X] = tile_byte(k, sh, tv, X - e, ent >> 16, rcp_w1);
+        }
+    }
+    __syncthreads();
+
+    // ---- snp: scatter the substituted bases
+    {
+        const float rcp_bpl = tl_rcp(bpl);
+        for (uint32_t i = tid; i < k.n_snp; i += SPLICE_THREADS) {
+            const Snp8 sp = sh.snp[i];
+            image[e + tile_snp_offset(k, sp.out, rcp_bpl)] = (uint8_t)sp.alt;
+        }
+    }
+    fence_proxy_async();
+    __syncthreads();
+
+    // ---- store: the aligned middle of the piece leaves with one bulk copy, the ragged ends byte-wise
+    if (tid == 0 && xb > xa) {
+        tma_store_1d(fasta + g0 + xa, image + xa, xb - xa);
+        tma_store_wait_read();
+    } else if (tid >= 32) {
+        const uint32_t h_end = xa < img_end ? xa : img_end;                 // head bytes [e, h_end)
+        const uint32_t t_lo = xb >= xa ? xb : img_end;                       // tail bytes [t_lo, img_end)
+        const uint32_t n_head = h_end - e, n_tail = img_end - t_lo;
+        for (uint32_t y = (uint32_t)tid - 32u; y < n_head + n_tail; y += SPLICE_THREADS - 32) {
+            const uint32_t X = y < n_head ? e + y : t_lo + (y - n_head);
+            fasta[g0 + X] = image[X];
         }
     }
 }
@@ -955,9 +762,10 @@ k_rec_sizes(VcfView v, const Rec* recs, int64_t n, const Contig* contigs, int32_
     vsize[i] = vcf_line_size(v, contigs[r.contig], r);
 }
 
-__global__ void k_store_total2(const I64x2* total, int64_t* S_end, int64_t* V_end) {
+__global__ void k_store_total3(const I64x3* total, int64_t* S_end, int64_t* V_end, uint32_t* N_end) {
     *S_end = total->a;
     *V_end = total->b;
+    *N_end = (uint32_t)total->c;
 }
 
 // ---- image -> bases (chained RMT -> IT without the file round trip) ---------------------------------------------
@@ -1032,11 +840,13 @@ static int plan_stage(ms_ctx* c, bool vcf_sizes) {
     MS_CUDA(c, cudaMemsetAsync(d_tot, 0, sizeof(Totals), st));
     MS_CUDA(c, c->svec.ensure((size_t)(M + 1) * sizeof(int64_t)));
     MS_CUDA(c, c->vcf_off.ensure((size_t)(M + 1) * sizeof(int64_t)));
+    MS_CUDA(c, c->nvec.ensure((size_t)(M + 1) * sizeof(uint32_t)));
     MS_CUDA(c, c->piece_lo.ensure((size_t)(c->n_contigs + 1) * sizeof(int64_t)));
     MS_CUDA(c, c->recs.ensure(32));  // M == 0: keep pointers valid
     Rec* d_recs = c->recs.as<Rec>();
     int64_t* S = c->svec.as<int64_t>();
     int64_t* V = c->vcf_off.as<int64_t>();
+    uint32_t* N = c->nvec.as<uint32_t>();
 
     k_rec_bounds<<<(unsigned)ceil_div(c->n_contigs + 1, 128), 128, 0, st>>>(d_recs, M, d_contigs, c->n_contigs);
     MS_LAUNCH_CHECK(c);
@@ -1060,22 +870,22 @@ static int plan_stage(ms_ctx* c, bool vcf_sizes) {
             k_rec_sizes<<<(unsigned)ceil_div(M, 256), 256, 0, st>>>(vv, d_recs, M, d_contigs, d_delta, d_vsize);
             MS_LAUNCH_CHECK(c);
         }
-        auto in = [=] __device__(int64_t i) -> I64x2 { return I64x2{(int64_t)d_delta[i], (int64_t)d_vsize[i]}; };
-        auto out = [=] __device__(int64_t i, I64x2 ex, I64x2) { S[i] = ex.a; V[i] = ex.b; };
-        I64x2* d_total = nullptr;
-        MS_CUDA(c, (device_scan<I64x2>(c, in, out, M, I64x2{0, 0}, SumOp(), c->scan_tmp, &d_total)));
-        k_store_total2<<<1, 1, 0, st>>>(d_total, S + M, V + M);
+        // one pass: output shift (S), VCF offset (V) and SvRec-stream slot (N) of every record
+        auto in = [=] __device__(int64_t i) -> I64x3 {
+            const uint32_t kw = reinterpret_cast<const uint32_t*>(d_recs + i)[6];
+            return I64x3{(int64_t)d_delta[i], (int64_t)d_vsize[i], (kw & 0xFFu) != K_SNP ? 1 : 0};
+        };
+        auto out = [=] __device__(int64_t i, I64x3 ex, I64x3) { S[i] = ex.a; V[i] = ex.b; N[i] = (uint32_t)ex.c; };
+        I64x3* d_total = nullptr;
+        MS_CUDA(c, (device_scan<I64x3>(c, in, out, M, I64x3{0, 0, 0}, SumOp(), c->scan_tmp, &d_total)));
+        k_store_total3<<<1, 1, 0, st>>>(d_total, S + M, V + M, N + M);
         MS_LAUNCH_CHECK(c);
     }
-    // gap list capacity is bounded by the block count; size it from the input side (exact bound needs out_len)
-    const int64_t gap_cap = c->total_bases / (BLK_BASES * GAP_INLINE) + 4 * (int64_t)c->n_contigs + M / GAP_INLINE + 1024;
-    MS_CUDA(c, c->long_gaps.ensure((size_t)gap_cap * sizeof(Gap)));
     if (c->n_contigs <= 2048) {
-        k_contig_layout<<<1, SCAN_THREADS, 0, st>>>(d_contigs, c->n_contigs, S, c->piece_lo.as<int64_t>(), (int64_t)c->tile_bytes,
-                                                    c->long_gaps.as<Gap>(), gap_cap, d_tot, M, V);
+        k_contig_layout<<<1, SCAN_THREADS, 0, st>>>(d_contigs, c->n_contigs, S, c->piece_lo.as<int64_t>(), (int64_t)c->tile_bytes, d_tot, M, V, N);
         MS_LAUNCH_CHECK(c);
     } else {
-        int rc = layout_by_scan(c, d_contigs, S, V, M, d_tot);
+        int rc = layout_by_scan(c, d_contigs, S, V, N, M, d_tot);
         if (rc) return rc;
     }
     MS_CUDA(c, cudaMemcpyAsync(c->h_totals, d_tot, sizeof(Totals), cudaMemcpyDeviceToHost, st));
@@ -1083,37 +893,34 @@ static int plan_stage(ms_ctx* c, bool vcf_sizes) {
     MS_CUDA(c, cudaStreamSynchronize(st));
     Totals t = *c->h_totals;
     if (t.error) MS_FAIL(c, (int)t.error, "ms_apply: layout failed (code %lld at contig %lld)", (long long)t.error, (long long)t.error_arg);
-    c->fasta_bytes = t.fasta_bytes; c->vcf_bytes = t.vcf_bytes; c->n_blk = t.n_blk; c->n_pieces = t.n_pieces;
+    c->fasta_bytes = t.fasta_bytes; c->vcf_bytes = t.vcf_bytes; c->n_sv = t.n_blk; c->n_pieces = t.n_pieces;
 
-    MS_CUDA(c, c->blk.ensure((size_t)(t.n_blk + 1) * sizeof(uint32_t)));
     MS_CUDA(c, c->fasta.ensure((size_t)t.fasta_bytes + 64));
     MS_CUDA(c, c->vcf.ensure((size_t)t.vcf_bytes + 64));
     MS_CUDA(c, c->piece_desc.ensure((size_t)(t.n_pieces + 1) * sizeof(PieceDesc)));
+    MS_CUDA(c, c->sv_stream.ensure((size_t)(c->n_sv + 4) * sizeof(SvRec)));
+    MS_CUDA(c, c->snp_stream.ensure((size_t)(M - c->n_sv + 4) * sizeof(Snp8)));
     return MS_OK;
 }
 
-// index: record output positions, coarse block index, per-tile descriptors
+// index: record output positions, the SvRec / Snp8 streams, per-tile descriptors
 static int index_stage(ms_ctx* c) {
     const int64_t M = c->n_recs;
     Contig* d_contigs = c->contigs.as<Contig>();
     Rec* d_recs = c->recs.as<Rec>();
     Totals* d_tot = c->totals.as<Totals>();
-    uint32_t* d_blk = c->blk.as<uint32_t>();
     const int64_t* S = c->svec.as<int64_t>();
-    const int64_t gap_cap = (int64_t)(c->long_gaps.cap / sizeof(Gap));
+    const uint32_t* N = c->nvec.as<uint32_t>();
     cudaStream_t st = c->stream;
     stage_begin(c, ST_INDEX);
     if (M > 0) {
-        k_rec_out<<<(unsigned)ceil_div(M, 256), 256, 0, st>>>(d_recs, M, d_contigs, S, d_blk, c->long_gaps.as<Gap>(), gap_cap, d_tot);
+        k_rec_out<<<(unsigned)ceil_div(M, 256), 256, 0, st>>>(d_recs, M, d_contigs, S, N, c->sv_stream.as<SvRec>(), c->snp_stream.as<Snp8>(), d_tot);
         MS_LAUNCH_CHECK(c);
     }
-    k_empty_contig_gaps<<<(unsigned)ceil_div(c->n_contigs, 128), 128, 0, st>>>(d_contigs, c->n_contigs, d_blk, c->long_gaps.as<Gap>(), gap_cap, d_tot);
-    MS_LAUNCH_CHECK(c);
-    k_fill_gaps<<<NUM_SMS_B200 * 4, 256, 0, st>>>(d_blk, c->long_gaps.as<Gap>(), d_tot);
-    MS_LAUNCH_CHECK(c);
     if (c->n_pieces > 0) {
         k_piece_desc<<<(unsigned)ceil_div(c->n_pieces, 256), 256, 0, st>>>(d_contigs, c->n_contigs, c->piece_lo.as<int64_t>(), c->n_pieces,
-                                                                          d_recs, d_blk, d_tot, c->piece_desc.as<PieceDesc>());
+                                                                          c->sv_stream.as<SvRec>(), c->snp_stream.as<Snp8>(), N, d_tot,
+                                                                          c->piece_desc.as<PieceDesc>());
         MS_LAUNCH_CHECK(c);
     }
     stage_end(c, ST_INDEX);
@@ -1123,19 +930,19 @@ static int index_stage(ms_ctx* c) {
 // splice: tiles [piece_lo, piece_lo + n_pieces) and the headers of contigs [ctg_lo, ctg_lo + n_ctg)
 static int splice_launch(ms_ctx* c, int64_t piece_lo, int64_t n_pieces, int32_t ctg_lo, int32_t n_ctg, int64_t w_lo = 0,
                          int64_t w_hi = INT64_MAX) {
-    if (c->tile_bytes != SP_TILE_MAX) MS_FAIL(c, MS_ERR_INTERNAL, "tile_bytes must equal %d", SP_TILE_MAX);
+    if (c->tile_bytes != TL_TILE) MS_FAIL(c, MS_ERR_INTERNAL, "tile_bytes must equal %d", TL_TILE);
     const Tables* d_tab = c->tables.as<Tables>();
     Contig* d_contigs = c->contigs.as<Contig>();
     cudaStream_t st = c->stream;
-    SpliceView sv{c->genome.as<uint8_t>(), c->lit.as<uint8_t>(), c->recs.as<Rec>(), c->blk.as<uint32_t>(), d_tab->conv, d_tab->comp, c->seed_last};
+    SpliceView sv{c->genome.as<uint8_t>(), c->lit.as<uint8_t>(), c->recs.as<Rec>(), d_tab->conv, d_tab->comp, c->seed_last};
     if (n_pieces > 0) {
-        constexpr int SP_DYN = SP_TILE_MAX + 64 + (int)SP_STAGE_CAP + 32;
         if (!c->splice_attr_set) {   // per context: the attribute is per device, and a process may hold contexts on several
             MS_CUDA(c, cudaFuncSetAttribute(k_splice, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_DYN));
             c->splice_attr_set = true;
         }
-        k_splice<<<(unsigned)n_pieces, SPLICE_THREADS, SP_DYN, st>>>(sv, d_contigs, c->piece_desc.as<PieceDesc>() + piece_lo, d_tab,
-                                                                   c->fasta.as<uint8_t>());
+        k_splice<<<(unsigned)n_pieces, SPLICE_THREADS, SP_DYN, st>>>(sv, d_contigs, c->piece_desc.as<PieceDesc>() + piece_lo,
+                                                                   c->sv_stream.as<SvRec>(), c->snp_stream.as<Snp8>(), d_tab,
+                                                                   c->fasta.as<uint8_t>(), n_pieces);
         MS_LAUNCH_CHECK(c);
     }
     if (n_ctg > 0) {
@@ -1264,7 +1071,8 @@ __global__ void __launch_bounds__(256) k_upper_range(uint8_t* g, int64_t lo, int
 
 // ref/alt of the SNP records [lo, hi): the part of record building that needs the bases (mutator.py:429-455)
 __global__ void __launch_bounds__(256)
-k_snp_fill(Rec* recs, int64_t lo, int64_t hi, const Contig* contigs, const uint8_t* genome, const Tables* tab, Seed seed, double p_ti) {
+k_snp_fill(Rec* recs, int64_t lo, int64_t hi, const Contig* contigs, const uint8_t* genome, const Tables* tab, Seed seed, double p_ti,
+           Snp8* snp) {
     const int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= hi) return;
     const uint32_t kind_type = reinterpret_cast<const uint32_t*>(recs + i)[6];   // kind | type<<8 | ref<<16 | alt<<24
@@ -1274,6 +1082,7 @@ k_snp_fill(Rec* recs, int64_t lo, int64_t hi, const Contig* contigs, const uint8
     const uint8_t ref = tab->conv[genome[ct.goff + pos]];
     const uint8_t alt = draw_snp(seed, ct.gid, pos, ref, p_ti, tab->trans);
     reinterpret_cast<uint32_t*>(recs + i)[6] = (kind_type & 0xFFFFu) | ((uint32_t)ref << 16) | ((uint32_t)alt << 24);
+    snp[recs[i].src].alt = (uint32_t)alt;      // k_rec_out left the record's Snp8 slot in its (otherwise unused) src
 }
 
 // VCF bytes written up to the end of a contig group: vend[1] = vend[0] + this group's bytes
@@ -1379,7 +1188,7 @@ int mutate_streamed(ms_ctx* c, uint64_t seed, const uint8_t* h_bases, uint8_t* h
         MS_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_up[g], 0));
         if (r1 > r0) {
             k_snp_fill<<<(unsigned)ceil_div(r1 - r0, 256), 256, 0, c->stream>>>(c->recs.as<Rec>(), r0, r1, c->contigs.as<Contig>(), d_genome, d_tab,
-                                                                             c->seed_last, c->p_ti);
+                                                                             c->seed_last, c->p_ti, c->snp_stream.as<Snp8>());
             MS_LAUNCH_CHECK(c);
         }
         if ((rc = splice_launch(c, h_piece_lo[c0], h_piece_lo[c1] - h_piece_lo[c0], c0, c1 - c0))) return rc;

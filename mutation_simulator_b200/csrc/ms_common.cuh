@@ -34,7 +34,7 @@ struct DevBuf {
 struct Totals {
     int64_t fasta_bytes;
     int64_t vcf_bytes;
-    int64_t n_blk;
+    int64_t n_blk;        // (number of SvRecs of the last plan)
     int64_t n_pieces;
     int64_t n_recs;       // records after sampling / linking
     int64_t lit_bytes;
@@ -96,8 +96,8 @@ struct ms_ctx {
     ms::Seed seed_last{0, 0};     // seed of the last ms_sample (K_RAND payloads are a function of it)
 
     // records + outputs
-    ms::DevBuf recs, lit, blk, piece_lo, piece_desc, long_gaps, fasta, vcf, vcf_off, totals;
-    int64_t n_recs = 0, lit_bytes = 0, fasta_bytes = 0, vcf_bytes = 0, n_pieces = 0, n_blk = 0;
+    ms::DevBuf recs, lit, piece_lo, piece_desc, fasta, vcf, vcf_off, totals, nvec, sv_stream, snp_stream;
+    int64_t n_recs = 0, lit_bytes = 0, fasta_bytes = 0, vcf_bytes = 0, n_pieces = 0, n_sv = 0;
     ms::Totals* h_totals = nullptr;  // pinned
     static constexpr int N_STAGE = 6;            // pinned staging buffers of ms_download_to_fd / ms_fasta_ingest_fd:
     static constexpr int64_t STAGE_BYTES = 16 << 20;   // one file read / write per buffer in flight, each on its own thread

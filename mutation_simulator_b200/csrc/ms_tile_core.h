@@ -20,6 +20,10 @@
 
 namespace ms {
 
+#if defined(__CUDACC__) && defined(MS_TILE_RAND_OOL)
+__device__ uint8_t rand_base_ool(Seed seed, uint32_t gid, uint32_t pos, uint32_t j);
+#endif
+
 struct alignas(16) SvRec {
     uint32_t out;      // contig-relative output base index where the payload starts
     uint32_t prod;     // payload bases
@@ -182,7 +186,13 @@ MS_HD uint8_t tile_byte(const PieceDesc& d, const TileShared& sh, const TileView
         case K_LIT:  return v.lit[q.src + rel];
         case K_CONV: return v.conv[v.genome[q.src + rel]];
         case K_RC:   return v.comp[v.conv[v.genome[q.src + (int64_t)(q.prod - 1u - rel)]]];
-        case K_RAND: return rel < 32u ? cached_insert_base(q.src, rel) : rand_insert_base(v.seed, d.gid, q.pos, rel);
+        case K_RAND:
+            if (rel < 32u) return cached_insert_base(q.src, rel);
+#if defined(__CUDA_ARCH__) && defined(MS_TILE_RAND_OOL)
+            return rand_base_ool(v.seed, d.gid, q.pos, rel);      // Philox out of line: rare, and it would cost registers here
+#else
+            return rand_insert_base(v.seed, d.gid, q.pos, rel);
+#endif
         default:     return (uint8_t)'?';
     }
 }

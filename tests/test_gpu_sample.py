@@ -101,11 +101,19 @@ def test_results_do_not_depend_on_contig_partition():
     ("stats_all", [0.01, 0.001, 0.001, 0.0005, 0.0005, 0.0005], [1, 1, 1, 2, 1, 1, 1], [1, 10, 10, 50, 50, 50, 50], [1] * 7),
     ("stats_dense", [0.05, 0.02, 0.02, 0.01, 0.01, 0.04], [1, 1, 1, 2, 1, 1, 1], [1, 20, 40, 40, 40, 30, 30], [2, 1, 10, 1, 1, 1, 1]),
 ])
+def gate(pvalues: dict, alpha: float = 0.01):
+    """The north star's tolerance — chi-square / KS at p > 0.01 — applied FAMILY-WISE: the m tests of one
+    configuration pass together iff every p exceeds alpha / m (Bonferroni), so that a correct sampler fails a
+    configuration with probability <= 1 % however many statistics are checked."""
+    m = len(pvalues)
+    bad = {k: v for k, v in pvalues.items() if not v > alpha / m}
+    assert not bad, (f"family of {m} tests at family-wise alpha={alpha}: threshold {alpha / m:.2e}", bad)
+
+
 def test_statistics_match_reference_runs(name, rates6, minlen, maxlen, block):
-    """Per-type counts (chi-square), SV length histograms (chi-square), TL/TLI pairing loss,
-    reversed fraction, positional uniformity — against the reference's own runs, p > 0.001
-    (several tests per config; each individual threshold is far below the 0.01 the north star quotes
-    to keep the family-wise false-alarm rate low)."""
+    """Per-type counts (chi-square), SV length histograms (chi-square), TL/TLI reversed fraction (Fisher) — against the
+    reference's own runs — and positional uniformity of the candidates of EVERY contig (Kolmogorov-Smirnov against
+    util.py:94-109's uniform k-subset), at family-wise p > 0.01 (see gate())."""
     g = json.loads((GOLDEN / f"{name}.json").read_text())
     lens = g["lengths"]
     contigs = random_contigs(lens, seed=7)
@@ -128,9 +136,16 @@ def test_statistics_match_reference_runs(name, rates6, minlen, maxlen, block):
     my_counts = np.zeros(7)
     my_lens = {t: {} for t in TYPES}
     my_rev = my_tli = 0
-    deciles = np.zeros(10)
+    pv = {}
+    goff = np.concatenate(([0], np.cumsum(lens)))
     for seed in range(len(g["runs"])):
         recs, _ = sample(eng, ranges, block, titv * (1 / (titv + 1)), seed=100 + seed)
+        if seed == 0:      # start positions of the candidates (before rejection): uniform over each contig
+            gpos, _, _, _ = eng.debug_candidates()
+            for ci, L in enumerate(lens):
+                pos = gpos[(gpos >= goff[ci]) & (gpos < goff[ci + 1])] - goff[ci]
+                assert len(pos) == ranges[ci]["k"]
+                pv[f"KS positions contig {ci}"] = stats.kstest((pos + 0.5) / L, "uniform").pvalue
         check_invariants(recs, lens, block)
         my_counts += np.bincount(recs["type"], minlength=8)[:7]
         for ti, t in enumerate(TYPES):
@@ -143,22 +158,17 @@ def test_statistics_match_reference_runs(name, rates6, minlen, maxlen, block):
         tli = recs[recs["type"] == 6]
         my_tli += len(tli)
         my_rev += int((tli["kind"] == 5).sum())
-        r0 = recs[recs["contig"] == 0]
-        deciles += np.histogram(r0["pos"], bins=10, range=(0, lens[0]))[0]
     keep = (ref_counts + my_counts) > 0
-    chi2, p, _, _ = stats.chi2_contingency(np.vstack([ref_counts[keep], my_counts[keep]]))
-    assert p > 1e-3, ("type counts", ref_counts, my_counts, p)
+    pv["type counts"] = stats.chi2_contingency(np.vstack([ref_counts[keep], my_counts[keep]]))[1]
     for t in TYPES[1:]:
         if t == "TLI" or not ref_lens[t]:
             continue
         keys = sorted(set(ref_lens[t]) | set(my_lens[t]))
         a = np.array([ref_lens[t].get(k, 0) for k in keys]); b = np.array([my_lens[t].get(k, 0) for k in keys])
-        chi2, p, _, _ = stats.chi2_contingency(np.vstack([a, b]) + 1e-9)
-        assert p > 1e-3, ("lengths", t, a, b, p)
+        pv[f"lengths {t}"] = stats.chi2_contingency(np.vstack([a, b]) + 1e-9)[1]
     if ref_tli:
-        p = stats.fisher_exact([[ref_rev, ref_tli - ref_rev], [my_rev, my_tli - my_rev]])[1]
-        assert p > 1e-3, ("reversed", ref_rev, ref_tli, my_rev, my_tli)
-    assert stats.chisquare(deciles)[1] > 1e-3
+        pv["TLI reversed"] = stats.fisher_exact([[ref_rev, ref_tli - ref_rev], [my_rev, my_tli - my_rev]])[1]
+    gate(pv)
     eng.close()
 
 
@@ -169,6 +179,7 @@ def test_titv_ratio_matches_reference():
     eng, genome, goff, _ = engine_for(contigs)
     ranges = args_ranges([L], [0.05, 0, 0, 0, 0, 0], [1, 1, 1, 2, 1, 1, 1], [1, 2, 2, 3, 2, 2, 2])
     trans = {ord("A"): ord("G"), ord("G"): ord("A"), ord("C"): ord("T"), ord("T"): ord("C")}
+    pv = {}
     for titv_s, res in g["result"].items():
         titv = float(titv_s)
         recs, _ = sample(eng, ranges, [1] * 7, titv * (1 / (titv + 1)), seed=int(titv * 10) + 1)
@@ -180,9 +191,41 @@ def test_titv_ratio_matches_reference():
             for c in res[base]:
                 ref_ti += c.get(chr(trans[ord(base)]), 0)
                 ref_n += sum(c.values())
-        p = stats.fisher_exact([[ref_ti, ref_n - ref_ti], [ti, len(sn) - ti]])[1]
-        assert p > 1e-3, (titv, ref_ti, ref_n, ti, len(sn))
+        pv[f"titv {titv}"] = stats.fisher_exact([[ref_ti, ref_n - ref_ti], [ti, len(sn) - ti]])[1]
+        # ... and against the nominal probability itself (mutator.py:436: p_ti = titv * (1 / (titv + 1)))
+        pv[f"titv {titv} nominal"] = stats.binomtest(ti, len(sn), titv * (1 / (titv + 1))).pvalue
         assert (sn["alt"] != sn["ref"]).all()
+    gate(pv)
+    eng.close()
+
+
+def test_random_insert_bases_are_uniform_in_the_gpu_output():
+    """mutator.py:466-471: every inserted base is an independent uniform draw from [A, T, G, C].  The bases are read
+    back from the FASTA image the GPU wrote (at the records' output positions), not from a host re-computation:
+    composition (chi-square, 3 dof), independence of neighbouring bases (16 cells) and uniformity of the first base
+    of an insert — family-wise p > 0.01."""
+    L = 3_000_000
+    contigs = random_contigs([L], seed=21, bpl=100_000_000)       # one line: output base index == file offset - header
+    eng, *_ = engine_for(contigs)
+    ranges = args_ranges([L], [0.0, 0.02, 0, 0, 0, 0], [1, 1, 1, 2, 1, 1, 1], [1, 12, 2, 3, 2, 2, 2])
+    recs, _ = sample(eng, ranges, [1] * 7, 0.5, seed=4)
+    eng.apply()
+    body = np.frombuffer(eng.fasta(), np.uint8)[len(contigs[0][1]) + 2:]
+    recs = eng.records()
+    ins = recs[recs["type"] == 1]
+    assert len(ins) > 40_000 and (ins["prod"] >= 1).all() and (ins["prod"] <= 12).all()
+    first = body[ins["out"]]
+    allb = np.concatenate([body[o:o + n] for o, n in zip(ins["out"].astype(np.int64), ins["prod"].astype(np.int64))])
+    assert set(np.unique(allb)) == set(b"ACGT")
+    code = np.zeros(256, np.int64); code[list(b"ACGT")] = range(4)
+    pv = {"composition": stats.chisquare(np.bincount(code[allb], minlength=4)).pvalue,
+          "first base": stats.chisquare(np.bincount(code[first], minlength=4)).pvalue}
+    two = ins[ins["prod"] >= 2]
+    pairs = code[body[two["out"]]] * 4 + code[body[two["out"].astype(np.int64) + 1]]
+    pv["neighbouring bases"] = stats.chisquare(np.bincount(pairs, minlength=16)).pvalue
+    # lengths are uniform on [min, max] (mutator.py:229-265)
+    pv["insert lengths"] = stats.chisquare(np.bincount(ins["prod"], minlength=13)[1:]).pvalue
+    gate(pv)
     eng.close()
 
 
