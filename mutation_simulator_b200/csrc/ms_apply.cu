@@ -149,11 +149,10 @@ static int layout_by_scan(ms_ctx* c, Contig* d_contigs, const int64_t* S, const 
 // Record i lands in slot N[i] of the SvRec stream or slot i - N[i] of the Snp8 stream; a contig's entries are
 // [N[rec_lo], N[rec_hi]) resp. [rec_lo - N[rec_lo], rec_hi - N[rec_hi]).  A SNP's stream slot is also left in its
 // (otherwise unused) Rec.src so that k_snp_fill can patch the substituted base in later (streamed runs).
-__global__ void __launch_bounds__(256)
-k_rec_out(Rec* recs, int64_t n_recs, const Contig* contigs, const int64_t* S, const uint32_t* N, SvRec* sv, Snp8* snp, Totals* tot) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_recs) return;
+__device__ __forceinline__ void rec_out_one(Rec* recs, int64_t i, const Contig* contigs, const int64_t* S, const uint32_t* N, SvRec* sv,
+                                            Snp8* snp, Totals* tot, unsigned int* hist) {
     const Rec r = recs[i];
+    if (r.type < 8) atomicAdd(&hist[r.type], 1u);
     const Contig& k = contigs[r.contig];
     const int64_t out = (int64_t)r.pos + (S[i] - S[k.rec_lo]);
     if ((int64_t)r.pos + r.cons > k.len) raise_error(tot, MS_ERR_OVERLAP, i);
@@ -176,10 +175,23 @@ k_rec_out(Rec* recs, int64_t n_recs, const Contig* contigs, const int64_t* S, co
     }
 }
 
+
+__global__ void __launch_bounds__(256)
+k_rec_out(Rec* recs, int64_t n_recs, const Contig* contigs, const int64_t* S, const uint32_t* N, SvRec* sv, Snp8* snp, Totals* tot) {
+    __shared__ unsigned int hist[8];          // records per mutation type (ms_get_stats), counted on the way
+    if (threadIdx.x < 8) hist[threadIdx.x] = 0u;
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_recs) rec_out_one(recs, i, contigs, S, N, sv, snp, tot, hist);
+    __syncthreads();
+    if (threadIdx.x < 8 && hist[threadIdx.x]) atomicAdd((unsigned long long*)&tot->counts[threadIdx.x], (unsigned long long)hist[threadIdx.x]);
+}
+
 // ---- K6: splice + SNP + line wrap -----------------------------------------------------
 // One CTA per piece (= 16 KiB tile of the output file image intersected with one contig body); the index logic lives in
 // ms_tile_core.h (shared with the CPU emulation in tests/emu), this file supplies the memory operations.
-constexpr int SPLICE_THREADS = 256;
+constexpr int SPLICE_THREADS = TL_TILE >= 16384 ? 256 : 192;
+constexpr int SPLICE_CTAS = TL_TILE >= 16384 ? 4 : 6;        // per SM (shared memory and registers allow it)
 
 // bytes [o, o+16) of the 32-byte window (a, b)
 __device__ __forceinline__ uint4 shift16(const uint4 a, const uint4 b, uint32_t o) {
@@ -224,8 +236,8 @@ k_piece_desc(const Contig* contigs, int32_t n_contigs, const int64_t* piece_lo, 
         if (piece_lo[mid] <= p) lo = mid; else hi = mid;
     }
     const Contig k = contigs[lo];
-    const int64_t tile_i = (k.body_off >> 14) + (p - k.piece_lo);
-    int64_t f_lo = tile_i << 14, f_hi = f_lo + TL_TILE;
+    const int64_t tile_i = (k.body_off >> TL_TILE_SHIFT) + (p - k.piece_lo);
+    int64_t f_lo = tile_i << TL_TILE_SHIFT, f_hi = f_lo + TL_TILE;
     if (f_lo < k.body_off) f_lo = k.body_off;
     if (f_hi > k.body_off + k.body_bytes) f_hi = k.body_off + k.body_bytes;
     const int64_t n_lo = (int64_t)N[k.rec_lo], n_hi = (int64_t)N[k.rec_hi];
@@ -269,35 +281,104 @@ __device__ __forceinline__ void tma_store_1d(void* dst_global, const void* src_s
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// n (<= 127) bytes shared -> shared with arbitrary alignment on both sides: up to 3 bytes to the destination's word
+// boundary, whole words through a funnel shift (constant along the copy), up to 3 tail bytes.  Head and tail are
+// predicated, not loops: the lanes of a warp run this on different pieces and must stay in step.
+__device__ __forceinline__ void copy_smem(uint8_t* __restrict__ image, uint32_t d, const uint8_t* __restrict__ stage, uint32_t s, uint32_t n) {
+    uint32_t h = (0u - d) & 3u;
+    if (h > n) h = n;
+#pragma unroll
+    for (uint32_t t = 0; t < 3u; ++t) if (t < h) image[d + t] = stage[s + t];
+    d += h; s += h; n -= h;
+    const uint32_t nw = n >> 2;
+    const uint32_t sh = (s & 3u) * 8u;
+    const uint32_t* sp = reinterpret_cast<const uint32_t*>(stage + (s & ~3u));
+    uint32_t* dp = reinterpret_cast<uint32_t*>(image + d);
+    uint32_t w0 = sp[0];
+#pragma unroll 4
+    for (uint32_t i = 0; i < nw; ++i) {
+        const uint32_t w1 = sp[i + 1u];
+        dp[i] = __funnelshift_r(w0, w1, sh);
+        w0 = w1;
+    }
+    d += nw << 2; s += nw << 2; n &= 3u;
+#pragma unroll
+    for (uint32_t t = 0; t < 3u; ++t) if (t < n) image[d + t] = stage[s + t];
+}
+// the same from global memory (sources outside the staged span: far copies, spans stretched by long deletions)
+__device__ __forceinline__ void copy_gmem(uint8_t* __restrict__ image, uint32_t d, const uint8_t* __restrict__ genome, int64_t g, uint32_t n) {
+    while ((d & 3u) && n) { image[d] = __ldg(genome + g); ++d; ++g; --n; }
+    const uint32_t nw = n >> 2;
+    if (nw) {
+        const uint32_t sh = (uint32_t)(g & 3) * 8u;
+        const uint32_t* sp = reinterpret_cast<const uint32_t*>(genome + (g & ~(int64_t)3));
+        uint32_t* dp = reinterpret_cast<uint32_t*>(image + d);
+        uint32_t w0 = __ldg(sp);
+#pragma unroll 4
+        for (uint32_t i = 0; i < nw; ++i) {
+            const uint32_t w1 = __ldg(sp + i + 1u);
+            dp[i] = __funnelshift_r(w0, w1, sh);
+            w0 = w1;
+        }
+        d += nw << 2; g += nw << 2; n &= 3u;
+    }
+    while (n) { image[d] = __ldg(genome + g); ++d; ++g; --n; }
+}
+
+// memory operations of the cell walk (ms_tile_core.h: tile_cell / tile_emit_bases)
+struct SpliceOps {
+    uint8_t* image; const uint8_t* stage; const uint8_t* genome; uint2* jobs; int* n_jobs; uint2* pieces; int* n_pieces;
+    const PieceDesc* d; const TileShared* sh; const TileView* tv;
+    __device__ __forceinline__ void put(uint32_t x, uint8_t c) { image[x] = c; }
+    __device__ __forceinline__ void copy_stage(uint32_t x, uint32_t s, uint32_t n) {
+        // queued: the copies themselves run in a second phase where every lane has exactly one piece
+        while (n) {
+            const uint32_t m = n < 124u ? n : 124u;
+            const int slot = atomicAdd(n_pieces, 1);
+            if (slot < TL_PIECE_CAP) pieces[slot] = make_uint2(x | (m << 16), s);
+            else copy_smem(image, x, stage, s, m);
+            x += m; s += m; n -= m;
+        }
+    }
+    __device__ __forceinline__ void copy_global(uint32_t x, int64_t g, uint32_t n) { copy_gmem(image, x, genome, g, n); }
+    __device__ __forceinline__ void job(uint32_t x, uint32_t j, uint32_t r, uint32_t n) {
+        const int slot = atomicAdd(n_jobs, 1);
+        if (slot < TL_JOB_CAP) jobs[slot] = make_uint2(x | (n << 16), r | (j << 16));
+        else for (uint32_t t = 0; t < n; ++t) image[x + t] = tile_payload_byte(*d, *sh, *tv, j, r + t);   // queue full: do it here
+    }
+};
+
 // dynamic shared memory of k_splice
 constexpr int SP_OFF_STAGE = 0;
 constexpr int SP_OFF_IMAGE = SP_OFF_STAGE + TL_STAGE_CAP + 32;
 constexpr int SP_OFF_POOL = SP_OFF_IMAGE + TL_TILE + 32;
 constexpr int SP_OFF_RS = SP_OFF_POOL + TL_POOL;
 constexpr int SP_OFF_DV = SP_OFF_RS + ((TL_SV_CAP + 1) * 4 + 15) / 16 * 16;
-constexpr int SP_OFF_DIRTY = SP_OFF_DV + TL_SV_CAP * 16;
-constexpr int SP_OFF_TAB = SP_OFF_DIRTY + TL_DIRTY_CAP * 4;
+constexpr int SP_OFF_JOBS = SP_OFF_DV + TL_SV_CAP * 16;
+constexpr int SP_OFF_PIECES = SP_OFF_JOBS + TL_JOB_CAP * 8;
+constexpr int SP_OFF_TAB = SP_OFF_PIECES + TL_PIECE_CAP * 8;
 constexpr int SP_DYN = SP_OFF_TAB + 512;
 
-__global__ void __launch_bounds__(SPLICE_THREADS, 4)
+__global__ void __launch_bounds__(SPLICE_THREADS, SPLICE_CTAS)
 k_splice(SpliceView v, const Contig* contigs, const PieceDesc* pieces, const SvRec* sv_stream, const Snp8* snp_stream,
          const Tables* tables, uint8_t* fasta, int64_t n_pieces) {
     extern __shared__ __align__(128) uint8_t sp_dyn[];
     __shared__ __align__(16) PieceDesc sd;
     __shared__ __align__(8) uint64_t bar;
-    __shared__ int n_dirty;
+    __shared__ int n_jobs, n_cp;
     __shared__ Contig sc;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t p = blockIdx.x;
     uint8_t* const stage = sp_dyn + SP_OFF_STAGE;
     uint8_t* const image = sp_dyn + SP_OFF_IMAGE;
     uint8_t* const pool = sp_dyn + SP_OFF_POOL;
-    uint32_t* const dirty = reinterpret_cast<uint32_t*>(sp_dyn + SP_OFF_DIRTY);
+    uint2* const jobs = reinterpret_cast<uint2*>(sp_dyn + SP_OFF_JOBS);
+    uint2* const cpq = reinterpret_cast<uint2*>(sp_dyn + SP_OFF_PIECES);
     uint8_t* const s_tab = sp_dyn + SP_OFF_TAB;
 
     if (warp == 0) {
         reinterpret_cast<uint32_t*>(&sd)[lane] = __ldg(reinterpret_cast<const uint32_t*>(pieces + p) + lane);
-        if (lane == 0) { n_dirty = 0; mbar_init(&bar, 1u); }
+        if (lane == 0) { n_jobs = 0; n_cp = 0; mbar_init(&bar, 1u); }
         __syncwarp();
         if (lane == 0 && !(sd.flags & PD_FALLBACK)) {
             // everything the tile reads arrives by bulk copies issued before any thread does anything else
@@ -313,7 +394,7 @@ k_splice(SpliceView v, const Contig* contigs, const PieceDesc* pieces, const SvR
             mbar_arrive_expect_tx(&bar, nb_in + nb_sv + nb_snp + 512u);
             if (virt) *reinterpret_cast<SvRec*>(pool) = SvRec{0u, 0u, 0u, 0u, 0, (uint32_t)K_NONE, 0u};
         }
-        if (lane == 1 && p + 592 < n_pieces) prefetch_l2(pieces + p + 592);   // the descriptor of a CTA of the next wave
+        if (lane == 1 && p + 148 * SPLICE_CTAS < n_pieces) prefetch_l2(pieces + p + 148 * SPLICE_CTAS);   // the descriptor of a CTA of the next wave
     }
     __syncthreads();
     const PieceDesc& k = sd;
@@ -325,8 +406,7 @@ k_splice(SpliceView v, const Contig* contigs, const PieceDesc* pieces, const SvR
     if (k.flags & PD_FALLBACK) {
         // ---- generic per-byte path: tiles with more records than the pool holds, lines shorter than a chunk
         if (tid == 0) sc = contigs[k.cidx];
-        s_tab[tid] = tables->conv[tid];
-        s_tab[256 + tid] = tables->comp[tid];
+        for (int i = tid; i < 256; i += SPLICE_THREADS) { s_tab[i] = tables->conv[i]; s_tab[256 + i] = tables->comp[i]; }
         __syncthreads();
         v.conv = s_tab; v.comp = s_tab + 256;
         const int ngroups = (int)((img_end + 15u) >> 4);
@@ -352,8 +432,7 @@ k_splice(SpliceView v, const Contig* contigs, const PieceDesc* pieces, const SvR
     sh.dv = reinterpret_cast<TileRec*>(sp_dyn + SP_OFF_DV);
     TileView tv{v.genome, v.lit, s_tab, s_tab + 256, v.seed};
     const uint32_t n_sv = k.n_sv;
-    const uint32_t bpl = k.bpl, w1 = bpl + 1u;
-    const float rcp_w1 = tl_rcp(w1);
+    const uint32_t bpl = k.bpl;
 
     // one warp waits on the mbarrier (the bulk copies); the others park at the CTA barrier instead of spinning
     if (warp == 0) mbar_wait(&bar, 0u);
@@ -364,98 +443,39 @@ k_splice(SpliceView v, const Contig* contigs, const PieceDesc* pieces, const SvR
     if (tid == 0) sh.rs[n_sv] = k.b_hi - k.b_lo;
     __syncthreads();
 
-    // ---- copy: one thread per full 16-byte chunk of the image; a warp owns a contiguous stretch of chunks
-    const uint32_t xa = (e + 15u) & ~15u, xb = img_end & ~15u;
+    // ---- walk: one thread per cell (a line of the file); consecutive lanes take consecutive lines
+    const TileGeom geo = tile_geom(k);
     {
-        const uint32_t n_full = xb > xa ? (xb - xa) >> 4 : 0u;
-        const uint32_t per_warp = ((n_full + 8u * 32u - 1u) / (8u * 32u)) * 32u;      // chunks per warp, a multiple of 32
-        const uint32_t c_lo = (uint32_t)warp * per_warp;
-        const uint32_t c_hi = c_lo + per_warp < n_full ? c_lo + per_warp : n_full;
-        const uint32_t step_line = 512u / w1, step_col = 512u - step_line * w1;        // a lane's chunks are 512 bytes apart
-        uint32_t c = c_lo + (uint32_t)lane;
-        uint32_t d0 = 0u, dl = 0u, col = 0u, j = 0u;
-        if (c < c_hi) {
-            d0 = xa + (c << 4) - e;
-            dl = div_small(k.col_lo + d0, w1, rcp_w1);
-            col = k.col_lo + d0 - dl * w1;
-            j = tile_find(sh.rs, n_sv, d0 - dl);
-        }
-        for (; c_lo < c_hi && (c - (uint32_t)lane) < c_hi; c += 32u, d0 += 512u) {   // warp-uniform trip count
-            const bool valid = c < c_hi;
-            bool is_dirty = false;
-            if (valid) {
-                const uint32_t rF = d0 - dl;
-                while (rF >= sh.rs[j + 1u]) ++j;
-                const uint32_t j_nl = bpl - col;
-                const uint32_t nb = j_nl < 16u ? 15u : 16u;
-                int32_t s_off; int64_t g_src = 0;
-                if (tile_chunk_source(k, sh, j, rF, nb, &s_off, &g_src)) {
-                    uint4 x;
-                    if (s_off != TL_DIRECT) {
-                        const uint4* w = reinterpret_cast<const uint4*>(stage + ((uint32_t)s_off & ~15u));
-                        x = shift16(w[0], w[1], (uint32_t)s_off & 15u);
-                    } else {
-                        const uint4* w = reinterpret_cast<const uint4*>(v.genome + (g_src & ~(int64_t)15));
-                        x = shift16(__ldg(w), __ldg(w + 1), (uint32_t)(g_src & 15));
-                    }
-                    if (j_nl < 16u) x = insert_nl(x, j_nl);
-                    *reinterpret_cast<uint4*>(image + xa + ((c) << 4)) = x;
-                } else {
-                    is_dirty = true;
-                }
-                // next chunk of this lane
-                dl += step_line; col += step_col;
-                if (col >= w1) { col -= w1; ++dl; }
-            }
-            const uint32_t m = __ballot_sync(0xffffffffu, is_dirty);
-            if (m) {
-                int b0 = 0;
-                const int leader = __ffs(m) - 1;
-                if (lane == leader) b0 = atomicAdd(&n_dirty, __popc(m));
-                b0 = __shfl_sync(0xffffffffu, b0, leader);
-                if (is_dirty) {
-                    const int slot = b0 + __popc(m & ((1u << lane) - 1u));
-                    const uint32_t x0 = xa + (c << 4);
-                    if (slot < TL_DIRTY_CAP) dirty[slot] = (x0 >> 4) | (j << 16);
-                    else {   // queue full (pathologically fragmented tile): the discovering thread does the chunk itself
-                        for (uint32_t t = 0; t < 16u; ++t) image[x0 + t] = tile_byte(k, sh, tv, x0 + t - e, j, rcp_w1);
-                    }
-                }
-            }
-        }
-        // piece edges: the partial chunks at both ends go byte-wise (and are stored byte-wise below)
-        if (tid == 0 && e != 0u) {
-            const int slot = atomicAdd(&n_dirty, 1);
-            if (slot < TL_DIRTY_CAP) dirty[slot] = 0u;               // chunk 0, first base of the piece: SvRec 0
-            else for (uint32_t X = e; X < 16u && X < img_end; ++X) image[X] = tile_byte(k, sh, tv, X - e, 0u, rcp_w1);
-        }
-        if (tid == 32 && (img_end & 15u) != 0u && (xb != 0u || e == 0u) && xb >= xa) {
-            const uint32_t dd = xb - e;
-            const uint32_t dl2 = div_small(k.col_lo + dd, w1, rcp_w1);
-            const uint32_t j2 = tile_find(sh.rs, n_sv, dd - dl2);
-            const int slot = atomicAdd(&n_dirty, 1);
-            if (slot < TL_DIRTY_CAP) dirty[slot] = (xb >> 4) | (j2 << 16);
-            else for (uint32_t X = xb; X < img_end; ++X) image[X] = tile_byte(k, sh, tv, X - e, j2, rcp_w1);
-        }
+        SpliceOps ops{image, stage, v.genome, jobs, &n_jobs, cpq, &n_cp, &k, &sh, &tv};
+        for (uint32_t cell = tid; cell < geo.n_cells; cell += SPLICE_THREADS) tile_cell(k, sh, geo, ops, cell);
     }
     __syncthreads();
 
-    // ---- dirty: one thread per byte of the queued chunks (run boundaries, generated payloads, piece edges)
+    // ---- copy: one thread per queued piece (a contiguous stretch of one run inside one line)
     {
-        const int nd = n_dirty < TL_DIRTY_CAP ? n_dirty : TL_DIRTY_CAP;
+        const int np = n_cp < TL_PIECE_CAP ? n_cp : TL_PIECE_CAP;
+        for (int i = tid; i < np; i += SPLICE_THREADS) {
+            const uint2 pc = cpq[i];
+            copy_smem(image, pc.x & 0xFFFFu, stage, pc.y, pc.x >> 16);
+        }
+    }
+
+    // ---- jobs: generated payload pieces (inserts, inversions, translocation inserts), half a warp each
+    {
+        const int nj = n_jobs < TL_JOB_CAP ? n_jobs : TL_JOB_CAP;
         const int half = tid >> 4;
         const uint32_t hl = (uint32_t)tid & 15u;
-        for (int i = half; i < nd; i += SPLICE_THREADS / 16) {
-            const uint32_t ent = dirty[i];
-            const uint32_t X = ((ent & 0xFFFFu) << 4) + hl;
-            if (X >= e && X < img_end) image[X] = tile_byte(k, sh, tv, X - e, ent >> 16, rcp_w1);
+        for (int i = half; i < nj; i += SPLICE_THREADS / 16) {
+            const uint2 jb = jobs[i];
+            const uint32_t x = jb.x & 0xFFFFu, n = jb.x >> 16, r = jb.y & 0xFFFFu, j = jb.y >> 16;
+            for (uint32_t t = hl; t < n; t += 16u) image[x + t] = tile_payload_byte(k, sh, tv, j, r + t);
         }
     }
+    const uint32_t xa = (e + 15u) & ~15u, xb = img_end & ~15u;
     __syncthreads();
-
-    // ---- snp: scatter the substituted bases
+    // ---- snp: scatter the substituted bases (they fall on copied bases, never on a payload)
     {
-        const float rcp_bpl = tl_rcp(bpl);
+        const float rcp_bpl = k.rcp_bpl;
         for (uint32_t i = tid; i < k.n_snp; i += SPLICE_THREADS) {
             const Snp8 sp = sh.snp[i];
             image[e + tile_snp_offset(k, sp.out, rcp_bpl)] = (uint8_t)sp.alt;
@@ -759,7 +779,7 @@ k_rec_sizes(VcfView v, const Rec* recs, int64_t n, const Contig* contigs, int32_
     if (i >= n) return;
     const Rec r = recs[i];
     delta[i] = (int32_t)r.prod - (int32_t)r.cons;
-    vsize[i] = vcf_line_size(v, contigs[r.contig], r);
+    vsize[i] = vcf_line_size(v, contigs[r.contig], r) | (r.kind != K_SNP ? VSIZE_SV : 0u);   // bit 31: the record moves bases (SvRec)
 }
 
 __global__ void k_store_total3(const I64x3* total, int64_t* S_end, int64_t* V_end, uint32_t* N_end) {
@@ -871,9 +891,9 @@ static int plan_stage(ms_ctx* c, bool vcf_sizes) {
             MS_LAUNCH_CHECK(c);
         }
         // one pass: output shift (S), VCF offset (V) and SvRec-stream slot (N) of every record
-        auto in = [=] __device__(int64_t i) -> I64x3 {
-            const uint32_t kw = reinterpret_cast<const uint32_t*>(d_recs + i)[6];
-            return I64x3{(int64_t)d_delta[i], (int64_t)d_vsize[i], (kw & 0xFFu) != K_SNP ? 1 : 0};
+        auto in = [=] __device__(int64_t i) -> I64x3 {      // 8 bytes per record: the records themselves are not touched
+            const uint32_t vs = d_vsize[i];
+            return I64x3{(int64_t)d_delta[i], (int64_t)(vs & ~VSIZE_SV), (int64_t)(vs >> 31)};
         };
         auto out = [=] __device__(int64_t i, I64x3 ex, I64x3) { S[i] = ex.a; V[i] = ex.b; N[i] = (uint32_t)ex.c; };
         I64x3* d_total = nullptr;
@@ -978,6 +998,8 @@ static int finish_apply(ms_ctx* c) {
     c->last_totals.fasta_bytes = c->fasta_bytes;
     c->last_totals.vcf_bytes = c->vcf_bytes;
     c->last_totals.n_recs = c->n_recs;
+    for (int k = 0; k < 8; ++k) c->last_totals.counts[k] = t.counts[k];     // counted by k_rec_out
+    c->counts_valid = true;
     return MS_OK;
 }
 
@@ -1203,7 +1225,7 @@ int mutate_streamed(ms_ctx* c, uint64_t seed, const uint8_t* h_bases, uint8_t* h
                                                                               d_delta + r0, d_vsize + r0);
             MS_LAUNCH_CHECK(c);
             const int64_t* carry = d_vend + g;
-            auto in = [=] __device__(int64_t i) -> I64x2 { return I64x2{0, (int64_t)d_vsize[r0 + i]}; };
+            auto in = [=] __device__(int64_t i) -> I64x2 { return I64x2{0, (int64_t)(d_vsize[r0 + i] & ~VSIZE_SV)}; };
             auto out = [=] __device__(int64_t i, I64x2 ex, I64x2) { V[r0 + i] = ex.b + *carry; };
             MS_CUDA(c, (device_scan<I64x2>(c, in, out, r1 - r0, I64x2{0, 0}, SumOp(), c->scan_tmp, &d_total)));
         }

@@ -7,6 +7,7 @@
 #include <vector>
 #include "ms_records.h"
 #include "ms_sample_core.h"
+#include "ms_tile_core.h"
 #include "../../include/mutsim_b200.h"
 
 namespace ms {
@@ -80,7 +81,7 @@ struct ms_ctx {
 
     // ranges / sampling
     ms::DevBuf ranges, cand_val, cand_sorted, bucket_cnt, bucket_off, cand_type, cand_len, cand_reach, cand_pm,
-               cand_accept, acc_idx, tl_list, tli_list, link, keep, contig_tl, scan_tmp, scan_tmp2, svec, vvec, lvec, bucket_range;
+               cand_accept, acc_idx, tl_list, tli_list, link, keep, contig_tl, scan_tmp, scan_tmp2, scan_mid, svec, vvec, lvec, bucket_range;
     std::vector<ms::Range> h_ranges;
     int32_t n_ranges = 0;
     int64_t n_candidates = 0;
@@ -110,7 +111,7 @@ struct ms_ctx {
     bool ev_used[ms::ST_COUNT];
     float stage_ms[ms::ST_COUNT];
     int64_t kernel_launches = 0;
-    int tile_bytes = 16384;
+    int tile_bytes = ms::TL_TILE;
     bool splice_attr_set = false, vcf_attr_set = false;   // cudaFuncSetAttribute done on this context's device
 
     // device FASTA ingest (ms_fasta_ingest_fd .. ms_fasta_commit)

@@ -71,6 +71,9 @@ struct Tables {
     uint8_t trans[256];  // transitions
 };
 
+// per-record VCF line size arrays carry in bit 31 whether the record moves bases (goes to the SvRec stream) or is a SNP
+constexpr uint32_t VSIZE_SV = 0x80000000u;
+
 // first 32 bases of the random insert at `pos`, 2 bits each (what Rec.src caches for K_RAND)
 MS_HD int64_t rand_insert_cache(Seed seed, uint32_t gid, uint32_t pos) {
     const U4 blk = draw(seed, gid, P_INSERT, pos);

@@ -397,7 +397,7 @@ k_build_records(int64_t n_acc, const uint32_t* acc_slot, const int64_t* gpos, co
     }
     recs[e] = r;
     delta[e] = (int32_t)r.prod - (int32_t)r.cons;
-    vsize[e] = defer_bases ? vcf_line_bound(vv, ct, r) : vcf_line_size(vv, ct, r);
+    vsize[e] = (defer_bases ? vcf_line_bound(vv, ct, r) : vcf_line_size(vv, ct, r)) | (r.kind != K_SNP ? VSIZE_SV : 0u);
 }
 
 __global__ void __launch_bounds__(256) k_count_types(const Rec* recs, int64_t n, Totals* tot) {

@@ -1,8 +1,8 @@
-// ms_scan.cuh — generic, order-preserving device-wide scan in ONE pass (chained scan with decoupled look-back).
+// ms_scan.cuh — generic, order-preserving device-wide scan (reduce-then-scan; a single-pass variant is kept below).
 //
 // in(i) -> T produces the i-th input (any fused transform), out(i, excl, val)
-// consumes the exclusive prefix, so compaction / scatter fuses into the same
-// pass.  Works for non-commutative associative operators.
+// consumes the exclusive prefix, so compaction / scatter fuses into the
+// down-sweep.  Works for non-commutative associative operators.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -59,11 +59,90 @@ __device__ inline T block_excl_scan(T v, T identity, Op op, T& total, T* sm /* 2
     return r;
 }
 
+template <class T, class Op, class InF>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(InF in, int64_t n, T identity, Op op, T* tile_sums) {
+    __shared__ T sm[2 * SCAN_THREADS / 32];
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    T acc = identity;
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; ++j) {
+        const int64_t i = base + j;
+        if (i < n) acc = op(acc, in(i));
+    }
+    T total;
+    block_excl_scan(acc, identity, op, total, sm);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+// In place: tile_sums[0..nt) -> exclusive prefixes, tile_sums[nt] = grand total.  One CTA of 1024 threads, each owning a
+// contiguous stretch of the tile sums (a 256-thread CTA walking 20 k sums 256 at a time took 80-98 us of an otherwise
+// 0.4 ms scan, profiles/r1n_launches.csv).
+constexpr int SCAN_MID_THREADS = 1024;
+template <class T, class Op>
+__global__ void __launch_bounds__(SCAN_MID_THREADS) k_scan_tiles(T* tile_sums, int64_t nt, T identity, Op op) {
+    __shared__ T warp_tot[SCAN_MID_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int64_t per = (nt + SCAN_MID_THREADS - 1) / SCAN_MID_THREADS;
+    const int64_t lo = (int64_t)tid * per, hi = lo + per < nt ? lo + per : nt;
+    T acc = identity;
+    for (int64_t i = lo; i < hi; ++i) acc = op(acc, tile_sums[i]);
+    T inc = acc;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        T o = shfl_up_t(inc, d);
+        if (lane >= d) inc = op(o, inc);
+    }
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        T w = warp_tot[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            T o = shfl_up_t(w, d);
+            if (lane >= d) w = op(o, w);
+        }
+        warp_tot[lane] = w;       // inclusive over warps
+    }
+    __syncthreads();
+    T ex = shfl_up_t(inc, 1);
+    if (lane == 0) ex = identity;
+    T run = wid ? op(warp_tot[wid - 1], ex) : ex;
+    for (int64_t i = lo; i < hi; ++i) {
+        const T v = tile_sums[i];
+        tile_sums[i] = run;
+        run = op(run, v);
+    }
+    if (tid == SCAN_MID_THREADS - 1) tile_sums[nt] = op(warp_tot[SCAN_MID_THREADS / 32 - 1], identity);
+}
+
+template <class T, class Op, class InF, class OutF>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_down(InF in, OutF out, int64_t n, T identity, Op op, const T* tile_prefix) {
+    __shared__ T sm[2 * SCAN_THREADS / 32];
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    T v[SCAN_ITEMS];
+    T acc = identity;
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; ++j) {
+        const int64_t i = base + j;
+        v[j] = i < n ? in(i) : identity;
+        acc = op(acc, v[j]);
+    }
+    T total;
+    T ex = block_excl_scan(acc, identity, op, total, sm);
+    T run = op(tile_prefix[blockIdx.x], ex);
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; ++j) {
+        const int64_t i = base + j;
+        if (i < n) out(i, run, v[j]);
+        run = op(run, v[j]);
+    }
+}
+
 // ---- single pass: chained scan with decoupled look-back ----------------------------------------------------------
 // One launch: tiles are numbered by an atomic ticket (so a tile only ever waits for tiles that already run), each
 // publishes its aggregate, then its inclusive prefix, in global memory; a tile's first warp looks back over its
 // predecessors 32 at a time.  The input is read once (the reduce / scan-of-totals / down-sweep form above reads it
-// twice and has a single-CTA middle kernel).  Works for non-commutative operators: look-back values are combined
+// twice).  Works for non-commutative operators: look-back values are combined
 // oldest-first.
 template <class T> __device__ __forceinline__ T ld_cg_t(const T* p) {
     static_assert(sizeof(T) % 8 == 0, "scan value must be a multiple of 8 bytes");
@@ -168,9 +247,8 @@ k_scan_1p(InF in, OutF out, int64_t n, T identity, Op op, uint32_t* ticket, uint
 
 template <class T> __global__ void k_scan_store(T* dst, T v) { *dst = v; }
 
-// Returns a device pointer to the grand total (valid until tmp is reused).
 template <class T, class Op, class InF, class OutF>
-inline cudaError_t device_scan(ms_ctx* c, InF in, OutF out, int64_t n, T identity, Op op, DevBuf& tmp, T** d_total) {
+inline cudaError_t device_scan_1p(ms_ctx* c, InF in, OutF out, int64_t n, T identity, Op op, DevBuf& tmp, T** d_total) {
     const int64_t nt = ceil_div(n, SCAN_TILE);
     const size_t status_bytes = ((size_t)nt * 4 + 15) & ~(size_t)15;
     cudaError_t e = tmp.ensure(16 + status_bytes + (size_t)(2 * nt + 1) * sizeof(T) + 16);
@@ -190,6 +268,44 @@ inline cudaError_t device_scan(ms_ctx* c, InF in, OutF out, int64_t n, T identit
     }
     c->kernel_launches++;
     if (d_total) *d_total = total;
+    return cudaGetLastError();
+}
+
+// Returns a device pointer to the grand total (valid until tmp is reused).
+// Three launches: tile reduce, one-CTA scan of the tile sums, down-sweep (the input is evaluated twice).  The single
+// pass above is kept for reference: on this part it LOSES (0.78 vs 0.39 ms for the compaction scan, 1.02 vs 0.55 ms
+// for the plan scan, profiles/r2c_scan_metrics.txt) — with ~300 tiles resident every look-back has to walk ~9 windows
+// of 32 predecessors before it meets a finished one, each window two dependent L2 round trips plus a fence, while the
+// other seven warps of the tile wait at the barrier (stall_barrier 52).
+template <class T, class Op, class InF, class OutF>
+inline cudaError_t device_scan(ms_ctx* c, InF in, OutF out, int64_t n, T identity, Op op, DevBuf& tmp, T** d_total) {
+    const int64_t nt = ceil_div(n, SCAN_TILE);
+    cudaError_t e = tmp.ensure((size_t)(nt + 1) * sizeof(T));
+    if (e != cudaSuccess) return e;
+    T* ts = tmp.as<T>();
+    if (nt > 0) { k_scan_reduce<T, Op, InF><<<(unsigned)nt, SCAN_THREADS, 0, c->stream>>>(in, n, identity, op, ts); c->kernel_launches++; }
+    if (nt > 4096) {
+        // many tile sums: scan them with the single-pass kernel (a handful of tiles: its look-back is one window deep);
+        // one CTA walking 20 k sums costs 65-98 us (profiles/r1n_launches.csv, r2e_launches.csv)
+        const int64_t nt2 = ceil_div(nt, SCAN_TILE);
+        const size_t status_bytes = ((size_t)nt2 * 4 + 15) & ~(size_t)15;
+        cudaError_t e2 = c->scan_mid.ensure(16 + status_bytes + (size_t)(2 * nt2 + 1) * sizeof(T) + 16);
+        if (e2 != cudaSuccess) return e2;
+        uint8_t* base = c->scan_mid.as<uint8_t>();
+        uint32_t* status = reinterpret_cast<uint32_t*>(base + 16);
+        T* agg = reinterpret_cast<T*>(base + 16 + status_bytes);
+        e2 = cudaMemsetAsync(base, 0, 16 + status_bytes, c->stream);
+        if (e2 != cudaSuccess) return e2;
+        auto in2 = [=] __device__(int64_t i) -> T { return ts[i]; };
+        auto out2 = [=] __device__(int64_t i, T ex, T) { ts[i] = ex; };
+        k_scan_1p<T, Op, decltype(in2), decltype(out2)><<<(unsigned)nt2, SCAN_THREADS, 0, c->stream>>>(
+            in2, out2, nt, identity, op, reinterpret_cast<uint32_t*>(base), status, agg, agg + nt2, ts + nt, nt2);
+    } else {
+        k_scan_tiles<T, Op><<<1, SCAN_MID_THREADS, 0, c->stream>>>(ts, nt, identity, op);
+    }
+    c->kernel_launches++;
+    if (nt > 0) { k_scan_down<T, Op, InF, OutF><<<(unsigned)nt, SCAN_THREADS, 0, c->stream>>>(in, out, n, identity, op, ts); c->kernel_launches++; }
+    if (d_total) *d_total = ts + nt;
     return cudaGetLastError();
 }
 

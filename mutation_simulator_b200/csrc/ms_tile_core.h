@@ -8,11 +8,11 @@
 //                    consecutive SvRecs the output is ONE shifted copy of the input ("run", ~290 bases at human rates).
 // A tile is assembled in shared memory as the final file bytes (bases AND line breaks) and leaves with one bulk store:
 //   prep   one thread per SvRec: span start, payload end, and the offset of its run in the staged input span
-//   copy   one thread per 16-byte chunk of the image: find the governing SvRec (sorted starts, short forward walk),
-//          chunk inside one run (or one raw payload) -> one shifted 16-byte copy with the line break inserted;
-//          anything else (run boundaries, generated payloads, piece edges) is queued as "dirty"
-//   dirty  one thread per byte of the queued chunks
-//   snp    one thread per Snp8: scatter the substituted base
+//   walk   one thread per CELL (= one line of the file, or 60 bytes of a long line): find the governing SvRec (sorted
+//          starts), then copy the cell's bases run by run — each piece is one contiguous byte copy with a constant
+//          shift, so no line break is ever inserted into a vector and run boundaries need no special pass; payloads
+//          that have to be generated (inserts, inversions, translocation inserts) are queued as jobs
+//   jobs   half a warp per queued payload piece;  snp: one thread per Snp8 scatters the substituted base
 // This header holds everything that is index arithmetic, so tests/emu runs exactly this code on the CPU against the
 // reference's golden files; the CUDA kernel (ms_apply.cu) supplies the memory operations.
 #pragma once
@@ -38,11 +38,16 @@ static_assert(sizeof(SvRec) == 32, "SvRec must be 32 bytes");
 struct alignas(8) Snp8 { uint32_t out; uint32_t alt; };   // alt: substituted base in the low byte
 static_assert(sizeof(Snp8) == 8, "Snp8 must be 8 bytes");
 
-constexpr int TL_TILE = 16384;                 // file bytes per tile
-constexpr int TL_STAGE_CAP = 18 * 1024;        // staged input span (tile + what deletions skip + alignment slack)
-constexpr int TL_SV_CAP = 256;                 // SvRecs per tile held in shared memory (incl. the governing one)
-constexpr int TL_POOL = 10 * 1024;             // bytes of SvRec + Snp8 per tile
-constexpr int TL_DIRTY_CAP = 768;              // queued chunks per tile
+#ifndef MS_TILE_SHIFT
+#define MS_TILE_SHIFT 13
+#endif
+constexpr int TL_TILE_SHIFT = MS_TILE_SHIFT;
+constexpr int TL_TILE = 1 << TL_TILE_SHIFT;    // file bytes per tile
+constexpr int TL_STAGE_CAP = TL_TILE + TL_TILE / 8 + 512;   // staged input span (tile + what deletions skip + alignment slack)
+constexpr int TL_SV_CAP = TL_TILE / 64;        // SvRecs per tile held in shared memory (incl. the governing one)
+constexpr int TL_POOL = TL_TILE / 2;           // bytes of SvRec + Snp8 per tile
+constexpr int TL_JOB_CAP = TL_TILE / 64;       // queued generated-payload pieces per tile
+constexpr int TL_PIECE_CAP = TL_TILE / 32 + TL_TILE / 128;   // queued copy pieces per tile
 constexpr int32_t TL_DIRECT = INT32_MIN;       // source lies outside the staged span: read from global memory
 
 enum : uint32_t { PD_GOV_VIRTUAL = 1u, PD_FALLBACK = 2u };
@@ -64,7 +69,8 @@ struct alignas(16) PieceDesc {
     uint32_t line_lo, col_lo;  // f_lo - body_off = line_lo * (bpl + 1) + col_lo
     uint32_t cb;             // b_lo % bpl
     int32_t  k0;             // (b_lo + b_lo / bpl) - (f_lo - body_off): 1 if the piece starts on a line break, else 0
-    uint32_t pad[5];
+    float rcp_w1, rcp_bpl;   // tl_rcp(bpl + 1), tl_rcp(bpl)
+    uint32_t pad[3];
 };
 static_assert(sizeof(PieceDesc) == 128, "PieceDesc layout");
 
@@ -137,55 +143,55 @@ MS_HD uint32_t tile_find(const uint32_t* rs, uint32_t n, uint32_t r) {
     return lo;
 }
 
-// ---- copy: is the chunk whose nb bases start at tile-relative base rF one shifted copy? --------------------------
-// j: governing SvRec of rF (rs[j] <= rF < rs[j+1], the caller walked it forward).  On success *s_off = offset of the
-// first source byte in the staged span, or *g_src = its genome index when the source is not staged (*s_off = TL_DIRECT).
-MS_HD bool tile_chunk_source(const PieceDesc& d, const TileShared& sh, uint32_t j, uint32_t rF, uint32_t nb, int32_t* s_off,
-                             int64_t* g_src) {
-    const TileRec t = sh.dv[j];
-    const uint32_t end = sh.rs[j + 1u];
-    if (rF >= t.pe) {                                  // in the trailing run
-        if (rF + nb > end) return false;
-        if (t.ro != TL_DIRECT) { *s_off = t.ro + (int32_t)(rF - t.pe); return true; }
-        const SvRec r = sh.sv[j];
-        *s_off = TL_DIRECT;
-        *g_src = d.goff + (int64_t)r.run_in + ((int64_t)t.pe + (int64_t)d.b_lo - (int64_t)(r.out + r.prod)) + (int64_t)(rF - t.pe);
-        return true;
+// ---- walk: the piece is cut into CELLS, one thread each ------------------------------------------------------------
+// Lines of up to 96 bytes: a cell is one line of the file (its bases + the line break), so the shift between source
+// and destination is constant along the whole cell and nothing ever has to be inserted into a vector of bases; with
+// the usual odd line pitch (61, 71, 81 bytes) the threads of a warp also fall on different shared-memory banks.
+// Longer lines are cut into 60-byte cells counted from the piece start (a cell then holds at most one line break).
+struct TileGeom {
+    uint32_t e, img_end;     // image bytes [e, img_end) belong to the piece (image byte 0 = file offset f_lo & ~15)
+    uint32_t w1, bpl;
+    uint32_t cw;             // cell pitch in bytes
+    int32_t  x_org;          // image offset of cell 0 (row-aligned: may lie before e)
+    uint32_t n_cells;
+    float rcp_w1;
+};
+
+MS_HD TileGeom tile_geom(const PieceDesc& d) {
+    TileGeom g;
+    const int64_t g0 = d.f_lo & ~(int64_t)15;
+    g.e = (uint32_t)(d.f_lo - g0); g.img_end = (uint32_t)(d.f_hi - g0);
+    g.bpl = d.bpl; g.w1 = d.bpl + 1u;
+    g.rcp_w1 = d.rcp_w1;
+    const uint32_t len = g.img_end - g.e;
+    if (g.w1 <= 96u) {
+        g.cw = g.w1;
+        g.x_org = (int32_t)g.e - (int32_t)d.col_lo;
+        g.n_cells = len ? div_small(d.col_lo + len - 1u, g.w1, g.rcp_w1) + 1u : 0u;
+    } else {
+        g.cw = 60u;
+        g.x_org = (int32_t)g.e;
+        g.n_cells = (len + 59u) / 60u;
     }
-    if (t.kind != K_RAW || rF + nb > t.pe) return false;   // generated payload, or payload end inside the chunk
-    const uint32_t rs = sh.rs[j];
-    if (t.po != TL_DIRECT) { *s_off = t.po + (int32_t)(rF - rs); return true; }
-    const SvRec r = sh.sv[j];
-    *s_off = TL_DIRECT;
-    *g_src = r.src + ((int64_t)rs + (int64_t)d.b_lo - (int64_t)r.out) + (int64_t)(rF - rs);
-    return true;
+    return g;
 }
 
-// ---- dirty: the file byte at offset dd from f_lo ----------------------------------------------------------------
-// j: any SvRec index at or before the governing one of this byte (walked forward here).
-MS_HD uint8_t tile_byte(const PieceDesc& d, const TileShared& sh, const TileView& v, uint32_t dd, uint32_t j, float rcp_w1) {
-    const uint32_t w1 = d.bpl + 1u;
-    const uint32_t x = d.col_lo + dd;
-    const uint32_t dl = div_small(x, w1, rcp_w1);
-    if (x - dl * w1 == d.bpl) return (uint8_t)'\n';
-    const uint32_t r = dd - dl;
-    while (r >= sh.rs[j + 1u]) ++j;
-    const TileRec t = sh.dv[j];
-    if (r >= t.pe) {
-        const uint32_t off = r - t.pe;
-        if (t.ro != TL_DIRECT) return sh.stage[t.ro + (int32_t)off];
-        const SvRec q = sh.sv[j];
-        return v.genome[d.goff + (int64_t)q.run_in + ((int64_t)t.pe + (int64_t)d.b_lo - (int64_t)(q.out + q.prod)) + (int64_t)off];
-    }
+// genome byte g: from the staged span when it lies inside (an inversion's source is the stretch it replaces, so it
+// usually does), else from global memory
+MS_HD uint8_t tile_genome_byte(const PieceDesc& d, const TileShared& sh, const TileView& v, int64_t g) {
+    const int64_t rel = g - d.in_lo;
+    return (rel >= 0 && rel < (int64_t)d.in_bytes) ? sh.stage[rel] : v.genome[g];
+}
+
+// byte r of SvRec j's payload region, r = tile-relative base index (generated payloads; raw ones are copied)
+MS_HD uint8_t tile_payload_byte(const PieceDesc& d, const TileShared& sh, const TileView& v, uint32_t j, uint32_t r) {
     const SvRec q = sh.sv[j];
     const uint32_t rel = (r + d.b_lo) - q.out;
     switch (q.kind) {
-        case K_RAW:
-            if (t.po != TL_DIRECT) return sh.stage[t.po + (int32_t)(r - sh.rs[j])];
-            return v.genome[q.src + rel];
+        case K_RAW:  return tile_genome_byte(d, sh, v, q.src + rel);
         case K_LIT:  return v.lit[q.src + rel];
-        case K_CONV: return v.conv[v.genome[q.src + rel]];
-        case K_RC:   return v.comp[v.conv[v.genome[q.src + (int64_t)(q.prod - 1u - rel)]]];
+        case K_CONV: return v.conv[tile_genome_byte(d, sh, v, q.src + rel)];
+        case K_RC:   return v.comp[v.conv[tile_genome_byte(d, sh, v, q.src + (int64_t)(q.prod - 1u - rel))]];
         case K_RAND:
             if (rel < 32u) return cached_insert_base(q.src, rel);
 #if defined(__CUDA_ARCH__) && defined(MS_TILE_RAND_OOL)
@@ -194,6 +200,67 @@ MS_HD uint8_t tile_byte(const PieceDesc& d, const TileShared& sh, const TileView
             return rand_insert_base(v.seed, d.gid, q.pos, rel);
 #endif
         default:     return (uint8_t)'?';
+    }
+}
+
+// n bases starting at tile-relative base r go to image offset x.  Ops supplies the memory operations:
+//   copy_stage(x, s_off, n)   n bytes from the staged span at s_off
+//   copy_global(x, g, n)      n bytes from genome index g
+//   job(x, j, r, n)           n generated payload bytes of SvRec j from base r (queued; produced by tile_payload_byte)
+// j: the SvRec governing r on entry, the one governing r + n (or the next) on exit.
+template <class Ops>
+MS_HD void tile_emit_bases(const PieceDesc& d, const TileShared& sh, Ops& ops, uint32_t x, uint32_t r, uint32_t n, uint32_t& j) {
+    while (n) {
+        while (r >= sh.rs[j + 1u]) ++j;
+        const TileRec t = sh.dv[j];
+        const uint32_t end = sh.rs[j + 1u];
+        uint32_t m;
+        if (r < t.pe) {                                        // inside the payload
+            m = t.pe - r < n ? t.pe - r : n;
+            if (t.kind == K_RAW) {
+                const uint32_t rs = sh.rs[j];
+                if (t.po != TL_DIRECT) ops.copy_stage(x, (uint32_t)(t.po + (int32_t)(r - rs)), m);
+                else { const SvRec q = sh.sv[j]; ops.copy_global(x, q.src + ((int64_t)r + (int64_t)d.b_lo - (int64_t)q.out), m); }
+            } else {
+                ops.job(x, j, r, m);
+            }
+        } else {                                               // in the trailing copy run
+            m = end - r < n ? end - r : n;
+            if (t.ro != TL_DIRECT) ops.copy_stage(x, (uint32_t)(t.ro + (int32_t)(r - t.pe)), m);
+            else {
+                const SvRec q = sh.sv[j];
+                ops.copy_global(x, d.goff + (int64_t)q.run_in + ((int64_t)r + (int64_t)d.b_lo - (int64_t)(q.out + q.prod)), m);
+            }
+        }
+        x += m; r += m; n -= m;
+    }
+}
+
+// One cell: its bases (through tile_emit_bases) and line breaks (ops.put(x, '\n')).
+template <class Ops>
+MS_HD void tile_cell(const PieceDesc& d, const TileShared& sh, const TileGeom& g, Ops& ops, uint32_t cell) {
+    int32_t xs = g.x_org + (int32_t)(cell * g.cw);
+    int32_t xe = xs + (int32_t)g.cw;
+    if (xs < (int32_t)g.e) xs = (int32_t)g.e;
+    if (xe > (int32_t)g.img_end) xe = (int32_t)g.img_end;
+    if (xe <= xs) return;
+    uint32_t x = (uint32_t)xs, left = (uint32_t)(xe - xs);
+    const uint32_t dd = x - g.e;                                // offset from f_lo
+    uint32_t dl = div_small(d.col_lo + dd, g.w1, g.rcp_w1);
+    uint32_t col = d.col_lo + dd - dl * g.w1;
+    uint32_t r = dd - dl;                                       // tile-relative index of the next base
+    uint32_t j = 0u;
+    bool have = false;
+    while (left) {
+        if (col == g.bpl) {
+            ops.put(x, (uint8_t)'\n');
+            ++x; --left; col = 0u;
+            continue;
+        }
+        const uint32_t nb = g.bpl - col < left ? g.bpl - col : left;
+        if (!have) { j = tile_find(sh.rs, d.n_sv, r); have = true; }
+        tile_emit_bases(d, sh, ops, x, r, nb, j);
+        x += nb; r += nb; left -= nb; col += nb;
     }
 }
 
@@ -217,6 +284,7 @@ MS_HD PieceDesc tile_describe(const Contig& k, uint32_t cidx, int64_t f_lo, int6
     d.b_lo = q_lo - d.line_lo; d.b_hi = q_hi - q_hi / w1;
     d.cb = d.b_lo % d.bpl;
     d.k0 = (int32_t)((int64_t)d.b_lo + (int64_t)(d.b_lo / d.bpl) - (int64_t)q_lo);
+    d.rcp_w1 = tl_rcp(w1); d.rcp_bpl = tl_rcp(d.bpl);
     // governing SvRec: the last one with out <= b_lo
     int64_t lo = sv_c0, hi = sv_c1;          // first index with out > b_lo
     while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (sv[mid].out <= d.b_lo) lo = mid + 1; else hi = mid; }
@@ -236,7 +304,7 @@ MS_HD PieceDesc tile_describe(const Contig& k, uint32_t cidx, int64_t f_lo, int6
     const int64_t n_snp = lo - s0;
     // pool layout: SvRecs first (32 B each), then the Snp8s from an even stream index (16-byte aligned bulk copy)
     const int64_t pool = 32 * n_sv + 8 * (n_snp + 2);
-    if (n_sv > TL_SV_CAP || pool > TL_POOL || d.bpl < 16u) d.flags |= PD_FALLBACK;
+    if (n_sv > TL_SV_CAP || pool > TL_POOL) d.flags |= PD_FALLBACK;
     d.n_sv = (uint32_t)(n_sv > 0x7fffffff ? 0x7fffffff : n_sv);
     d.n_snp = (uint32_t)(n_snp > 0x7fffffff ? 0x7fffffff : n_snp);
     // staged span: the contiguous, monotone stretch of input the tile's copy runs read — from the source of its first

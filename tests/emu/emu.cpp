@@ -198,38 +198,23 @@ int emu_apply_tiles(const uint8_t* genome, int32_t n_contigs, const int64_t* gof
             TileShared sh{stage.data(), image.data(), ssv.data(), snp.data() + d.snp_lo, rs.data(), dv.data()};
             for (uint32_t j = 0; j < d.n_sv; ++j) tile_prep_rec(d, sh, j);
             rs[d.n_sv] = d.b_hi - d.b_lo;
-            const uint32_t w1 = d.bpl + 1u;
-            const float rcp_w1 = tl_rcp(w1), rcp_bpl = tl_rcp(d.bpl);
-            const uint32_t e = (uint32_t)(f_lo - g0), img_end = (uint32_t)(f_hi - g0);
-            const uint32_t xa = (e + 15u) & ~15u, xb = img_end & ~15u;
-            std::vector<std::pair<uint32_t, uint32_t>> dirty;
-            for (uint32_t x = 0; x < img_end; x += 16u) {
-                const bool full = x >= e && x + 16u <= img_end;
-                const uint32_t d0 = (x > e ? x : e) - e;                       // offset from f_lo of the chunk's first byte
-                const uint32_t dl = div_small(d.col_lo + d0, w1, rcp_w1);
-                const uint32_t col = d.col_lo + d0 - dl * w1;
-                const uint32_t rF = d0 - dl;
-                const uint32_t j = tile_find(rs.data(), d.n_sv, rF);
-                if (!full) { dirty.push_back({x, j}); continue; }               // piece edge: byte-wise
-                const uint32_t j_nl = d.bpl - col;
-                const uint32_t nb = j_nl < 16u ? 15u : 16u;
-                int32_t s_off; int64_t g_src = 0;
-                if (tile_chunk_source(d, sh, j, rF, nb, &s_off, &g_src)) {
-                    ++nc;
-                    const uint8_t* src = s_off != TL_DIRECT ? stage.data() + s_off : genome + g_src;
-                    uint32_t si = 0;
-                    for (uint32_t t2 = 0; t2 < 16u; ++t2) image[x + t2] = (t2 == j_nl) ? (uint8_t)'\n' : src[si++];
-                } else {
-                    dirty.push_back({x, j});
-                }
-            }
-            for (auto& q : dirty) {
+            const float rcp_bpl = d.rcp_bpl;
+            const TileGeom geo = tile_geom(d);
+            const uint32_t e = geo.e, img_end = geo.img_end;
+            struct Job { uint32_t x, j, r, n; };
+            struct HostOps {
+                uint8_t* image; const uint8_t* stage; const uint8_t* genome; std::vector<Job>* jobs; int64_t* nc;
+                void copy_stage(uint32_t x, uint32_t s, uint32_t n) { memcpy(image + x, stage + s, n); ++*nc; }
+                void copy_global(uint32_t x, int64_t g, uint32_t n) { memcpy(image + x, genome + g, n); ++*nc; }
+                void job(uint32_t x, uint32_t j, uint32_t r, uint32_t n) { jobs->push_back(Job{x, j, r, n}); }
+                void put(uint32_t x, uint8_t c) { image[x] = c; }
+            };
+            std::vector<Job> jobs;
+            HostOps ops{image.data(), stage.data(), genome, &jobs, &nc};
+            for (uint32_t cell = 0; cell < geo.n_cells; ++cell) tile_cell(d, sh, geo, ops, cell);
+            for (const Job& q : jobs) {
                 ++nd;
-                for (uint32_t t2 = 0; t2 < 16u; ++t2) {
-                    const uint32_t X = q.first + t2;
-                    if (X < e || X >= img_end) continue;
-                    image[X] = tile_byte(d, sh, tv, X - e, q.second, rcp_w1);
-                }
+                for (uint32_t t2 = 0; t2 < q.n; ++t2) image[q.x + t2] = tile_payload_byte(d, sh, tv, q.j, q.r + t2);
             }
             for (uint32_t i = 0; i < d.n_snp; ++i) {
                 const Snp8 sp = sh.snp[i];

@@ -96,11 +96,6 @@ def test_results_do_not_depend_on_contig_partition():
         e2.close()
 
 
-@pytest.mark.parametrize("name,rates6,minlen,maxlen,block", [
-    ("stats_c1", [0.01, 0.001, 0.001, 0, 0, 0], [1, 1, 1, 2, 1, 1, 1], [1, 10, 10, 3, 2, 2, 2], [1] * 7),
-    ("stats_all", [0.01, 0.001, 0.001, 0.0005, 0.0005, 0.0005], [1, 1, 1, 2, 1, 1, 1], [1, 10, 10, 50, 50, 50, 50], [1] * 7),
-    ("stats_dense", [0.05, 0.02, 0.02, 0.01, 0.01, 0.04], [1, 1, 1, 2, 1, 1, 1], [1, 20, 40, 40, 40, 30, 30], [2, 1, 10, 1, 1, 1, 1]),
-])
 def gate(pvalues: dict, alpha: float = 0.01):
     """The north star's tolerance — chi-square / KS at p > 0.01 — applied FAMILY-WISE: the m tests of one
     configuration pass together iff every p exceeds alpha / m (Bonferroni), so that a correct sampler fails a
@@ -110,6 +105,11 @@ def gate(pvalues: dict, alpha: float = 0.01):
     assert not bad, (f"family of {m} tests at family-wise alpha={alpha}: threshold {alpha / m:.2e}", bad)
 
 
+@pytest.mark.parametrize("name,rates6,minlen,maxlen,block", [
+    ("stats_c1", [0.01, 0.001, 0.001, 0, 0, 0], [1, 1, 1, 2, 1, 1, 1], [1, 10, 10, 3, 2, 2, 2], [1] * 7),
+    ("stats_all", [0.01, 0.001, 0.001, 0.0005, 0.0005, 0.0005], [1, 1, 1, 2, 1, 1, 1], [1, 10, 10, 50, 50, 50, 50], [1] * 7),
+    ("stats_dense", [0.05, 0.02, 0.02, 0.01, 0.01, 0.04], [1, 1, 1, 2, 1, 1, 1], [1, 20, 40, 40, 40, 30, 30], [2, 1, 10, 1, 1, 1, 1]),
+])
 def test_statistics_match_reference_runs(name, rates6, minlen, maxlen, block):
     """Per-type counts (chi-square), SV length histograms (chi-square), TL/TLI reversed fraction (Fisher) — against the
     reference's own runs — and positional uniformity of the candidates of EVERY contig (Kolmogorov-Smirnov against
