@@ -188,10 +188,20 @@ k_rec_out(Rec* recs, int64_t n_recs, const Contig* contigs, const int64_t* S, co
 }
 
 // ---- K6: splice + SNP + line wrap -----------------------------------------------------
-// One CTA per piece (= 16 KiB tile of the output file image intersected with one contig body); the index logic lives in
-// ms_tile_core.h (shared with the CPU emulation in tests/emu), this file supplies the memory operations.
-constexpr int SPLICE_THREADS = TL_TILE >= 16384 ? 256 : 192;
-constexpr int SPLICE_CTAS = TL_TILE >= 16384 ? 4 : 6;        // per SM (shared memory and registers allow it)
+// One CTA per piece (= 16 KiB tile of the output file image intersected with one contig body).
+//
+// Run-centric splice over the two record streams of the plan pass.  SNPs move nothing, so between two consecutive
+// SvRecs the output is one shifted copy of the input ("run", ~290 bases at human-like rates).  A CTA assembles the
+// mutated bases of its tile in shared memory:
+//   segs one thread per SvRec of the tile: its raw payload (tandem duplication, interchromosomal segment) and its
+//        trailing run become copy segments — the SvRec stream IS the run list, no pass over the SNP records
+//   S1   every segment is a shifted copy staged-input -> tile, 16 bytes per lane, half a warp per segment
+//   S2   one thread per Snp8 scatters the substituted base; one thread per SvRec queues the payloads that have to be
+//        generated (random inserts, inversions, translocation inserts) as byte jobs for warps
+//   S3   line breaks are inserted while the tile is written out, 16 aligned bytes per lane
+// The tile's contiguous input span arrives by ONE bulk copy (TMA) issued before anything else.
+constexpr int SPLICE_THREADS = 256;
+struct SegC { int64_t src; uint32_t dst; uint32_t n; };   // copy n bytes genome[src..] -> tile[dst..]; jobs: n | kind << 24
 
 // bytes [o, o+16) of the 32-byte window (a, b)
 __device__ __forceinline__ uint4 shift16(const uint4 a, const uint4 b, uint32_t o) {
@@ -204,20 +214,10 @@ __device__ __forceinline__ uint4 shift16(const uint4 a, const uint4 b, uint32_t 
                       __funnelshift_r(u3, u4, bs));
 }
 
-// the 16 file bytes made of x's first 15 bases with a line break inserted at byte j (< 16): one PRMT per word
-__device__ __forceinline__ uint4 insert_nl(const uint4 x, uint32_t j) {
-    //   word w <  jw : untouched
-    //   word w == jw : byte t becomes '\n', the bytes above it take x_w[t..]
-    //   word w >  jw : shifted up by one byte, filled from x_{w-1}
-    const uint32_t jw = j >> 2, t = j & 3u;
-    const uint32_t selnl = (uint32_t)(0x4210241021402104ull >> (16u * t)) & 0xFFFFu;
-    uint4 y;
-    y.x = __byte_perm(x.x, 0x0Au, jw == 0u ? selnl : 0x3210u);
-    y.y = __byte_perm(x.y, jw == 1u ? 0x0Au : x.x, jw > 1u ? 0x3210u : (jw == 1u ? selnl : 0x2107u));
-    y.z = __byte_perm(x.z, jw == 2u ? 0x0Au : x.y, jw > 2u ? 0x3210u : (jw == 2u ? selnl : 0x2107u));
-    y.w = __byte_perm(x.w, jw == 3u ? 0x0Au : x.z, jw == 3u ? selnl : 0x2107u);
-    return y;
-}
+constexpr int SP_SEG_CAP = 320;
+constexpr int SP_JOB_CAP = 192;
+constexpr uint32_t SP_DIRECT = 0xFFFFFFFFu;        // segment did not fit the staging buffer: copied straight from global
+constexpr uint32_t SP_SEG_SPLIT = 2048;
 
 __global__ void __launch_bounds__(256)
 k_piece_desc(const Contig* contigs, int32_t n_contigs, const int64_t* piece_lo, int64_t n_pieces, const SvRec* sv, const Snp8* snp,
@@ -270,146 +270,325 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_glob
                  "l"(src_global), "r"(bytes), "r"(smem_addr(bar))
                  : "memory");
 }
-// shared -> global bulk store (one thread issues it; everything the CTA wrote to the source with ordinary stores must
-// have been made visible to the async proxy with fence_proxy_async() before the barrier that precedes the store)
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_1d(void* dst_global, const void* src_smem, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_global), "r"(smem_addr(src_smem)), "r"(bytes)
-                 : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
-// n (<= 127) bytes shared -> shared with arbitrary alignment on both sides: up to 3 bytes to the destination's word
-// boundary, whole words through a funnel shift (constant along the copy), up to 3 tail bytes.  Head and tail are
-// predicated, not loops: the lanes of a warp run this on different pieces and must stay in step.
-__device__ __forceinline__ void copy_smem(uint8_t* __restrict__ image, uint32_t d, const uint8_t* __restrict__ stage, uint32_t s, uint32_t n) {
-    uint32_t h = (0u - d) & 3u;
-    if (h > n) h = n;
-#pragma unroll
-    for (uint32_t t = 0; t < 3u; ++t) if (t < h) image[d + t] = stage[s + t];
-    d += h; s += h; n -= h;
-    const uint32_t nw = n >> 2;
-    const uint32_t sh = (s & 3u) * 8u;
-    const uint32_t* sp = reinterpret_cast<const uint32_t*>(stage + (s & ~3u));
-    uint32_t* dp = reinterpret_cast<uint32_t*>(image + d);
-    uint32_t w0 = sp[0];
-#pragma unroll 4
-    for (uint32_t i = 0; i < nw; ++i) {
-        const uint32_t w1 = sp[i + 1u];
-        dp[i] = __funnelshift_r(w0, w1, sh);
-        w0 = w1;
-    }
-    d += nw << 2; s += nw << 2; n &= 3u;
-#pragma unroll
-    for (uint32_t t = 0; t < 3u; ++t) if (t < n) image[d + t] = stage[s + t];
-}
-// the same from global memory (sources outside the staged span: far copies, spans stretched by long deletions)
-__device__ __forceinline__ void copy_gmem(uint8_t* __restrict__ image, uint32_t d, const uint8_t* __restrict__ genome, int64_t g, uint32_t n) {
-    while ((d & 3u) && n) { image[d] = __ldg(genome + g); ++d; ++g; --n; }
-    const uint32_t nw = n >> 2;
-    if (nw) {
-        const uint32_t sh = (uint32_t)(g & 3) * 8u;
-        const uint32_t* sp = reinterpret_cast<const uint32_t*>(genome + (g & ~(int64_t)3));
-        uint32_t* dp = reinterpret_cast<uint32_t*>(image + d);
-        uint32_t w0 = __ldg(sp);
-#pragma unroll 4
-        for (uint32_t i = 0; i < nw; ++i) {
-            const uint32_t w1 = __ldg(sp + i + 1u);
-            dp[i] = __funnelshift_r(w0, w1, sh);
-            w0 = w1;
-        }
-        d += nw << 2; g += nw << 2; n &= 3u;
-    }
-    while (n) { image[d] = __ldg(genome + g); ++d; ++g; --n; }
+// `bytes` (a multiple of 16) from a 16-byte aligned global address into L2, no destination
+__device__ __forceinline__ void bulk_prefetch_l2(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
-// memory operations of the cell walk (ms_tile_core.h: tile_cell / tile_emit_bases)
-struct SpliceOps {
-    uint8_t* image; const uint8_t* stage; const uint8_t* genome; uint2* jobs; int* n_jobs; uint2* pieces; int* n_pieces;
-    const PieceDesc* d; const TileShared* sh; const TileView* tv;
-    __device__ __forceinline__ void put(uint32_t x, uint8_t c) { image[x] = c; }
-    __device__ __forceinline__ void copy_stage(uint32_t x, uint32_t s, uint32_t n) {
-        // queued: the copies themselves run in a second phase where every lane has exactly one piece
-        while (n) {
-            const uint32_t m = n < 124u ? n : 124u;
-            const int slot = atomicAdd(n_pieces, 1);
-            if (slot < TL_PIECE_CAP) pieces[slot] = make_uint2(x | (m << 16), s);
-            else copy_smem(image, x, stage, s, m);
-            x += m; s += m; n -= m;
-        }
+// byte x of a clipped generated payload; s0 as prepared in S2 (RC: last source index, RAND: the cached 2-bit bases
+// shifted to the first byte, RANDL (insert reaching past its 32 cached bases): pos << 32 | first byte index)
+constexpr uint32_t K_RANDL = 7;
+__device__ __forceinline__ uint8_t payload_at(const SpliceView& v, uint32_t kind, int64_t s0, uint32_t x, uint32_t gid) {
+    switch (kind) {
+        case K_LIT:   return v.lit[s0 + x];
+        case K_CONV:  return v.conv[v.genome[s0 + x]];
+        case K_RAND:  return cached_insert_base(s0, x);
+        case K_RANDL: return rand_base_ool(v.seed, gid, (uint32_t)((uint64_t)s0 >> 32), (uint32_t)s0 + x);
+        default:      return v.comp[v.conv[v.genome[s0 - (int64_t)x]]];
     }
-    __device__ __forceinline__ void copy_global(uint32_t x, int64_t g, uint32_t n) { copy_gmem(image, x, genome, g, n); }
-    __device__ __forceinline__ void job(uint32_t x, uint32_t j, uint32_t r, uint32_t n) {
-        const int slot = atomicAdd(n_jobs, 1);
-        if (slot < TL_JOB_CAP) jobs[slot] = make_uint2(x | (n << 16), r | (j << 16));
-        else for (uint32_t t = 0; t < n; ++t) image[x + t] = tile_payload_byte(*d, *sh, *tv, j, r + t);   // queue full: do it here
+}
+
+// 16 lanes per segment (the average run is ~270 bytes = 17 chunks, so a full warp per segment leaves half of the
+// lanes idle).  hl = lane within the half-warp; n == 0 makes the half idle.
+__device__ __forceinline__ void half_copy_stage_to_tile(uint8_t* tile, const uint8_t* stage, uint32_t so, uint32_t d0, uint32_t n, int hl) {
+    const uint32_t d1 = d0 + n;
+    const uint32_t a0 = (d0 + 15u) & ~15u, a1 = d1 & ~15u;
+    if (a0 >= a1) {                                   // no aligned chunk inside: at most 30 bytes
+        for (uint32_t x = d0 + hl; x < d1; x += 16u) tile[x] = stage[so + (x - d0)];
+        return;
     }
-};
+#pragma unroll
+    for (int e = hl; e < 30; e += 16) {               // <= 15 head bytes (slots 0..14) and <= 15 tail bytes (slots 15..29)
+        const uint32_t x = e < 15 ? d0 + e : a1 + (e - 15);
+        if (x < (e < 15 ? a0 : d1)) tile[x] = stage[so + (x - d0)];
+    }
+    for (uint32_t c = a0 + 16u * hl; c < a1; c += 256u) {
+        const uint32_t s = so + (c - d0);
+        const uint4* w = reinterpret_cast<const uint4*>(stage + (s & ~15u));
+        *reinterpret_cast<uint4*>(tile + c) = shift16(w[0], w[1], s & 15u);
+    }
+}
 
-// dynamic shared memory of k_splice
-constexpr int SP_OFF_STAGE = 0;
-constexpr int SP_OFF_IMAGE = SP_OFF_STAGE + TL_STAGE_CAP + 32;
-constexpr int SP_OFF_POOL = SP_OFF_IMAGE + TL_TILE + 32;
-constexpr int SP_OFF_RS = SP_OFF_POOL + TL_POOL;
-constexpr int SP_OFF_DV = SP_OFF_RS + ((TL_SV_CAP + 1) * 4 + 15) / 16 * 16;
-constexpr int SP_OFF_JOBS = SP_OFF_DV + TL_SV_CAP * 16;
-constexpr int SP_OFF_PIECES = SP_OFF_JOBS + TL_JOB_CAP * 8;
-constexpr int SP_OFF_TAB = SP_OFF_PIECES + TL_PIECE_CAP * 8;
-constexpr int SP_DYN = SP_OFF_TAB + 512;
+__device__ __forceinline__ void warp_copy_to_tile(uint8_t* tile, const uint8_t* __restrict__ genome, const SegC sg, int lane) {
+    const uint32_t d0 = sg.dst, d1 = sg.dst + sg.n;
+    const uint32_t a0 = (d0 + 15u) & ~15u, a1 = d1 & ~15u;
+    if (a0 >= a1) {   // no aligned 16-byte chunk inside: at most 30 bytes
+        const uint32_t x = d0 + lane;
+        if (x < d1) tile[x] = __ldg(genome + sg.src + lane);
+        return;
+    }
+    {   // <= 15 head bytes on lanes 0..15, <= 15 tail bytes on lanes 16..31
+        const uint32_t x = lane < 16 ? d0 + lane : a1 + (lane - 16);
+        if (x < (lane < 16 ? a0 : d1)) tile[x] = __ldg(genome + sg.src + (x - d0));
+    }
+    for (uint32_t c = a0 + 16u * lane; c < a1; c += 512u) {
+        const int64_t s = sg.src + (int64_t)(c - d0);
+        const uint4* w = reinterpret_cast<const uint4*>(genome + (s & ~(int64_t)15));
+        const uint4 wa = __ldg(w), wb = __ldg(w + 1);
+        *reinterpret_cast<uint4*>(tile + c) = shift16(wa, wb, (uint32_t)(s & 15));
+    }
+}
 
-__global__ void __launch_bounds__(SPLICE_THREADS, SPLICE_CTAS)
+constexpr int SP_DYN = TL_TILE + 64 + TL_STAGE_CAP + 32;       // [tile | stage]
+
+__global__ void __launch_bounds__(SPLICE_THREADS, 5)
 k_splice(SpliceView v, const Contig* contigs, const PieceDesc* pieces, const SvRec* sv_stream, const Snp8* snp_stream,
          const Tables* tables, uint8_t* fasta, int64_t n_pieces) {
-    extern __shared__ __align__(128) uint8_t sp_dyn[];
-    __shared__ __align__(16) PieceDesc sd;
-    __shared__ __align__(8) uint64_t bar;
-    __shared__ int n_jobs, n_cp;
     __shared__ Contig sc;
+    __shared__ __align__(16) PieceDesc sd;
+    extern __shared__ __align__(16) uint8_t sp_dyn[];
+    uint8_t* const tile = sp_dyn;
+    uint8_t* const stage = sp_dyn + TL_TILE + 64;
+    __shared__ SegC segs[SP_SEG_CAP];
+    __shared__ uint32_t seg_stage[SP_SEG_CAP];     // offset of the segment's input in `stage`, or SP_DIRECT
+    SegC* const jobs = reinterpret_cast<SegC*>(stage);   // payload jobs are queued after S1, when the staging buffer is dead
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ int n_segs, n_jobs, fallback;
+    __shared__ uint8_t s_conv[256], s_comp[256];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t p = blockIdx.x;
-    uint8_t* const stage = sp_dyn + SP_OFF_STAGE;
-    uint8_t* const image = sp_dyn + SP_OFF_IMAGE;
-    uint8_t* const pool = sp_dyn + SP_OFF_POOL;
-    uint2* const jobs = reinterpret_cast<uint2*>(sp_dyn + SP_OFF_JOBS);
-    uint2* const cpq = reinterpret_cast<uint2*>(sp_dyn + SP_OFF_PIECES);
-    uint8_t* const s_tab = sp_dyn + SP_OFF_TAB;
-
     if (warp == 0) {
         reinterpret_cast<uint32_t*>(&sd)[lane] = __ldg(reinterpret_cast<const uint32_t*>(pieces + p) + lane);
-        if (lane == 0) { n_jobs = 0; n_cp = 0; mbar_init(&bar, 1u); }
+        if (lane == 0) { n_segs = 0; n_jobs = 0; fallback = 0; mbar_init(&bar, 1u); }
         __syncwarp();
+        // the tile's whole input span as ONE TMA bulk copy, issued before anything else so that it overlaps the
+        // segment pass below (S1 waits for it)
         if (lane == 0 && !(sd.flags & PD_FALLBACK)) {
-            // everything the tile reads arrives by bulk copies issued before any thread does anything else
-            const uint32_t virt = (sd.flags & PD_GOV_VIRTUAL) ? 1u : 0u;
-            const uint32_t nb_in = sd.in_bytes;
-            const uint32_t nb_sv = 32u * (sd.n_sv - virt);
-            const uint32_t skip = (uint32_t)(sd.snp_lo & 1);
-            const uint32_t nb_snp = sd.n_snp ? 8u * ((sd.n_snp + skip + 1u) & ~1u) : 0u;
-            if (nb_in) tma_load_1d(stage, v.genome + sd.in_lo, nb_in, &bar);
-            if (nb_sv) tma_load_1d(pool + 32u * virt, sv_stream + sd.sv_lo, nb_sv, &bar);
-            if (nb_snp) tma_load_1d(pool + 32u * sd.n_sv, snp_stream + (sd.snp_lo - skip), nb_snp, &bar);
-            tma_load_1d(s_tab, tables, 512u, &bar);
-            mbar_arrive_expect_tx(&bar, nb_in + nb_sv + nb_snp + 512u);
-            if (virt) *reinterpret_cast<SvRec*>(pool) = SvRec{0u, 0u, 0u, 0u, 0, (uint32_t)K_NONE, 0u};
+            const uint32_t nb = sd.in_bytes;
+            if (nb) tma_load_1d(stage, v.genome + sd.in_lo, nb, &bar);
+            mbar_arrive_expect_tx(&bar, nb);
         }
-        if (lane == 1 && p + 148 * SPLICE_CTAS < n_pieces) prefetch_l2(pieces + p + 148 * SPLICE_CTAS);   // the descriptor of a CTA of the next wave
+    } else if (warp == 1) {
+        // software wave prefetch: the descriptor of the tile that runs in this SM slot two waves from now, and the input
+        // span + records of the one a wave from now (its descriptor was requested a wave ago), go to L2
+        constexpr int64_t W = 148 * 5;
+        if (lane == 0 && p + 2 * W < n_pieces) prefetch_l2(pieces + p + 2 * W);
+        if (lane < 3 && p + W < n_pieces) {
+            const PieceDesc* nx = pieces + p + W;
+            if (lane == 0) {
+                const uint32_t nb = __ldg(&nx->in_bytes);
+                if (nb) bulk_prefetch_l2(v.genome + __ldg(&nx->in_lo), nb);
+            } else if (lane == 1) {
+                const uint32_t nsv = __ldg(&nx->n_sv);
+                if (nsv) bulk_prefetch_l2(sv_stream + __ldg(&nx->sv_lo), 32u * nsv);
+            } else {
+                const uint32_t nsnp = __ldg(&nx->n_snp);
+                if (nsnp) bulk_prefetch_l2(snp_stream + (__ldg(&nx->snp_lo) & ~(int64_t)1), 8u * ((nsnp + 2u) & ~1u));
+            }
+        }
     }
+    s_conv[tid] = tables->conv[tid];
+    s_comp[tid] = tables->comp[tid];
     __syncthreads();
     const PieceDesc& k = sd;
+    v.conv = s_conv;
+    v.comp = s_comp;
     const int64_t f_lo = k.f_lo, f_hi = k.f_hi;
     if (f_hi <= f_lo) return;
     const int64_t g0 = f_lo & ~(int64_t)15;
-    const uint32_t e = (uint32_t)(f_lo - g0), img_end = (uint32_t)(f_hi - g0);
+    const int ngroups = (int)((f_hi - g0 + 15) >> 4);
+    const uint32_t bpl = k.bpl, w1 = bpl + 1u;
+    const uint32_t b_lo = k.b_lo, b_hi = k.b_hi;   // mutated bases [b_lo, b_hi) live in this tile
+    const uint32_t virt = (k.flags & PD_GOV_VIRTUAL) ? 1u : 0u;
+    const int n_sv = (int)k.n_sv;                  // slot 0 = the governing record (virtual: the start of the contig)
+    const SvRec* const sv = sv_stream + k.sv_lo;   // slot j >= virt is sv[j - virt]
+    bool use_fallback = (k.flags & PD_FALLBACK) != 0u;
 
-    if (k.flags & PD_FALLBACK) {
-        // ---- generic per-byte path: tiles with more records than the pool holds, lines shorter than a chunk
-        if (tid == 0) sc = contigs[k.cidx];
-        for (int i = tid; i < 256; i += SPLICE_THREADS) { s_tab[i] = tables->conv[i]; s_tab[256 + i] = tables->comp[i]; }
+    if (!use_fallback) {
+        // ---- segs: copy segments of every run (raw payload + trailing shifted copy), clipped to the tile
+        for (int j = tid; j < n_sv; j += SPLICE_THREADS) {
+            uint32_t o = 0u, pr = 0u, kind = K_NONE;
+            int64_t run_src = k.goff, psrc = 0;   // source of the base right after the payload
+            if (j >= (int)virt) {
+                const uint4 a = __ldg(reinterpret_cast<const uint4*>(sv + (j - virt)));        // out, prod, run_in, pos
+                const uint4 b = __ldg(reinterpret_cast<const uint4*>(sv + (j - virt)) + 1);    // src, kind
+                o = a.x; pr = a.y; kind = b.z;
+                run_src = k.goff + (int64_t)a.z;
+                psrc = (int64_t)(((uint64_t)b.y << 32) | b.x);
+            }
+            uint32_t end = j + 1 < n_sv ? __ldg(&sv[j + 1 - virt].out) : b_hi;
+            if (end > b_hi) end = b_hi;
+#pragma unroll
+            for (int part = 0; part < 2; ++part) {
+                uint32_t lo, hi;
+                int64_t src;
+                if (part == 0) {  // raw payload [o, o+pr)
+                    if (kind != K_RAW || pr == 0u) continue;
+                    lo = o > b_lo ? o : b_lo;
+                    hi = o + pr < end ? o + pr : end;
+                    src = psrc + (int64_t)(lo - o);
+                } else {          // trailing run [o+pr, end)
+                    lo = o + pr > b_lo ? o + pr : b_lo;
+                    hi = end;
+                    src = run_src + (int64_t)(lo - (o + pr));
+                }
+                while (lo < hi) {
+                    const uint32_t n = hi - lo < SP_SEG_SPLIT ? hi - lo : SP_SEG_SPLIT;
+                    const int slot = atomicAdd(&n_segs, 1);
+                    if (slot < SP_SEG_CAP) {
+                        segs[slot] = SegC{src, lo - b_lo, n};
+                        // staged iff the segment's source lies inside the span the prologue's TMA copy brings in
+                        const int64_t rel = src - k.in_lo;
+                        seg_stage[slot] = (rel >= 0 && rel + (int64_t)n <= (int64_t)k.in_bytes) ? (uint32_t)rel : SP_DIRECT;
+                    } else {
+                        fallback = 1;
+                    }
+                    lo += n; src += n;
+                }
+            }
+        }
+        // one warp waits on the mbarrier (the TMA copy of the input span); the others park at the CTA barrier instead of
+        // spinning on try_wait (8 spinning warps were 11.6 % of all issued instructions, profiles/r1h).  The same barrier
+        // publishes the segment list.
+        if (warp == 0) mbar_wait(&bar, 0u);
         __syncthreads();
-        v.conv = s_tab; v.comp = s_tab + 256;
-        const int ngroups = (int)((img_end + 15u) >> 4);
+        use_fallback = fallback != 0;
+    }
+
+    if (!use_fallback) {
+        const int ns = n_segs;
+        // ---- S1: shifted copies shared -> shared, one half-warp per segment
+        {
+            const int half = lane >> 4, hl = lane & 15;
+            bool any_direct = false;
+            for (int s0 = 2 * warp; s0 < ns; s0 += 2 * (SPLICE_THREADS / 32)) {
+                const int sidx = s0 + half;
+                uint32_t so = 0u, d0 = 0u, n = 0u;
+                if (sidx < ns) {
+                    const uint32_t off = seg_stage[sidx];
+                    if (off == SP_DIRECT) any_direct = true;
+                    else { const SegC sg = segs[sidx]; so = off; d0 = sg.dst; n = sg.n; }
+                }
+                half_copy_stage_to_tile(tile, stage, so, d0, n, hl);
+            }
+            if (__any_sync(0xffffffffu, any_direct)) {   // segments that did not fit the staging buffer (rare)
+                for (int s0 = 2 * warp; s0 < ns; s0 += 2 * (SPLICE_THREADS / 32))
+                    for (int h = 0; h < 2; ++h)
+                        if (s0 + h < ns && seg_stage[s0 + h] == SP_DIRECT) warp_copy_to_tile(tile, v.genome, segs[s0 + h], lane);
+            }
+        }
+        __syncthreads();
+        // ---- S2: SNP bases (one thread per Snp8 of the tile) ...
+        {
+            const Snp8* snp = snp_stream + k.snp_lo;
+            for (uint32_t i = tid; i < k.n_snp; i += SPLICE_THREADS) {
+                const uint2 s = __ldg(reinterpret_cast<const uint2*>(snp + i));
+                tile[s.x - b_lo] = (uint8_t)s.y;
+            }
+        }
+        // ... and generated payloads (one thread per SvRec; short ones written on the spot, the others queued)
+        for (int j = tid + (int)virt; j < n_sv; j += SPLICE_THREADS) {
+            const uint4 a = __ldg(reinterpret_cast<const uint4*>(sv + (j - virt)));
+            const uint4 b = __ldg(reinterpret_cast<const uint4*>(sv + (j - virt)) + 1);
+            const uint32_t o = a.x, pr = a.y, kind = b.z;
+            uint32_t pkind = kind;
+            if (pr > 0u && kind != K_RAW) {
+                const uint32_t lo = o > b_lo ? o : b_lo, hi = o + pr < b_hi ? o + pr : b_hi;
+                if (lo < hi) {
+                    const int64_t src = (int64_t)(((uint64_t)b.y << 32) | b.x);
+                    const uint32_t rel = lo - o, n = hi - lo;
+                    // RC walks backwards; a random insert is addressed by (position, first byte index)
+                    int64_t s0;
+                    if (kind == K_RC) s0 = src + (int64_t)(pr - 1u - rel);
+                    else if (kind != K_RAND) s0 = src + rel;
+                    else if (rel + n <= 32u) s0 = (int64_t)((uint64_t)src >> (2u * rel));
+                    else { s0 = (int64_t)(((uint64_t)a.w << 32) | rel); pkind = K_RANDL; }
+                    if (n <= 3u) {
+                        for (uint32_t x = 0; x < n; ++x) {
+                            const uint8_t ch = payload_at(v, pkind, s0, x, k.gid);
+                            tile[lo - b_lo + x] = ch;
+                        }
+                    } else {
+                        const int slot = atomicAdd(&n_jobs, 1);
+                        if (slot < SP_JOB_CAP) jobs[slot] = SegC{s0, lo - b_lo, n | (pkind << 24)};
+                        else {
+                            for (uint32_t x = 0; x < n; ++x) {
+                                const uint8_t ch = payload_at(v, pkind, s0, x, k.gid);
+                                tile[lo - b_lo + x] = ch;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        const int nj = n_jobs < SP_JOB_CAP ? n_jobs : SP_JOB_CAP;
+        for (int jb = warp; jb < nj; jb += SPLICE_THREADS / 32) {
+            const SegC job = jobs[jb];
+            const uint32_t n = job.n & 0xFFFFFFu, kind = job.n >> 24;
+            uint8_t* d = tile + job.dst;
+            if (kind == K_RC) {
+                const uint8_t* g = v.genome + job.src;
+                for (uint32_t x = lane; x < n; x += 32u) d[x] = s_comp[s_conv[g[-(int)x]]];
+            } else if (kind == K_CONV) {
+                const uint8_t* g = v.genome + job.src;
+                for (uint32_t x = lane; x < n; x += 32u) d[x] = s_conv[g[x]];
+            } else if (kind == K_RAND || kind == K_RANDL) {
+                for (uint32_t x = lane; x < n; x += 32u) d[x] = payload_at(v, kind, job.src, x, k.gid);
+            } else {
+                const uint8_t* g = v.lit + job.src;
+                for (uint32_t x = lane; x < n; x += 32u) d[x] = g[x];
+            }
+        }
+        __syncthreads();
+        // ---- S3: insert line breaks, write the file image
+        // line / column of a thread's groups advance by a constant per iteration: one division per thread
+        const int g_first = (int)((f_lo - g0 + 15) >> 4);                 // first full group
+        const int g_end = (int)((f_hi - g0) >> 4);                        // one past the last full group
+        if (bpl >= 16u && g_end > g_first) {
+            const uint32_t step_q = 16u * SPLICE_THREADS;
+            const uint32_t step_line = step_q / w1, step_col = step_q - step_line * w1;
+            int gi = g_first + tid;
+            uint32_t q0 = (uint32_t)(g0 - k.body_off) + ((uint32_t)gi << 4);
+            uint32_t line = q0 / w1, col = q0 - line * w1;
+            uint8_t* out = fasta + g0 + ((int64_t)gi << 4);
+            for (; gi < g_end; gi += SPLICE_THREADS) {
+                const uint32_t j = bpl - col;                             // lane of the line break (if < 16)
+                const uint32_t so = (q0 - line) - b_lo;                   // tile offset of the group's first base
+                const uint32_t* w = reinterpret_cast<const uint32_t*>(tile + (so & ~3u));
+                const uint32_t bs = (so & 3u) * 8u;
+                const uint32_t u0 = w[0], u1 = w[1], u2 = w[2], u3 = w[3], u4 = w[4];
+                uint4 y = make_uint4(__funnelshift_r(u0, u1, bs), __funnelshift_r(u1, u2, bs), __funnelshift_r(u2, u3, bs),
+                                     __funnelshift_r(u3, u4, bs));
+                if (j < 16u) {
+                    // one PRMT per word: word w = prmt(x_w, other, sel) with
+                    //   w <  jw : sel 0x3210 (untouched)
+                    //   w == jw : other = '\n', byte t becomes '\n', bytes above it take x_w[t..]
+                    //   w >  jw : other = x_{w-1}, sel 0x2107 (shifted up by one byte)
+                    const uint32_t jw = j >> 2, t = j & 3u;
+                    const uint32_t selnl = (uint32_t)(0x4210241021402104ull >> (16u * t)) & 0xFFFFu;
+                    const uint32_t x0 = y.x, x1 = y.y, x2 = y.z, x3 = y.w;
+                    y.x = __byte_perm(x0, 0x0Au, jw == 0u ? selnl : 0x3210u);
+                    y.y = __byte_perm(x1, jw == 1u ? 0x0Au : x0, jw > 1u ? 0x3210u : (jw == 1u ? selnl : 0x2107u));
+                    y.z = __byte_perm(x2, jw == 2u ? 0x0Au : x1, jw > 2u ? 0x3210u : (jw == 2u ? selnl : 0x2107u));
+                    y.w = __byte_perm(x3, jw == 3u ? 0x0Au : x2, jw == 3u ? selnl : 0x2107u);
+                }
+                __stcs(reinterpret_cast<uint4*>(out), y);
+                out += step_q;
+                q0 += step_q;
+                line += step_line; col += step_col;
+                if (col >= w1) { col -= w1; ++line; }
+            }
+        }
+        // edge bytes of the piece (and everything when lines are shorter than a group)
+        {
+            const int64_t e0 = bpl >= 16u ? g0 + ((int64_t)g_first << 4) : f_lo;   // [f_lo, e0) and [e1, f_hi) go byte-wise
+            const int64_t e1 = bpl >= 16u ? (g_end > g_first ? g0 + ((int64_t)g_end << 4) : e0) : f_lo;
+            const int64_t n_head = (e0 < f_hi ? e0 : f_hi) - f_lo;
+            const int64_t n_tail = f_hi - (e1 > f_lo ? e1 : f_lo);
+            for (int64_t y = tid; y < n_head + (n_tail > 0 ? n_tail : 0); y += SPLICE_THREADS) {
+                const int64_t x = y < n_head ? f_lo + y : e1 + (y - n_head);
+                if (x >= f_hi) continue;
+                const uint32_t q = (uint32_t)(x - k.body_off);
+                const uint32_t ln = q / w1;
+                fasta[x] = (q - ln * w1 == bpl) ? (uint8_t)'\n' : tile[(q - ln) - b_lo];
+            }
+        }
+    } else {
+        // ---- fallback for tiles with more runs than the staging lists hold: generic per-byte path
+        if (tid == 0) sc = contigs[k.cidx];
+        __syncthreads();
         for (int gi = tid; gi < ngroups; gi += SPLICE_THREADS) {
             const int64_t g = g0 + ((int64_t)gi << 4);
             const int64_t a = g < f_lo ? f_lo : g;
@@ -420,81 +599,6 @@ k_splice(SpliceView v, const Contig* contigs, const PieceDesc* pieces, const SvR
                 const int ln = (int)(x - g);
                 fasta[x] = (uint8_t)(w[ln >> 2] >> (8 * (ln & 3)));
             }
-        }
-        return;
-    }
-
-    TileShared sh;
-    sh.stage = stage; sh.image = image;
-    sh.sv = reinterpret_cast<SvRec*>(pool);
-    sh.snp = reinterpret_cast<const Snp8*>(pool + 32u * k.n_sv) + (k.snp_lo & 1);
-    sh.rs = reinterpret_cast<uint32_t*>(sp_dyn + SP_OFF_RS);
-    sh.dv = reinterpret_cast<TileRec*>(sp_dyn + SP_OFF_DV);
-    TileView tv{v.genome, v.lit, s_tab, s_tab + 256, v.seed};
-    const uint32_t n_sv = k.n_sv;
-    const uint32_t bpl = k.bpl;
-
-    // one warp waits on the mbarrier (the bulk copies); the others park at the CTA barrier instead of spinning
-    if (warp == 0) mbar_wait(&bar, 0u);
-    __syncthreads();
-
-    // ---- prep: one thread per SvRec
-    for (uint32_t j = tid; j < n_sv; j += SPLICE_THREADS) tile_prep_rec(k, sh, j);
-    if (tid == 0) sh.rs[n_sv] = k.b_hi - k.b_lo;
-    __syncthreads();
-
-    // ---- walk: one thread per cell (a line of the file); consecutive lanes take consecutive lines
-    const TileGeom geo = tile_geom(k);
-    {
-        SpliceOps ops{image, stage, v.genome, jobs, &n_jobs, cpq, &n_cp, &k, &sh, &tv};
-        for (uint32_t cell = tid; cell < geo.n_cells; cell += SPLICE_THREADS) tile_cell(k, sh, geo, ops, cell);
-    }
-    __syncthreads();
-
-    // ---- copy: one thread per queued piece (a contiguous stretch of one run inside one line)
-    {
-        const int np = n_cp < TL_PIECE_CAP ? n_cp : TL_PIECE_CAP;
-        for (int i = tid; i < np; i += SPLICE_THREADS) {
-            const uint2 pc = cpq[i];
-            copy_smem(image, pc.x & 0xFFFFu, stage, pc.y, pc.x >> 16);
-        }
-    }
-
-    // ---- jobs: generated payload pieces (inserts, inversions, translocation inserts), half a warp each
-    {
-        const int nj = n_jobs < TL_JOB_CAP ? n_jobs : TL_JOB_CAP;
-        const int half = tid >> 4;
-        const uint32_t hl = (uint32_t)tid & 15u;
-        for (int i = half; i < nj; i += SPLICE_THREADS / 16) {
-            const uint2 jb = jobs[i];
-            const uint32_t x = jb.x & 0xFFFFu, n = jb.x >> 16, r = jb.y & 0xFFFFu, j = jb.y >> 16;
-            for (uint32_t t = hl; t < n; t += 16u) image[x + t] = tile_payload_byte(k, sh, tv, j, r + t);
-        }
-    }
-    const uint32_t xa = (e + 15u) & ~15u, xb = img_end & ~15u;
-    __syncthreads();
-    // ---- snp: scatter the substituted bases (they fall on copied bases, never on a payload)
-    {
-        const float rcp_bpl = k.rcp_bpl;
-        for (uint32_t i = tid; i < k.n_snp; i += SPLICE_THREADS) {
-            const Snp8 sp = sh.snp[i];
-            image[e + tile_snp_offset(k, sp.out, rcp_bpl)] = (uint8_t)sp.alt;
-        }
-    }
-    fence_proxy_async();
-    __syncthreads();
-
-    // ---- store: the aligned middle of the piece leaves with one bulk copy, the ragged ends byte-wise
-    if (tid == 0 && xb > xa) {
-        tma_store_1d(fasta + g0 + xa, image + xa, xb - xa);
-        tma_store_wait_read();
-    } else if (tid >= 32) {
-        const uint32_t h_end = xa < img_end ? xa : img_end;                 // head bytes [e, h_end)
-        const uint32_t t_lo = xb >= xa ? xb : img_end;                       // tail bytes [t_lo, img_end)
-        const uint32_t n_head = h_end - e, n_tail = img_end - t_lo;
-        for (uint32_t y = (uint32_t)tid - 32u; y < n_head + n_tail; y += SPLICE_THREADS - 32) {
-            const uint32_t X = y < n_head ? e + y : t_lo + (y - n_head);
-            fasta[g0 + X] = image[X];
         }
     }
 }

@@ -39,12 +39,12 @@ struct alignas(8) Snp8 { uint32_t out; uint32_t alt; };   // alt: substituted ba
 static_assert(sizeof(Snp8) == 8, "Snp8 must be 8 bytes");
 
 #ifndef MS_TILE_SHIFT
-#define MS_TILE_SHIFT 13
+#define MS_TILE_SHIFT 14
 #endif
 constexpr int TL_TILE_SHIFT = MS_TILE_SHIFT;
 constexpr int TL_TILE = 1 << TL_TILE_SHIFT;    // file bytes per tile
 constexpr int TL_STAGE_CAP = TL_TILE + TL_TILE / 8 + 512;   // staged input span (tile + what deletions skip + alignment slack)
-constexpr int TL_SV_CAP = TL_TILE / 64;        // SvRecs per tile held in shared memory (incl. the governing one)
+constexpr int TL_SV_CAP = TL_TILE / 32;        // SvRecs per tile the staged path handles (incl. the governing one)
 constexpr int TL_POOL = TL_TILE / 2;           // bytes of SvRec + Snp8 per tile
 constexpr int TL_JOB_CAP = TL_TILE / 64;       // queued generated-payload pieces per tile
 constexpr int TL_PIECE_CAP = TL_TILE / 32 + TL_TILE / 128;   // queued copy pieces per tile
@@ -304,7 +304,8 @@ MS_HD PieceDesc tile_describe(const Contig& k, uint32_t cidx, int64_t f_lo, int6
     const int64_t n_snp = lo - s0;
     // pool layout: SvRecs first (32 B each), then the Snp8s from an even stream index (16-byte aligned bulk copy)
     const int64_t pool = 32 * n_sv + 8 * (n_snp + 2);
-    if (n_sv > TL_SV_CAP || pool > TL_POOL) d.flags |= PD_FALLBACK;
+    (void)pool;
+    if (n_sv > TL_SV_CAP) d.flags |= PD_FALLBACK;
     d.n_sv = (uint32_t)(n_sv > 0x7fffffff ? 0x7fffffff : n_sv);
     d.n_snp = (uint32_t)(n_snp > 0x7fffffff ? 0x7fffffff : n_snp);
     // staged span: the contiguous, monotone stretch of input the tile's copy runs read — from the source of its first
