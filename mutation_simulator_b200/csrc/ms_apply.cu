@@ -289,21 +289,36 @@ __device__ __forceinline__ uint8_t payload_at(const SpliceView& v, uint32_t kind
     }
 }
 
-// 16 lanes per segment (the average run is ~270 bytes = 17 chunks, so a full warp per segment leaves half of the
-// lanes idle).  hl = lane within the half-warp; n == 0 makes the half idle.
-__device__ __forceinline__ void half_copy_stage_to_tile(uint8_t* tile, const uint8_t* stage, uint32_t so, uint32_t d0, uint32_t n, int hl) {
+// 8 lanes per segment (the average run is ~270 bytes = 17 chunks: 16 lanes left a third of them idle and paid the
+// per-segment fixed cost twice as often, profiles/r2m).  ql = lane within the quarter-warp; n == 0 makes it idle.
+// The ragged ends go in 12 slots — <= 3 bytes and <= 3 words up to the first aligned chunk, <= 3 words and <= 3
+// bytes after the last — each read as one unaligned word through a funnel shift.
+__device__ __forceinline__ void quarter_copy_stage_to_tile(uint8_t* tile, const uint8_t* stage, uint32_t so, uint32_t d0, uint32_t n, int ql) {
     const uint32_t d1 = d0 + n;
     const uint32_t a0 = (d0 + 15u) & ~15u, a1 = d1 & ~15u;
     if (a0 >= a1) {                                   // no aligned chunk inside: at most 30 bytes
-        for (uint32_t x = d0 + hl; x < d1; x += 16u) tile[x] = stage[so + (x - d0)];
+        for (uint32_t x = d0 + ql; x < d1; x += 8u) tile[x] = stage[so + (x - d0)];
         return;
     }
+    const uint32_t h4 = (d0 + 3u) & ~3u;              // (<= a0) head: bytes [d0, h4), words [h4, a0)
+    const uint32_t t4 = a1 + ((d1 - a1) & ~3u);       // tail: words [a1, t4), bytes [t4, d1)
 #pragma unroll
-    for (int e = hl; e < 30; e += 16) {               // <= 15 head bytes (slots 0..14) and <= 15 tail bytes (slots 15..29)
-        const uint32_t x = e < 15 ? d0 + e : a1 + (e - 15);
-        if (x < (e < 15 ? a0 : d1)) tile[x] = stage[so + (x - d0)];
+    for (int r = 0; r < 2; ++r) {
+        const int slot = ql + 8 * r;                  // 0-2 head bytes, 3-5 head words, 6-8 tail words, 9-11 tail bytes
+        if (slot < 12) {
+            const uint32_t k = (uint32_t)slot % 3u;
+            const bool word = slot >= 3 && slot < 9;
+            const uint32_t x = slot < 3 ? d0 + k : slot < 6 ? h4 + 4u * k : slot < 9 ? a1 + 4u * k : t4 + k;
+            const uint32_t lim = slot < 3 ? h4 : slot < 6 ? a0 : slot < 9 ? t4 : d1;
+            if (x < lim) {
+                const uint32_t s = so + (x - d0);
+                const uint32_t* w = reinterpret_cast<const uint32_t*>(stage + (s & ~3u));
+                const uint32_t v = __funnelshift_r(w[0], w[1], (s & 3u) * 8u);
+                if (word) *reinterpret_cast<uint32_t*>(tile + x) = v; else tile[x] = (uint8_t)v;
+            }
+        }
     }
-    for (uint32_t c = a0 + 16u * hl; c < a1; c += 256u) {
+    for (uint32_t c = a0 + 16u * ql; c < a1; c += 128u) {
         const uint32_t s = so + (c - d0);
         const uint4* w = reinterpret_cast<const uint4*>(stage + (s & ~15u));
         *reinterpret_cast<uint4*>(tile + c) = shift16(w[0], w[1], s & 15u);
@@ -448,23 +463,23 @@ k_splice(SpliceView v, const Contig* contigs, const PieceDesc* pieces, const SvR
 
     if (!use_fallback) {
         const int ns = n_segs;
-        // ---- S1: shifted copies shared -> shared, one half-warp per segment
+        // ---- S1: shifted copies shared -> shared, a quarter of a warp per segment
         {
-            const int half = lane >> 4, hl = lane & 15;
+            const int quarter = lane >> 3, ql = lane & 7;
             bool any_direct = false;
-            for (int s0 = 2 * warp; s0 < ns; s0 += 2 * (SPLICE_THREADS / 32)) {
-                const int sidx = s0 + half;
+            for (int s0 = 4 * warp; s0 < ns; s0 += 4 * (SPLICE_THREADS / 32)) {
+                const int sidx = s0 + quarter;
                 uint32_t so = 0u, d0 = 0u, n = 0u;
                 if (sidx < ns) {
                     const uint32_t off = seg_stage[sidx];
                     if (off == SP_DIRECT) any_direct = true;
                     else { const SegC sg = segs[sidx]; so = off; d0 = sg.dst; n = sg.n; }
                 }
-                half_copy_stage_to_tile(tile, stage, so, d0, n, hl);
+                quarter_copy_stage_to_tile(tile, stage, so, d0, n, ql);
             }
             if (__any_sync(0xffffffffu, any_direct)) {   // segments that did not fit the staging buffer (rare)
-                for (int s0 = 2 * warp; s0 < ns; s0 += 2 * (SPLICE_THREADS / 32))
-                    for (int h = 0; h < 2; ++h)
+                for (int s0 = 4 * warp; s0 < ns; s0 += 4 * (SPLICE_THREADS / 32))
+                    for (int h = 0; h < 4; ++h)
                         if (s0 + h < ns && seg_stage[s0 + h] == SP_DIRECT) warp_copy_to_tile(tile, v.genome, segs[s0 + h], lane);
             }
         }
