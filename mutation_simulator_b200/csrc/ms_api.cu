@@ -327,6 +327,7 @@ int ms_load_records(ms_ctx* c, const ms_rec* recs, int64_t n_recs, const uint8_t
     c->lit_bytes = lit_bytes;
     c->counts_valid = false;
     c->sizes_valid = false;
+    c->rec_out_valid = true;
     return MS_OK;
 }
 
@@ -351,7 +352,8 @@ static int which_buffer(ms_ctx* c, int which, void** p, int64_t* n) {
     switch (which) {
         case 0: *p = c->fasta.p; *n = c->fasta_bytes; return MS_OK;
         case 1: *p = c->vcf.p; *n = c->vcf_bytes; return MS_OK;
-        case 2: *p = c->recs.p; *n = c->n_recs * (int64_t)sizeof(Rec); return MS_OK;
+        case 2: { int rc = fill_record_out(c); if (rc) return rc; }
+                *p = c->recs.p; *n = c->n_recs * (int64_t)sizeof(Rec); return MS_OK;
         case 3: *p = c->lit.p; *n = c->lit_bytes; return MS_OK;
         case 4: *p = c->genome.p; *n = c->total_bases; return MS_OK;
         default: MS_FAIL(c, MS_ERR_ARG, "unknown buffer id %d", which);

@@ -147,9 +147,8 @@ static int layout_by_scan(ms_ctx* c, Contig* d_contigs, const int64_t* S, const 
 // ---- out positions, validation, and the two record streams the splice kernel reads -----------------------------
 // S[i] = sum of length deltas before record i, N[i] = number of non-SNP records before i (both over all contigs).
 // Record i lands in slot N[i] of the SvRec stream or slot i - N[i] of the Snp8 stream; a contig's entries are
-// [N[rec_lo], N[rec_hi]) resp. [rec_lo - N[rec_lo], rec_hi - N[rec_hi]).  A SNP's stream slot is also left in its
-// (otherwise unused) Rec.src so that k_snp_fill can patch the substituted base in later (streamed runs).
-__device__ __forceinline__ void rec_out_one(Rec* recs, int64_t i, const Contig* contigs, const int64_t* S, const uint32_t* N, SvRec* sv,
+// [N[rec_lo], N[rec_hi]) resp. [rec_lo - N[rec_lo], rec_hi - N[rec_hi]).  The record table itself is only read.
+__device__ __forceinline__ void rec_out_one(const Rec* recs, int64_t i, const Contig* contigs, const int64_t* S, const uint32_t* N, SvRec* sv,
                                             Snp8* snp, Totals* tot, unsigned int* hist) {
     const Rec r = recs[i];
     if (r.type < 8) atomicAdd(&hist[r.type], 1u);
@@ -161,23 +160,31 @@ __device__ __forceinline__ void rec_out_one(Rec* recs, int64_t i, const Contig* 
         if ((int64_t)r.pos < (int64_t)p.pos + p.cons || r.pos == p.pos) raise_error(tot, MS_ERR_OVERLAP, i);
     }
     const uint32_t nsv = N[i];
-    if (r.kind == K_SNP) {
-        const int64_t slot = i - (int64_t)nsv;
-        snp[slot] = Snp8{(uint32_t)out, (uint32_t)r.alt};
-        uint4 lo4 = *reinterpret_cast<const uint4*>(&r);
-        lo4.w = (uint32_t)out;
-        uint4* dst = reinterpret_cast<uint4*>(recs + i);
-        dst[0] = lo4;
-        reinterpret_cast<int64_t*>(recs + i)[2] = slot;
-    } else {
-        sv[nsv] = SvRec{(uint32_t)out, r.prod, r.pos + r.cons, r.pos, r.src, (uint32_t)r.kind, 0u};
-        recs[i].out = (uint32_t)out;
-    }
+    if (r.kind == K_SNP) snp[i - (int64_t)nsv] = Snp8{(uint32_t)out, (uint32_t)r.alt};
+    else sv[nsv] = SvRec{(uint32_t)out, r.prod, r.pos + r.cons, r.pos, r.src, (uint32_t)r.kind, 0u};
+}
+
+// Rec.out is not needed on the device any more (the streams carry it); it is filled in when the records are handed out
+// (ms_download / ms_device_ptr of the record table).
+__global__ void __launch_bounds__(256) k_fill_out(Rec* recs, int64_t n_recs, const Contig* contigs, const int64_t* S) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_recs) return;
+    const Contig& k = contigs[recs[i].contig];
+    recs[i].out = (uint32_t)((int64_t)recs[i].pos + (S[i] - S[k.rec_lo]));
+}
+
+int fill_record_out(ms_ctx* c) {
+    if (c->rec_out_valid || c->n_recs <= 0) return MS_OK;
+    k_fill_out<<<(unsigned)ceil_div(c->n_recs, 256), 256, 0, c->stream>>>(c->recs.as<Rec>(), c->n_recs, c->contigs.as<Contig>(), c->svec.as<int64_t>());
+    MS_LAUNCH_CHECK(c);
+    c->rec_out_valid = true;
+    return MS_OK;
 }
 
 
+
 __global__ void __launch_bounds__(256)
-k_rec_out(Rec* recs, int64_t n_recs, const Contig* contigs, const int64_t* S, const uint32_t* N, SvRec* sv, Snp8* snp, Totals* tot) {
+k_rec_out(const Rec* recs, int64_t n_recs, const Contig* contigs, const int64_t* S, const uint32_t* N, SvRec* sv, Snp8* snp, Totals* tot) {
     __shared__ unsigned int hist[8];          // records per mutation type (ms_get_stats), counted on the way
     if (threadIdx.x < 8) hist[threadIdx.x] = 0u;
     __syncthreads();
@@ -1062,6 +1069,7 @@ static int index_stage(ms_ctx* c) {
                                                                           c->piece_desc.as<PieceDesc>());
         MS_LAUNCH_CHECK(c);
     }
+    c->rec_out_valid = false;
     stage_end(c, ST_INDEX);
     return MS_OK;
 }
@@ -1073,7 +1081,7 @@ static int splice_launch(ms_ctx* c, int64_t piece_lo, int64_t n_pieces, int32_t 
     const Tables* d_tab = c->tables.as<Tables>();
     Contig* d_contigs = c->contigs.as<Contig>();
     cudaStream_t st = c->stream;
-    SpliceView sv{c->genome.as<uint8_t>(), c->lit.as<uint8_t>(), c->recs.as<Rec>(), d_tab->conv, d_tab->comp, c->seed_last};
+    SpliceView sv{c->genome.as<uint8_t>(), c->lit.as<uint8_t>(), c->recs.as<Rec>(), c->svec.as<int64_t>(), d_tab->conv, d_tab->comp, c->seed_last};
     if (n_pieces > 0) {
         if (!c->splice_attr_set) {   // per context: the attribute is per device, and a process may hold contexts on several
             MS_CUDA(c, cudaFuncSetAttribute(k_splice, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_DYN));
@@ -1213,7 +1221,7 @@ __global__ void __launch_bounds__(256) k_upper_range(uint8_t* g, int64_t lo, int
 // ref/alt of the SNP records [lo, hi): the part of record building that needs the bases (mutator.py:429-455)
 __global__ void __launch_bounds__(256)
 k_snp_fill(Rec* recs, int64_t lo, int64_t hi, const Contig* contigs, const uint8_t* genome, const Tables* tab, Seed seed, double p_ti,
-           Snp8* snp) {
+           Snp8* snp, const uint32_t* N) {
     const int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= hi) return;
     const uint32_t kind_type = reinterpret_cast<const uint32_t*>(recs + i)[6];   // kind | type<<8 | ref<<16 | alt<<24
@@ -1223,7 +1231,7 @@ k_snp_fill(Rec* recs, int64_t lo, int64_t hi, const Contig* contigs, const uint8
     const uint8_t ref = tab->conv[genome[ct.goff + pos]];
     const uint8_t alt = draw_snp(seed, ct.gid, pos, ref, p_ti, tab->trans);
     reinterpret_cast<uint32_t*>(recs + i)[6] = (kind_type & 0xFFFFu) | ((uint32_t)ref << 16) | ((uint32_t)alt << 24);
-    snp[recs[i].src].alt = (uint32_t)alt;      // k_rec_out left the record's Snp8 slot in its (otherwise unused) src
+    snp[i - (int64_t)N[i]].alt = (uint32_t)alt;      // the record's slot in the Snp8 stream
 }
 
 // VCF bytes written up to the end of a contig group: vend[1] = vend[0] + this group's bytes
@@ -1329,7 +1337,7 @@ int mutate_streamed(ms_ctx* c, uint64_t seed, const uint8_t* h_bases, uint8_t* h
         MS_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_up[g], 0));
         if (r1 > r0) {
             k_snp_fill<<<(unsigned)ceil_div(r1 - r0, 256), 256, 0, c->stream>>>(c->recs.as<Rec>(), r0, r1, c->contigs.as<Contig>(), d_genome, d_tab,
-                                                                             c->seed_last, c->p_ti, c->snp_stream.as<Snp8>());
+                                                                             c->seed_last, c->p_ti, c->snp_stream.as<Snp8>(), c->nvec.as<uint32_t>());
             MS_LAUNCH_CHECK(c);
         }
         if ((rc = splice_launch(c, h_piece_lo[c0], h_piece_lo[c1] - h_piece_lo[c0], c0, c1 - c0))) return rc;

@@ -93,6 +93,7 @@ struct ms_ctx {
     int64_t maxspan = 2;          // longest blocking span of any candidate (set with the ranges)
     int any_small = 0, any_large = 0;
     bool counts_valid = false;
+    bool rec_out_valid = false;   // Rec.out of the device table is filled in (done lazily when the records are handed out)
     bool sizes_valid = false;     // keep/cand_val hold (delta, vcf size) of the current records (written by k_build_records)
     ms::Seed seed_last{0, 0};     // seed of the last ms_sample (K_RAND payloads are a function of it)
 
@@ -170,5 +171,6 @@ int sample_pipeline(ms_ctx* c, uint64_t seed, bool defer_bases = false);
 int mutate_streamed(ms_ctx* c, uint64_t seed, const uint8_t* h_bases, uint8_t* h_fasta, int64_t fasta_cap, uint8_t* h_vcf,
                     int64_t vcf_cap, int64_t* fasta_bytes, int64_t* vcf_bytes, int64_t group_min);
 int count_types(ms_ctx* c);
+int fill_record_out(ms_ctx* c);
 int hash_ranges(ms_ctx* c, const uint8_t* buf, int32_t n, const int64_t* start, const int64_t* end, uint64_t* out);
 }  // namespace ms

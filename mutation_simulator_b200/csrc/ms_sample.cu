@@ -590,6 +590,7 @@ int sample_pipeline(ms_ctx* c, uint64_t seed64, bool defer_bases) {
     c->last_totals.lit_bytes = 0;
     c->counts_valid = false;
     c->sizes_valid = true;
+    c->rec_out_valid = true;      // nothing to fill in until the next plan (svec is the candidates' scratch here)
     return MS_OK;
 }
 

@@ -17,6 +17,7 @@ struct SpliceView {
     const uint8_t* genome;  // padded base array (>= 32 readable bytes past the last base)
     const uint8_t* lit;     // literal pool
     const Rec* recs;
+    const int64_t* S;       // running length delta before each record (device plan); NULL: Rec.out is filled in (emulation)
     const uint8_t* conv;    // 256-entry tables (global or shared memory)
     const uint8_t* comp;
     Seed seed;              // for K_RAND payloads
@@ -28,6 +29,11 @@ MS_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {
 #else
     return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
 #endif
+}
+
+// contig-relative output base index of record i's payload: its position shifted by the length deltas before it
+MS_HD uint32_t rec_out_of(const SpliceView& v, const Contig& c, int64_t i) {
+    return v.S ? (uint32_t)((int64_t)v.recs[i].pos + (v.S[i] - v.S[c.rec_lo])) : v.recs[i].out;
 }
 
 // Record cursor: the record governing output base b and its cached fields.
@@ -50,10 +56,10 @@ MS_HD void cursor_load(const SpliceView& v, const Contig& c, int64_t i, Cursor& 
         k.run_src = c.goff;
     } else {
         const Rec r = v.recs[i];
-        k.out = r.out; k.prod = r.prod; k.kind = r.kind; k.alt = r.alt; k.src = r.src; k.pos = r.pos;
+        k.out = rec_out_of(v, c, i); k.prod = r.prod; k.kind = r.kind; k.alt = r.alt; k.src = r.src; k.pos = r.pos;
         k.run_src = c.goff + (int64_t)r.pos + (int64_t)r.cons;
     }
-    k.next = (i + 1 < c.rec_hi) ? v.recs[i + 1].out : (uint32_t)c.out_len;
+    k.next = (i + 1 < c.rec_hi) ? rec_out_of(v, c, i + 1) : (uint32_t)c.out_len;
 }
 
 // the record governing output base b: the last one of the contig with out <= b (rec_lo - 1 if none)
@@ -61,7 +67,7 @@ MS_HD int64_t rec_find(const SpliceView& v, const Contig& c, uint32_t b) {
     int64_t lo = c.rec_lo, hi = c.rec_hi;   // first record with out > b
     while (lo < hi) {
         const int64_t mid = (lo + hi) >> 1;
-        if (v.recs[mid].out <= b) lo = mid + 1; else hi = mid;
+        if (rec_out_of(v, c, mid) <= b) lo = mid + 1; else hi = mid;
     }
     return lo - 1;
 }
@@ -74,7 +80,7 @@ MS_HD void cursor_seek(const SpliceView& v, const Contig& c, uint32_t b, Cursor&
 MS_HD void cursor_advance(const SpliceView& v, const Contig& c, uint32_t b, Cursor& k) {
     if (b < k.next) return;
     int64_t i = k.i;
-    while (i + 1 < c.rec_hi && v.recs[i + 1].out <= b) ++i;
+    while (i + 1 < c.rec_hi && rec_out_of(v, c, i + 1) <= b) ++i;
     cursor_load(v, c, i, k);
 }
 
@@ -147,7 +153,7 @@ MS_HD bool group_fast(const SpliceView& v, const Contig& c, uint32_t q0, uint32_
         src0 = c.goff + (int64_t)bF;
     } else {
         const Rec r = v.recs[i];
-        const uint32_t rel = bF - r.out;
+        const uint32_t rel = bF - rec_out_of(v, c, i);
         if (rel < r.prod) {
             if (r.kind == K_RAW) {
                 if (rel + nb > r.prod) return false;
@@ -165,7 +171,7 @@ MS_HD bool group_fast(const SpliceView& v, const Contig& c, uint32_t q0, uint32_
     }
     if (scan_next) {
         for (int64_t n = i + 1; n < c.rec_hi; ++n) {
-            const uint32_t o = v.recs[n].out;
+            const uint32_t o = rec_out_of(v, c, n);
             if (o > bL) break;
             const Rec r = v.recs[n];
             if (r.kind != K_SNP || npatch == 4) return false;

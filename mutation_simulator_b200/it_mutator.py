@@ -223,7 +223,7 @@ class ITMutator:
         self._src_of.update({p: total + 64 + off for p, off in stage_off.items()})
         self.exchange_bytes = self.exchange_ms = 0
 
-    MAX_INTERVAL_OPS = 512      # beyond this many intervals per direction the whole contig goes as one transfer
+    MAX_INTERVAL_OPS = 64      # beyond this many intervals per direction the whole contig goes as one transfer
 
     def step_partitioned(self):
         """Breakpoints (identical on every rank: keyed by the global contig id), exchange, records, splice."""

@@ -67,7 +67,7 @@ int emu_apply(const uint8_t* genome, int32_t n_contigs, const int64_t* goff, con
     }
     if (file > fasta_cap) return -1;
     *fasta_len = file;
-    SpliceView v{genome, lit, recs, tab.conv, tab.comp, Seed{0, 0}};
+    SpliceView v{genome, lit, recs, nullptr, tab.conv, tab.comp, Seed{0, 0}};
     memset(fasta, 0, (size_t)file);
     int64_t nf = 0, ns = 0;
     for (int c = 0; c < n_contigs; ++c) {
@@ -158,7 +158,7 @@ int emu_apply_tiles(const uint8_t* genome, int32_t n_contigs, const int64_t* gof
     if (file > fasta_cap) return -1;
     *fasta_len = file;
     memset(fasta, 0, (size_t)file);
-    SpliceView v{genome, lit, recs, tab.conv, tab.comp, Seed{0, 0}};
+    SpliceView v{genome, lit, recs, nullptr, tab.conv, tab.comp, Seed{0, 0}};
     TileView tv{genome, lit, tab.conv, tab.comp, Seed{0, 0}};
     int64_t nc = 0, nd = 0, nf = 0;
     std::vector<uint8_t> stage(TL_STAGE_CAP + 64), image(tile_bytes + 64);
