@@ -381,15 +381,21 @@ class Fasta:
             raise FastaIndexingError(f"Line length of fasta file is not consistent! Inconsistent line found in record {i + 1}")
 
     def _write_fai(self):
-        """pyfaidx leaves <file>.fai next to the input (README 'Notes'); keep that side effect when the directory is writable."""
-        p = Path(self.filename + ".fai")
-        if p.exists():
+        """pyfaidx leaves <file>.fai next to the input (README 'Notes') and rebuilds it when it is older than the FASTA;
+        keep that side effect when the directory is writable.  One process per GPU: only rank 0 writes it, through a
+        temporary file, so that concurrent readers never see a partial index."""
+        if int(os.environ.get("RANK", "0")) != 0:
             return
+        p = Path(self.filename + ".fai")
         try:
-            with open(p, "w") as fh:
+            if p.exists() and p.stat().st_mtime >= Path(self.filename).stat().st_mtime:
+                return
+            tmp = Path(f"{p}.{os.getpid()}.tmp")
+            with open(tmp, "w") as fh:
                 for nm in self.names:
                     e = self.faidx.index[nm]
                     fh.write(f"{nm}\t{e.rlen}\t{e.offset}\t{e.lenc}\t{e.lenb}\n")
+            os.replace(tmp, p)
         except OSError:
             pass
 

@@ -34,6 +34,9 @@ class Mutator:
         self._engine = None
         self.stats = None
         self._replay = None
+        # plan the ranges (and reject overlapping ones) BEFORE any output file is opened and truncated: a settings
+        # error must not leave partial *_ms.fa / *_ms.vcf behind (the reference dies later, with both files cut)
+        self._planned = build_ranges(sim, fasta.lengths, None) if sim.has_mutations else None
         if self._world > 1:      # one process per GPU: files are assembled by write_partitioned()
             self._fasta_writer = self._vcf_writer = None
             return
@@ -93,7 +96,8 @@ class Mutator:
                                              skip_unknown=world > 1 and not tiles)
                 eng.load_records(recs, lit)
             else:
-                ranges, n = build_ranges(sim, fasta.lengths, my_ids)
+                ranges, n = self._planned if (self._planned is not None and len(my_ids) == n_contigs) \
+                    else build_ranges(sim, fasta.lengths, my_ids)
                 eng.set_ranges_array(ranges, n, block_list(sim), min(sim.mut_block.values()), p_transition(sim.titv))
                 eng.sample(seed)
             if tiles:

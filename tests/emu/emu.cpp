@@ -242,6 +242,13 @@ void emu_rand_insert(uint64_t seed, uint32_t gid, uint32_t pos, uint32_t n, uint
     for (uint32_t j = 0; j < n; ++j) out[j] = rand_insert_base(make_seed(seed), gid, pos, j);
 }
 
+// the same for many inserts at once: insert i = n[i] bases at out + off[i] (full-size parity tests)
+void emu_rand_inserts(uint64_t seed, uint32_t gid, int64_t count, const uint32_t* pos, const uint32_t* n, const int64_t* off, uint8_t* out) {
+    const Seed s = make_seed(seed);
+    for (int64_t i = 0; i < count; ++i)
+        for (uint32_t j = 0; j < n[i]; ++j) out[off[i] + j] = rand_insert_base(s, gid, pos[i], j);
+}
+
 int emu_snp(uint64_t seed, uint32_t gid, uint32_t pos, uint8_t ref, double p_ti, uint8_t* alt) {
     Tables tab; fill_tables(tab);
     *alt = draw_snp(make_seed(seed), gid, pos, ref, p_ti, tab.trans);

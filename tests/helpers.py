@@ -131,3 +131,63 @@ def recs_to_muts(recs, lit, goff, seed=0, gids=None):
             m.reverse = int(r["kind"]) == R.K_RC
         out[c].append(m)
     return out
+
+
+def oracle_contig_from_recs(seq: bytes, name: bytes, long_name: bytes, bpl: int, recs, lit, goff_c: int, seed: int, gid: int,
+                            written):
+    """One contig through the C oracle (orc_walk + orc_wrap) given the device's records of that contig — the vectorised
+    form of recs_to_muts + c_oracle.mutate_genome for chromosome-sized contigs.  `written` is the ctypes line state that
+    orc_wrap carries from contig to contig.  -> (fasta bytes of this contig as the oracle's writer emits them, vcf bytes)"""
+    import ctypes as C
+    import numpy as np
+    from mutation_simulator_b200 import records as R
+    from oracle import c_oracle
+    lib = c_oracle.lib()
+    n = len(recs)
+    dt = np.dtype([("key", "<i8"), ("start", "<i8"), ("stop", "<i8"), ("lit_off", "<i8"),
+                   ("type", "<i4"), ("reverse", "u1"), ("alt", "u1"), ("pad", "u1", 2)])
+    m = np.zeros(max(n, 1), dtype=dt)
+    pos = recs["pos"].astype(np.int64); cons = recs["cons"].astype(np.int64); prod = recs["prod"].astype(np.int64)
+    typ = recs["type"].astype(np.int32)
+    m["key"][:n] = pos
+    m["type"][:n] = typ
+    start = pos.copy()
+    tli = typ == R.T_TLI
+    start[tli] = recs["src"][tli] - goff_c
+    stop = pos.copy()
+    by_prod = (typ == R.T_IN) | (typ == R.T_DU)
+    stop[by_prod] = pos[by_prod] + prod[by_prod] - 1
+    by_cons = (typ == R.T_DE) | (typ == R.T_TL) | (typ == R.T_IV)
+    stop[by_cons] = pos[by_cons] + cons[by_cons] - 1
+    stop[tli] = start[tli] + prod[tli] - 1
+    m["start"][:n] = start; m["stop"][:n] = stop
+    m["reverse"][:n] = (tli & (recs["kind"] == R.K_RC)).astype(np.uint8)
+    m["alt"][:n] = np.where(typ == R.T_SN, recs["alt"], 0)
+    # insert strings: literal ones from the pool, random ones regenerated from (seed, contig id, position)
+    ins = np.flatnonzero(typ == R.T_IN)
+    ilen = prod[ins]
+    off = np.concatenate(([0], np.cumsum(ilen)[:-1])).astype(np.int64) if len(ins) else np.zeros(0, np.int64)
+    pool = np.zeros(int(ilen.sum()) + 16, dtype=np.uint8)
+    m["lit_off"][ins] = off
+    rnd = recs["kind"][ins] == 6
+    if rnd.any():
+        p32 = np.ascontiguousarray(recs["pos"][ins][rnd], np.uint32); n32 = np.ascontiguousarray(ilen[rnd], np.uint32)
+        o64 = np.ascontiguousarray(off[rnd], np.int64)
+        P = lambda a: a.ctypes.data_as(C.c_void_p)
+        emu_lib().emu_rand_inserts(C.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), C.c_uint32(gid), C.c_int64(len(p32)), P(p32), P(n32), P(o64), P(pool))
+    litb = np.asarray(lit, dtype=np.uint8)
+    for i in np.flatnonzero(~rnd):
+        r = recs[ins[i]]
+        pool[off[i]:off[i] + ilen[i]] = litb[int(r["src"]):int(r["src"]) + int(r["prod"])]
+    body, vcf = C.c_void_p(), C.c_void_p()
+    bl, vl = C.c_int64(), C.c_int64()
+    rc = lib.orc_walk(seq, C.c_int64(len(seq)), name, m.ctypes.data_as(C.c_void_p), C.c_int64(n), pool.ctypes.data_as(C.c_void_p),
+                      C.byref(body), C.byref(bl), C.byref(vcf), C.byref(vl))
+    assert rc == 0, rc
+    dst = C.create_string_buffer(bl.value + bl.value // max(1, bpl) + len(long_name) + 8)
+    k = lib.orc_wrap(long_name, C.c_int64(len(long_name)), body, C.c_int64(bl.value), C.c_int64(bpl), C.byref(written), dst)
+    fa = dst.raw[:k]
+    lib.orc_free(body)
+    lines = C.string_at(vcf, vl.value) if vl.value else b""
+    lib.orc_free(vcf)
+    return fa, lines

@@ -149,3 +149,73 @@ def test_c3_shaped_rmt_hot_cold_ranges_and_blocked_centromeres(tmp_path):
     for ci, L in enumerate(lens):
         assert int(eng.contig_out_len()[ci]) == L + int(d[recs["contig"] == ci].sum())
     eng.close()
+
+
+def _compare_with_oracle(eng, names, lens, bpl, seed):
+    """Every contig of the resident genome through the C oracle with the device's own records; FASTA image and VCF body
+    must be byte-identical.  Bases come back from HBM one contig at a time."""
+    import ctypes as C
+    from tests.helpers import oracle_contig_from_recs
+    recs, lit = eng.records(), eng.literals()
+    image, vcf = eng.download(0), eng.download(1)
+    goff = np.concatenate(([0], np.cumsum(lens))).astype(np.int64)
+    written = C.c_int64(0)
+    fpos = vpos = 0
+    lo = np.searchsorted(recs["contig"], np.arange(len(lens)), "left"); hi = np.searchsorted(recs["contig"], np.arange(len(lens)), "right")
+    for ci, L in enumerate(lens):
+        seq = eng.read_genome(int(goff[ci]), int(L)).tobytes()
+        fa, lines = oracle_contig_from_recs(seq, names[ci], names[ci], bpl, recs[lo[ci]:hi[ci]], lit, int(goff[ci]), seed, ci, written)
+        assert image[fpos:fpos + len(fa)].tobytes() == fa, f"FASTA of contig {ci} differs from the oracle"
+        assert vcf[vpos:vpos + len(lines)].tobytes() == lines, f"VCF of contig {ci} differs from the oracle"
+        fpos += len(fa); vpos += len(lines)
+    assert fpos == len(image) and vpos == len(vcf)
+
+
+def test_chromosome_sized_contig_bit_exact_against_c_oracle():
+    """GRCh38 chr1 size (250 Mbp, N runs, all mutation types) sampled and applied on the GPU, then walked by the C
+    oracle from the same records: both files byte for byte (full-size oracle compare, not only invariants)."""
+    from mutation_simulator_b200.engine import Engine
+    L = 250_000_000
+    eng = Engine(0)
+    eng.synth_genome(3, [L], [60], [b"chr1"], [b"chr1"], n_fraction=0.03, telomere_n=10000)
+    ranges = args_ranges([L], [0.01, 0.001, 0.001, 0.0005, 0.0005, 0.0005], [1, 1, 1, 2, 1, 1, 1], [1, 10, 10, 50, 50, 50, 50])
+    eng.set_ranges(ranges, [1] * 7, 1, 2.0 / 3.0)
+    eng.sample(21)
+    eng.apply()
+    _compare_with_oracle(eng, [b"chr1"], [L], 60, 21)
+    eng.close()
+
+
+def test_c3_full_size_rmt_bit_exact_against_c_oracle():
+    """BASELINE config 3 in full: the GRCh38-shaped 3.09 Gbp genome, 10 k hot / cold RMT ranges + blocked centromeres through
+    from_rmt -> plan.build_ranges (bench.py's generator), sampled and applied on the GPU; every contig is then walked by
+    the C oracle from the device's records and compared byte for byte; no record starts or reaches into a None range."""
+    import bench
+    from mutation_simulator_b200 import plan
+    from mutation_simulator_b200.engine import Engine
+    from mutation_simulator_b200.rmt import SimulationSettings
+    wl = bench.WORKLOADS["c3"]
+    lens, names = list(wl["lengths"]), [n.encode() for n in wl["names"]]
+    text, n_explicit = bench.c3_rmt_text(lens, wl["n_rmt_ranges"], wl["n_fraction"])
+    assert n_explicit > 9000
+    import tempfile, os
+    with tempfile.NamedTemporaryFile("w", suffix=".rmt", delete=False) as fh:
+        fh.write(text)
+    try:
+        sim = SimulationSettings.from_rmt(__import__("pathlib").Path(fh.name), bench.LenFasta(wl["names"], lens), True)
+    finally:
+        os.unlink(fh.name)
+    arr, n = plan.build_ranges(sim, lens)
+    eng = Engine(0)
+    eng.synth_genome(bench.GENOME_SEED, lens, [60] * len(lens), names, names, wl["n_fraction"], wl["telomere"])
+    eng.set_ranges_array(arr, n, plan.block_list(sim), min(sim.mut_block.values()), plan.p_transition(sim.titv))
+    eng.sample(5)
+    eng.apply()
+    recs = eng.records()
+    pos = recs["pos"].astype(np.int64); ext = pos + np.maximum(recs["cons"].astype(np.int64), 1)
+    for ci, L in enumerate(lens):                       # the centromere of every contig is a None range
+        lo, hi = (L * 2) // 5, (L * 2) // 5 + int(wl["n_fraction"] * L)
+        m = recs["contig"] == ci
+        assert not ((pos[m] >= lo) & (pos[m] < hi)).any() and not ((pos[m] < lo) & (ext[m] > lo)).any()
+    _compare_with_oracle(eng, names, lens, 60, 5)
+    eng.close()

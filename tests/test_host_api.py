@@ -200,3 +200,35 @@ def test_it_pairing_reproduces_the_reference_pair_count():
             hits[a] += 1
     from scipy import stats
     assert stats.chisquare(hits).pvalue > 0.01
+
+
+def test_overlapping_ranges_fail_before_the_output_files_are_touched(tmp_path):
+    """the overlap check runs in Mutator.__init__ before the writers open (and truncate) the outputs."""
+    from argparse import Namespace
+    from mutation_simulator_b200 import Mutator
+    from mutation_simulator_b200.plan import RangeOverlapError
+    fa = tmp_path / "g.fa"
+    fa.write_text(">c1\n" + "ACGT" * 500 + "\n")
+    rmt = tmp_path / "g.rmt"
+    rmt.write_text("std\nit None\nsn 0.01\n\nchr 1\n1-1200 sn 0.05\n400-1500 sn 0.05\n")
+    fasta = Fasta(str(fa))
+    sim = SimulationSettings.from_rmt(rmt, fasta, True)
+    out_fa, out_vcf = tmp_path / "o.fa", tmp_path / "o.vcf"
+    out_fa.write_text("precious")
+    args = Namespace(outfasta=out_fa, outvcf=out_vcf, infile=fa, ignore_warnings=True, no_color=True, no_progress=True, seed=1, device=0)
+    with pytest.raises(RangeOverlapError):
+        Mutator(args, fasta, sim)
+    assert out_fa.read_text() == "precious" and not out_vcf.exists()
+
+
+def test_fai_is_rebuilt_when_older_than_the_fasta(tmp_path):
+    import os
+    fa = tmp_path / "g.fa"
+    fa.write_text(">c1\nACGTACGT\nACG\n")
+    Fasta(str(fa))
+    fai = tmp_path / "g.fa.fai"
+    assert fai.read_text().split("\t")[1] == "11"
+    fa.write_text(">c1\nACGTACGT\nACGTA\n")
+    os.utime(fai, (1, 1))                       # the index predates the file
+    Fasta(str(fa))
+    assert fai.read_text().split("\t")[1] == "13"
