@@ -151,7 +151,11 @@ static int layout_by_scan(ms_ctx* c, Contig* d_contigs, const int64_t* S, const 
 __device__ __forceinline__ void rec_out_one(const Rec* recs, int64_t i, const Contig* contigs, const int64_t* S, const uint32_t* N, SvRec* sv,
                                             Snp8* snp, Totals* tot, unsigned int* hist) {
     const Rec r = recs[i];
-    if (r.type < 8) atomicAdd(&hist[r.type], 1u);
+    {   // one shared-memory atomic per (warp, type): three quarters of a warp's lanes hold the same type
+        const uint32_t t = r.type < 8 ? r.type : 8u;
+        const uint32_t peers = __match_any_sync(__activemask(), t);
+        if (t < 8u && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[t], (unsigned)__popc(peers));
+    }
     const Contig& k = contigs[r.contig];
     const int64_t out = (int64_t)r.pos + (S[i] - S[k.rec_lo]);
     if ((int64_t)r.pos + r.cons > k.len) raise_error(tot, MS_ERR_OVERLAP, i);

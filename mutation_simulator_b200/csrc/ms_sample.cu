@@ -307,29 +307,57 @@ k_resolve_local(int64_t K, const int64_t* gpos, const int64_t* reach, const uint
     }
 }
 
-__global__ void k_contig_tl_bounds(const Contig* contigs, int32_t n_contigs, const int64_t* gpos, const uint32_t* tl_list, int64_t n_tl,
-                                   const uint32_t* tli_list, int64_t n_tli, int64_t* tl_base, int64_t* tli_base) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c > n_contigs) return;
-    if (c == n_contigs) { tl_base[c] = n_tl; tli_base[c] = n_tli; return; }
+// first TL / TLI list entry of every contig.  One warp per (contig, list): a 32-ary search (each round the lanes probe
+// 32 evenly spaced entries) finishes in 4-5 rounds of two dependent loads; the one-thread-per-contig binary search it
+// replaces took 50 us on 24 contigs — a fixed cost that did not shrink with the GPU count (SCALE_r01).
+__global__ void __launch_bounds__(128)
+k_contig_tl_bounds(const Contig* contigs, int32_t n_contigs, const int64_t* gpos, const uint32_t* tl_list, const uint32_t* tli_list,
+                   const Totals* tot, int64_t* tl_base, int64_t* tli_base) {
+    const int w = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (w >= 2 * (n_contigs + 1)) return;
+    const int c = w >> 1;
+    const bool tli = (w & 1) != 0;
+    const uint32_t* list = tli ? tli_list : tl_list;
+    const int64_t n = tli ? tot->pad[1] : tot->pad[0];
+    int64_t* out = tli ? tli_base : tl_base;
+    if (c == n_contigs) { if (lane == 0) out[c] = n; return; }
     const int64_t key = contigs[c].goff;
-    int64_t lo = 0, hi = n_tl;
-    while (lo < hi) { const int64_t m = (lo + hi) >> 1; if (gpos[tl_list[m]] < key) lo = m + 1; else hi = m; }
-    tl_base[c] = lo;
-    lo = 0; hi = n_tli;
-    while (lo < hi) { const int64_t m = (lo + hi) >> 1; if (gpos[tli_list[m]] < key) lo = m + 1; else hi = m; }
-    tli_base[c] = lo;
+    int64_t lo = 0, hi = n;                       // first entry with gpos >= key lies in [lo, hi]
+    while (hi - lo > 0) {
+        const int64_t span = hi - lo;
+        const int64_t probe = lo + (span * (lane + 1)) / 33;          // 32 probes inside [lo, hi)
+        const bool less = probe < hi && gpos[list[probe]] < key;
+        const uint32_t m = __ballot_sync(0xffffffffu, less);
+        const int k = __popc(m);                  // probes are ascending: the first k are "less"
+        const int64_t p_lo = k ? lo + (span * k) / 33 + 1 : lo;
+        const int64_t p_hi = k < 32 ? lo + (span * (k + 1)) / 33 : hi;
+        if (p_lo == lo && p_hi == hi) {           // span too small for the probes to split it
+            if (gpos[list[lo]] < key) lo = lo + 1; else hi = lo;
+        } else { lo = p_lo; hi = p_hi < p_lo ? p_lo : p_hi; }
+    }
+    if (lane == 0) out[c] = lo;
 }
 
 // K4: element j of the smaller list is paired with element rho(j) of the larger one,
 // rho a keyed permutation of the larger list: a uniform random injection, which is
 // what "remove random surplus, shuffle, zip" (mutator.py:277-304) produces.
 // link[slot]: -1 unlinked (dropped), -2 kept TL, >= 0 (TLI) candidate slot of its TL.
+__device__ __forceinline__ void link_one(int64_t x, const Contig* contigs, const Range* ranges, const uint32_t* cand_range,
+                                         const uint32_t* tl_list, int64_t n_tl, const uint32_t* tli_list, int64_t n_tli,
+                                         const int64_t* tl_base, const int64_t* tli_base, Seed seed, int32_t* link);
+
 __global__ void __launch_bounds__(256)
-k_link(const Contig* contigs, const Range* ranges, const uint32_t* cand_range, const uint32_t* tl_list, int64_t n_tl,
-       const uint32_t* tli_list, int64_t n_tli, const int64_t* tl_base, const int64_t* tli_base, Seed seed, int32_t* link) {
-    const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= n_tl + n_tli) return;
+k_link(const Contig* contigs, const Range* ranges, const uint32_t* cand_range, const uint32_t* tl_list, const uint32_t* tli_list,
+       const Totals* tot, const int64_t* tl_base, const int64_t* tli_base, Seed seed, int32_t* link) {
+    const int64_t n_tl = tot->pad[0], n_tli = tot->pad[1];
+    if (n_tl == 0 || n_tli == 0) return;
+    for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n_tl + n_tli; x += (int64_t)gridDim.x * blockDim.x)
+        link_one(x, contigs, ranges, cand_range, tl_list, n_tl, tli_list, n_tli, tl_base, tli_base, seed, link);
+}
+
+__device__ __forceinline__ void link_one(int64_t x, const Contig* contigs, const Range* ranges, const uint32_t* cand_range,
+                                         const uint32_t* tl_list, int64_t n_tl, const uint32_t* tli_list, int64_t n_tli,
+                                         const int64_t* tl_base, const int64_t* tli_base, Seed seed, int32_t* link) {
     const bool is_tl = x < n_tl;
     const int64_t idx = is_tl ? x : x - n_tl;
     const uint32_t slot = is_tl ? tl_list[idx] : tli_list[idx];
@@ -357,12 +385,12 @@ k_link(const Contig* contigs, const Range* ranges, const uint32_t* cand_range, c
 #include "ms_vcf_core.h"
 namespace ms {
 
-__global__ void __launch_bounds__(256)
-k_build_records(int64_t n_acc, const uint32_t* acc_slot, const int64_t* gpos, const uint8_t* type, const uint32_t* len,
+__global__ void __launch_bounds__(256, 8)      // 32 registers: the SNP reference gather needs all 64 warps to hide its latency
+k_build_records(const Totals* tot, const uint32_t* acc_slot, const int64_t* gpos, const uint8_t* type, const uint32_t* len,
                 const uint32_t* cand_range, const int32_t* link, const Range* ranges, const Contig* contigs, VcfView vv,
                 const Tables* tab, Seed seed, double p_ti, Rec* recs, int32_t* delta, uint32_t* vsize, bool defer_bases) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n_acc) return;
+    if (e >= tot->n_accepted) return;             // the grid is sized from the candidate count (an upper bound)
     const uint32_t s = acc_slot[e];
     const uint32_t cidx = ranges[cand_range[s]].contig;
     const Contig& ct = contigs[cidx];
@@ -411,6 +439,7 @@ __global__ void __launch_bounds__(256) k_count_types(const Rec* recs, int64_t n,
 }
 
 template <class T> __global__ void k_copy_scalar(const T* src, T* dst) { *dst = *src; }
+__global__ void k_store_counts(const I64x3* total, Totals* tot) { tot->n_accepted = total->a; tot->pad[0] = total->b; tot->pad[1] = total->c; }
 
 // ---- host orchestration --------------------------------------------------------------
 static int draw_and_sort(ms_ctx* c, Seed seed, uint32_t purpose, int32_t min_dist, int positions_only, const Contig* d_ctg) {
@@ -539,44 +568,40 @@ int sample_pipeline(ms_ctx* c, uint64_t seed64, bool defer_bases) {
         };
         I64x3* d_total = nullptr;
         MS_CUDA(c, (device_scan<I64x3>(c, in, out, K, I64x3{0, 0, 0}, SumOp(), c->scan_tmp, &d_total)));
-        MS_CUDA(c, cudaMemcpyAsync(c->h_totals, d_total, sizeof(I64x3), cudaMemcpyDeviceToHost, st));
+        k_store_counts<<<1, 1, 0, st>>>(d_total, d_tot);      // accepted / TL / TLI counts stay on the device: no host round trip
+        MS_LAUNCH_CHECK(c);
     }
     stage_end(c, ST_SAMPLE_RESOLVE);
-    MS_CUDA(c, cudaStreamSynchronize(st));
-    const I64x3 cnt = *reinterpret_cast<const I64x3*>(c->h_totals);
-    const int64_t n_acc = cnt.a, n_tl = cnt.b, n_tli = cnt.c;
-    c->last_totals.n_accepted = n_acc;
 
     // ---- K4: TL <-> TLI linking -------------------------------------------------------
     stage_begin(c, ST_SAMPLE_LINK);
     MS_CUDA(c, c->link.ensure((size_t)K * 4 + 16));
     int32_t* d_link = c->link.as<int32_t>();
     MS_CUDA(c, cudaMemsetAsync(d_link, 0xFF, (size_t)K * 4, st));
-    if (n_tl > 0 && n_tli > 0) {
+    {
         MS_CUDA(c, c->contig_tl.ensure((size_t)(c->n_contigs + 1) * 16));
         int64_t* d_tlb = c->contig_tl.as<int64_t>();
         int64_t* d_tlib = d_tlb + (c->n_contigs + 1);
-        k_contig_tl_bounds<<<(unsigned)ceil_div(c->n_contigs + 1, 128), 128, 0, st>>>(d_contigs, c->n_contigs, d_gpos, d_tl, n_tl, d_tli,
-                                                                                     n_tli, d_tlb, d_tlib);
+        k_contig_tl_bounds<<<(unsigned)ceil_div(2 * (int64_t)(c->n_contigs + 1) * 32, 128), 128, 0, st>>>(d_contigs, c->n_contigs, d_gpos, d_tl, d_tli,
+                                                                                                     d_tot, d_tlb, d_tlib);
         MS_LAUNCH_CHECK(c);
-        k_link<<<(unsigned)ceil_div(n_tl + n_tli, 256), 256, 0, st>>>(d_contigs, d_ranges, d_crange, d_tl, n_tl, d_tli, n_tli, d_tlb, d_tlib,
-                                                                      seed, d_link);
+        k_link<<<NUM_SMS_B200 * 8, 256, 0, st>>>(d_contigs, d_ranges, d_crange, d_tl, d_tli, d_tot, d_tlb, d_tlib, seed, d_link);
         MS_LAUNCH_CHECK(c);
     }
     stage_end(c, ST_SAMPLE_LINK);
 
-    // ---- K4b: records -----------------------------------------------------------------
+    // ---- K4b: records (buffers sized from the candidate count, an upper bound of the accepted count) ------------------
     stage_begin(c, ST_SAMPLE_FINAL);
     c->seed_last = seed;
-    MS_CUDA(c, c->recs.ensure((size_t)(n_acc + 1) * sizeof(Rec)));
-    MS_CUDA(c, c->keep.ensure((size_t)(n_acc + 1) * 4));
-    MS_CUDA(c, c->cand_val.ensure((size_t)(n_acc + 1) * 4));
-    if (n_acc > 0) {
+    MS_CUDA(c, c->recs.ensure((size_t)(K + 1) * sizeof(Rec)));
+    MS_CUDA(c, c->keep.ensure((size_t)(K + 1) * 4));
+    MS_CUDA(c, c->cand_val.ensure((size_t)(K + 1) * 4));
+    {
         const Tables* d_tab = c->tables.as<Tables>();
         VcfView vv{c->genome.as<uint8_t>(), c->lit.as<uint8_t>(), c->names.as<uint8_t>(), d_tab->conv, d_tab->comp, seed};
-        k_build_records<<<(unsigned)ceil_div(n_acc, 256), 256, 0, st>>>(n_acc, d_acc, d_gpos, d_type, d_len, d_crange, d_link, d_ranges,
-                                                                        d_contigs, vv, d_tab, seed, c->p_ti, c->recs.as<Rec>(),
-                                                                        c->keep.as<int32_t>(), c->cand_val.as<uint32_t>(), defer_bases);
+        k_build_records<<<(unsigned)ceil_div(K, 256), 256, 0, st>>>(d_tot, d_acc, d_gpos, d_type, d_len, d_crange, d_link, d_ranges,
+                                                                    d_contigs, vv, d_tab, seed, c->p_ti, c->recs.as<Rec>(),
+                                                                    c->keep.as<int32_t>(), c->cand_val.as<uint32_t>(), defer_bases);
         MS_LAUNCH_CHECK(c);
     }
     MS_CUDA(c, cudaMemcpyAsync(c->h_totals, d_tot, sizeof(Totals), cudaMemcpyDeviceToHost, st));
@@ -584,6 +609,8 @@ int sample_pipeline(ms_ctx* c, uint64_t seed64, bool defer_bases) {
     MS_CUDA(c, cudaStreamSynchronize(st));
     if (c->h_totals->error) MS_FAIL(c, (int)c->h_totals->error, "ms_sample: kernel error %lld (arg %lld)", (long long)c->h_totals->error,
                                     (long long)c->h_totals->error_arg);
+    const int64_t n_acc = c->h_totals->n_accepted;
+    c->last_totals.n_accepted = n_acc;
     c->n_recs = n_acc;
     c->lit_bytes = 0;
     c->last_totals.n_recs = n_acc;
