@@ -118,6 +118,13 @@ int ms_genome_adopt_output(ms_ctx* ctx);
  * not fit the index (ragged or blank lines) — nothing is resident then.  ms_genome_read copies a slice of the resident
  * bases to the host (the lazy per-record views of the Python Fasta object). */
 int ms_fasta_ingest_fd(ms_ctx* ctx, int fd, int64_t nbytes, int32_t* n_records, int32_t* regular);
+/* The same for a SUBSET of the file: the image is the concatenation of the byte ranges [off[r], off[r] + len[r]), each
+ * made of whole records ('>' ... up to the next record).  With one process per GPU every rank finds the record starts
+ * of its 1/N slice of the file, the ranks exchange them, and each then reads only the records of its own contigs
+ * (mutator.py:111 iterates contigs independently) — ingest time and host traffic shrink with the GPU count instead of
+ * every rank reading the whole file.  seq_off of ms_fasta_index is then relative to the image, not the file. */
+int ms_fasta_ingest_ranges(ms_ctx* ctx, int fd, int32_t n_ranges, const int64_t* off, const int64_t* len,
+                           int32_t* n_records, int32_t* regular);
 int ms_fasta_index(ms_ctx* ctx, int64_t* hdr_off, int64_t* seq_off, int64_t* length, int32_t* lenc, int32_t* lenb,
                    uint8_t* hdr_blob, int64_t blob_cap);
 int ms_fasta_commit(ms_ctx* ctx, const uint32_t* gid, const uint8_t* headers, const int64_t* hdr_off,
@@ -131,7 +138,8 @@ int ms_genome_declare(ms_ctx* ctx, int64_t total_bases, int32_t n_contigs, const
                       const int32_t* bpl, const uint32_t* gid, const uint8_t* headers, const int64_t* hdr_off,
                       const uint8_t* names, const int64_t* name_off);
 /* Reserve `extra_bytes` of staging space behind the genome for bases of contigs that live on another GPU
- * (interchromosomal partners, it_mutator.py:133-137).  Call before ms_genome_upload.  The region starts at
+ * (interchromosomal partners, it_mutator.py:133-137).  Call before ms_genome_upload (a genome that is already resident
+ * is moved into a buffer with the extra space).  The region starts at
  * genome index total_bases + 64 (ms_device_ptr(4) gives the base pointer); K_RAW records may point into it,
  * so a peer's ncclSend can land directly where the splice kernel gathers from. */
 int ms_genome_reserve(ms_ctx* ctx, int64_t extra_bytes);

@@ -52,6 +52,7 @@ PROTOTYPES = {
     "ms_genome_reserve": (C.c_int, [_P, _I64]),
     "ms_genome_adopt_output": (C.c_int, [_P]),
     "ms_fasta_ingest_fd": (C.c_int, [_P, C.c_int, _I64, _P, _P]),
+    "ms_fasta_ingest_ranges": (C.c_int, [_P, C.c_int, _I32, _P, _P, _P, _P]),
     "ms_fasta_index": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64]),
     "ms_fasta_commit": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     "ms_genome_read": (C.c_int, [_P, _I64, _I64, _P]),

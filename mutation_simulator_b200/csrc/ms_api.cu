@@ -209,7 +209,17 @@ int ms_mutate_streamed(ms_ctx* c, uint64_t seed, const uint8_t* bases, uint8_t* 
 int ms_fasta_ingest_fd(ms_ctx* c, int fd, int64_t nbytes, int32_t* n_records, int32_t* regular) {
     if (!c || fd < 0 || nbytes < 0 || !n_records || !regular) return MS_ERR_ARG;
     MS_CUDA(c, cudaSetDevice(c->device));
-    return fasta_ingest(c, fd, nbytes, n_records, regular);
+    const int64_t off = 0;
+    return fasta_ingest(c, fd, 1, &off, &nbytes, n_records, regular);
+}
+
+int ms_fasta_ingest_ranges(ms_ctx* c, int fd, int32_t n_ranges, const int64_t* off, const int64_t* len, int32_t* n_records,
+                           int32_t* regular) {
+    if (!c || fd < 0 || n_ranges < 0 || (n_ranges > 0 && (!off || !len)) || !n_records || !regular) return MS_ERR_ARG;
+    for (int32_t r = 0; r < n_ranges; ++r)
+        if (off[r] < 0 || len[r] < 0) MS_FAIL(c, MS_ERR_ARG, "ms_fasta_ingest_ranges: range %d is negative", r);
+    MS_CUDA(c, cudaSetDevice(c->device));
+    return fasta_ingest(c, fd, n_ranges, off, len, n_records, regular);
 }
 
 int ms_fasta_index(ms_ctx* c, int64_t* hdr_off, int64_t* seq_off, int64_t* length, int32_t* lenc, int32_t* lenb, uint8_t* hdr_blob,
@@ -285,6 +295,17 @@ int ms_genome_read(ms_ctx* c, int64_t off, int64_t n, uint8_t* dst) {
 int ms_genome_reserve(ms_ctx* c, int64_t extra_bytes) {
     if (!c || extra_bytes < 0) return MS_ERR_ARG;
     c->foreign_cap = extra_bytes;
+    // a genome that is already resident (ingested straight from the file) moves into a buffer with the staging space
+    const size_t need = (size_t)c->total_bases + 64 + (size_t)extra_bytes + 64;
+    if (c->n_contigs > 0 && c->genome.p && c->genome.cap < need) {
+        MS_CUDA(c, cudaSetDevice(c->device));
+        DevBuf fresh;
+        MS_CUDA(c, fresh.ensure(need));
+        MS_CUDA(c, cudaMemcpyAsync(fresh.p, c->genome.p, (size_t)c->total_bases + 64, cudaMemcpyDeviceToDevice, c->stream));
+        MS_CUDA(c, cudaStreamSynchronize(c->stream));
+        c->genome.release();
+        c->genome = fresh;
+    }
     return MS_OK;
 }
 

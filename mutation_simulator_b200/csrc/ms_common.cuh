@@ -163,7 +163,7 @@ int apply_pipeline(ms_ctx* c);
 int apply_window(ms_ctx* c, int part, int n_parts, int64_t* win);
 int adopt_output(ms_ctx* c);
 int ensure_stage_buffers(ms_ctx* c);
-int fasta_ingest(ms_ctx* c, int fd, int64_t nbytes, int32_t* n_records, int32_t* regular);
+int fasta_ingest(ms_ctx* c, int fd, int32_t n_ranges, const int64_t* off, const int64_t* len, int32_t* n_records, int32_t* regular);
 int fasta_index(ms_ctx* c, int64_t* hdr_off, int64_t* seq_off, int64_t* length, int32_t* lenc, int32_t* lenb, uint8_t* hdr_blob,
                 int64_t blob_cap);
 int fasta_strip(ms_ctx* c, int64_t total, int32_t* regular);

@@ -141,33 +141,45 @@ static int pread_all(int fd, uint8_t* dst, int64_t n, int64_t off) {
 }
 
 // file -> device image -> record index.  The image lives in the FASTA output buffer (dead until the next ms_apply).
-int fasta_ingest(ms_ctx* c, int fd, int64_t nbytes, int32_t* n_records, int32_t* regular) {
+// The image is the concatenation of the file's byte ranges [off[r], off[r] + len[r]) (whole records each: one process per
+// GPU reads only the records of its own contigs); a single range [0, nbytes) is the whole file.
+int fasta_ingest(ms_ctx* c, int fd, int32_t n_ranges, const int64_t* off, const int64_t* len, int32_t* n_records, int32_t* regular) {
     cudaStream_t st = c->stream;
     *n_records = 0; *regular = 0;
     c->fa_recs.clear(); c->fa_bytes = 0;
     c->fasta_bytes = 0; c->vcf_bytes = 0;      // the image takes over the FASTA output buffer: earlier outputs are gone
-    if (nbytes <= 0) return MS_OK;
     constexpr int64_t CH = ms_ctx::STAGE_BYTES;
     constexpr int NS = ms_ctx::N_STAGE;
+    struct Chunk { int64_t foff, doff, n; };
+    std::vector<Chunk> chunks;
+    int64_t nbytes = 0;
+    for (int32_t r = 0; r < n_ranges; ++r) {
+        for (int64_t done = 0; done < len[r]; done += CH) {
+            const int64_t n = len[r] - done < CH ? len[r] - done : CH;
+            chunks.push_back(Chunk{off[r] + done, nbytes + done, n});
+        }
+        nbytes += len[r] > 0 ? len[r] : 0;
+    }
+    if (nbytes <= 0) return MS_OK;
     int rc = ensure_stage_buffers(c);
     if (rc) return rc;
     MS_CUDA(c, c->fasta.ensure((size_t)nbytes + 64));
     uint8_t* d_raw = c->fasta.as<uint8_t>();
     stage_begin(c, ST_UPLOAD);
     // page-cache reads manage a few GB/s per thread: NS reads are kept in flight, each into its own pinned buffer;
-    // the H2D copies are issued in file order as the reads complete
-    const int64_t nch = (nbytes + CH - 1) / CH;
+    // the H2D copies are issued in image order as the reads complete
+    const int64_t nch = (int64_t)chunks.size();
     std::future<int> reader[NS];
     auto start_read = [&](int64_t i) {
         const int s = (int)(i % NS);
-        const int64_t n = (i + 1) * CH <= nbytes ? CH : nbytes - i * CH;
+        const Chunk ck = chunks[(size_t)i];
         uint8_t* buf = c->h_stage[s];
         cudaEvent_t ev = c->h_stage_ev[s];
         const bool reuse = i >= NS;
         const int device = c->device;
         reader[s] = std::async(std::launch::async, [=]() -> int {
             if (reuse) { cudaSetDevice(device); if (cudaEventSynchronize(ev) != cudaSuccess) return EIO; }   // previous H2D out of this buffer
-            return pread_all(fd, buf, n, i * CH);
+            return pread_all(fd, buf, ck.n, ck.foff);
         });
     };
     for (int64_t i = 0; i < nch && i < NS; ++i) start_read(i);
@@ -177,8 +189,8 @@ int fasta_ingest(ms_ctx* c, int fd, int64_t nbytes, int32_t* n_records, int32_t*
         const int e = reader[s].get();
         if (e && !rerr) rerr = e;
         if (!rerr) {
-            const int64_t n = (i + 1) * CH <= nbytes ? CH : nbytes - i * CH;
-            cudaError_t ce = cudaMemcpyAsync(d_raw + i * CH, c->h_stage[s], (size_t)n, cudaMemcpyHostToDevice, st);
+            const Chunk ck = chunks[(size_t)i];
+            cudaError_t ce = cudaMemcpyAsync(d_raw + ck.doff, c->h_stage[s], (size_t)ck.n, cudaMemcpyHostToDevice, st);
             if (ce == cudaSuccess) ce = cudaEventRecord(c->h_stage_ev[s], st);
             if (ce != cudaSuccess) rerr = EIO;
         }

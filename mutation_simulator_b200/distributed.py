@@ -93,6 +93,16 @@ def shard_mode(lengths, n) -> str:
     return "contigs"
 
 
+def partition_of(fasta, n):
+    """The contig partition of a run: the one the FASTA was ingested with (every rank read only its own records), else
+    LPT on the contig lengths."""
+    return getattr(fasta, "partition", None) or lpt_partition(fasta.lengths, n)
+
+
+def shard_of(fasta, n) -> str:
+    return getattr(fasta, "shard", None) or shard_mode(fasta.lengths, n)
+
+
 def owners(parts, n_contigs):
     own = np.zeros(n_contigs, dtype=np.int64)
     for r, ids in enumerate(parts):

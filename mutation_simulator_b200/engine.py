@@ -108,12 +108,18 @@ class Engine:
             self._check(self._lib.ms_hash_ranges(self._h, which, len(start), _ptr(start), _ptr(end), _ptr(out)))
         return out
 
-    def ingest_fasta(self, fd: int, nbytes: int):
+    def ingest_fasta(self, fd: int, nbytes: int, ranges=None):
         """Raw FASTA file -> device image + record index (ms_fasta_ingest_fd / ms_fasta_index).  Returns None when the
         file is not regularly wrapped (the host parser then takes over), else a dict with length, seq_off, lenc, lenb
-        (numpy arrays) and long_names (deflines without '>')."""
+        (numpy arrays) and long_names (deflines without '>').  ranges = [(file offset, bytes)] of whole records: only
+        those are read (ms_fasta_ingest_ranges); seq_off is then relative to their concatenation."""
         n, reg = C.c_int32(0), C.c_int32(0)
-        self._check(self._lib.ms_fasta_ingest_fd(self._h, int(fd), int(nbytes), C.byref(n), C.byref(reg)))
+        if ranges is None:
+            self._check(self._lib.ms_fasta_ingest_fd(self._h, int(fd), int(nbytes), C.byref(n), C.byref(reg)))
+        else:
+            off = np.ascontiguousarray([r[0] for r in ranges], dtype=np.int64)
+            ln = np.ascontiguousarray([r[1] for r in ranges], dtype=np.int64)
+            self._check(self._lib.ms_fasta_ingest_ranges(self._h, int(fd), len(ranges), _ptr(off), _ptr(ln), C.byref(n), C.byref(reg)))
         if not reg.value:
             return None
         n = n.value

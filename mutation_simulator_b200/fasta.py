@@ -131,8 +131,92 @@ class Fasta:
             self._write_fai()
 
     # -- parsing -----------------------------------------------------------
+    def _ingest_device_sliced(self, device: int, rank: int, world: int):
+        """One process per GPU: every rank looks for record starts in its 1/world slice of the file, the ranks exchange
+        them, and each reads and indexes only the records of its own contigs (ms_fasta_ingest_ranges); names, lengths
+        and line layout of all contigs are then gathered, so the object describes the whole file while only this rank's
+        bases are resident.  Returns True / None (None: use the whole-file path — a genome that will be sharded by
+        tiles, or a file the device indexer declines; decided identically on all ranks)."""
+        from . import distributed as D
+        from .engine import Engine
+        D.init()
+        size = os.path.getsize(self.filename)
+        if size == 0:
+            return None
+        with open(self.filename, "rb") as fh:
+            mm = mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ)
+            try:
+                lo, hi = size * rank // world, size * (rank + 1) // world
+                starts = [0] if (rank == 0 and mm[0:1] == b">") else []
+                pos = max(lo - 1, 0)
+                while True:                       # "\n>" whose '>' lies in [lo, hi)
+                    k = mm.find(b"\n>", pos, hi)
+                    if k < 0:
+                        break
+                    starts.append(k + 1)
+                    pos = k + 1
+            finally:
+                mm.close()
+            every = sorted(set(x for part in D.all_gather_object(starts) for x in part))
+            if not every or every[0] != 0:
+                return None
+            sizes = [b - a for a, b in zip(every, every[1:] + [size])]
+            if D.shard_mode(sizes, world) != "contigs":
+                return None
+            parts = D.lpt_partition(sizes, world)
+            mine = parts[rank]
+            ranges = []                           # consecutive records become one read
+            for g in mine:
+                if ranges and ranges[-1][0] + ranges[-1][1] == every[g]:
+                    ranges[-1][1] += sizes[g]
+                else:
+                    ranges.append([every[g], sizes[g]])
+            eng = Engine(device)
+            ok, info, names, long_names = False, None, [], []
+            try:
+                info = eng.ingest_fasta(fh.fileno(), size, ranges)
+                if info is not None and len(info["long_names"]) == len(mine):
+                    long_names = info["long_names"]
+                    names = [(ln.split() or [""])[0] for ln in long_names]
+                    ok = eng.commit_fasta(info["length"], info["lenc"], [ln.encode("latin-1") for ln in long_names],
+                                          [nm.encode("latin-1") for nm in names], gid=mine)
+            except Exception:
+                eng.close()
+                raise
+        mine_off = np.concatenate(([0], np.cumsum([sizes[g] for g in mine])[:-1])).astype(np.int64) if mine else np.zeros(0, np.int64)
+        payload = None
+        if ok:
+            payload = (mine, names, long_names, info["length"].tolist(), info["lenc"].tolist(), info["lenb"].tolist(),
+                       [int(every[g] + (so - mo)) for g, so, mo in zip(mine, info["seq_off"].tolist(), mine_off.tolist())])
+        gathered = D.all_gather_object(payload)
+        n = len(every)
+        all_names = [None] * n
+        if any(p is None for p in gathered):
+            eng.close()
+            return None
+        all_long = [None] * n
+        length = np.zeros(n, np.int64); lenc = np.zeros(n, np.int32); lenb = np.zeros(n, np.int64); seq_off = np.zeros(n, np.int64)
+        for ids, nm, ln, L, lc, lb, so in gathered:
+            for j, g in enumerate(ids):
+                all_names[g], all_long[g], length[g], lenc[g], lenb[g], seq_off[g] = nm[j], ln[j], L[j], lc[j], lb[j], so[j]
+        if len(set(all_names)) != n:              # duplicate keys: the host parser owns pyfaidx's error message
+            eng.close()
+            return None
+        self.engine = eng
+        self.names, self.long_names = all_names, all_long
+        self.lengths, self.bpl, self._lenb, self._seq_off = length, lenc, lenb, seq_off
+        self.goff = np.zeros(n + 1, np.int64)
+        np.cumsum(self.lengths, out=self.goff[1:])
+        self.partition, self.shard = parts, "contigs"     # Mutator / ITMutator keep this partition
+        self._resident_ids = list(mine)
+        return True
+
     def _ingest_device(self, device: int) -> bool:
         from .engine import Engine
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        if world > 1 and not os.environ.get("MS_FULL_INGEST"):
+            if self._ingest_device_sliced(device, int(os.environ.get("RANK", "0")), world):
+                return True
         with open(self.filename, "rb") as fh:
             size = os.fstat(fh.fileno()).st_size
             if size == 0:

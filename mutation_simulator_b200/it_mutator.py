@@ -188,7 +188,7 @@ class ITMutator:
         """One process per GPU: contigs are partitioned; a pair that straddles two GPUs swaps the intervals each
         member takes from the other over NCCL P2P, straight into the staging region behind the receiver's genome
         (SURVEY.md §8e)."""
-        if D.shard_mode(self._fasta.lengths, self._world) == "tiles":
+        if D.shard_of(self._fasta, self._world) == "tiles":
             return self._mutate_tiles()
         self.setup_partitioned()
         self.step_partitioned()
@@ -199,7 +199,7 @@ class ITMutator:
         """Partition, staging space for foreign partner intervals, upload of this rank's contigs."""
         fasta, rank, world = self._fasta, self._rank, self._world
         n_contigs = len(fasta.names)
-        parts = D.lpt_partition(fasta.lengths, world)
+        parts = D.partition_of(fasta, world)
         self._own = own = D.owners(parts, n_contigs)
         self._my_ids = my_ids = parts[rank]
         self._device = device = D.local_device()

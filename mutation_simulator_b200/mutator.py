@@ -78,9 +78,9 @@ class Mutator:
         n_contigs = len(fasta.names)
         # several GPUs: whole contigs per rank (every stage sharded, no exchange), or — when contigs are too few or too
         # uneven for that — the same table on every rank and the output cut at tile boundaries (distributed.shard_mode)
-        mode = D.shard_mode(fasta.lengths, world)
+        mode = D.shard_of(fasta, world)
         tiles = world > 1 and mode == "tiles"
-        my_ids = D.lpt_partition(fasta.lengths, world)[self._rank] if world > 1 and not tiles else list(range(n_contigs))
+        my_ids = D.partition_of(fasta, world)[self._rank] if world > 1 and not tiles else list(range(n_contigs))
         seed = D.broadcast_object(run_seed(args))
         eng = self._engine = getattr(fasta, "engine", None) or \
             Engine(D.local_device(getattr(args, "device", 0)) if world > 1 else getattr(args, "device", 0))
