@@ -660,6 +660,10 @@ __global__ void k_headers(const Contig* contigs, int32_t n_contigs, const uint8_
 // loops ran on 1.5 lanes and were half of all instructions).
 constexpr int VCF_THREADS = 256;
 constexpr int VCF_SMEM = 13 * 1024;
+#ifndef MS_VCF_INLINE
+#define MS_VCF_INLINE 3
+#endif
+constexpr uint32_t VCF_INLINE_MAX = MS_VCF_INLINE;   // REF / ALT pieces up to this long are written by the record's own thread
 constexpr int VCF_MAX_JOBS = 192;
 enum SegMode : uint32_t { SM_IMM = 0, SM_RAW = 1, SM_CONV = 2, SM_RC = 3, SM_LIT = 4, SM_RAND = 5, SM_RANDL = 6 };   // RAND: src = cached 2-bit bases (<= 32); RANDL: src = gid << 32 | pos
 struct Seg { int64_t src; uint32_t len; uint32_t mode; };
@@ -756,7 +760,7 @@ __device__ __forceinline__ void vcf_emit_uniform(const VcfView& v, const Contig&
     for (int q = 0; q < 4; ++q) {
         if (q == 1) *p++ = '\t';
         const Seg g = sg[q];
-        if (g.len <= 3u) {
+        if (g.len <= VCF_INLINE_MAX) {
             for (uint32_t i = 0; i < g.len; ++i) *p++ = seg_byte(v, g.mode, g.src, g.len, i);
         } else {
             const int slot = atomicAdd(n_jobs, 1);
