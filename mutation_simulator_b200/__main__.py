@@ -56,12 +56,18 @@ def main():
         try:
             mutator = Mutator(args, fasta, sim)
             mutator.mutate()
-            # one GPU: the mutated genome stays in HBM for the IT step (MS_NO_CHAIN=1 forces the reference's reload)
-            if sim.has_it and distributed.rank_world()[1] == 1 and not os.environ.get("MS_NO_CHAIN") \
-                    and int(mutator._engine.contig_out_len().min()) > 0:
-                from .fasta import ResidentFasta
-                resident = ResidentFasta(mutator.detach_engine(), fasta)
-                fasta.detach_engine()
+            # the mutated genome stays in HBM for the IT step (MS_NO_CHAIN=1 forces the reference's reload of *_ms.fa);
+            # with several GPUs every rank keeps the contigs it mutated and the IT step reuses the partition
+            if sim.has_it and not os.environ.get("MS_NO_CHAIN"):
+                world = distributed.rank_world()[1]
+                ok = mutator._engine is not None and mutator.shard == "contigs" and len(mutator.my_ids) > 0 \
+                    and int(mutator._engine.contig_out_len().min()) > 0
+                if world > 1:
+                    ok = all(distributed.all_gather_object(bool(ok)))
+                if ok:
+                    from .fasta import ResidentFasta
+                    resident = ResidentFasta(mutator.detach_engine(), fasta, mutator.my_ids if world > 1 else None, mutator.parts)
+                    fasta.detach_engine()
             mutator.close()
             fasta.close()
         except (FastaWriterError, VcfWriterError, MutSimError, RangeOverlapError) as e:

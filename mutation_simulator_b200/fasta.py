@@ -546,12 +546,24 @@ class ResidentFasta:
     load_fasta(args.outfasta) between Mutator and ITMutator (__main__.py:88-95), without the trip through the file.
     Exposes the part of the Fasta surface ITMutator uses (names, lengths, records with len()/name)."""
 
-    def __init__(self, engine, source: "Fasta"):
-        lens = engine.adopt_output()
+    def __init__(self, engine, source: "Fasta", my_ids=None, parts=None):
+        """my_ids / parts: one process per GPU — the engine holds the contigs my_ids (global indices) of the partition
+        `parts`; the mutated lengths of the others are gathered from their ranks, and the IT step keeps the partition."""
+        lens = np.asarray(engine.adopt_output(), dtype=np.int64)
         self.engine = engine
         self.names = list(source.names)
         self.long_names = list(source.long_names)
-        self.lengths = np.asarray(lens, dtype=np.int64)
+        if my_ids is None:
+            self.lengths = lens
+            self._my_ids = None
+        else:
+            from . import distributed as D
+            self.lengths = np.zeros(len(self.names), dtype=np.int64)
+            for ids, ln in D.all_gather_object((list(my_ids), lens.tolist())):
+                if len(ids):
+                    self.lengths[ids] = ln
+            self._my_ids = list(my_ids)
+            self.partition, self.shard = parts, "contigs"
         self.goff = np.concatenate(([0], np.cumsum(self.lengths)[:-1])).astype(np.int64)
         self._records = {nm: FastaRecord(nm, ln, None, 0, length=int(n))
                          for nm, ln, n in zip(self.names, self.long_names, self.lengths)}
@@ -571,6 +583,7 @@ class ResidentFasta:
         pass
 
     def upload(self, engine, contig_ids=None):
-        if engine is not self.engine or contig_ids is not None:
+        mine = getattr(self, "_my_ids", None)
+        if engine is not self.engine or (contig_ids is not None and list(contig_ids) != (mine if mine is not None else list(range(len(self.names))))):
             raise ValueError("a resident genome lives on the engine that produced it")
-        return list(range(len(self.names)))
+        return mine if mine is not None else list(range(len(self.names)))

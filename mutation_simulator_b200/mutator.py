@@ -81,6 +81,8 @@ class Mutator:
         mode = D.shard_of(fasta, world)
         tiles = world > 1 and mode == "tiles"
         my_ids = D.partition_of(fasta, world)[self._rank] if world > 1 and not tiles else list(range(n_contigs))
+        self.shard, self.my_ids = ("tiles" if tiles else "contigs"), my_ids
+        self.parts = D.partition_of(fasta, world) if world > 1 and not tiles else None
         seed = D.broadcast_object(run_seed(args))
         eng = self._engine = getattr(fasta, "engine", None) or \
             Engine(D.local_device(getattr(args, "device", 0)) if world > 1 else getattr(args, "device", 0))

@@ -101,3 +101,24 @@ def test_one_contig_is_cut_into_tiles_over_the_gpus(tmp_path):
     for f in ("g_ms_it.fa", "g_ms_it.bedpe"):
         _same(tmp_path / "it_a", tmp_path / "it_b", f)
     assert (tmp_path / "it_a" / "g_ms_it.bedpe").stat().st_size > 0
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
+def test_rmt_with_it_chained_in_hbm_on_several_gpus(tmp_path):
+    """RMT mode with mutations AND interchromosomal translocations (__main__.py:88-102): every rank keeps the contigs
+    it mutated in HBM and the IT step runs on them with the same partition; all four output files equal the 1-GPU
+    run, and the run that reloads *_ms.fa instead (MS_NO_CHAIN=1)."""
+    n = min(_ngpu(), 4)
+    lens = [90_000, 70_011, 65_000, 40_000, 33_333, 20_000, 3_000, 1_000]
+    make_genome(tmp_path / "g.fa", lens, 9)
+    (tmp_path / "g.rmt").write_text("titv=2.0\nstd\nit 0.0008\nsn 0.01 in 0.002 inmin 1 inmax 9 de 0.002 demin 1 demax 9 tl 0.002 tlmin 2 tlmax 20\n\n"
+                                    "chr 1\n1000-20000 None\n30001-60000 sn 0.05\nchr 3\n1-2000 None\n")
+    runs = {"a": (1, {}), "b": (n, {}), "c": (n, {"MS_NO_CHAIN": "1"})}
+    for d, (k, env) in runs.items():
+        (tmp_path / d).mkdir()
+        cli([str(tmp_path / "g.fa"), "-o", str(tmp_path / d / "g"), "-q", "--seed", "31", "rmt", str(tmp_path / "g.rmt")], k,
+            29571 + ord(d), **env)
+    for d in ("b", "c"):
+        for f in ("g_ms.fa", "g_ms.vcf", "g_ms_it.fa", "g_ms_it.bedpe"):
+            _same(tmp_path / "a", tmp_path / d, f)
+    assert (tmp_path / "a" / "g_ms_it.bedpe").stat().st_size > 0
