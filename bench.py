@@ -639,13 +639,14 @@ def roofline_of(run: Run, res):
     ach = alg / (splice_ms * 1e-3) / 1e9 if splice_ms > 0 else 0.0
     both_ms = splice_ms + vcf_ms
     ach_both = (alg + alg_vcf) / (both_ms * 1e-3) / 1e9 if both_ms > 0 else 0.0
-    traffic = None
+    traffic, traffic_src = None, None
     tf = REPO / "profiles" / "k_splice_traffic.json"
     if tf.exists() and run.name == "c2" and run.world == 1:   # ncu --set full capture of this kernel on this workload
         t_ = json.loads(tf.read_text())
         traffic = t_["dram_bytes_read"] + t_["dram_bytes_write"]
+        traffic_src = t_.get("capture")
     return {"bound": "hbm", "kernel": "k_splice", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak if peak else None,
-            "traffic": traffic, "peak_source": peak_src, "alg_bytes_per_launch": alg, "kernel_ms": splice_ms,
+            "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "alg_bytes_per_launch": alg, "kernel_ms": splice_ms,
             "emit": {"kernels": "k_splice + k_vcf_write", "alg_bytes": alg + alg_vcf, "ms": both_ms, "achieved": ach_both,
                      "frac": ach_both / peak if peak else None},
             "all_kernels_frac": ((my_bases + fasta_bytes * share + vcf_bytes * share + 64 * recs_n) / (res["ms_per_step"] * 1e-3) / 1e9) / peak}
