@@ -616,7 +616,12 @@ def measure(run: Run, steps, warmup, barrier, stream, local_rank, with_clocks=Fa
            "wall_ms_per_step": wall / steps * 1e3}
     if run.it is not None and world > 1:
         exm, exb = reduce_over_ranks([ex_ms / steps], "max", world)[0], reduce_over_ranks([float(ex_bytes) / steps], "sum", world)[0]
-        res["exchange"] = {"ms_per_step": exm, "bytes_per_step": int(exb), "transport": "NCCL P2P (batch_isend_irecv), odd intervals only"}
+        route = getattr(run.it, "_route", "nccl")
+        res["exchange"] = {"ms_per_step": exm if route == "nccl" else None, "bytes_per_step": int(exb), "route": route,
+                           "transport": {"nccl": "NCCL P2P (batch_isend_irecv) into a staging region, odd intervals only",
+                                         "pull": "copy engine, peer genome mapped with CUDA IPC -> staging region, odd intervals only",
+                                         "direct": "none: k_splice gathers the odd intervals from the peer's HBM (CUDA IPC "
+                                                   "mapping) over NVLink; bytes_per_step = bytes read remotely"}[route]}
     return res
 
 

@@ -143,6 +143,18 @@ int ms_genome_declare(ms_ctx* ctx, int64_t total_bases, int32_t n_contigs, const
  * genome index total_bases + 64 (ms_device_ptr(4) gives the base pointer); K_RAW records may point into it,
  * so a peer's ncclSend can land directly where the splice kernel gathers from. */
 int ms_genome_reserve(ms_ctx* ctx, int64_t extra_bytes);
+/* Peer windows: with one process per GPU the partner contig of an interchromosomal pair (it_mutator.py:91-102 picks
+ * the pairs, :133-142 swaps the odd intervals) may live in another process.  The owner exports its resident genome
+ * buffer (a 64-byte CUDA IPC handle; valid until the owner uploads, reserves or destroys), the reader maps it and gets
+ * `rel_off` = (mapped base - its own genome pointer): a K_RAW record whose src = rel_off + the interval's index in the
+ * owner's genome makes the splice kernel gather those bases in place over NVLink — no staging copy, no collective.
+ * ms_peer_pull instead copies intervals (src relative like above) into the staging region of ms_genome_reserve
+ * (dst = genome index >= total_bases + 64) on the context's stream.  The caller orders the two processes: export after
+ * the owner's genome is final, close every window before the owner frees it. */
+int ms_genome_export(ms_ctx* ctx, uint8_t* handle64, int64_t* nbytes);
+int ms_peer_open(ms_ctx* ctx, const uint8_t* handle64, int64_t nbytes, int64_t* rel_off);
+int ms_peer_pull(ms_ctx* ctx, int32_t n, const int64_t* src, const int64_t* dst, const int64_t* nbytes);
+int ms_peer_close(ms_ctx* ctx);
 
 /* ---- fresh sampling ----------------------------------------------------
  * Replaces Mutator.__get_mutations / __get_mut_positions / __get_stop_position /

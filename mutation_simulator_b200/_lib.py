@@ -50,6 +50,10 @@ PROTOTYPES = {
     "ms_hash_ranges": (C.c_int, [_P, C.c_int, _I32, _P, _P, _P]),
     "ms_genome_download": (C.c_int, [_P, _P, _I64]),
     "ms_genome_reserve": (C.c_int, [_P, _I64]),
+    "ms_genome_export": (C.c_int, [_P, _P, _P]),
+    "ms_peer_open": (C.c_int, [_P, _P, _I64, _P]),
+    "ms_peer_pull": (C.c_int, [_P, C.c_int32, _P, _P, _P]),
+    "ms_peer_close": (C.c_int, [_P]),
     "ms_genome_adopt_output": (C.c_int, [_P]),
     "ms_fasta_ingest_fd": (C.c_int, [_P, C.c_int, _I64, _P, _P]),
     "ms_fasta_ingest_ranges": (C.c_int, [_P, C.c_int, _I32, _P, _P, _P, _P]),

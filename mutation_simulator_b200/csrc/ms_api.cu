@@ -59,10 +59,21 @@ int ms_create(int device, ms_ctx** out) {
     return MS_OK;
 }
 
+// [src, src + n) — relative to this context's genome pointer — lies inside one of the mapped peer buffers
+static bool source_in_peer_window(const ms_ctx* c, int64_t src, int64_t n) {
+    if (c->peer_anchor != c->genome.p) return false;   // the genome moved since ms_peer_open
+    const uint8_t* a = (const uint8_t*)c->genome.p + src;
+    for (const auto& w : c->peers)
+        if (a >= (const uint8_t*)w.base && a + n <= (const uint8_t*)w.base + w.bytes) return true;
+    return false;
+}
+
 int ms_destroy(ms_ctx* c) {
     if (!c) return MS_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    for (auto& w : c->peers) cudaIpcCloseMemHandle(w.base);
+    c->peers.clear();
     DevBuf* bufs[] = {&c->genome, &c->contigs, &c->headers, &c->names, &c->tables, &c->ranges, &c->cand_val, &c->cand_sorted,
                       &c->bucket_cnt, &c->bucket_off, &c->cand_type, &c->cand_len, &c->cand_reach, &c->cand_pm, &c->cand_accept,
                       &c->acc_idx, &c->tl_list, &c->tli_list, &c->link, &c->keep, &c->contig_tl, &c->scan_tmp, &c->scan_tmp2,
@@ -309,6 +320,61 @@ int ms_genome_reserve(ms_ctx* c, int64_t extra_bytes) {
     return MS_OK;
 }
 
+// ---- peer windows: a partner contig that lives on another GPU is read in place over NVLink ------------------------
+static void close_peers(ms_ctx* c) {
+    for (auto& w : c->peers) cudaIpcCloseMemHandle(w.base);
+    c->peers.clear();
+}
+
+int ms_genome_export(ms_ctx* c, uint8_t* handle, int64_t* nbytes) {
+    if (!c || !handle || !nbytes) return MS_ERR_ARG;
+    if (c->n_contigs <= 0 || !c->genome.p) MS_FAIL(c, MS_ERR_STATE, "ms_genome_export: no resident genome");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    MS_CUDA(c, cudaSetDevice(c->device));
+    MS_CUDA(c, cudaStreamSynchronize(c->stream));     // peers read what earlier calls on this stream wrote
+    cudaIpcMemHandle_t h;
+    MS_CUDA(c, cudaIpcGetMemHandle(&h, c->genome.p));
+    memcpy(handle, &h, 64);
+    *nbytes = c->total_bases + 64;
+    return MS_OK;
+}
+
+int ms_peer_open(ms_ctx* c, const uint8_t* handle, int64_t nbytes, int64_t* rel_off) {
+    if (!c || !handle || !rel_off || nbytes <= 0) return MS_ERR_ARG;
+    if (!c->genome.p) MS_FAIL(c, MS_ERR_STATE, "ms_peer_open: upload this rank's genome first (sources are relative to it)");
+    MS_CUDA(c, cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    void* base = nullptr;
+    MS_CUDA(c, cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    if (c->peer_anchor != c->genome.p) close_peers(c);   // offsets handed out earlier are void
+    c->peer_anchor = c->genome.p;
+    c->peers.push_back({base, nbytes});
+    *rel_off = (int64_t)((const uint8_t*)base - (const uint8_t*)c->genome.p);
+    return MS_OK;
+}
+
+int ms_peer_pull(ms_ctx* c, int32_t n, const int64_t* src, const int64_t* dst, const int64_t* nbytes) {
+    if (!c || n < 0 || (n > 0 && (!src || !dst || !nbytes))) return MS_ERR_ARG;
+    MS_CUDA(c, cudaSetDevice(c->device));
+    uint8_t* g = (uint8_t*)c->genome.p;
+    for (int32_t i = 0; i < n; ++i) {
+        if (nbytes[i] < 0 || dst[i] < c->total_bases + 64 || dst[i] + nbytes[i] > c->total_bases + 64 + c->foreign_cap)
+            MS_FAIL(c, MS_ERR_ARG, "ms_peer_pull: copy %d lands outside the staging region", i);
+        if (!source_in_peer_window(c, src[i], nbytes[i])) MS_FAIL(c, MS_ERR_ARG, "ms_peer_pull: copy %d reads outside every peer window", i);
+        if (nbytes[i]) MS_CUDA(c, cudaMemcpyAsync(g + dst[i], g + src[i], (size_t)nbytes[i], cudaMemcpyDefault, c->stream));
+    }
+    return MS_OK;
+}
+
+int ms_peer_close(ms_ctx* c) {
+    if (!c) return MS_ERR_ARG;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    close_peers(c);
+    return MS_OK;
+}
+
 int ms_genome_adopt_output(ms_ctx* c) {
     if (!c) return MS_ERR_ARG;
     MS_CUDA(c, cudaSetDevice(c->device));
@@ -335,7 +401,8 @@ int ms_load_records(ms_ctx* c, const ms_rec* recs, int64_t n_recs, const uint8_t
         if (recs[i].kind == K_LIT && (recs[i].src < 0 || recs[i].src + recs[i].prod > lit_bytes))
             MS_FAIL(c, MS_ERR_ARG, "record %lld: literal range outside the pool", (long long)i);
         if ((recs[i].kind == K_RAW || recs[i].kind == K_CONV || recs[i].kind == K_RC) &&
-            (recs[i].src < 0 || recs[i].src + recs[i].prod > c->total_bases + 64 + c->foreign_cap))
+            (recs[i].src < 0 || recs[i].src + recs[i].prod > c->total_bases + 64 + c->foreign_cap) &&
+            !(recs[i].kind == K_RAW && source_in_peer_window(c, recs[i].src, recs[i].prod)))
             MS_FAIL(c, MS_ERR_ARG, "record %lld: source range outside the genome", (long long)i);
     }
     MS_CUDA(c, cudaSetDevice(c->device));

@@ -394,7 +394,11 @@ k_splice(SpliceView v, const Contig* contigs, const PieceDesc* pieces, const SvR
             const PieceDesc* nx = pieces + p + W;
             if (lane == 0) {
                 const uint32_t nb = __ldg(&nx->in_bytes);
-                if (nb) bulk_prefetch_l2(v.genome + __ldg(&nx->in_lo), nb);
+                const int64_t lo = __ldg(&nx->in_lo);
+                // not for a span in a peer's HBM (interchromosomal partner on another GPU): the TMA copy of such a span
+                // runs at NVLink speed, but an L2 prefetch of a peer address completes one at a time, ≈ 1.6 µs each
+                // (measured: 41 ms instead of 1.1 ms for the 26 k remote tiles of C4, profiles/r2w_*)
+                if (nb && lo >= 0 && lo < v.local_cap) bulk_prefetch_l2(v.genome + lo, nb);
             } else if (lane == 1) {
                 const uint32_t nsv = __ldg(&nx->n_sv);
                 if (nsv) bulk_prefetch_l2(sv_stream + __ldg(&nx->sv_lo), 32u * nsv);
@@ -1090,6 +1094,7 @@ static int splice_launch(ms_ctx* c, int64_t piece_lo, int64_t n_pieces, int32_t 
     Contig* d_contigs = c->contigs.as<Contig>();
     cudaStream_t st = c->stream;
     SpliceView sv{c->genome.as<uint8_t>(), c->lit.as<uint8_t>(), c->recs.as<Rec>(), c->svec.as<int64_t>(), d_tab->conv, d_tab->comp, c->seed_last};
+    sv.local_cap = (int64_t)c->genome.cap;
     if (n_pieces > 0) {
         if (!c->splice_attr_set) {   // per context: the attribute is per device, and a process may hold contexts on several
             MS_CUDA(c, cudaFuncSetAttribute(k_splice, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_DYN));

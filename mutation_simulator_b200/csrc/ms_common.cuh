@@ -77,6 +77,9 @@ struct ms_ctx {
     int32_t n_contigs = 0;
     int64_t total_bases = 0;
     int64_t foreign_cap = 0;   // staging bytes behind the genome (ms_genome_reserve)
+    struct PeerWindow { void* base; int64_t bytes; };   // another GPU's genome buffer, mapped with CUDA IPC (ms_peer_open)
+    std::vector<PeerWindow> peers;
+    const void* peer_anchor = nullptr;   // genome pointer the windows' offsets are relative to (stale once it moves)
     ms::DevBuf tmp_contigs;
 
     // ranges / sampling

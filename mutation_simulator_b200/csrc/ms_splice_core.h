@@ -21,6 +21,7 @@ struct SpliceView {
     const uint8_t* conv;    // 256-entry tables (global or shared memory)
     const uint8_t* comp;
     Seed seed;              // for K_RAND payloads
+    int64_t local_cap = INT64_MAX;   // genome indices outside [0, local_cap) address another GPU's buffer (ms_peer_open)
 };
 
 MS_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {

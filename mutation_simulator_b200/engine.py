@@ -178,6 +178,28 @@ class Engine:
         """Staging space behind the genome for partner contigs owned by another GPU (call before upload)."""
         self._check(self._lib.ms_genome_reserve(self._h, int(nbytes)))
 
+    def export_genome(self):
+        """-> (64-byte CUDA IPC handle of the resident genome buffer, its size): another process maps it with open_peer."""
+        h = np.zeros(64, dtype=np.uint8)
+        n = C.c_int64(0)
+        self._check(self._lib.ms_genome_export(self._h, _ptr(h), C.byref(n)))
+        return h.tobytes(), n.value
+
+    def open_peer(self, handle: bytes, nbytes: int) -> int:
+        """Map another GPU's genome buffer; -> offset of its base relative to this engine's genome (for Rec.src)."""
+        h = np.frombuffer(handle, dtype=np.uint8).copy()
+        rel = C.c_int64(0)
+        self._check(self._lib.ms_peer_open(self._h, _ptr(h), int(nbytes), C.byref(rel)))
+        return rel.value
+
+    def pull_peer(self, src, dst, nbytes):
+        """Async copies peer window -> staging region on the engine's stream (src relative like open_peer's offset)."""
+        src, dst, nbytes = (np.ascontiguousarray(a, dtype=np.int64) for a in (src, dst, nbytes))
+        self._check(self._lib.ms_peer_pull(self._h, len(src), _ptr(src), _ptr(dst), _ptr(nbytes)))
+
+    def close_peers(self):
+        self._check(self._lib.ms_peer_close(self._h))
+
     def adopt_output(self) -> np.ndarray:
         """The mutated genome of the last apply() becomes the resident genome; returns the new contig lengths."""
         self._check(self._lib.ms_genome_adopt_output(self._h))

@@ -8,6 +8,7 @@ FASTA image comes back complete.  Contigs without a partner are written once wit
 line wrapping (the reference's duplicated header is treated as a bug)."""
 from __future__ import annotations
 
+import os
 import random
 
 import numpy as np
@@ -18,6 +19,7 @@ from .engine import BUF_FASTA, Engine
 from .fasta_writer import FastaWriter
 from .mutator import run_seed
 from .records import K_RAW, REC_DTYPE, T_IT
+from ._lib import MS_ERR_ARG, MutSimError
 from .util import print_warning
 
 
@@ -76,6 +78,10 @@ class ITMutator:
             self._fasta_writer.close()
             self._bedpe_writer.close()
         if self._engine is not None:
+            if getattr(self, "_peer_src", None):     # mapped peer buffers go before their owners free them
+                self._engine.close_peers()
+            if getattr(self, "_route", "nccl") != "nccl":
+                D.barrier()
             self._engine.close()
             self._engine = None
 
@@ -196,31 +202,56 @@ class ITMutator:
 
     # The three phases are separate so that bench.py can time the step (breakpoints -> exchange -> splice) alone.
     def setup_partitioned(self):
-        """Partition, staging space for foreign partner intervals, upload of this rank's contigs."""
+        """Partition, upload of this rank's contigs, and the route to partner contigs owned by a peer:
+        ``direct`` (default) maps the owner's genome buffer (CUDA IPC) so the splice kernel gathers the swapped intervals
+        in place over NVLink; ``pull`` copies them from the mapped buffer into a staging region behind this rank's genome;
+        ``nccl`` has the owner send them there (MS_IT_EXCHANGE selects; all three write identical files)."""
         fasta, rank, world = self._fasta, self._rank, self._world
         n_contigs = len(fasta.names)
         parts = D.partition_of(fasta, world)
         self._own = own = D.owners(parts, n_contigs)
         self._my_ids = my_ids = parts[rank]
         self._device = device = D.local_device()
+        self._route = route = os.environ.get("MS_IT_EXCHANGE", "direct")
+        if route not in ("direct", "pull", "nccl"):
+            raise MutSimError(MS_ERR_ARG, f"MS_IT_EXCHANGE={route}: expected direct, pull or nccl")
         eng = self._engine = getattr(fasta, "engine", None) or Engine(device)
-        # partner contigs owned by a peer get a slot in the staging region (sized for the whole contig: an interval
-        # lands at its own coordinate, so the records' sources need no translation table)
         foreign = sorted(self._partners[c] for c in my_ids if c in self._partners and own[self._partners[c]] != rank)
+        # staging (pull, nccl): a slot per foreign partner, sized for the whole contig — an interval lands at its own
+        # coordinate, so the records' sources need no translation table
         stage_off, acc = {}, 0
-        for p in foreign:
-            stage_off[p] = acc
-            acc += int(fasta.lengths[p]) + 64
+        if route != "direct":
+            for p in foreign:
+                stage_off[p] = acc
+                acc += int(fasta.lengths[p]) + 64
         eng.reserve_foreign(acc)
         if my_ids:
             fasta.upload(eng, my_ids)
         total = int(sum(int(fasta.lengths[g]) for g in my_ids))
-        self._local_goff, o = {}, 0
-        for g in my_ids:
-            self._local_goff[g] = o
-            o += int(fasta.lengths[g])
-        self._src_of = {p: self._local_goff[p] for p in my_ids}
-        self._src_of.update({p: total + 64 + off for p, off in stage_off.items()})
+        goff_on = {}                       # contig -> index of its base 0 in its owner's genome
+        for part in parts:
+            o = 0
+            for g in part:
+                goff_on[g] = o
+                o += int(fasta.lengths[g])
+        self._local_goff = {g: goff_on[g] for g in my_ids}
+        self._src_of = {p: goff_on[p] for p in my_ids}
+        self._peer_src = {}
+        if route == "nccl":
+            self._src_of.update({p: total + 64 + off for p, off in stage_off.items()})
+        else:
+            # every rank with contigs exports its buffer; a reader maps only the owners of its foreign partners
+            mine = eng.export_genome() if my_ids else None
+            handles = D.all_gather_object(mine)
+            rel = {}
+            if my_ids:
+                for r in sorted({int(own[p]) for p in foreign}):
+                    rel[r] = eng.open_peer(*handles[r])
+            self._peer_src = {p: rel[int(own[p])] + goff_on[p] for p in foreign}
+            if route == "direct":
+                self._src_of.update(self._peer_src)
+            else:
+                self._src_of.update({p: total + 64 + off for p, off in stage_off.items()})
         self.exchange_bytes = self.exchange_ms = 0
 
     MAX_INTERVAL_OPS = 64      # beyond this many intervals per direction the whole contig goes as one transfer
@@ -229,11 +260,11 @@ class ITMutator:
         """Breakpoints (identical on every rank: keyed by the global contig id), exchange, records, splice."""
         fasta, rank = self._fasta, self._rank
         own, my_ids, src_of, local_goff = self._own, self._my_ids, self._src_of, self._local_goff
-        eng = self._engine
+        eng, route = self._engine, self._route
         bps = self.breakpoints = self._generate_all_breakpoints(eng)
         # globally agreed order: ascending (min, max) of each straddling pair; for each member the intervals the
         # OTHER one takes from it (odd-numbered intervals of its own breakpoint list, it_mutator.py:133-137)
-        sends, recvs = [], []
+        sends, recvs, pulls, remote = [], [], [], 0
         for a in sorted(bps):
             b = self._partners[a]
             if a < b and own[a] != own[b]:
@@ -244,14 +275,27 @@ class ITMutator:
                     cut = np.concatenate(([0], bps[mine]["self"].astype(np.int64), [int(fasta.lengths[mine])]))
                     cut_t = np.concatenate(([0], bps[theirs]["self"].astype(np.int64), [int(fasta.lengths[theirs])]))
                     odd = np.arange(1, len(cut) - 1, 2)
-                    if len(odd) <= self.MAX_INTERVAL_OPS:
+                    remote += int(sum(int(cut_t[i + 1] - cut_t[i]) for i in odd))
+                    if route == "pull" and len(odd) <= self.MAX_INTERVAL_OPS:
+                        pulls += [(self._peer_src[theirs] + int(cut_t[i]), src_of[theirs] + int(cut_t[i]),
+                                   int(cut_t[i + 1] - cut_t[i])) for i in odd]
+                    elif route == "pull":
+                        pulls.append((self._peer_src[theirs], src_of[theirs], int(fasta.lengths[theirs])))
+                    elif len(odd) <= self.MAX_INTERVAL_OPS:
                         sends += [(peer, local_goff[mine] + int(cut[i]), int(cut[i + 1] - cut[i])) for i in odd]
                         recvs += [(peer, src_of[theirs] + int(cut_t[i]), int(cut_t[i + 1] - cut_t[i])) for i in odd]
                     else:
                         sends.append((peer, local_goff[mine], int(fasta.lengths[mine])))
                         recvs.append((peer, src_of[theirs], int(fasta.lengths[theirs])))
-        self.exchange_bytes = sum(n for _, _, n in recvs)
-        self.exchange_ms = D.exchange_contigs(eng, self._device, sends, recvs)
+        if route == "nccl":
+            self.exchange_bytes = sum(n for _, _, n in recvs)
+            self.exchange_ms = D.exchange_contigs(eng, self._device, sends, recvs)
+        elif route == "pull":
+            self.exchange_bytes = sum(n for _, _, n in pulls)
+            if pulls:
+                eng.pull_peer(*zip(*pulls))        # on the engine's stream, ahead of the splice that reads the staging
+        else:                                      # direct: the splice kernel reads the peers' HBM (bytes it gathers remotely)
+            self.exchange_bytes = remote
         if my_ids:
             eng.load_records(self._records(bps, my_ids, src_of))
             eng.apply()

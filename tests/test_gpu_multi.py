@@ -1,5 +1,5 @@
 """N-GPU output == 1-GPU output, byte for byte (needs >= 2 GPUs; run with `gpurun --gpus 2`).
-ARGS mode shards contigs with no collective; IT mode swaps partner contigs over NCCL P2P."""
+ARGS mode shards contigs with no collective; IT mode reads partner contigs from the owning GPU."""
 import os
 import shutil
 import subprocess
@@ -57,16 +57,18 @@ def test_partitioned_runs_equal_single_gpu(tmp_path):
             a = b"".join(l for l in a.splitlines(keepends=True) if not l.startswith(b"##filedate"))
             b = b"".join(l for l in b.splitlines(keepends=True) if not l.startswith(b"##filedate"))
         assert a == b, f
-    # IT: several seeds so that at least one pairing straddles the GPUs
-    for seed in (1, 2, 3):
+    # IT: several seeds so that at least one pairing straddles the GPUs; the partner's intervals reach the splice
+    # kernel in place over NVLink (direct, the default), through a copy-engine pull, or over NCCL — same files
+    for seed, route in ((1, "direct"), (2, "direct"), (3, "direct"), (2, "pull"), (3, "nccl")):
         for d in ("a", "b"):
             for f in (tmp_path / d).glob("*_it*"):
                 f.unlink()
         it = ["-q", "--seed", str(seed), "it", "0.001"]
         cli([str(tmp_path / "g.fa"), "-o", str(tmp_path / "a" / "g")] + it, 1, 0)
-        cli([str(tmp_path / "g.fa"), "-o", str(tmp_path / "b" / "g")] + it, n, 29542 + seed)
+        cli([str(tmp_path / "g.fa"), "-o", str(tmp_path / "b" / "g")] + it, n, 29542 + seed + (10 if route != "direct" else 0),
+            MS_IT_EXCHANGE=route)
         for f in ("g_ms_it.fa", "g_ms_it.bedpe"):
-            assert (tmp_path / "a" / f).read_bytes() == (tmp_path / "b" / f).read_bytes(), (seed, f)
+            assert (tmp_path / "a" / f).read_bytes() == (tmp_path / "b" / f).read_bytes(), (seed, route, f)
         assert (tmp_path / "a" / "g_ms_it.bedpe").stat().st_size > 0
 
 
