@@ -83,13 +83,14 @@ struct ms_ctx {
     ms::DevBuf tmp_contigs;
 
     // ranges / sampling
-    ms::DevBuf ranges, cand_val, cand_sorted, bucket_cnt, bucket_off, cand_type, cand_len, cand_reach, cand_pm,
+    ms::DevBuf ranges, cand_val, big_ranges, bucket_cnt, bucket_off, cand_type, cand_len, cand_reach, cand_pm,
                cand_accept, acc_idx, tl_list, tli_list, link, keep, contig_tl, scan_tmp, scan_tmp2, scan_mid, svec, vvec, lvec, bucket_range;
     std::vector<ms::Range> h_ranges;
     int32_t n_ranges = 0;
     int64_t n_candidates = 0;
     int64_t n_buckets = 0;
-    int64_t store_entries = 0;
+    int split_levels = 0;         // levels k_split_top runs (bucket-tree nodes wider than SPLIT_LEAF)
+    int32_t n_big = 0;            // ranges that have such nodes
     int32_t block[7] = {1, 1, 1, 1, 1, 1, 1};
     double p_ti = 0.5;
     int32_t min_dist = 1;

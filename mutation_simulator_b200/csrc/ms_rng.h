@@ -4,10 +4,8 @@
 //    pure function of (seed, contig, purpose, index), so results do not depend
 //    on the GPU count, the partition of contigs over GPUs, or launch geometry
 //    (BASELINE.json north_star (a)).
-//  * A Philox-keyed Feistel permutation with cycle walking gives the k distinct
-//    start positions of util.py:94-109 (random.sample of a range) without any
-//    duplicate/redraw round: pi(0..k-1) of a random permutation of range(n) is
-//    a uniform k-subset.
+//  * A Philox-keyed Feistel permutation with cycle walking (a uniform random
+//    injection without any redraw round) pairs TLs with TLIs (mutator.py:277-285).
 #pragma once
 #include <stdint.h>
 #include <math.h>
@@ -69,6 +67,7 @@ enum Purpose : uint32_t {
     P_TL_REV    = 6,   // inversion coin of one translocation                       (mutator.py:307-316)
     P_IT_PRP    = 7,   // breakpoint permutations of an interchromosomal pair       (it_mutator.py:94-118)
     P_GENOME    = 8,   // synthetic genome generator (bench only)
+    P_RANGE_KEY = 9,   // sub-key of one RMT range: bucket-count splits and in-bucket position draws   (util.py:104)
 };
 
 struct Seed { uint32_t k0, k1; };

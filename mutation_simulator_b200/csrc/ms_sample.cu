@@ -1,9 +1,11 @@
 // ms_sample.cu — K1..K4: fresh sampling of mutations for all ranges of all contigs.
 //
-//   K1  positions   util.py:94-109 sample_with_minimum_distance: pi(0..k-1) of a
-//                   Philox-keyed permutation of range(n) (distinct by construction),
-//                   then a uniform bucket sort (count / scan / scatter / in-smem
-//                   bitonic) — keys are uniform, so equal-width buckets balance.
+//   K1  positions   util.py:94-109 sample_with_minimum_distance: a uniform k-subset of
+//                   range(n), generated IN ORDER: the value span is cut into equal sort
+//                   buckets, a hypergeometric split tree gives every bucket its count
+//                   (no value is drawn or scattered for that), a scan turns counts into
+//                   candidate slots, and each bucket draws its values as a uniform subset
+//                   of its span in shared memory (bitmap rank / bitonic sort).
 //   K2  type+length mutator.py:166-182, 229-265 (fused into the sort's write-back)
 //   K3  rejection   mutator.py:184-213 first-come greedy acceptance, in parallel:
 //                   exclusive prefix-max of the blocking reach marks "anchors"
@@ -20,8 +22,7 @@
 namespace ms {
 
 constexpr int BUCKET_TARGET = 384;   // mean keys per sort bucket of a multi-bucket range
-constexpr int BUCKET_CAP = 640;      // storage per such bucket: mean + 13 sigma of Binomial(k, 1/nb); overflow raises MS_ERR_INTERNAL
-constexpr int SORT_CAP = 1024;
+constexpr int SORT_CAP = 1024;       // keys one sort CTA can hold: mean + 32 sigma of a bucket's count; beyond raises MS_ERR_INTERNAL
 constexpr int SORT_THREADS = 512;
 
 __device__ inline void raise_error_s(Totals* t, int64_t code, int64_t arg) {
@@ -38,61 +39,87 @@ __device__ inline int upper_idx(const int64_t* key, int n, int64_t x) {
     return lo;
 }
 
-__global__ void k_make_prps(const Range* ranges, int32_t n_ranges, const Contig* contigs, Seed seed, uint32_t purpose, Prp* prps) {
+// Everything a sort CTA needs to start, built on the host with the range table (the lookups it replaces were a
+// chain of dependent loads and two 64-bit divisions on one thread at the head of every CTA, profiles/r1m).
+struct BucketInfo {
+    uint32_t ridx;        // its range
+    uint32_t vlo;         // smallest value that falls into it
+    uint32_t width;       // number of values in its span
+    uint32_t nw;          // 32-bit bitmap words its span needs
+};
+
+// K1a: per-range sub-key, and the root of the range's bucket tree gets all k samples
+__global__ void k_range_keys(const Range* ranges, int32_t n_ranges, const Contig* contigs, Seed seed, uint32_t purpose, Seed* keys,
+                             uint32_t* bucket_cnt) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_ranges) return;
     const Range& g = ranges[r];
-    prps[r] = make_prp(seed, contigs[g.contig].gid, purpose, g.start, g.n);
+    const U4 k = draw(seed, contigs[g.contig].gid, purpose, g.start);
+    keys[r] = Seed{k.x, k.y};
+    bucket_cnt[g.bucket_lo] = g.k;
 }
 
-__device__ inline uint32_t bucket_of(const Range& g, uint32_t v) {
-    const uint32_t b = mulhi32(v, g.bscale);   // nb == 1: bscale = 0
-    return g.bucket_lo + (b < g.nb ? b : g.nb - 1);
+// K1b: bucket counts.  bucket_cnt[first bucket of a node] holds the node's sample count; a split leaves the left
+// child's count in that slot and puts the right child's into its own first bucket.
+//   k_split_top   the few nodes that span more than SPLIT_LEAF buckets (ranges with > 98 k candidates: at most
+//                 ~2 * buckets / SPLIT_LEAF nodes in the whole table), level by level inside ONE CTA;
+//   k_split_leaf  one thread per bucket walks from its SPLIT_LEAF-sized ancestor down to itself, drawing the splits
+//                 on the way (threads of a warp share most of the path and run it in lock step; no barriers, no
+//                 level launches).  Leaf counts go to a second array because the ancestors' slots are still being
+//                 read by their other descendants.
+constexpr uint32_t SPLIT_LEAF = 256;
+
+__device__ __forceinline__ uint32_t node_split(const Range& g, const BucketInfo* bi, Seed key, uint32_t lo, uint32_t hi, uint32_t mid, uint32_t n_node) {
+    const uint32_t v_lo = bi[lo].vlo, v_mid = bi[mid].vlo, v_hi = hi < g.nb ? bi[hi].vlo : g.n;
+    return split_left(key, lo, hi, v_hi - v_lo, v_mid - v_lo, n_node);
 }
 
-// K1a: draw and drop each value straight into its sort bucket.  Keys are uniform, so equal-width buckets
-// are balanced and a fixed capacity per bucket replaces the usual count / scan / scatter passes.
-__device__ inline int64_t bucket_store(const Range& g, uint32_t b) {
-    const uint32_t cap = g.nb == 1u ? g.k : (uint32_t)BUCKET_CAP;
-    return g.store_lo + (int64_t)(b - g.bucket_lo) * cap;
-}
-
-// A CTA draws DRAW_TILE consecutive candidate slots: the range lookup (a chain of dependent loads) is paid once
-// per 2048 candidates, and a thread's successive candidates are independent chains the scheduler can overlap
-// (profiles/r1k: with one candidate per thread the kernel sat at 48 % issue utilisation behind that prologue and
-// the bucket atomics).
-constexpr int DRAW_THREADS = 256, DRAW_PER_THREAD = 8, DRAW_TILE = DRAW_THREADS * DRAW_PER_THREAD;
-__global__ void __launch_bounds__(DRAW_THREADS)
-k_draw(const Range* ranges, const int64_t* cand_lo, int32_t n_ranges, const Prp* prps, int64_t K, uint32_t* store, uint32_t* bucket_cnt,
-       Totals* tot) {
-    __shared__ int r0;
-    const int64_t s0 = (int64_t)blockIdx.x * DRAW_TILE;
-    if (threadIdx.x == 0) r0 = upper_idx(cand_lo, n_ranges, s0);
-    __syncthreads();
-    int r = r0, r_have = -1;
-    Prp p;
-    int64_t g_cand_lo = 0, g_store_lo = 0;
-    uint32_t g_nb = 1u, g_bscale = 0u, g_bucket_lo = 0u, g_k = 0u;
-    // (issuing a thread's eight bucket atomics back to back before the stores was measured: slower, 0.99 -> 1.11 ms)
-#pragma unroll 2
-    for (int it = 0; it < DRAW_PER_THREAD; ++it) {
-        const int64_t s = s0 + (int64_t)it * DRAW_THREADS + threadIdx.x;
-        if (s >= K) break;
-        while (s >= cand_lo[r + 1]) ++r;
-        if (r != r_have) {
-            const Range& g = ranges[r];
-            p = prps[r];
-            g_cand_lo = g.cand_lo; g_store_lo = g.store_lo; g_nb = g.nb; g_bscale = g.bscale; g_bucket_lo = g.bucket_lo; g_k = g.k;
-            r_have = r;
+__global__ void __launch_bounds__(1024)
+k_split_top(const Range* ranges, const BucketInfo* binfo, const Seed* keys, const uint32_t* big, int32_t n_big, int levels, uint32_t* bucket_cnt) {
+    for (int level = 0; level < levels; ++level) {
+        const int64_t items = (int64_t)n_big << level;
+        for (int64_t idx = threadIdx.x; idx < items; idx += blockDim.x) {
+            const uint32_t ridx = big[idx >> level];
+            const Range& g = ranges[ridx];
+            if ((uint32_t)level >= g.top_levels) continue;
+            const uint32_t j = (uint32_t)(idx & (((int64_t)1 << level) - 1));
+            uint32_t lo = 0u, hi = g.nb;
+            for (int s = level - 1; s >= 0; --s) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if ((j >> s) & 1u) lo = mid; else hi = mid;
+            }
+            const uint32_t mid = (lo + hi) >> 1;
+            uint32_t* cnt = bucket_cnt + g.bucket_lo;
+            const uint32_t n_node = cnt[lo];
+            const uint32_t left = node_split(g, binfo + g.bucket_lo, keys[ridx], lo, hi, mid, n_node);
+            cnt[lo] = left;
+            cnt[mid] = n_node - left;
         }
-        const uint32_t v = prp_apply(p, (uint32_t)(s - g_cand_lo));
-        uint32_t bl = mulhi32(v, g_bscale);   // nb == 1: bscale = 0
-        if (bl >= g_nb) bl = g_nb - 1u;
-        const uint32_t cap = g_nb == 1u ? g_k : (uint32_t)BUCKET_CAP;
-        const uint32_t slot = atomicAdd(&bucket_cnt[g_bucket_lo + bl], 1u);
-        if (slot < cap) store[g_store_lo + (int64_t)bl * cap + slot] = v;
-        else raise_error_s(tot, MS_ERR_INTERNAL, 200 + (int64_t)(g_bucket_lo + bl));
+        __syncthreads();
     }
+}
+
+__global__ void __launch_bounds__(256)
+k_split_leaf(const Range* ranges, const BucketInfo* binfo, const Seed* keys, int64_t n_buckets, const uint32_t* bucket_cnt, uint32_t* leaf_cnt) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_buckets) return;
+    const uint32_t ridx = binfo[b].ridx;
+    const Range& g = ranges[ridx];
+    const uint32_t bl = (uint32_t)(b - (int64_t)g.bucket_lo);
+    uint32_t lo = 0u, hi = g.nb;
+    for (uint32_t s = 0; s < g.top_levels; ++s) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (bl < mid) hi = mid; else lo = mid;
+    }
+    uint32_t cnt = bucket_cnt[(int64_t)g.bucket_lo + lo];
+    const Seed key = keys[ridx];
+    const BucketInfo* bi = binfo + g.bucket_lo;
+    while (hi - lo >= 2u) {
+        const uint32_t mid = (lo + hi) >> 1;
+        const uint32_t left = node_split(g, bi, key, lo, hi, mid, cnt);
+        if (bl < mid) { hi = mid; cnt = left; } else { lo = mid; cnt -= left; }
+    }
+    leaf_cnt[b] = cnt;
 }
 
 template <int K, int J>
@@ -128,16 +155,6 @@ __device__ __forceinline__ uint32_t bitonic_sorted(uint32_t v, int tid, uint32_t
     return v;
 }
 
-// Everything a sort CTA needs to start, built on the host with the range table (the lookups it replaces were a
-// chain of dependent loads and two 64-bit divisions on one thread at the head of every CTA, profiles/r1m).
-struct BucketInfo {
-    int64_t store_base;   // first slot of the bucket in the bucket store
-    uint32_t ridx;        // its range
-    uint32_t vlo;         // smallest value that falls into it
-    uint32_t nw;          // 32-bit bitmap words its value span needs
-    uint32_t pad;
-};
-
 constexpr int SMALL_BUCKET = 128;   // buckets of at most this many keys are sorted four per CTA (k_sort_emit_small)
 
 // position, type, length and blocking reach of the candidate that ends up in `slot` (K2)
@@ -158,67 +175,105 @@ __device__ __forceinline__ void emit_candidate(const Range& g, const Contig& ct,
     cand_range[slot] = r_idx;
 }
 
+// The values of one bucket are a uniform c-subset of its span: draw c values; while some coincide, keep the distinct
+// ones and draw as many new values as were lost, from streams numbered by (round, j) — WHICH thread redraws does not
+// matter, only how many do, so the resulting set is a pure function of the range key and invariant under any
+// relabelling of the span's values, i.e. uniform over c-subsets.
+
 // Small buckets (many-small-contig genomes: a 5 kbp contig has ~67 candidates): four buckets per CTA, 128 threads
 // each, instead of one mostly idle 512-thread CTA per bucket (C5: 4.0 ms -> see profiles).
 __global__ void __launch_bounds__(SORT_THREADS)
-k_sort_emit_small(const Range* ranges, const BucketInfo* binfo, const Contig* contigs, const int64_t* bucket_off,
-                  int64_t n_buckets, const uint32_t* store, Seed seed, int32_t min_dist, const int32_t* block7, int positions_only,
+k_sort_emit_small(const Range* ranges, const BucketInfo* binfo, const Seed* keys, const Contig* contigs, const int64_t* bucket_off,
+                  int64_t n_buckets, Seed seed, int32_t min_dist, const int32_t* block7, int positions_only,
                   int64_t* cand_gpos, uint8_t* cand_type, uint32_t* cand_len, int64_t* cand_reach, uint32_t* cand_range) {
+    constexpr int G = SORT_THREADS / SMALL_BUCKET;
     __shared__ uint32_t sm[SORT_THREADS];
-    __shared__ Range g4[SORT_THREADS / SMALL_BUCKET];
-    __shared__ uint32_t ridx4[SORT_THREADS / SMALL_BUCKET];
+    __shared__ Range g4[G];
+    __shared__ BucketInfo bi4[G];
+    __shared__ Seed key4[G];
     __shared__ int32_t blk[7];
+    __shared__ uint32_t n_redraw[G];
     const int tid = threadIdx.x, grp = tid / SMALL_BUCKET, t = tid % SMALL_BUCKET;
-    const int64_t b = (int64_t)blockIdx.x * (SORT_THREADS / SMALL_BUCKET) + grp;
+    const int64_t b = (int64_t)blockIdx.x * G + grp;
     int64_t lo = 0;
     int cnt = 0;
     if (b < n_buckets) { lo = bucket_off[b]; cnt = (int)(bucket_off[b + 1] - lo); }
     const bool mine = cnt > 0 && cnt <= SMALL_BUCKET;
-    if (mine && t == 0) { ridx4[grp] = binfo[b].ridx; g4[grp] = ranges[ridx4[grp]]; }
+    if (t == 0) {
+        n_redraw[grp] = 0u;
+        if (mine) { bi4[grp] = binfo[b]; g4[grp] = ranges[bi4[grp].ridx]; key4[grp] = keys[bi4[grp].ridx]; }
+    }
     if (tid < 7) blk[tid] = block7[tid];
     __syncthreads();
+    uint32_t* const my = sm + grp * SMALL_BUCKET;
+    const uint32_t bl = mine ? (uint32_t)(b - (int64_t)g4[grp].bucket_lo) : 0u;
     uint32_t v = 0xFFFFFFFFu;
-    if (mine && t < cnt) v = store[bucket_store(g4[grp], (uint32_t)b) + t];
-    v = bitonic_sorted<SMALL_BUCKET>(v, t, sm + grp * SMALL_BUCKET);   // CTA-wide barriers inside: every thread takes part
+    if (mine && t < cnt) v = bi4[grp].vlo + bucket_value(key4[grp], bl, 0u, (uint32_t)t, bi4[grp].width);
+    for (uint32_t round = 1u;; ++round) {
+        v = bitonic_sorted<SMALL_BUCKET>(v, t, my);   // CTA-wide barriers inside: every thread takes part
+        my[t] = v;
+        __syncthreads();
+        const bool dup = mine && t > 0 && t < cnt && my[t - 1] == v;
+        if (dup) v = bi4[grp].vlo + bucket_value(key4[grp], bl, round, atomicAdd(&n_redraw[grp], 1u), bi4[grp].width);
+        const int any = __syncthreads_or(dup);
+        if (!any) break;
+        if (t == 0) n_redraw[grp] = 0u;               // (ordered before the next round's atomics by the barriers in the sort)
+    }
     if (mine && t < cnt)
-        emit_candidate(g4[grp], contigs[g4[grp].contig], ridx4[grp], lo + t, v, seed, min_dist, blk, positions_only, cand_gpos, cand_type,
-                       cand_len, cand_reach, cand_range);
+        emit_candidate(g4[grp], contigs[g4[grp].contig], bi4[grp].ridx, lo + t, v, seed, min_dist, blk, positions_only, cand_gpos,
+                       cand_type, cand_len, cand_reach, cand_range);
 }
 
-// K1d + K2: sort one bucket in shared memory, then write position, type, length and reach.
+// K1c + K2: draw one bucket's values in shared memory, in order, then write position, type, length and reach.
 __global__ void __launch_bounds__(SORT_THREADS, 4)
-k_sort_emit(const Range* ranges, const BucketInfo* binfo, const Contig* contigs, const int64_t* bucket_off,
-            const uint32_t* store, Seed seed, int32_t min_dist, const int32_t* block7, int positions_only,
+k_sort_emit(const Range* ranges, const BucketInfo* binfo, const Seed* keys, const Contig* contigs, const int64_t* bucket_off,
+            Seed seed, int32_t min_dist, const int32_t* block7, int positions_only,
             int64_t* cand_gpos, uint8_t* cand_type, uint32_t* cand_len, int64_t* cand_reach, uint32_t* cand_range, Totals* tot,
             int skip_small) {
     __shared__ uint32_t sm[SORT_CAP];
     __shared__ int32_t blk[7];
     __shared__ uint32_t warp_tot[SORT_THREADS / 32];
+    __shared__ uint32_t n_redraw[2];
     const int tid = threadIdx.x;
     const int64_t b = blockIdx.x;
     const int64_t lo = bucket_off[b], hi = bucket_off[b + 1];
     const int cnt = (int)(hi - lo);
     if (cnt <= 0 || (skip_small && cnt <= SMALL_BUCKET)) return;
     if (cnt > SORT_CAP) { if (tid == 0) raise_error_s(tot, MS_ERR_INTERNAL, 100 + b); return; }
-    const BucketInfo bi = binfo[b];                 // one 24-byte broadcast load; no per-CTA lookups, no barrier
+    const BucketInfo bi = binfo[b];                 // one 16-byte broadcast load; no per-CTA lookups
     const Range& g = ranges[bi.ridx];               // fields are read where they are needed (L1 broadcast)
-    const uint32_t s_ridx = bi.ridx, s_nw = bi.nw, s_vlo = bi.vlo;
+    const Seed key = keys[bi.ridx];
+    const uint32_t s_ridx = bi.ridx, s_nw = bi.nw, s_vlo = bi.vlo, width = bi.width;
+    const uint32_t bl = (uint32_t)(b - (int64_t)g.bucket_lo);
     if (tid < 7) blk[tid] = block7[tid];
+    if (tid < 2) n_redraw[tid] = 0u;
     int n2 = 32;
     while (n2 < cnt) n2 <<= 1;
-    const uint32_t* src = store + bi.store_base;
     if (cnt >= 64 && s_nw <= (uint32_t)SORT_CAP) {
-        // Dense bucket: the keys are distinct (a permutation's values) and span at most 32 Ki positions, so the
-        // sorted order is read off a bitmap — set one bit per key, prefix-sum the popcounts, write each key to
-        // its rank.  ~100 instructions per thread instead of the ~360 of the 512-key bitonic network.
+        // Dense bucket (span of at most 32 Ki values): one bit per value in a bitmap; a draw that finds its bit set
+        // is a coincidence and is redrawn in the next round.  The sorted order is then read off the bitmap —
+        // prefix-sum the popcounts, write each value to its rank (~100 instructions per thread instead of the ~360
+        // of the 512-key bitonic network).
         const uint32_t vlo = s_vlo, nw = s_nw;
         for (uint32_t i = tid; i < nw; i += SORT_THREADS) sm[i] = 0u;
         __syncthreads();
-        for (int i = tid; i < cnt; i += SORT_THREADS) {
-            const uint32_t d = src[i] - vlo;
-            atomicOr(&sm[d >> 5], 1u << (d & 31u));
+        uint32_t n_draw = (uint32_t)cnt;
+        for (uint32_t round = 0u; n_draw > 0u; ++round) {
+            for (uint32_t jp = tid; 2u * jp < n_draw; jp += SORT_THREADS) {      // one Philox block per two draws
+                const U4 r = bucket_block(key, bl, round, jp);
+#pragma unroll
+                for (uint32_t h = 0; h < 2u; ++h) {
+                    if (2u * jp + h >= n_draw) break;
+                    const uint32_t d = bucket_value_of(r, h, width);
+                    const uint32_t bit = 1u << (d & 31u);
+                    if (atomicOr(&sm[d >> 5], bit) & bit) atomicAdd(&n_redraw[round & 1u], 1u);
+                }
+            }
+            __syncthreads();
+            n_draw = n_redraw[round & 1u];
+            if (tid == 0) n_redraw[(round + 1u) & 1u] = 0u;
+            __syncthreads();
         }
-        __syncthreads();
         const uint32_t i0 = 2u * (uint32_t)tid;
         uint32_t w0 = i0 < nw ? sm[i0] : 0u, w1 = i0 + 1u < nw ? sm[i0 + 1u] : 0u;
         const uint32_t mine = (uint32_t)(__popc(w0) + __popc(w1));
@@ -238,31 +293,50 @@ k_sort_emit(const Range* ranges, const BucketInfo* binfo, const Contig* contigs,
         // one key per thread: strides below 32 are exchanged with shuffles, only the
         // 10 cross-warp phases of a 512-key bitonic network go through shared memory;
         // the network is unrolled at compile time (loop control was 22 % of the kernel, profiles/r1e)
-        uint32_t v = tid < cnt ? src[tid] : 0xFFFFFFFFu;
-        switch (n2) {
-            case 32:  v = bitonic_sorted<32>(v, tid, sm); break;
-            case 64:  v = bitonic_sorted<64>(v, tid, sm); break;
-            case 128: v = bitonic_sorted<128>(v, tid, sm); break;
-            case 256: v = bitonic_sorted<256>(v, tid, sm); break;
-            default:  v = bitonic_sorted<512>(v, tid, sm); break;
-        }
-        sm[tid] = v;
-        __syncthreads();
-    } else {
-        for (int i = tid; i < n2; i += SORT_THREADS) sm[i] = i < cnt ? src[i] : 0xFFFFFFFFu;
-        __syncthreads();
-        for (int k = 2; k <= n2; k <<= 1) {
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                for (int i = tid; i < n2; i += SORT_THREADS) {
-                    const int x = i ^ j;
-                    if (x > i) {
-                        const uint32_t a = sm[i], c = sm[x];
-                        const bool asc = (i & k) == 0;
-                        if ((a > c) == asc) { sm[i] = c; sm[x] = a; }
-                    }
-                }
-                __syncthreads();
+        uint32_t v = tid < cnt ? s_vlo + bucket_value(key, bl, 0u, (uint32_t)tid, width) : 0xFFFFFFFFu;
+        for (uint32_t round = 1u;; ++round) {
+            switch (n2) {
+                case 32:  v = bitonic_sorted<32>(v, tid, sm); break;
+                case 64:  v = bitonic_sorted<64>(v, tid, sm); break;
+                case 128: v = bitonic_sorted<128>(v, tid, sm); break;
+                case 256: v = bitonic_sorted<256>(v, tid, sm); break;
+                default:  v = bitonic_sorted<512>(v, tid, sm); break;
             }
+            sm[tid] = v;
+            __syncthreads();
+            const bool dup = tid > 0 && tid < cnt && sm[tid - 1] == v;
+            if (dup) v = s_vlo + bucket_value(key, bl, round, atomicAdd(&n_redraw[round & 1u], 1u), width);
+            const int any = __syncthreads_or(dup);
+            if (!any) break;
+            if (tid == 0) n_redraw[(round + 1u) & 1u] = 0u;
+        }
+    } else {
+        for (int i = tid; i < n2; i += SORT_THREADS) sm[i] = i < cnt ? s_vlo + bucket_value(key, bl, 0u, (uint32_t)i, width) : 0xFFFFFFFFu;
+        __syncthreads();
+        for (uint32_t round = 1u;; ++round) {
+            for (int k = 2; k <= n2; k <<= 1) {
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    for (int i = tid; i < n2; i += SORT_THREADS) {
+                        const int x = i ^ j;
+                        if (x > i) {
+                            const uint32_t a = sm[i], c = sm[x];
+                            const bool asc = (i & k) == 0;
+                            if ((a > c) == asc) { sm[i] = c; sm[x] = a; }
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+            // (two keys per thread: decide on both before either is replaced)
+            const int i0 = tid, i1 = tid + SORT_THREADS;
+            const bool d0 = i0 > 0 && i0 < cnt && sm[i0 - 1] == sm[i0];
+            const bool d1 = i1 < cnt && sm[i1 - 1] == sm[i1];
+            const int any = __syncthreads_or(d0 || d1);
+            if (!any) break;
+            if (d0) sm[i0] = s_vlo + bucket_value(key, bl, round, atomicAdd(&n_redraw[round & 1u], 1u), width);
+            if (d1) sm[i1] = s_vlo + bucket_value(key, bl, round, atomicAdd(&n_redraw[round & 1u], 1u), width);
+            if (tid == 0) n_redraw[(round + 1u) & 1u] = 0u;
+            __syncthreads();
         }
     }
     const Contig& ct = contigs[g.contig];
@@ -450,12 +524,12 @@ static int draw_and_sort(ms_ctx* c, Seed seed, uint32_t purpose, int32_t min_dis
     // side arrays kept right behind the Range table
     int64_t* d_cand_lo = reinterpret_cast<int64_t*>(c->ranges.as<uint8_t>() + sizeof(Range) * (size_t)R);
     int64_t* d_bucket_lo = d_cand_lo + (R + 1);
-    Prp* d_prps = reinterpret_cast<Prp*>(d_bucket_lo + (R + 1));
-    int32_t* d_block = reinterpret_cast<int32_t*>(d_prps + R);
+    Seed* d_keys = reinterpret_cast<Seed*>(d_bucket_lo + (R + 1));
+    int32_t* d_block = reinterpret_cast<int32_t*>(d_keys + R);
     Totals* d_tot = c->totals.as<Totals>();
+    const BucketInfo* d_binfo = c->bucket_range.as<BucketInfo>();
 
-    MS_CUDA(c, c->cand_sorted.ensure((size_t)c->store_entries * 4 + 16));
-    MS_CUDA(c, c->bucket_cnt.ensure((size_t)(c->n_buckets + 1) * 4));
+    MS_CUDA(c, c->bucket_cnt.ensure((size_t)(c->n_buckets + 1) * 8));   // node counts, then leaf counts
     MS_CUDA(c, c->bucket_off.ensure((size_t)(c->n_buckets + 1) * 8));
     MS_CUDA(c, c->cand_reach.ensure((size_t)K * 8 + 16));   // cand_gpos lives in svec
     MS_CUDA(c, c->svec.ensure((size_t)(K + 1) * 8));
@@ -466,13 +540,17 @@ static int draw_and_sort(ms_ctx* c, Seed seed, uint32_t purpose, int32_t min_dis
     int64_t* d_boff = c->bucket_off.as<int64_t>();
 
     stage_begin(c, ST_SAMPLE_POS);
-    k_make_prps<<<(unsigned)ceil_div(R, 128), 128, 0, st>>>(d_ranges, R, d_ctg, seed, purpose, d_prps);
+    k_range_keys<<<(unsigned)ceil_div(R, 128), 128, 0, st>>>(d_ranges, R, d_ctg, seed, purpose, d_keys, d_cnt);
     MS_LAUNCH_CHECK(c);
-    MS_CUDA(c, cudaMemsetAsync(d_cnt, 0, (size_t)(c->n_buckets + 1) * 4, st));
-    k_draw<<<(unsigned)ceil_div(K, DRAW_TILE), DRAW_THREADS, 0, st>>>(d_ranges, d_cand_lo, R, d_prps, K, c->cand_sorted.as<uint32_t>(), d_cnt, d_tot);
+    if (c->n_big > 0) {
+        k_split_top<<<1, 1024, 0, st>>>(d_ranges, d_binfo, d_keys, c->big_ranges.as<uint32_t>(), c->n_big, c->split_levels, d_cnt);
+        MS_LAUNCH_CHECK(c);
+    }
+    uint32_t* d_leaf = d_cnt + (c->n_buckets + 1);
+    k_split_leaf<<<(unsigned)ceil_div(c->n_buckets, 256), 256, 0, st>>>(d_ranges, d_binfo, d_keys, c->n_buckets, d_cnt, d_leaf);
     MS_LAUNCH_CHECK(c);
     {
-        const uint32_t* cnt = d_cnt;
+        const uint32_t* cnt = d_leaf;
         auto in = [=] __device__(int64_t i) -> int64_t { return (int64_t)cnt[i]; };
         auto out = [=] __device__(int64_t i, int64_t ex, int64_t) { d_boff[i] = ex; };
         int64_t* d_total = nullptr;
@@ -486,16 +564,16 @@ static int draw_and_sort(ms_ctx* c, Seed seed, uint32_t purpose, int32_t min_dis
     const int any_small = c->any_small, any_large = c->any_large;
     if (any_small) {
         k_sort_emit_small<<<(unsigned)ceil_div(c->n_buckets, SORT_THREADS / SMALL_BUCKET), SORT_THREADS, 0, st>>>(
-            d_ranges, c->bucket_range.as<BucketInfo>(), d_ctg, d_boff, c->n_buckets, c->cand_sorted.as<uint32_t>(), seed, min_dist, d_block, positions_only,
+            d_ranges, d_binfo, d_keys, d_ctg, d_boff, c->n_buckets, seed, min_dist, d_block, positions_only,
             c->svec.as<int64_t>(), c->cand_type.as<uint8_t>(), c->cand_len.as<uint32_t>(), c->cand_reach.as<int64_t>(),
             c->lvec.as<uint32_t>());
         MS_LAUNCH_CHECK(c);
     }
     if (any_large) {
-        k_sort_emit<<<(unsigned)c->n_buckets, SORT_THREADS, 0, st>>>(d_ranges, c->bucket_range.as<BucketInfo>(), d_ctg, d_boff,
-                                                                     c->cand_sorted.as<uint32_t>(), seed, min_dist, d_block, positions_only,
-                                                                     c->svec.as<int64_t>(), c->cand_type.as<uint8_t>(), c->cand_len.as<uint32_t>(),
-                                                                     c->cand_reach.as<int64_t>(), c->lvec.as<uint32_t>(), d_tot, any_small);
+        k_sort_emit<<<(unsigned)c->n_buckets, SORT_THREADS, 0, st>>>(d_ranges, d_binfo, d_keys, d_ctg, d_boff, seed, min_dist, d_block,
+                                                                     positions_only, c->svec.as<int64_t>(), c->cand_type.as<uint8_t>(),
+                                                                     c->cand_len.as<uint32_t>(), c->cand_reach.as<int64_t>(),
+                                                                     c->lvec.as<uint32_t>(), d_tot, any_small);
         MS_LAUNCH_CHECK(c);
     }
     stage_end(c, ST_SAMPLE_TYPE);
@@ -640,7 +718,9 @@ int count_types(ms_ctx* c) {
 static int upload_ranges(ms_ctx* c, int32_t min_dist, const std::vector<Contig>& ctg) {
     const int32_t R = (int32_t)c->h_ranges.size();
     std::vector<int64_t> cand_lo(R + 1), bucket_lo(R + 1);
-    int64_t K = 0, NB = 0, STORE = 0;
+    int64_t K = 0, NB = 0;
+    uint32_t max_top = 0;
+    std::vector<uint32_t> big;                             // ranges with more than SPLIT_LEAF buckets
     for (int32_t r = 0; r < R; ++r) {
         Range& g = c->h_ranges[r];
         const int64_t n = (int64_t)g.stop - ((int64_t)g.k - 1) * min_dist - (int64_t)g.start;   // util.py:104
@@ -652,8 +732,9 @@ static int upload_ranges(ms_ctx* c, int32_t min_dist, const std::vector<Contig>&
         g.nb = (uint32_t)std::max<int64_t>(1, ceil_div(g.k, BUCKET_TARGET));
         g.bscale = g.nb == 1u ? 0u : (uint32_t)((((uint64_t)g.nb) << 32) / (uint64_t)n);
         g.bucket_lo = (uint32_t)NB;
-        g.store_lo = STORE;
-        STORE += (int64_t)g.nb * (g.nb == 1u ? g.k : (uint32_t)BUCKET_CAP);
+        g.top_levels = 0u;                                 // halvings until every node spans at most SPLIT_LEAF buckets
+        while ((((uint64_t)g.nb + (1ull << g.top_levels) - 1) >> g.top_levels) > SPLIT_LEAF) ++g.top_levels;
+        if (g.top_levels) { big.push_back((uint32_t)r); max_top = std::max(max_top, g.top_levels); }
         g.gstart = ctg[g.contig].goff + g.start;
         cand_lo[r] = K; bucket_lo[r] = NB;
         K += g.k; NB += g.nb;
@@ -669,8 +750,11 @@ static int upload_ranges(ms_ctx* c, int32_t min_dist, const std::vector<Contig>&
         if (g.nb == 1u && g.k <= (uint32_t)SMALL_BUCKET) c->any_small = 1; else c->any_large = 1;
     }
     if (K >= (int64_t)0x7FFFFFF0) MS_FAIL(c, MS_ERR_LIMIT, "more than 2^31 candidates in one call");
-    c->n_ranges = R; c->n_candidates = K; c->n_buckets = NB; c->min_dist = min_dist; c->store_entries = STORE;
-    const size_t bytes = sizeof(Range) * (size_t)R + 2 * sizeof(int64_t) * (size_t)(R + 1) + sizeof(Prp) * (size_t)R + 64;
+    c->n_ranges = R; c->n_candidates = K; c->n_buckets = NB; c->min_dist = min_dist;
+    c->split_levels = (int)max_top; c->n_big = (int32_t)big.size();
+    MS_CUDA(c, c->big_ranges.ensure(big.size() * 4 + 16));
+    if (!big.empty()) MS_CUDA(c, cudaMemcpyAsync(c->big_ranges.p, big.data(), big.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    const size_t bytes = sizeof(Range) * (size_t)R + 2 * sizeof(int64_t) * (size_t)(R + 1) + sizeof(Seed) * (size_t)R + 64;
     MS_CUDA(c, c->ranges.ensure(bytes));
     uint8_t* base = c->ranges.as<uint8_t>();
     cudaStream_t st = c->stream;
@@ -678,20 +762,18 @@ static int upload_ranges(ms_ctx* c, int32_t min_dist, const std::vector<Contig>&
     int64_t* d_cand_lo = reinterpret_cast<int64_t*>(base + sizeof(Range) * (size_t)R);
     MS_CUDA(c, cudaMemcpyAsync(d_cand_lo, cand_lo.data(), sizeof(int64_t) * (size_t)(R + 1), cudaMemcpyHostToDevice, st));
     MS_CUDA(c, cudaMemcpyAsync(d_cand_lo + (R + 1), bucket_lo.data(), sizeof(int64_t) * (size_t)(R + 1), cudaMemcpyHostToDevice, st));
-    int32_t* d_block = reinterpret_cast<int32_t*>(reinterpret_cast<Prp*>(d_cand_lo + 2 * (R + 1)) + R);
+    int32_t* d_block = reinterpret_cast<int32_t*>(reinterpret_cast<Seed*>(d_cand_lo + 2 * (R + 1)) + R);
     MS_CUDA(c, cudaMemcpyAsync(d_block, c->block, sizeof(int32_t) * 7, cudaMemcpyHostToDevice, st));
-    std::vector<BucketInfo> br((size_t)NB + 1, BucketInfo{});   // per sort bucket: range, storage, value span
+    std::vector<BucketInfo> br((size_t)NB + 1, BucketInfo{});   // per sort bucket: range and value span
     for (int32_t r = 0; r < R; ++r) {
         const Range& g = c->h_ranges[r];
         const uint64_t sc = g.bscale;
-        const uint32_t cap = g.nb == 1u ? g.k : (uint32_t)BUCKET_CAP;
         for (uint64_t bl = 0; bl < g.nb; ++bl) {
             // values of bucket bl: mulhi32(v, bscale) == bl  <=>  ceil(bl * 2^32 / bscale) <= v < ceil((bl + 1) * 2^32 / bscale)
             const uint64_t vlo = (g.nb == 1u || bl == 0) ? 0ull : ((bl << 32) + sc - 1) / sc;
             const uint64_t vhi = (g.nb == 1u || bl + 1 == g.nb) ? (uint64_t)g.n : (((bl + 1) << 32) + sc - 1) / sc;
             BucketInfo& bi = br[(size_t)(bucket_lo[r] + (int64_t)bl)];
-            bi.store_base = g.store_lo + (int64_t)bl * cap;
-            bi.ridx = (uint32_t)r; bi.vlo = (uint32_t)vlo; bi.nw = (uint32_t)((vhi - vlo + 31) >> 5); bi.pad = 0u;
+            bi.ridx = (uint32_t)r; bi.vlo = (uint32_t)vlo; bi.width = (uint32_t)(vhi - vlo); bi.nw = (uint32_t)((vhi - vlo + 31) >> 5);
         }
     }
     MS_CUDA(c, c->bucket_range.ensure(br.size() * sizeof(BucketInfo)));

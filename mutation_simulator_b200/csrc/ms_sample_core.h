@@ -11,7 +11,6 @@ namespace ms {
 struct Range {
     int64_t gstart;     // genome index of the range's first base
     int64_t cand_lo;    // first candidate slot of this range
-    int64_t store_lo;   // first slot of this range's sort buckets in the bucket store
     int64_t limit;      // contig-relative end (exclusive) an SV may extend to: contig length,
                         // or the start of the next blocked (None) range — SURVEY.md Q3 stance
     uint32_t start;     // contig-relative, inclusive
@@ -22,6 +21,8 @@ struct Range {
     uint32_t bucket_lo; // first sort bucket
     uint32_t nb;        // number of sort buckets
     uint32_t bscale;    // floor(2^32 * nb / n): bucket of value v = mulhi32(v, bscale) (monotone, < nb)
+    uint32_t top_levels; // levels of the bucket tree whose nodes span more than SPLIT_LEAF buckets (k_split_top); 0 for most ranges
+    uint32_t pad;
     double cdf[7];      // cumulative mut_chances in canonical type order (numpy.random.choice, mutator.py:170-174)
     int32_t minlen[7];
     int32_t maxlen[7];
@@ -33,6 +34,92 @@ struct RangeParams {
     int32_t maxlen[7];
     int64_t limit;
 };
+
+// ---- k distinct positions of a range, generated in order (util.py:94-109: random.sample(range(n), k), sorted) --------
+// The value span [0, n) of a range is cut into nb equal sort buckets.  A uniform k-subset of [0, n) puts a
+// multivariate-hypergeometric number of values into each bucket; those counts come from a binary split tree over
+// the buckets (the samples of a node go left with a hypergeometric law), each split a pure function of
+// (range key, node) — so every bucket knows its count without any value having been drawn or scattered.  Inside a
+// bucket the values are then a uniform c-subset of its span (k_sort_emit).
+//
+// hypergeom(): number of marked items among `n` drawn without replacement from `N` of which `K` are marked.
+//   variance >= 900: rounded normal with the exact mean and variance (splits are near p = 1/2, so the skewness
+//     (1-2p)/sigma is ~0 and the pmf is matched to O(1/sigma^2) < 1e-3 relative);
+//   otherwise: inversion by walking outwards from the mode with the exact pmf ratios, the mode's pmf from lgamma
+//     (relative error of the normalisation <= ~2e-5 for N ~ 2^31, ~1e-9 for the node sizes that take this path when
+//     the range is dense) — a shortfall of the walked mass falls back to the mode.
+MS_HD double log_choose(double n, double k) { return lgamma(n + 1.0) - lgamma(k + 1.0) - lgamma(n - k + 1.0); }
+
+MS_HD uint32_t hypergeom(const U4& r, uint32_t N, uint32_t K, uint32_t n) {
+    if (n == 0u || K == 0u) return 0u;
+    if (K >= N) return n;
+    if (n >= N) return K;
+    const int64_t lo = (int64_t)n + (int64_t)K - (int64_t)N > 0 ? (int64_t)n + (int64_t)K - (int64_t)N : 0;
+    const int64_t hi = n < K ? n : K;
+    if (lo == hi) return (uint32_t)lo;
+    const double dN = (double)N, dK = (double)K, dn = (double)n;
+    const double p = dK / dN;
+    const double mean = dn * p;
+    const double var = mean * (1.0 - p) * ((dN - dn) / (dN - 1.0));
+    if (var >= 900.0) {
+        const double u1 = ((double)(u64_of(r.x, r.y) >> 11) + 1.0) * (1.0 / 9007199254740992.0);   // (0, 1]
+        const double u2 = unit_double(r.z, r.w);
+        const double z = sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2);
+        double x = floor(mean + sqrt(var) * z + 0.5);
+        if (x < (double)lo) x = (double)lo;
+        if (x > (double)hi) x = (double)hi;
+        return (uint32_t)x;
+    }
+    int64_t m = (int64_t)(((dn + 1.0) * (dK + 1.0)) / (dN + 2.0));
+    if (m < lo) m = lo;
+    if (m > hi) m = hi;
+    const double pm = exp(log_choose(dK, (double)m) + log_choose(dN - dK, dn - (double)m) - log_choose(dN, dn));
+    // walk outwards, up and down alternately: any fixed order of the support is an inversion as long as it is the same
+    // for every u; a side stops once its pmf is below 1e-19
+    const double u = unit_double(r.x, r.y);
+    double acc = pm;
+    if (u < acc) return (uint32_t)m;
+    int64_t a = m, b = m;       // [a, b] walked so far
+    double pa = pm, pb = pm;    // pmf at a and at b
+    bool up = b < hi, down = a > lo;
+    while (up || down) {
+        if (up) {               // p(x+1)/p(x) = (K-x)(n-x) / ((x+1)(N-K-n+x+1))
+            const double x = (double)b;
+            pb *= ((dK - x) * (dn - x)) / ((x + 1.0) * (dN - dK - dn + x + 1.0));
+            ++b;
+            acc += pb;
+            if (u < acc) return (uint32_t)b;
+            up = b < hi && pb > 1e-19;
+        }
+        if (down) {             // p(x-1)/p(x) = x (N-K-n+x) / ((K-x+1)(n-x+1))
+            const double x = (double)a;
+            pa *= (x * (dN - dK - dn + x)) / ((dK - x + 1.0) * (dn - x + 1.0));
+            --a;
+            acc += pa;
+            if (u < acc) return (uint32_t)a;
+            down = a > lo && pa > 1e-19;
+        }
+    }
+    return (uint32_t)m;
+}
+
+// samples of the bucket-tree node [lo, hi) that go to its left child [lo, mid): N values in the node, K of them left
+MS_HD uint32_t split_left(Seed range_key, uint32_t lo, uint32_t hi, uint32_t N, uint32_t K, uint32_t n) {
+    const U4 r = philox4x32_10(U4{lo, hi, 0x53504C54u, 0u}, range_key.k0, range_key.k1);
+    return hypergeom(r, N, K, n);
+}
+
+// j-th value drawn in redraw round `round` for sort bucket `bl` of a range: uniform in [0, width).  One Philox block
+// serves draws 2i and 2i+1.
+MS_HD U4 bucket_block(Seed range_key, uint32_t bl, uint32_t round, uint32_t pair) {
+    return philox4x32_10(U4{bl, round, pair, 0x56414C55u}, range_key.k0, range_key.k1);
+}
+MS_HD uint32_t bucket_value_of(const U4& r, uint32_t j, uint32_t width) {
+    return (uint32_t)bounded((j & 1u) ? u64_of(r.z, r.w) : u64_of(r.x, r.y), (uint64_t)width);
+}
+MS_HD uint32_t bucket_value(Seed range_key, uint32_t bl, uint32_t round, uint32_t j, uint32_t width) {
+    return bucket_value_of(bucket_block(range_key, bl, round, j >> 1), j, width);
+}
 
 // Type and length of the candidate at contig-relative `pos`.
 // type = T_DEAD for an inversion that does not fit (mutator.py:243-244).

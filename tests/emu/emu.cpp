@@ -7,6 +7,7 @@
 // and is never imported by the product package (which has no CPU fallback).
 #include <cstdint>
 #include <cstring>
+#include <utility>
 #include <vector>
 #include "../../mutation_simulator_b200/csrc/ms_rng.h"
 #include "../../mutation_simulator_b200/csrc/ms_records.h"
@@ -27,6 +28,34 @@ void emu_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
 void emu_prp(uint64_t seed, uint32_t contig, uint32_t purpose, uint64_t idx, uint32_t n, uint32_t count, uint32_t* out) {
     Prp p = make_prp(make_seed(seed), contig, purpose, idx, n);
     for (uint32_t j = 0; j < count; ++j) out[j] = prp_apply(p, j);
+}
+
+// count draws of hypergeom(N, K, n), draw i from Philox counter (i, 0, 0, 0) under `seed`
+void emu_hypergeom(uint64_t seed, uint32_t N, uint32_t K, uint32_t n, uint32_t count, uint32_t* out) {
+    const Seed s = make_seed(seed);
+    for (uint32_t i = 0; i < count; ++i) out[i] = hypergeom(philox4x32_10(U4{i, 0, 0, 0}, s.k0, s.k1), N, K, n);
+}
+
+// Bucket counts of one range through the split tree, the way k_range_keys + k_split_level compute them on the device:
+// nb buckets with value spans starting at vlo[0..nb) (vlo[nb] = n), k samples in total.
+void emu_split_counts(uint64_t seed, uint32_t gid, uint32_t start, uint32_t nb, const uint32_t* vlo, uint32_t k, uint32_t* cnt) {
+    const U4 kk = draw(make_seed(seed), gid, P_RANGE_KEY, start);
+    const Seed key{kk.x, kk.y};
+    std::vector<std::pair<uint32_t, uint32_t>> nodes{{0u, nb}};
+    cnt[0] = k;
+    while (!nodes.empty()) {
+        std::vector<std::pair<uint32_t, uint32_t>> next;
+        for (auto [lo, hi] : nodes) {
+            if (hi - lo < 2u) continue;
+            const uint32_t mid = (lo + hi) >> 1;
+            const uint32_t left = split_left(key, lo, hi, vlo[hi] - vlo[lo], vlo[mid] - vlo[lo], cnt[lo]);
+            cnt[mid] = cnt[lo] - left;
+            cnt[lo] = left;
+            next.push_back({lo, mid});
+            next.push_back({mid, hi});
+        }
+        nodes.swap(next);
+    }
 }
 
 // Layout + splice + VCF for a whole (small) genome.

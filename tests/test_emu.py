@@ -76,6 +76,76 @@ def test_prp_subset_is_uniform_over_positions(emu):
     assert p > 1e-3
 
 
+def hypergeom_draws(emu, seed, N, K, n, count):
+    out = (C.c_uint32 * count)()
+    emu.emu_hypergeom(C.c_uint64(seed), C.c_uint32(N), C.c_uint32(K), C.c_uint32(n), C.c_uint32(count), out)
+    return np.array(out, dtype=np.int64)
+
+
+@pytest.mark.parametrize("N,K,n", [
+    (20, 7, 5), (100, 50, 10), (1000, 3, 900), (56_000, 28_000, 768), (56_001, 27_999, 769), (2**31, 2**30, 400),
+    (300_000, 100_000, 3_000),                                   # variance 444: exact walk, asymmetric split
+    (248_956_422, 124_478_211, 3_360_000), (1_000_000, 500_001, 40_000), (10_000_000, 3_333_333, 123_457),  # normal regime
+])
+def test_hypergeometric_split_sampler_matches_the_exact_law(emu, N, K, n):
+    """The bucket counts of the in-order position sampler (util.py:104: random.sample(range(n), k)) rest on this
+    sampler: chi-square against scipy's exact pmf in the inversion regime and in the rounded-normal regime."""
+    from scipy import stats
+    draws = 40_000
+    x = hypergeom_draws(emu, 99, N, K, n, draws)
+    lo, hi = max(0, n + K - N), min(n, K)
+    assert x.min() >= lo and x.max() <= hi
+    rv = stats.hypergeom(N, K, n)
+    mean, sd = rv.mean(), rv.std()
+    assert abs(x.mean() - mean) < 5 * sd / np.sqrt(draws) + 1e-9
+    # cells: about 20 equal-probability groups of adjacent values
+    support = np.arange(max(lo, int(mean - 8 * sd) - 1), min(hi, int(mean + 8 * sd) + 1) + 1)
+    pmf = rv.pmf(support)
+    edges, acc = [support[0]], 0.0
+    for v, p in zip(support, pmf):
+        acc += p
+        if acc >= 0.05:
+            edges.append(v + 1); acc = 0.0
+    edges[-1] = support[-1] + 1 if edges[-1] <= support[-1] else edges[-1]
+    if len(edges) < 3:
+        return
+    obs = np.histogram(x, bins=edges)[0].astype(float)
+    exp = np.array([rv.cdf(edges[i + 1] - 1) - rv.cdf(edges[i] - 1) for i in range(len(edges) - 1)])
+    exp[0] += rv.cdf(edges[0] - 1); exp[-1] += rv.sf(edges[-1] - 1)
+    obs[0] += (x < edges[0]).sum(); obs[-1] += (x >= edges[-1]).sum()
+    chi2, p = stats.chisquare(obs, exp * draws)
+    assert p > 1e-4, (N, K, n, p, obs, exp * draws)
+
+
+def test_split_tree_bucket_counts(emu):
+    """Counts add up to k, respect every bucket's capacity, and each bucket's count has the hypergeometric marginal."""
+    from scipy import stats
+    nb, n, k = 13, 50_000, 5_000
+    vlo = np.array([(i * n + nb - 1) // nb for i in range(nb)] + [n], dtype=np.uint32)
+    trials = 3000
+    cnts = np.zeros((trials, nb), dtype=np.int64)
+    for s in range(trials):
+        out = (C.c_uint32 * nb)()
+        emu.emu_split_counts(C.c_uint64(s), C.c_uint32(3), C.c_uint32(17), C.c_uint32(nb), vlo.ctypes.data_as(C.c_void_p), C.c_uint32(k), out)
+        cnts[s] = out
+    assert (cnts.sum(axis=1) == k).all()
+    width = np.diff(vlo.astype(np.int64))
+    assert (cnts <= width).all()
+    for b in (0, 5, 12):
+        rv = stats.hypergeom(n, int(width[b]), k)
+        z = (cnts[:, b].mean() - rv.mean()) / (rv.std() / np.sqrt(trials))
+        assert abs(z) < 4.5, (b, z)
+        assert 0.9 < cnts[:, b].std() / rv.std() < 1.1
+    # neighbouring buckets are negatively correlated like a multivariate hypergeometric: cov = -k w_i w_j (n-k) / (n^2 (n-1))
+    c01 = np.cov(cnts[:, 0], cnts[:, 1])[0, 1]
+    exp = -k * width[0] * width[1] * (n - k) / (n * n * (n - 1))
+    assert abs(c01 - exp) < 6 * rv.var() / np.sqrt(trials)
+    # degenerate: k == n fills every bucket
+    out = (C.c_uint32 * nb)()
+    emu.emu_split_counts(C.c_uint64(1), C.c_uint32(0), C.c_uint32(0), C.c_uint32(nb), vlo.ctypes.data_as(C.c_void_p), C.c_uint32(n), out)
+    assert list(out) == list(width)
+
+
 def run_emu_apply(emu, contigs, tables, tile_bytes=4096, vcf_text=None):
     seqs = [c[2] for c in contigs]
     genome, goff = R.pack_genome(seqs)
