@@ -404,3 +404,45 @@ def test_streamed_run_with_nothing_to_mutate():
         fb, vb = eng.mutate_streamed(5, raw, fa, vcf)
         assert vb == 0 and fa[:fb].tobytes() == want
         eng.close()
+
+
+def test_position_sampler_is_a_uniform_subset_in_every_regime():
+    """ms_sample_positions = util.sample_with_minimum_distance (util.py:94-109) for many ranges at once.  The values are
+    generated in order (hypergeometric bucket counts, then a uniform subset inside each sort bucket): distinct, sorted,
+    inside the range, spaced by min_dist; saturated ranges (k == population) return every position; over many small
+    ranges every 2-subset of a 6-value span is equally likely; a single-bucket sparse range, a dense multi-bucket range
+    and one whose buckets are sparse (bitonic path) are uniform by KS."""
+    from mutation_simulator_b200.engine import Engine
+    eng = Engine(0)
+    # saturated: k == n for bitonic-sized, small-kernel-sized and bitmap-sized populations, and k = n - 1
+    n = np.array([1, 2, 5, 63, 64, 100, 129, 500, 2000, 2000], dtype=np.uint32)
+    k = n.copy(); k[-1] = 1999
+    out = eng.sample_positions(11, np.arange(len(n)), np.zeros(len(n)), n, k, 0)     # values in [start, stop) = [0, n)
+    o = 0
+    for ni, ki in zip(n, k):
+        v = out[o:o + ki]; o += int(ki)
+        assert (np.diff(v.astype(np.int64)) > 0).all() and v.min() >= 0 and v.max() < ni
+        if ki == ni:
+            assert np.array_equal(v, np.arange(ni))
+    # min distance: sample_with_minimum_distance(start, stop, k, d): gaps > d, all inside [start, stop)
+    v = eng.sample_positions(5, [0], [100], [100 + 50_000], [5_000], 3).astype(np.int64)
+    assert v.min() >= 100 and v.max() < 100 + 50_000 and (np.diff(v) > 3).all()
+    # all 15 two-subsets of a 6-value span, over 6000 independent ranges (keyed by contig id)
+    R = 6000
+    v = eng.sample_positions(7, np.arange(R), np.zeros(R), np.full(R, 6), np.full(R, 2), 0).reshape(R, 2)
+    cells = np.bincount(v[:, 0] * 6 + v[:, 1], minlength=36)
+    cells = cells[cells > 0]
+    assert len(cells) == 15
+    assert stats.chisquare(cells).pvalue > 1e-3
+    # KS against the uniform law: sparse single bucket, dense multi-bucket, multi-bucket with sparse buckets
+    for gid, (pop, kk) in enumerate([(2_000_000_000, 300), (5_000_000, 400_000), (2_000_000_000, 100_000)]):
+        v = eng.sample_positions(3, [gid], [0], [pop], [kk], 0).astype(np.float64)
+        assert len(np.unique(v)) == kk
+        assert stats.kstest(v / pop, "uniform").pvalue > 1e-3, (pop, kk)
+        # bucket counts are hypergeometric, not equal: the spread of per-bucket counts matches sqrt(mean)
+        if kk >= 100_000:
+            nb = -(-kk // 384)
+            cnt = np.histogram(v, bins=nb, range=(0, pop))[0]
+            ratio = cnt.var() / (cnt.mean() * (1 - 1 / nb) * (pop - kk) / (pop - 1))
+            assert 0.7 < ratio < 1.4, ratio
+    eng.close()
