@@ -59,15 +59,14 @@ MS_HD U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1) {
 
 // Purposes (second counter word).  One purpose per independent stream.
 enum Purpose : uint32_t {
-    P_RANGE_PRP = 1,   // round keys of the position permutation of one RMT range   (util.py:104)
+    P_RANGE_KEY = 1,   // sub-key of one RMT range: bucket-count splits and in-bucket position draws (util.py:104)
     P_TYPE_LEN  = 2,   // type + length of one candidate                            (mutator.py:170-174, 229-265)
     P_SNP       = 3,   // ti/tv decision + transversion coin of one SNP             (mutator.py:429-455)
     P_INSERT    = 4,   // random insert bases, 64 per Philox block                  (mutator.py:466-471)
     P_TL_PRP    = 5,   // round keys of the TL<->TLI pairing permutation of a contig (mutator.py:277-285)
     P_TL_REV    = 6,   // inversion coin of one translocation                       (mutator.py:307-316)
-    P_IT_PRP    = 7,   // breakpoint permutations of an interchromosomal pair       (it_mutator.py:94-118)
+    P_IT_KEY    = 7,   // the same for the breakpoint ranges of an interchromosomal pair (it_mutator.py:94-118)
     P_GENOME    = 8,   // synthetic genome generator (bench only)
-    P_RANGE_KEY = 9,   // sub-key of one RMT range: bucket-count splits and in-bucket position draws   (util.py:104)
 };
 
 struct Seed { uint32_t k0, k1; };

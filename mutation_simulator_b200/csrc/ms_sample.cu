@@ -595,7 +595,7 @@ int sample_pipeline(ms_ctx* c, uint64_t seed64, bool defer_bases) {
     MS_CUDA(c, c->lit.ensure(64));
     if (K == 0 || c->n_ranges == 0) return MS_OK;
 
-    int rc = draw_and_sort(c, seed, P_RANGE_PRP, c->min_dist, 0, c->contigs.as<Contig>());
+    int rc = draw_and_sort(c, seed, P_RANGE_KEY, c->min_dist, 0, c->contigs.as<Contig>());
     if (rc) return rc;
 
     const int64_t* d_gpos = c->svec.as<int64_t>();
@@ -850,7 +850,7 @@ int ms_sample_positions(ms_ctx* c, uint64_t seed, int32_t n, const uint32_t* gid
     MS_CUDA(c, c->tmp_contigs.ensure(sizeof(Contig) * (size_t)n));
     MS_CUDA(c, cudaMemcpyAsync(c->tmp_contigs.p, ctg.data(), sizeof(Contig) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     MS_CUDA(c, cudaMemsetAsync(c->totals.p, 0, sizeof(Totals), c->stream));
-    rc = draw_and_sort(c, make_seed(seed), P_IT_PRP, min_dist, 1, c->tmp_contigs.as<Contig>());
+    rc = draw_and_sort(c, make_seed(seed), P_IT_KEY, min_dist, 1, c->tmp_contigs.as<Contig>());
     c->n_ranges = -1;  // the range table now holds position-only ranges: ms_sample needs ms_set_ranges again
     if (rc) return rc;
     std::vector<int64_t> gpos((size_t)K);
