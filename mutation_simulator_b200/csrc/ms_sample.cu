@@ -230,9 +230,9 @@ k_sort_emit(const Range* ranges, const BucketInfo* binfo, const Seed* keys, cons
             Seed seed, int32_t min_dist, const int32_t* block7, int positions_only,
             int64_t* cand_gpos, uint8_t* cand_type, uint32_t* cand_len, int64_t* cand_reach, uint32_t* cand_range, Totals* tot,
             int skip_small) {
-    __shared__ uint32_t sm[SORT_CAP];
+    __shared__ __align__(16) uint32_t sm[SORT_CAP];
     __shared__ int32_t blk[7];
-    __shared__ uint32_t warp_tot[SORT_THREADS / 32];
+    __shared__ uint32_t warp_tot[32];
     __shared__ uint32_t n_redraw[2];
     const int tid = threadIdx.x;
     const int64_t b = blockIdx.x;
@@ -247,15 +247,15 @@ k_sort_emit(const Range* ranges, const BucketInfo* binfo, const Seed* keys, cons
     const uint32_t bl = (uint32_t)(b - (int64_t)g.bucket_lo);
     if (tid < 7) blk[tid] = block7[tid];
     if (tid < 2) n_redraw[tid] = 0u;
-    int n2 = 32;
-    while (n2 < cnt) n2 <<= 1;
+    const int n2 = cnt <= 32 ? 32 : 1 << (32 - __clz(cnt - 1));      // next power of two (bitonic paths)
     if (cnt >= 64 && s_nw <= (uint32_t)SORT_CAP) {
         // Dense bucket (span of at most 32 Ki values): one bit per value in a bitmap; a draw that finds its bit set
         // is a coincidence and is redrawn in the next round.  The sorted order is then read off the bitmap —
         // prefix-sum the popcounts, write each value to its rank (~100 instructions per thread instead of the ~360
         // of the 512-key bitonic network).
         const uint32_t vlo = s_vlo, nw = s_nw;
-        for (uint32_t i = tid; i < nw; i += SORT_THREADS) sm[i] = 0u;
+        static_assert(SORT_CAP / 4 <= SORT_THREADS, "one uint4 per thread clears the bitmap");
+        if (tid < SORT_CAP / 4) reinterpret_cast<uint4*>(sm)[tid] = make_uint4(0u, 0u, 0u, 0u);
         __syncthreads();
         uint32_t n_draw = (uint32_t)cnt;
         for (uint32_t round = 0u; n_draw > 0u; ++round) {
@@ -282,8 +282,8 @@ k_sort_emit(const Range* ranges, const BucketInfo* binfo, const Seed* keys, cons
         for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d); if ((tid & 31) >= d) incl += y; }
         if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
         __syncthreads();                                   // every thread holds its bitmap words: sm can be overwritten
-        uint32_t rank = incl - mine;
-        for (int w = 0; w < (tid >> 5); ++w) rank += warp_tot[w];
+        // + the totals of the warps before this one: lane l holds warp l's total (16 warps), summed across the warp
+        uint32_t rank = incl - mine + __reduce_add_sync(0xffffffffu, (tid & 31) < (tid >> 5) ? warp_tot[tid & 31] : 0u);
         uint32_t vb = vlo + (i0 << 5);
         while (w0) { const int bit = __ffs(w0) - 1; w0 &= w0 - 1u; sm[rank++] = vb + (uint32_t)bit; }
         vb += 32u;
