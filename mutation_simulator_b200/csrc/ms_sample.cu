@@ -474,15 +474,18 @@ k_build_records(const Totals* tot, const uint32_t* acc_slot, const int64_t* gpos
     const uint32_t l = len[s];
     Rec r;
     r.pos = pos; r.out = 0; r.src = 0; r.type = t; r.ref = 0; r.alt = 0; r.contig = cidx;
+    // SNP substitution, insert bases and the translocation coin are all Philox(contig, purpose of the type, pos): one
+    // block per thread ahead of the switch instead of three copies of the generator run by three lane subsets
+    const U4 rnd = draw(seed, ct.gid, t == T_SN ? (uint32_t)P_SNP : t == T_IN ? (uint32_t)P_INSERT : (uint32_t)P_TL_REV, pos);
     switch (t) {
         case T_SN: {
             r.cons = 1; r.prod = 1; r.kind = K_SNP;
             if (!defer_bases) {   // streamed runs fill these per contig group once its bases have arrived (k_snp_fill)
                 r.ref = tab->conv[vv.genome[g]];
-                r.alt = draw_snp(seed, ct.gid, pos, r.ref, p_ti, tab->trans);
+                r.alt = snp_of_block(rnd, r.ref, p_ti, tab->trans);
             }
         } break;
-        case T_IN: r.cons = 0; r.prod = l; r.kind = K_RAND; r.src = rand_insert_cache(seed, ct.gid, pos); break;
+        case T_IN: r.cons = 0; r.prod = l; r.kind = K_RAND; r.src = (int64_t)u64_of(rnd.x, rnd.y); break;   // = rand_insert_cache(seed, gid, pos)
         case T_DE: r.cons = l; r.prod = 0; r.kind = K_NONE; break;
         case T_IV: r.cons = l; r.prod = l; r.kind = K_RC; r.src = g; break;
         case T_DU: r.cons = 0; r.prod = l; r.kind = K_RAW; r.src = g; break;
@@ -493,7 +496,7 @@ k_build_records(const Totals* tot, const uint32_t* acc_slot, const int64_t* gpos
             else {
                 const uint32_t tl_len = len[lk];
                 r.cons = 0; r.prod = tl_len; r.src = gpos[lk];
-                r.kind = draw_tl_reverse(seed, ct.gid, pos, tl_len) ? K_RC : K_CONV;
+                r.kind = ((rnd.x & 1u) != 0 && tl_len >= 2) ? K_RC : K_CONV;              // = draw_tl_reverse(seed, gid, pos, tl_len)
             }
         } break;
     }

@@ -160,11 +160,13 @@ MS_HD int64_t block_reach(uint8_t type, uint32_t pos, uint32_t len, const int32_
 }
 
 // mutator.py:429-463.  `ref` is already IUPAC-converted.
-MS_HD uint8_t draw_snp(Seed seed, uint32_t gid, uint32_t pos, uint8_t ref, double p_ti, const uint8_t* trans) {
-    const U4 r = draw(seed, gid, P_SNP, pos);
+MS_HD uint8_t snp_of_block(const U4& r, uint8_t ref, double p_ti, const uint8_t* trans) {   // r = draw(seed, gid, P_SNP, pos)
     const double u = unit_double(r.x, r.y);
     if (u <= p_ti) return trans[ref];
     return transversion(ref, r.z & 1u);
+}
+MS_HD uint8_t draw_snp(Seed seed, uint32_t gid, uint32_t pos, uint8_t ref, double p_ti, const uint8_t* trans) {
+    return snp_of_block(draw(seed, gid, P_SNP, pos), ref, p_ti, trans);
 }
 
 // mutator.py:466-471: base j of the insert at `pos`; 64 bases per Philox block.

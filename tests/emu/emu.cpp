@@ -30,6 +30,8 @@ void emu_prp(uint64_t seed, uint32_t contig, uint32_t purpose, uint64_t idx, uin
     for (uint32_t j = 0; j < count; ++j) out[j] = prp_apply(p, j);
 }
 
+void emu_ndigits(uint32_t count, const uint32_t* v, uint32_t* out) { for (uint32_t i = 0; i < count; ++i) out[i] = ndigits(v[i]); }
+
 // count draws of hypergeom(N, K, n), draw i from Philox counter (i, 0, 0, 0) under `seed`
 void emu_hypergeom(uint64_t seed, uint32_t N, uint32_t K, uint32_t n, uint32_t count, uint32_t* out) {
     const Seed s = make_seed(seed);

@@ -76,6 +76,16 @@ def test_prp_subset_is_uniform_over_positions(emu):
     assert p > 1e-3
 
 
+def test_decimal_digit_count(emu):
+    """POS / END / SVLEN widths of the VCF line size pass (vcf_writer.py:118-126 formats them with str())."""
+    rng = np.random.default_rng(1)
+    v = np.concatenate([[0, 1, 9, 2**32 - 1, 2**31], [10**e + d for e in range(1, 10) for d in (-1, 0, 1)],
+                        [2**b + d for b in range(1, 32) for d in (-1, 0, 1)], rng.integers(0, 2**32, 20000)]).astype(np.uint32)
+    out = np.zeros(len(v), np.uint32)
+    emu.emu_ndigits(C.c_uint32(len(v)), v.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(out, [len(str(int(x))) for x in v])
+
+
 def hypergeom_draws(emu, seed, N, K, n, count):
     out = (C.c_uint32 * count)()
     emu.emu_hypergeom(C.c_uint64(seed), C.c_uint32(N), C.c_uint32(K), C.c_uint32(n), C.c_uint32(count), out)
