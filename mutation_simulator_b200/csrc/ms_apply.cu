@@ -868,26 +868,44 @@ k_vcf_write(VcfView v, const Rec* recs, int64_t rec_lo, int64_t n_recs, const Co
         else vcf_emit_uniform<false>(v, contigs[r.contig], r, line0, vcf + a, jobs, &n_jobs);
     }
     __syncthreads();
-    // pass 3: copy jobs, one warp per job; all warps together on jobs longer than 2 KiB
+    // pass 3: copy jobs.  Most are 4-50 bytes (a deleted stretch, a duplicated or inverted one, an insert): a quarter
+    // of a warp per job, so that one pass over the dispatch code serves four of them; jobs longer than 64 bytes take a
+    // whole warp, those longer than 2 KiB all warps together.
     const int nj = n_jobs < VCF_MAX_JOBS ? n_jobs : VCF_MAX_JOBS;
     const int warp = tid >> 5, lane = tid & 31;
-    bool any_big = false;
-    for (int jb = warp; jb < nj; jb += VCF_THREADS / 32) {
-        const CopyJob job = jobs[jb];
-        const uint32_t len = job.len_mode & 0x1FFFFFFFu, mode = job.len_mode >> 29;
-        if (len > 2048u) { any_big = true; continue; }
-        uint8_t* d = line0 + job.dst;
-        if (mode == SM_RC) {
-            const uint8_t* g = v.genome + job.src + (len - 1u);
-            for (uint32_t x = lane; x < len; x += 32u) d[x] = s_comp[s_conv[g[-(int)x]]];
-        } else if (mode == SM_CONV) {
-            const uint8_t* g = v.genome + job.src;
-            for (uint32_t x = lane; x < len; x += 32u) d[x] = s_conv[g[x]];
-        } else if (mode == SM_RAND || mode == SM_RANDL) {
-            for (uint32_t x = lane; x < len; x += 32u) d[x] = seg_byte(v, mode, job.src, len, x);
-        } else {
-            const uint8_t* g = (mode == SM_RAW ? v.genome : v.lit) + job.src;
-            for (uint32_t x = lane; x < len; x += 32u) d[x] = g[x];
+    bool any_big = false, any_mid = false;
+    {
+        const int quarter = lane >> 3, ql = lane & 7;
+        for (int j0 = 4 * warp; j0 < nj; j0 += 4 * (VCF_THREADS / 32)) {
+            const int jb = j0 + quarter;
+            if (jb >= nj) continue;
+            const CopyJob job = jobs[jb];
+            const uint32_t len = job.len_mode & 0x1FFFFFFFu, mode = job.len_mode >> 29;
+            if (len > 64u) { if (len > 2048u) any_big = true; else any_mid = true; continue; }
+            uint8_t* d = line0 + job.dst;
+            if (mode == SM_RAND || mode == SM_RANDL) {
+                for (uint32_t x = ql; x < len; x += 8u) d[x] = seg_byte(v, mode, job.src, len, x);
+            } else {
+                const uint8_t* g = (mode == SM_LIT ? v.lit : v.genome) + job.src;
+                const bool conv = mode == SM_CONV || mode == SM_RC, rc = mode == SM_RC;
+                for (uint32_t x = ql; x < len; x += 8u) {
+                    uint8_t ch = g[rc ? len - 1u - x : x];
+                    if (conv) ch = s_conv[ch];
+                    if (rc) ch = s_comp[ch];
+                    d[x] = ch;
+                }
+            }
+        }
+    }
+    if (__any_sync(0xffffffffu, any_mid)) {
+        for (int j0 = 4 * warp; j0 < nj; j0 += 4 * (VCF_THREADS / 32)) {
+            for (int h = 0; h < 4 && j0 + h < nj; ++h) {
+                const CopyJob job = jobs[j0 + h];
+                const uint32_t len = job.len_mode & 0x1FFFFFFFu, mode = job.len_mode >> 29;
+                if (len <= 64u || len > 2048u) continue;
+                uint8_t* d = line0 + job.dst;
+                for (uint32_t x = lane; x < len; x += 32u) d[x] = seg_byte(v, mode, job.src, len, x);
+            }
         }
     }
     if (__syncthreads_or(any_big)) {
