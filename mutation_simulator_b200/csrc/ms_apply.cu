@@ -886,13 +886,15 @@ k_vcf_write(VcfView v, const Rec* recs, int64_t rec_lo, int64_t n_recs, const Co
             if (mode == SM_RAND || mode == SM_RANDL) {
                 for (uint32_t x = ql; x < len; x += 8u) d[x] = seg_byte(v, mode, job.src, len, x);
             } else {
-                const uint8_t* g = (mode == SM_LIT ? v.lit : v.genome) + job.src;
                 const bool conv = mode == SM_CONV || mode == SM_RC, rc = mode == SM_RC;
-                for (uint32_t x = ql; x < len; x += 8u) {
-                    uint8_t ch = g[rc ? len - 1u - x : x];
-                    if (conv) ch = s_conv[ch];
-                    if (rc) ch = s_comp[ch];
-                    d[x] = ch;
+                // the lane's first source byte and its stride: forwards, or backwards from the end for a reverse complement
+                const uint8_t* g = (mode == SM_LIT ? v.lit : v.genome) + job.src + (rc ? (int64_t)len - 1 - ql : (int64_t)ql);
+                const int step = rc ? -8 : 8;
+                uint8_t* dq = d + ql;
+                for (int left = (int)len - ql; left > 0; left -= 8, g += step, dq += 8) {
+                    uint32_t ch = *g;
+                    if (conv) { ch = s_conv[ch]; if (rc) ch = s_comp[ch]; }
+                    *dq = (uint8_t)ch;
                 }
             }
         }
@@ -919,13 +921,17 @@ k_vcf_write(VcfView v, const Rec* recs, int64_t rec_lo, int64_t n_recs, const Co
     }
     if (!staged) return;
     __syncthreads();
-    int64_t al = (base + 15) & ~(int64_t)15;         // first 16-aligned destination offset
-    if (al > end) al = end;
-    const int64_t ah = al + ((end - al) & ~(int64_t)15);
-    for (int64_t x = base + tid; x < al; x += VCF_THREADS) vcf[x] = buf[shift + (x - base)];
-    for (int64_t x = al + 16 * (int64_t)tid; x < ah; x += 16 * VCF_THREADS)
-        *reinterpret_cast<uint4*>(vcf + x) = *reinterpret_cast<const uint4*>(buf + shift + (x - base));
-    for (int64_t x = ah + tid; x < end; x += VCF_THREADS) vcf[x] = buf[shift + (x - base)];
+    // (32-bit offsets from `base`: the staged lines are at most VCF_SMEM bytes)
+    const uint32_t total = (uint32_t)(end - base);
+    uint32_t al = (16u - shift) & 15u;               // first 16-aligned destination offset
+    if (al > total) al = total;
+    const uint32_t ah = al + ((total - al) & ~15u);
+    uint8_t* const out = vcf + base;
+    const uint8_t* const in = buf + shift;
+    if ((uint32_t)tid < al) out[tid] = in[tid];
+    for (uint32_t x = al + 16u * (uint32_t)tid; x < ah; x += 16u * VCF_THREADS)
+        *reinterpret_cast<uint4*>(out + x) = *reinterpret_cast<const uint4*>(in + x);
+    if (ah + (uint32_t)tid < total) out[ah + tid] = in[ah + tid];
 }
 
 // delta (prod - cons) and VCF line size of every record, computed once (the scan reads 8 bytes per record)
