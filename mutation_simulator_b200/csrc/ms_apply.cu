@@ -192,8 +192,12 @@ k_rec_out(const Rec* recs, int64_t n_recs, const Contig* contigs, const int64_t*
     __shared__ unsigned int hist[8];          // records per mutation type (ms_get_stats), counted on the way
     if (threadIdx.x < 8) hist[threadIdx.x] = 0u;
     __syncthreads();
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_recs) rec_out_one(recs, i, contigs, S, N, sv, snp, tot, hist);
+    // grid-stride: a few thousand CTAs flush their counts at the end instead of one CTA per 256 records (163 k CTAs
+    // x 8 atomics on the same eight words were 40 % of this kernel's stall samples, profiles/r3f)
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x; i0 < n_recs; i0 += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = i0 + threadIdx.x;
+        if (i < n_recs) rec_out_one(recs, i, contigs, S, N, sv, snp, tot, hist);
+    }
     __syncthreads();
     if (threadIdx.x < 8 && hist[threadIdx.x]) atomicAdd((unsigned long long*)&tot->counts[threadIdx.x], (unsigned long long)hist[threadIdx.x]);
 }
@@ -1096,7 +1100,7 @@ static int index_stage(ms_ctx* c) {
     cudaStream_t st = c->stream;
     stage_begin(c, ST_INDEX);
     if (M > 0) {
-        k_rec_out<<<(unsigned)ceil_div(M, 256), 256, 0, st>>>(d_recs, M, d_contigs, S, N, c->sv_stream.as<SvRec>(), c->snp_stream.as<Snp8>(), d_tot);
+        k_rec_out<<<(unsigned)std::min<int64_t>(ceil_div(M, 256), (int64_t)NUM_SMS_B200 * 32), 256, 0, st>>>(d_recs, M, d_contigs, S, N, c->sv_stream.as<SvRec>(), c->snp_stream.as<Snp8>(), d_tot);
         MS_LAUNCH_CHECK(c);
     }
     if (c->n_pieces > 0) {
