@@ -948,6 +948,58 @@ k_rec_sizes(VcfView v, const Rec* recs, int64_t n, const Contig* contigs, int32_
     vsize[i] = vcf_line_size(v, contigs[r.contig], r) | (r.kind != K_SNP ? VSIZE_SV : 0u);   // bit 31: the record moves bases (SvRec)
 }
 
+// Down-sweep of the plan scan, written out for its fixed types: a thread owns 8 consecutive records, reads their
+// (delta, size) words with 16-byte loads, keeps them as 32-bit values (the generic k_scan_down held eight I64x3 per
+// thread: 77 registers, 3 CTAs per SM, 0.55 ms for 1.1 GB) and writes S / V / N with 16-byte stores.
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_plan_down(const int32_t* __restrict__ delta, const uint32_t* __restrict__ vsize, int64_t n, const I64x3* __restrict__ tile_prefix,
+            int64_t* __restrict__ S, int64_t* __restrict__ V, uint32_t* __restrict__ N) {
+    __shared__ I64x3 sm[2 * SCAN_THREADS / 32];
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    static_assert(SCAN_ITEMS == 8, "two 16-byte loads per array");
+    int32_t d[8];
+    uint32_t vs[8];
+    const bool full = base + 8 <= n;
+    if (full) {
+        const int4 d0 = __ldg(reinterpret_cast<const int4*>(delta + base)), d1 = __ldg(reinterpret_cast<const int4*>(delta + base) + 1);
+        const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(vsize + base)), v1 = __ldg(reinterpret_cast<const uint4*>(vsize + base) + 1);
+        d[0] = d0.x; d[1] = d0.y; d[2] = d0.z; d[3] = d0.w; d[4] = d1.x; d[5] = d1.y; d[6] = d1.z; d[7] = d1.w;
+        vs[0] = v0.x; vs[1] = v0.y; vs[2] = v0.z; vs[3] = v0.w; vs[4] = v1.x; vs[5] = v1.y; vs[6] = v1.z; vs[7] = v1.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const bool ok = base + j < n; d[j] = ok ? delta[base + j] : 0; vs[j] = ok ? vsize[base + j] : 0u; }
+    }
+    I64x3 acc{0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { acc.a += d[j]; acc.b += (int64_t)(vs[j] & ~VSIZE_SV); acc.c += (int64_t)(vs[j] >> 31); }
+    I64x3 total;
+    const I64x3 ex = block_excl_scan(acc, I64x3{0, 0, 0}, SumOp(), total, sm);
+    I64x3 run = tile_prefix[blockIdx.x] + ex;
+    if (full) {
+        longlong2* const s2 = reinterpret_cast<longlong2*>(S + base);
+        longlong2* const v2 = reinterpret_cast<longlong2*>(V + base);
+        uint32_t nn[8];
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+            longlong2 a, b;
+            a.x = run.a; b.x = run.b; nn[j] = (uint32_t)run.c;
+            run.a += d[j]; run.b += (int64_t)(vs[j] & ~VSIZE_SV); run.c += (int64_t)(vs[j] >> 31);
+            a.y = run.a; b.y = run.b; nn[j + 1] = (uint32_t)run.c;
+            run.a += d[j + 1]; run.b += (int64_t)(vs[j + 1] & ~VSIZE_SV); run.c += (int64_t)(vs[j + 1] >> 31);
+            s2[j >> 1] = a;
+            v2[j >> 1] = b;
+        }
+        reinterpret_cast<uint4*>(N + base)[0] = make_uint4(nn[0], nn[1], nn[2], nn[3]);
+        reinterpret_cast<uint4*>(N + base)[1] = make_uint4(nn[4], nn[5], nn[6], nn[7]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (base + j < n) { S[base + j] = run.a; V[base + j] = run.b; N[base + j] = (uint32_t)run.c; }
+            run.a += d[j]; run.b += (int64_t)(vs[j] & ~VSIZE_SV); run.c += (int64_t)(vs[j] >> 31);
+        }
+    }
+}
+
 __global__ void k_store_total3(const I64x3* total, int64_t* S_end, int64_t* V_end, uint32_t* N_end) {
     *S_end = total->a;
     *V_end = total->b;
@@ -1061,9 +1113,14 @@ static int plan_stage(ms_ctx* c, bool vcf_sizes) {
             const uint32_t vs = d_vsize[i];
             return I64x3{(int64_t)d_delta[i], (int64_t)(vs & ~VSIZE_SV), (int64_t)(vs >> 31)};
         };
-        auto out = [=] __device__(int64_t i, I64x3 ex, I64x3) { S[i] = ex.a; V[i] = ex.b; N[i] = (uint32_t)ex.c; };
-        I64x3* d_total = nullptr;
-        MS_CUDA(c, (device_scan<I64x3>(c, in, out, M, I64x3{0, 0, 0}, SumOp(), c->scan_tmp, &d_total)));
+        I64x3* tile_prefix = nullptr;
+        int64_t nt = 0;
+        MS_CUDA(c, (scan_tile_sums<I64x3>(c, in, M, I64x3{0, 0, 0}, SumOp(), c->scan_tmp, &tile_prefix, &nt)));
+        if (nt > 0) {
+            k_plan_down<<<(unsigned)nt, SCAN_THREADS, 0, st>>>(d_delta, d_vsize, M, tile_prefix, S, V, N);
+            MS_LAUNCH_CHECK(c);
+        }
+        I64x3* d_total = tile_prefix + nt;
         k_store_total3<<<1, 1, 0, st>>>(d_total, S + M, V + M, N + M);
         MS_LAUNCH_CHECK(c);
     }

@@ -277,8 +277,10 @@ inline cudaError_t device_scan_1p(ms_ctx* c, InF in, OutF out, int64_t n, T iden
 // for the plan scan, profiles/r2c_scan_metrics.txt) — with ~300 tiles resident every look-back has to walk ~9 windows
 // of 32 predecessors before it meets a finished one, each window two dependent L2 round trips plus a fence, while the
 // other seven warps of the tile wait at the barrier (stall_barrier 52).
-template <class T, class Op, class InF, class OutF>
-inline cudaError_t device_scan(ms_ctx* c, InF in, OutF out, int64_t n, T identity, Op op, DevBuf& tmp, T** d_total) {
+// First two phases: per-tile reduce, then the exclusive scan of the tile sums.  *tile_prefix gets nt prefixes followed
+// by the grand total; the caller launches the down-sweep (the generic k_scan_down, or a kernel written for its types).
+template <class T, class Op, class InF>
+inline cudaError_t scan_tile_sums(ms_ctx* c, InF in, int64_t n, T identity, Op op, DevBuf& tmp, T** tile_prefix, int64_t* n_tiles) {
     const int64_t nt = ceil_div(n, SCAN_TILE);
     cudaError_t e = tmp.ensure((size_t)(nt + 1) * sizeof(T));
     if (e != cudaSuccess) return e;
@@ -304,6 +306,17 @@ inline cudaError_t device_scan(ms_ctx* c, InF in, OutF out, int64_t n, T identit
         k_scan_tiles<T, Op><<<1, SCAN_MID_THREADS, 0, c->stream>>>(ts, nt, identity, op);
     }
     c->kernel_launches++;
+    *tile_prefix = ts;
+    *n_tiles = nt;
+    return cudaGetLastError();
+}
+
+template <class T, class Op, class InF, class OutF>
+inline cudaError_t device_scan(ms_ctx* c, InF in, OutF out, int64_t n, T identity, Op op, DevBuf& tmp, T** d_total) {
+    T* ts = nullptr;
+    int64_t nt = 0;
+    cudaError_t e = scan_tile_sums<T>(c, in, n, identity, op, tmp, &ts, &nt);
+    if (e != cudaSuccess) return e;
     if (nt > 0) { k_scan_down<T, Op, InF, OutF><<<(unsigned)nt, SCAN_THREADS, 0, c->stream>>>(in, out, n, identity, op, ts); c->kernel_launches++; }
     if (d_total) *d_total = ts + nt;
     return cudaGetLastError();
