@@ -388,6 +388,56 @@ k_resolve_local(int64_t K, const int64_t* gpos, const int64_t* reach, const uint
     }
 }
 
+// Compaction of the accepted candidates and of the accepted TL / TLI among them (three lists in one scan), written for
+// its types: a thread owns 8 consecutive candidates and reads their accept / type bytes as two 8-byte words (the generic
+// scan kernels read them byte by byte and carried eight I64x3 per thread: 80 registers, 0.29 ms).
+__device__ __forceinline__ void compact_masks(const uint8_t* accept, const uint8_t* type, int64_t base, int64_t K, uint32_t& m_acc,
+                                              uint32_t& m_tl, uint32_t& m_tli) {
+    uint64_t a8 = 0ull, t8 = 0ull;
+    if (base + 8 <= K) {
+        a8 = __ldg(reinterpret_cast<const unsigned long long*>(accept + base));
+        t8 = __ldg(reinterpret_cast<const unsigned long long*>(type + base));
+    } else {
+        for (int j = 0; j < 8 && base + j < K; ++j) { a8 |= (uint64_t)accept[base + j] << (8 * j); t8 |= (uint64_t)type[base + j] << (8 * j); }
+    }
+    m_acc = m_tl = m_tli = 0u;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t a = (uint32_t)(a8 >> (8 * j)) & 0xffu, t = (uint32_t)(t8 >> (8 * j)) & 0xffu;
+        if (a) { m_acc |= 1u << j; if (t == T_TL) m_tl |= 1u << j; if (t == T_TLI) m_tli |= 1u << j; }
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_compact_reduce(const uint8_t* accept, const uint8_t* type, int64_t K, I64x3* tile_sums) {
+    __shared__ I64x3 sm[2 * SCAN_THREADS / 32];
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    uint32_t ma, mtl, mtli;
+    compact_masks(accept, type, base, K, ma, mtl, mtli);
+    I64x3 total;
+    block_excl_scan(I64x3{__popc(ma), __popc(mtl), __popc(mtli)}, I64x3{0, 0, 0}, SumOp(), total, sm);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_compact_down(const uint8_t* accept, const uint8_t* type, int64_t K, const I64x3* tile_prefix, uint32_t* acc_list, uint32_t* tl_list,
+               uint32_t* tli_list) {
+    __shared__ I64x3 sm[2 * SCAN_THREADS / 32];
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    uint32_t ma, mtl, mtli;
+    compact_masks(accept, type, base, K, ma, mtl, mtli);
+    I64x3 total;
+    const I64x3 ex = block_excl_scan(I64x3{__popc(ma), __popc(mtl), __popc(mtli)}, I64x3{0, 0, 0}, SumOp(), total, sm);
+    const I64x3 run = tile_prefix[blockIdx.x] + ex;
+    uint32_t* a = acc_list + run.a;
+    uint32_t* b = tl_list + run.b;
+    uint32_t* cc = tli_list + run.c;
+    const uint32_t i0 = (uint32_t)base;               // candidate slots fit 31 bits (ms_set_ranges checks)
+    while (ma) { const int j = __ffs(ma) - 1; ma &= ma - 1u; *a++ = i0 + (uint32_t)j; }
+    while (mtl) { const int j = __ffs(mtl) - 1; mtl &= mtl - 1u; *b++ = i0 + (uint32_t)j; }
+    while (mtli) { const int j = __ffs(mtli) - 1; mtli &= mtli - 1u; *cc++ = i0 + (uint32_t)j; }
+}
+
 // first TL / TLI list entry of every contig.  One warp per (contig, list): a 32-ary search (each round the lanes probe
 // 32 evenly spaced entries) finishes in 4-5 rounds of two dependent loads; the one-thread-per-contig binary search it
 // replaces took 50 us on 24 contigs — a fixed cost that did not shrink with the GPU count (SCALE_r01).
@@ -644,19 +694,15 @@ int sample_pipeline(ms_ctx* c, uint64_t seed64, bool defer_bases) {
     uint32_t* d_tl = c->tl_list.as<uint32_t>();
     uint32_t* d_tli = c->tli_list.as<uint32_t>();
     {
-        auto in = [=] __device__(int64_t i) -> I64x3 {
-            const int64_t a = d_accept[i];
-            const uint8_t t = d_type[i];
-            return I64x3{a, (a && t == T_TL) ? 1 : 0, (a && t == T_TLI) ? 1 : 0};
-        };
-        auto out = [=] __device__(int64_t i, I64x3 ex, I64x3 v) {
-            if (v.a) d_acc[ex.a] = (uint32_t)i;
-            if (v.b) d_tl[ex.b] = (uint32_t)i;
-            if (v.c) d_tli[ex.c] = (uint32_t)i;
-        };
-        I64x3* d_total = nullptr;
-        MS_CUDA(c, (device_scan<I64x3>(c, in, out, K, I64x3{0, 0, 0}, SumOp(), c->scan_tmp, &d_total)));
-        k_store_counts<<<1, 1, 0, st>>>(d_total, d_tot);      // accepted / TL / TLI counts stay on the device: no host round trip
+        const int64_t nt = ceil_div(K, SCAN_TILE);
+        MS_CUDA(c, c->scan_tmp.ensure((size_t)(nt + 1) * sizeof(I64x3)));
+        I64x3* ts = c->scan_tmp.as<I64x3>();
+        k_compact_reduce<<<(unsigned)nt, SCAN_THREADS, 0, st>>>(d_accept, d_type, K, ts);
+        MS_LAUNCH_CHECK(c);
+        MS_CUDA(c, (scan_mid_phase<I64x3>(c, ts, nt, I64x3{0, 0, 0}, SumOp())));
+        k_compact_down<<<(unsigned)nt, SCAN_THREADS, 0, st>>>(d_accept, d_type, K, ts, d_acc, d_tl, d_tli);
+        MS_LAUNCH_CHECK(c);
+        k_store_counts<<<1, 1, 0, st>>>(ts + nt, d_tot);      // accepted / TL / TLI counts stay on the device: no host round trip
         MS_LAUNCH_CHECK(c);
     }
     stage_end(c, ST_SAMPLE_RESOLVE);

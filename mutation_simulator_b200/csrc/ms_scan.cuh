@@ -279,13 +279,9 @@ inline cudaError_t device_scan_1p(ms_ctx* c, InF in, OutF out, int64_t n, T iden
 // other seven warps of the tile wait at the barrier (stall_barrier 52).
 // First two phases: per-tile reduce, then the exclusive scan of the tile sums.  *tile_prefix gets nt prefixes followed
 // by the grand total; the caller launches the down-sweep (the generic k_scan_down, or a kernel written for its types).
-template <class T, class Op, class InF>
-inline cudaError_t scan_tile_sums(ms_ctx* c, InF in, int64_t n, T identity, Op op, DevBuf& tmp, T** tile_prefix, int64_t* n_tiles) {
-    const int64_t nt = ceil_div(n, SCAN_TILE);
-    cudaError_t e = tmp.ensure((size_t)(nt + 1) * sizeof(T));
-    if (e != cudaSuccess) return e;
-    T* ts = tmp.as<T>();
-    if (nt > 0) { k_scan_reduce<T, Op, InF><<<(unsigned)nt, SCAN_THREADS, 0, c->stream>>>(in, n, identity, op, ts); c->kernel_launches++; }
+// middle phase alone: ts[0..nt) tile sums -> exclusive prefixes in place, ts[nt] = grand total
+template <class T, class Op>
+inline cudaError_t scan_mid_phase(ms_ctx* c, T* ts, int64_t nt, T identity, Op op) {
     if (nt > 4096) {
         // many tile sums: scan them with the single-pass kernel (a handful of tiles: its look-back is one window deep);
         // one CTA walking 20 k sums costs 65-98 us (profiles/r1n_launches.csv, r2e_launches.csv)
@@ -306,9 +302,19 @@ inline cudaError_t scan_tile_sums(ms_ctx* c, InF in, int64_t n, T identity, Op o
         k_scan_tiles<T, Op><<<1, SCAN_MID_THREADS, 0, c->stream>>>(ts, nt, identity, op);
     }
     c->kernel_launches++;
+    return cudaGetLastError();
+}
+
+template <class T, class Op, class InF>
+inline cudaError_t scan_tile_sums(ms_ctx* c, InF in, int64_t n, T identity, Op op, DevBuf& tmp, T** tile_prefix, int64_t* n_tiles) {
+    const int64_t nt = ceil_div(n, SCAN_TILE);
+    cudaError_t e = tmp.ensure((size_t)(nt + 1) * sizeof(T));
+    if (e != cudaSuccess) return e;
+    T* ts = tmp.as<T>();
+    if (nt > 0) { k_scan_reduce<T, Op, InF><<<(unsigned)nt, SCAN_THREADS, 0, c->stream>>>(in, n, identity, op, ts); c->kernel_launches++; }
     *tile_prefix = ts;
     *n_tiles = nt;
-    return cudaGetLastError();
+    return scan_mid_phase<T>(c, ts, nt, identity, op);
 }
 
 template <class T, class Op, class InF, class OutF>
