@@ -369,19 +369,38 @@ __device__ __forceinline__ bool is_anchor_local(int64_t j, const int64_t* gpos, 
     return true;
 }
 
-// Every candidate's anchor test is evaluated once: a warp covers 31 candidates plus the first one of the next warp,
-// whose flag tells lane 30 whether its chain ends right there (as it does for almost every candidate).
+// Every candidate's anchor test is evaluated once, on registers: a warp covers 28 candidates plus three before them
+// (their positions and reaches reach the owners by shuffle: a look-back of up to three candidates needs no memory;
+// deeper ones — under 1 % at genome-like densities — go on from memory) and the first one of the next warp, whose flag
+// tells lane 30 whether its chain ends right there (as it does for almost every candidate).
+constexpr int RESOLVE_OWN = 28, RESOLVE_BACK = 3;
 __global__ void __launch_bounds__(256)
 k_resolve_local(int64_t K, const int64_t* gpos, const int64_t* reach, const uint8_t* type, int64_t maxspan, uint8_t* accept) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t s = warp * 31 + lane;
-    const bool anchor = s < K && is_anchor_local(s, gpos, reach, type, maxspan);
-    const bool next_anchor = __shfl_down_sync(0xffffffffu, anchor, 1) != 0;     // (lane 31 owns nothing)
-    if (lane == 31 || !anchor) return;
+    const int64_t s = warp * RESOLVE_OWN - RESOLVE_BACK + lane;
+    const bool valid = s >= 0 && s < K;
+    const int64_t g = valid ? gpos[s] : INT64_MIN / 2;          // (an absent predecessor is infinitely far away)
+    const int64_t r = valid ? reach[s] : 0;
+    bool anchor = valid && type[s] != T_DEAD;
+    bool open = anchor;                                          // look-back not finished yet
+#pragma unroll
+    for (int d = 1; d <= RESOLVE_BACK; ++d) {
+        const int64_t gp = __shfl_up_sync(0xffffffffu, g, d), rp = __shfl_up_sync(0xffffffffu, r, d);
+        if (open && lane >= d) {
+            if (g - gp >= maxspan) open = false;
+            else if (rp > g) { anchor = false; open = false; }
+        }
+    }
+    if (open && lane >= RESOLVE_BACK) {
+        for (int64_t i = s - RESOLVE_BACK - 1; i >= 0 && g - gpos[i] < maxspan; --i)
+            if (reach[i] > g) { anchor = false; break; }
+    }
+    const bool next_anchor = __shfl_down_sync(0xffffffffu, anchor, 1) != 0;
+    if (lane < RESOLVE_BACK || lane == 31 || !anchor) return;   // the halo lanes own nothing
     accept[s] = 1;
     if (next_anchor || s + 1 >= K) return;
-    int64_t cur = reach[s];
+    int64_t cur = r;
     for (int64_t t = s + 1; t < K && (t == s + 1 || !is_anchor_local(t, gpos, reach, type, maxspan)); ++t) {
         if (type[t] == T_DEAD) continue;
         if (gpos[t] >= cur) { accept[t] = 1; cur = reach[t]; }
@@ -675,7 +694,7 @@ int sample_pipeline(ms_ctx* c, uint64_t seed64, bool defer_bases) {
     MS_CUDA(c, cudaMemsetAsync(d_accept, 0, (size_t)K, st));
     const int64_t maxspan = c->maxspan;   // (per-range host loops live in upload_ranges: C5 has 200 k ranges)
     if (maxspan <= 4096) {
-        k_resolve_local<<<(unsigned)ceil_div(ceil_div(K, 31) * 32, 256), 256, 0, st>>>(K, d_gpos, d_reach, d_type, maxspan, d_accept);
+        k_resolve_local<<<(unsigned)ceil_div(ceil_div(K, RESOLVE_OWN) * 32, 256), 256, 0, st>>>(K, d_gpos, d_reach, d_type, maxspan, d_accept);
         MS_LAUNCH_CHECK(c);
     } else {
         auto in = [=] __device__(int64_t i) -> int64_t { return d_reach[i]; };
