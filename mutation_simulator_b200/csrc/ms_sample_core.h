@@ -43,12 +43,54 @@ struct RangeParams {
 // bucket the values are then a uniform c-subset of its span (k_sort_emit).
 //
 // hypergeom(): number of marked items among `n` drawn without replacement from `N` of which `K` are marked.
-//   variance >= 900: rounded normal with the exact mean and variance (splits are near p = 1/2, so the skewness
-//     (1-2p)/sigma is ~0 and the pmf is matched to O(1/sigma^2) < 1e-3 relative);
-//   otherwise: inversion by walking outwards from the mode with the exact pmf ratios, the mode's pmf from lgamma
-//     (relative error of the normalisation <= ~2e-5 for N ~ 2^31, ~1e-9 for the node sizes that take this path when
-//     the range is dense) — a shortfall of the walked mass falls back to the mode.
-MS_HD double log_choose(double n, double k) { return lgamma(n + 1.0) - lgamma(k + 1.0) - lgamma(n - k + 1.0); }
+//   variance >= 900: rounded normal with the exact mean and variance (Sheppard-corrected for the rounding); splits are
+//     near p = 1/2, so the skewness (1-2p)/sigma is ~0 and the pmf is matched to O(1/sigma^2) < 1e-3 relative;
+//   otherwise: inversion by walking outwards from the mode with the exact pmf ratios.  The mode's pmf comes from log
+//     factorials (Stirling's series where every argument is >= 16: truncation < 3e-12; lgamma otherwise) — the
+//     normalisation is good to ~2e-5 for N ~ 2^31 and ~1e-9 for the node sizes that take this path when the range is
+//     dense; the ratios are formed in single precision (a walk of ~1.6 sigma <= 50 steps accumulates < 1e-5 relative).
+//     A shortfall of the walked mass falls back to the mode.
+MS_HD double log_fact_stirling(double x, double lx) {   // ln x!, x >= 16, lx = ln x
+    const double i = 1.0 / x, i2 = i * i;
+    return x * lx - x + 0.5 * lx + 0.9189385332046727 + i * (1.0 / 12.0 - i2 * (1.0 / 360.0 - i2 * (1.0 / 1260.0)));
+}
+MS_HD double log_choose(double n, double k) {
+    const double m = n - k;
+    if (k >= 16.0 && m >= 16.0) {
+        const double ln = log(n), lk = log(k), lm = log(m);
+        return log_fact_stirling(n, ln) - log_fact_stirling(k, lk) - log_fact_stirling(m, lm);
+    }
+    return lgamma(n + 1.0) - lgamma(k + 1.0) - lgamma(m + 1.0);
+}
+
+// u >= pmf(m): walk outwards from the mode, up and down alternately, until the accumulated mass passes u
+template <class F>
+MS_HD int64_t hypergeom_walk(double u, double pm, int64_t m, int64_t lo, int64_t hi, double dN, double dK, double dn) {
+    const F fK = (F)dK, fn = (F)dn, fR = (F)(dN - dK - dn);   // R = N - K - n
+    const F one = (F)1, tiny = (F)1e-19;
+    F xb = (F)m, xa = (F)m;      // [a, b] walked so far
+    F pa = (F)pm, pb = pa;       // pmf at a and at b
+    double acc = pm;
+    int64_t a = m, b = m;
+    bool up = b < hi, down = a > lo;
+    while (up || down) {
+        if (up) {               // p(x+1)/p(x) = (K-x)(n-x) / ((x+1)(N-K-n+x+1))
+            pb *= ((fK - xb) * (fn - xb)) / ((xb + one) * (fR + xb + one));
+            ++b; xb += one;
+            acc += (double)pb;
+            if (u < acc) return b;
+            up = b < hi && pb > tiny;
+        }
+        if (down) {             // p(x-1)/p(x) = x (N-K-n+x) / ((K-x+1)(n-x+1))
+            pa *= (xa * (fR + xa)) / ((fK - xa + one) * (fn - xa + one));
+            --a; xa -= one;
+            acc += (double)pa;
+            if (u < acc) return a;
+            down = a > lo && pa > tiny;
+        }
+    }
+    return m;
+}
 
 MS_HD uint32_t hypergeom(const U4& r, uint32_t N, uint32_t K, uint32_t n) {
     if (n == 0u || K == 0u) return 0u;
@@ -65,7 +107,7 @@ MS_HD uint32_t hypergeom(const U4& r, uint32_t N, uint32_t K, uint32_t n) {
         const double u1 = ((double)(u64_of(r.x, r.y) >> 11) + 1.0) * (1.0 / 9007199254740992.0);   // (0, 1]
         const double u2 = unit_double(r.z, r.w);
         const double z = sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2);
-        double x = floor(mean + sqrt(var) * z + 0.5);
+        double x = floor(mean + sqrt(var - 1.0 / 12.0) * z + 0.5);     // rounding adds 1/12 to the variance
         if (x < (double)lo) x = (double)lo;
         if (x > (double)hi) x = (double)hi;
         return (uint32_t)x;
@@ -79,28 +121,9 @@ MS_HD uint32_t hypergeom(const U4& r, uint32_t N, uint32_t K, uint32_t n) {
     const double u = unit_double(r.x, r.y);
     double acc = pm;
     if (u < acc) return (uint32_t)m;
-    int64_t a = m, b = m;       // [a, b] walked so far
-    double pa = pm, pb = pm;    // pmf at a and at b
-    bool up = b < hi, down = a > lo;
-    while (up || down) {
-        if (up) {               // p(x+1)/p(x) = (K-x)(n-x) / ((x+1)(N-K-n+x+1))
-            const double x = (double)b;
-            pb *= ((dK - x) * (dn - x)) / ((x + 1.0) * (dN - dK - dn + x + 1.0));
-            ++b;
-            acc += pb;
-            if (u < acc) return (uint32_t)b;
-            up = b < hi && pb > 1e-19;
-        }
-        if (down) {             // p(x-1)/p(x) = x (N-K-n+x) / ((K-x+1)(n-x+1))
-            const double x = (double)a;
-            pa *= (x * (dN - dK - dn + x)) / ((dK - x + 1.0) * (dn - x + 1.0));
-            --a;
-            acc += pa;
-            if (u < acc) return (uint32_t)a;
-            down = a > lo && pa > 1e-19;
-        }
-    }
-    return (uint32_t)m;
+    // (single precision holds the walked values exactly only below 2^24)
+    if (hi < (1 << 23)) return (uint32_t)hypergeom_walk<float>(u, pm, m, lo, hi, dN, dK, dn);
+    return (uint32_t)hypergeom_walk<double>(u, pm, m, lo, hi, dN, dK, dn);
 }
 
 // samples of the bucket-tree node [lo, hi) that go to its left child [lo, mid): N values in the node, K of them left

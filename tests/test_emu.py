@@ -95,6 +95,7 @@ def hypergeom_draws(emu, seed, N, K, n, count):
 @pytest.mark.parametrize("N,K,n", [
     (20, 7, 5), (100, 50, 10), (1000, 3, 900), (56_000, 28_000, 768), (56_001, 27_999, 769), (2**31, 2**30, 400),
     (300_000, 100_000, 3_000),                                   # variance 444: exact walk, asymmetric split
+    (2**31, 2**31 - 7, 2**30), (2**31, 2**30, 2**31 - 40),        # walked values beyond single precision
     (248_956_422, 124_478_211, 3_360_000), (1_000_000, 500_001, 40_000), (10_000_000, 3_333_333, 123_457),  # normal regime
 ])
 def test_hypergeometric_split_sampler_matches_the_exact_law(emu, N, K, n):
