@@ -440,7 +440,7 @@ k_compact_reduce(const uint8_t* accept, const uint8_t* type, int64_t K, I64x3* t
 
 __global__ void __launch_bounds__(SCAN_THREADS)
 k_compact_down(const uint8_t* accept, const uint8_t* type, int64_t K, const I64x3* tile_prefix, uint32_t* acc_list, uint32_t* tl_list,
-               uint32_t* tli_list) {
+               uint32_t* tli_list, int32_t* link) {
     __shared__ I64x3 sm[2 * SCAN_THREADS / 32];
     const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
     uint32_t ma, mtl, mtli;
@@ -459,8 +459,9 @@ k_compact_down(const uint8_t* accept, const uint8_t* type, int64_t K, const I64x
     for (uint32_t x = threadIdx.x; x < (uint32_t)total.a; x += SCAN_THREADS) a[x] = stage[x];
     uint32_t* b = tl_list + tp.b + ex.b;              // (2 % of the candidates: written directly)
     uint32_t* cc = tli_list + tp.c + ex.c;
-    while (mtl) { const int j = __ffs(mtl) - 1; mtl &= mtl - 1u; *b++ = i0 + (uint32_t)j; }
-    while (mtli) { const int j = __ffs(mtli) - 1; mtli &= mtli - 1u; *cc++ = i0 + (uint32_t)j; }
+    // (their link entries start out "unlinked"; k_link overwrites the paired ones: no 4-byte-per-candidate memset)
+    while (mtl) { const int j = __ffs(mtl) - 1; mtl &= mtl - 1u; *b++ = i0 + (uint32_t)j; link[i0 + j] = -1; }
+    while (mtli) { const int j = __ffs(mtli) - 1; mtli &= mtli - 1u; *cc++ = i0 + (uint32_t)j; link[i0 + j] = -1; }
 }
 
 // first TL / TLI list entry of every contig.  One warp per (contig, list): a 32-ary search (each round the lanes probe
@@ -712,6 +713,7 @@ int sample_pipeline(ms_ctx* c, uint64_t seed64, bool defer_bases) {
         MS_LAUNCH_CHECK(c);
     }
     // compaction of accepted candidates + TL / TLI lists in one pass
+    MS_CUDA(c, c->link.ensure((size_t)K * 4 + 16));
     MS_CUDA(c, c->acc_idx.ensure((size_t)K * 4 + 16));
     MS_CUDA(c, c->tl_list.ensure((size_t)K * 4 + 16));
     MS_CUDA(c, c->tli_list.ensure((size_t)K * 4 + 16));
@@ -725,7 +727,7 @@ int sample_pipeline(ms_ctx* c, uint64_t seed64, bool defer_bases) {
         k_compact_reduce<<<(unsigned)nt, SCAN_THREADS, 0, st>>>(d_accept, d_type, K, ts);
         MS_LAUNCH_CHECK(c);
         MS_CUDA(c, (scan_mid_phase<I64x3>(c, ts, nt, I64x3{0, 0, 0}, SumOp())));
-        k_compact_down<<<(unsigned)nt, SCAN_THREADS, 0, st>>>(d_accept, d_type, K, ts, d_acc, d_tl, d_tli);
+        k_compact_down<<<(unsigned)nt, SCAN_THREADS, 0, st>>>(d_accept, d_type, K, ts, d_acc, d_tl, d_tli, c->link.as<int32_t>());
         MS_LAUNCH_CHECK(c);
         k_store_counts<<<1, 1, 0, st>>>(ts + nt, d_tot);      // accepted / TL / TLI counts stay on the device: no host round trip
         MS_LAUNCH_CHECK(c);
@@ -734,9 +736,7 @@ int sample_pipeline(ms_ctx* c, uint64_t seed64, bool defer_bases) {
 
     // ---- K4: TL <-> TLI linking -------------------------------------------------------
     stage_begin(c, ST_SAMPLE_LINK);
-    MS_CUDA(c, c->link.ensure((size_t)K * 4 + 16));
-    int32_t* d_link = c->link.as<int32_t>();
-    MS_CUDA(c, cudaMemsetAsync(d_link, 0xFF, (size_t)K * 4, st));
+    int32_t* d_link = c->link.as<int32_t>();       // TL / TLI entries were set to -1 (unlinked) by the compaction
     {
         MS_CUDA(c, c->contig_tl.ensure((size_t)(c->n_contigs + 1) * 16));
         int64_t* d_tlb = c->contig_tl.as<int64_t>();

@@ -289,7 +289,12 @@ MS_HD PieceDesc tile_describe(const Contig& k, uint32_t cidx, int64_t f_lo, int6
     int64_t lo = sv_c0, hi = sv_c1;          // first index with out > b_lo
     while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (sv[mid].out <= d.b_lo) lo = mid + 1; else hi = mid; }
     const int64_t gov = lo - 1;
-    int64_t e = lo; hi = sv_c1;              // first index with out >= b_hi
+    // first index with out >= b_hi: a tile holds a few dozen SvRecs, so gallop from the start instead of bisecting
+    // the whole contig again (each probe is a dependent load: this kernel is pure latency)
+    int64_t e = lo; hi = sv_c1;
+    for (int64_t step = 64; e + step < hi; step <<= 1) {
+        if (sv[e + step].out < d.b_hi) e += step + 1; else { hi = e + step; break; }
+    }
     while (e < hi) { const int64_t mid = (e + hi) >> 1; if (sv[mid].out < d.b_hi) e = mid + 1; else hi = mid; }
     const bool virt = gov < sv_c0;
     d.flags = virt ? PD_GOV_VIRTUAL : 0u;
@@ -299,6 +304,9 @@ MS_HD PieceDesc tile_describe(const Contig& k, uint32_t cidx, int64_t f_lo, int6
     while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (snp[mid].out < d.b_lo) lo = mid + 1; else hi = mid; }
     const int64_t s0 = lo;
     hi = snp_c1;
+    for (int64_t step = 256; lo + step < hi; step <<= 1) {
+        if (snp[lo + step].out < d.b_hi) lo += step + 1; else { hi = lo + step; break; }
+    }
     while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (snp[mid].out < d.b_hi) lo = mid + 1; else hi = mid; }
     d.snp_lo = s0;
     const int64_t n_snp = lo - s0;
