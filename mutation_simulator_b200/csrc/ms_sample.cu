@@ -158,9 +158,9 @@ __device__ __forceinline__ uint32_t bitonic_sorted(uint32_t v, int tid, uint32_t
 constexpr int SMALL_BUCKET = 128;   // buckets of at most this many keys are sorted four per CTA (k_sort_emit_small)
 
 // position, type, length and blocking reach of the candidate that ends up in `slot` (K2)
-__device__ __forceinline__ void emit_candidate(const Range& g, const Contig& ct, uint32_t r_idx, int64_t slot, uint32_t v, Seed seed,
+__device__ __forceinline__ void emit_candidate(const Range& g, const Contig& ct, int64_t slot, uint32_t v, Seed seed,
                                                int32_t min_dist, const int32_t* blk, int positions_only, int64_t* cand_gpos,
-                                               uint8_t* cand_type, uint32_t* cand_len, int64_t* cand_reach, uint32_t* cand_range) {
+                                               uint8_t* cand_type, uint32_t* cand_len, int64_t* cand_reach, uint32_t* cand_contig) {
     const uint32_t rank = (uint32_t)(slot - g.cand_lo);
     const uint32_t pos = g.start + v + (uint32_t)min_dist * rank;   // util.py:106-108
     cand_gpos[slot] = ct.goff + pos;
@@ -172,7 +172,7 @@ __device__ __forceinline__ void emit_candidate(const Range& g, const Contig& ct,
     cand_type[slot] = type;
     cand_len[slot] = len;
     cand_reach[slot] = type == T_DEAD ? 0 : ct.goff + reach;
-    cand_range[slot] = r_idx;
+    cand_contig[slot] = g.contig;           // (its range is not needed again: the later stages only ask for the contig)
 }
 
 // The values of one bucket are a uniform c-subset of its span: draw c values; while some coincide, keep the distinct
@@ -185,7 +185,7 @@ __device__ __forceinline__ void emit_candidate(const Range& g, const Contig& ct,
 __global__ void __launch_bounds__(SORT_THREADS)
 k_sort_emit_small(const Range* ranges, const BucketInfo* binfo, const Seed* keys, const Contig* contigs, const int64_t* bucket_off,
                   int64_t n_buckets, Seed seed, int32_t min_dist, const int32_t* block7, int positions_only,
-                  int64_t* cand_gpos, uint8_t* cand_type, uint32_t* cand_len, int64_t* cand_reach, uint32_t* cand_range) {
+                  int64_t* cand_gpos, uint8_t* cand_type, uint32_t* cand_len, int64_t* cand_reach, uint32_t* cand_contig) {
     constexpr int G = SORT_THREADS / SMALL_BUCKET;
     __shared__ uint32_t sm[SORT_THREADS];
     __shared__ Range g4[G];
@@ -220,15 +220,15 @@ k_sort_emit_small(const Range* ranges, const BucketInfo* binfo, const Seed* keys
         if (t == 0) n_redraw[grp] = 0u;               // (ordered before the next round's atomics by the barriers in the sort)
     }
     if (mine && t < cnt)
-        emit_candidate(g4[grp], contigs[g4[grp].contig], bi4[grp].ridx, lo + t, v, seed, min_dist, blk, positions_only, cand_gpos,
-                       cand_type, cand_len, cand_reach, cand_range);
+        emit_candidate(g4[grp], contigs[g4[grp].contig], lo + t, v, seed, min_dist, blk, positions_only, cand_gpos,
+                       cand_type, cand_len, cand_reach, cand_contig);
 }
 
 // K1c + K2: draw one bucket's values in shared memory, in order, then write position, type, length and reach.
 __global__ void __launch_bounds__(SORT_THREADS, 4)
 k_sort_emit(const Range* ranges, const BucketInfo* binfo, const Seed* keys, const Contig* contigs, const int64_t* bucket_off,
             Seed seed, int32_t min_dist, const int32_t* block7, int positions_only,
-            int64_t* cand_gpos, uint8_t* cand_type, uint32_t* cand_len, int64_t* cand_reach, uint32_t* cand_range, Totals* tot,
+            int64_t* cand_gpos, uint8_t* cand_type, uint32_t* cand_len, int64_t* cand_reach, uint32_t* cand_contig, Totals* tot,
             int skip_small) {
     __shared__ __align__(16) uint32_t sm[SORT_CAP];
     __shared__ int32_t blk[7];
@@ -243,7 +243,7 @@ k_sort_emit(const Range* ranges, const BucketInfo* binfo, const Seed* keys, cons
     const BucketInfo bi = binfo[b];                 // one 16-byte broadcast load; no per-CTA lookups
     const Range& g = ranges[bi.ridx];               // fields are read where they are needed (L1 broadcast)
     const Seed key = keys[bi.ridx];
-    const uint32_t s_ridx = bi.ridx, s_nw = bi.nw, s_vlo = bi.vlo, width = bi.width;
+    const uint32_t s_nw = bi.nw, s_vlo = bi.vlo, width = bi.width;
     const uint32_t bl = (uint32_t)(b - (int64_t)g.bucket_lo);
     if (tid < 7) blk[tid] = block7[tid];
     if (tid < 2) n_redraw[tid] = 0u;
@@ -341,8 +341,8 @@ k_sort_emit(const Range* ranges, const BucketInfo* binfo, const Seed* keys, cons
     }
     const Contig& ct = contigs[g.contig];
     for (int i = tid; i < cnt; i += SORT_THREADS)
-        emit_candidate(g, ct, s_ridx, lo + i, sm[i], seed, min_dist, blk, positions_only, cand_gpos, cand_type, cand_len, cand_reach,
-                       cand_range);
+        emit_candidate(g, ct, lo + i, sm[i], seed, min_dist, blk, positions_only, cand_gpos, cand_type, cand_len, cand_reach,
+                       cand_contig);
 }
 
 // K3b: walk the chain that starts at each anchor (mutator.py:184-213).
@@ -499,26 +499,26 @@ k_contig_tl_bounds(const Contig* contigs, int32_t n_contigs, const int64_t* gpos
 // rho a keyed permutation of the larger list: a uniform random injection, which is
 // what "remove random surplus, shuffle, zip" (mutator.py:277-304) produces.
 // link[slot]: -1 unlinked (dropped), -2 kept TL, >= 0 (TLI) candidate slot of its TL.
-__device__ __forceinline__ void link_one(int64_t x, const Contig* contigs, const Range* ranges, const uint32_t* cand_range,
+__device__ __forceinline__ void link_one(int64_t x, const Contig* contigs, const Range* ranges, const uint32_t* cand_contig,
                                          const uint32_t* tl_list, int64_t n_tl, const uint32_t* tli_list, int64_t n_tli,
                                          const int64_t* tl_base, const int64_t* tli_base, Seed seed, int32_t* link);
 
 __global__ void __launch_bounds__(256)
-k_link(const Contig* contigs, const Range* ranges, const uint32_t* cand_range, const uint32_t* tl_list, const uint32_t* tli_list,
+k_link(const Contig* contigs, const Range* ranges, const uint32_t* cand_contig, const uint32_t* tl_list, const uint32_t* tli_list,
        const Totals* tot, const int64_t* tl_base, const int64_t* tli_base, Seed seed, int32_t* link) {
     const int64_t n_tl = tot->pad[0], n_tli = tot->pad[1];
     if (n_tl == 0 || n_tli == 0) return;
     for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n_tl + n_tli; x += (int64_t)gridDim.x * blockDim.x)
-        link_one(x, contigs, ranges, cand_range, tl_list, n_tl, tli_list, n_tli, tl_base, tli_base, seed, link);
+        link_one(x, contigs, ranges, cand_contig, tl_list, n_tl, tli_list, n_tli, tl_base, tli_base, seed, link);
 }
 
-__device__ __forceinline__ void link_one(int64_t x, const Contig* contigs, const Range* ranges, const uint32_t* cand_range,
+__device__ __forceinline__ void link_one(int64_t x, const Contig* contigs, const Range* ranges, const uint32_t* cand_contig,
                                          const uint32_t* tl_list, int64_t n_tl, const uint32_t* tli_list, int64_t n_tli,
                                          const int64_t* tl_base, const int64_t* tli_base, Seed seed, int32_t* link) {
     const bool is_tl = x < n_tl;
     const int64_t idx = is_tl ? x : x - n_tl;
     const uint32_t slot = is_tl ? tl_list[idx] : tli_list[idx];
-    const uint32_t c = ranges[cand_range[slot]].contig;
+    const uint32_t c = cand_contig[slot];
     const int64_t a = tl_base[c + 1] - tl_base[c], b = tli_base[c + 1] - tli_base[c];
     if (a == 0 || b == 0) return;
     // ties (a == b) are driven from the TL side
@@ -544,12 +544,12 @@ namespace ms {
 
 __global__ void __launch_bounds__(256, 8)      // 32 registers: the SNP reference gather needs all 64 warps to hide its latency
 k_build_records(const Totals* tot, const uint32_t* acc_slot, const int64_t* gpos, const uint8_t* type, const uint32_t* len,
-                const uint32_t* cand_range, const int32_t* link, const Range* ranges, const Contig* contigs, VcfView vv,
+                const uint32_t* cand_contig, const int32_t* link, const Range* ranges, const Contig* contigs, VcfView vv,
                 const Tables* tab, Seed seed, double p_ti, Rec* recs, int32_t* delta, uint32_t* vsize, bool defer_bases) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= tot->n_accepted) return;             // the grid is sized from the candidate count (an upper bound)
     const uint32_t s = acc_slot[e];
-    const uint32_t cidx = ranges[cand_range[s]].contig;
+    const uint32_t cidx = cand_contig[s];
     const Contig& ct = contigs[cidx];
     const int64_t g = gpos[s];
     const uint32_t pos = (uint32_t)(g - ct.goff);
@@ -621,7 +621,7 @@ static int draw_and_sort(ms_ctx* c, Seed seed, uint32_t purpose, int32_t min_dis
     MS_CUDA(c, c->svec.ensure((size_t)(K + 1) * 8));
     MS_CUDA(c, c->cand_type.ensure((size_t)K + 16));
     MS_CUDA(c, c->cand_len.ensure((size_t)K * 4 + 16));
-    MS_CUDA(c, c->lvec.ensure((size_t)K * 4 + 16));         // cand_range
+    MS_CUDA(c, c->lvec.ensure((size_t)K * 4 + 16));         // cand_contig
     uint32_t* d_cnt = c->bucket_cnt.as<uint32_t>();
     int64_t* d_boff = c->bucket_off.as<int64_t>();
 
