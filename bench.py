@@ -16,8 +16,9 @@ splice/emit FASTA image -> format VCF, all on the GPU (IT workloads: breakpoints
 `partition_invariant` (N > 1): every rank hashes its slices of the outputs on the device, rank 0 recomputes the
             whole genome alone with the same seed and compares — the N-GPU result IS the 1-GPU result.
 `--impl reference`: the reference's own CPU implementation on all host cores (one process per contig).
-N > 1 (torchrun): contigs are partitioned over ranks (LPT by length, no data-path collective; IT pairs that
-straddle ranks exchange their intervals over NCCL P2P); genomes with fewer contigs than ranks are cut at output
+N > 1 (torchrun): contigs are partitioned over ranks (LPT by length, no data-path collective; for an IT pair that
+straddles ranks the splice kernel reads the partner's intervals in place from the peer GPU over NVLink, or —
+MS_IT_EXCHANGE=pull|nccl — they are copied / sent into a staging region); genomes with fewer contigs than ranks are cut at output
 tile boundaries (ms_apply_window).  Total work is fixed, so scaling is "strong".
 """
 from __future__ import annotations
@@ -59,7 +60,7 @@ WORKLOADS = {
                                 "std sn .001, one None range over each centromere",
                lengths=GRCH38, names=GRCH38_NAMES, n_fraction=0.03, telomere=10000, n_rmt_ranges=10_000),
     # BASELINE.json configs[3]: interchromosomal translocations on the 24-contig genome
-    "c4": dict(kind="it", desc="C4: IT rate 1e-7 on the GRCh38-shaped genome (ceil(24/3) = 8 pairs like the reference's pairing; cross-GPU intervals over NCCL P2P)",
+    "c4": dict(kind="it", desc="C4: IT rate 1e-7 on the GRCh38-shaped genome (ceil(24/3) = 8 pairs like the reference's pairing; cross-GPU partners read in place over NVLink)",
                lengths=GRCH38, names=GRCH38_NAMES, n_fraction=0.03, telomere=10000, it_rate=1e-7),
     "c4d": dict(kind="it", desc="C4 dense: IT rate 1e-5 on the GRCh38-shaped genome (~2 k breakpoints per pair)",
                 lengths=GRCH38, names=GRCH38_NAMES, n_fraction=0.03, telomere=10000, it_rate=1e-5),
@@ -603,7 +604,7 @@ def measure(run: Run, steps, warmup, barrier, stream, local_rank, with_clocks=Fa
     barrier()
     wall = time.perf_counter() - t0
     dev_ms = ev0.elapsed_time(ev1)
-    if run.it is not None:       # IT steps contain host work (breakpoint download, record build, NCCL): wall clock is the honest one
+    if run.it is not None:       # IT steps contain host work (breakpoint download, record build): wall clock is the honest one
         dev_ms = max(dev_ms, wall * 1e3)
     clocks = sampler.stop() if sampler else None
     st = eng.stats()

@@ -141,7 +141,7 @@ int ms_genome_declare(ms_ctx* ctx, int64_t total_bases, int32_t n_contigs, const
  * (interchromosomal partners, it_mutator.py:133-137).  Call before ms_genome_upload (a genome that is already resident
  * is moved into a buffer with the extra space).  The region starts at
  * genome index total_bases + 64 (ms_device_ptr(4) gives the base pointer); K_RAW records may point into it,
- * so a peer's ncclSend can land directly where the splice kernel gathers from. */
+ * so a peer's ncclSend or ms_peer_pull can land directly where the splice kernel gathers from. */
 int ms_genome_reserve(ms_ctx* ctx, int64_t extra_bytes);
 /* Peer windows: with one process per GPU the partner contig of an interchromosomal pair (it_mutator.py:91-102 picks
  * the pairs, :133-142 swaps the odd intervals) may live in another process.  The owner exports its resident genome

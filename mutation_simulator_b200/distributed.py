@@ -3,10 +3,11 @@
 ARGS/RMT need no data-path collective: contigs are independent (mutator.py:111 carries no
 state between them) and the RNG is keyed by the global contig index, so every rank simply
 processes its share and the ranks' slices are written into one file at offsets derived
-from an all-gather of their sizes.  IT needs one exchange step: for a pair whose members
-live on different GPUs each owner sends its contig to the other (NCCL send/recv, grouped)
-straight into the staging region behind the receiver's genome, which is where the splice
-kernel's raw far-copy records point (it_mutator.py:133-142)."""
+from an all-gather of their sizes.  IT needs the partner's odd intervals: for a pair whose
+members live on different GPUs the reader maps the owner's genome buffer (CUDA IPC) and its
+raw far-copy records point straight into the peer's HBM (it_mutator.py:133-142; SURVEY.md
+§8e); exchange_contigs() below is the NCCL send/recv route into a staging region that the
+`nccl` setting of MS_IT_EXCHANGE keeps available."""
 from __future__ import annotations
 
 import os

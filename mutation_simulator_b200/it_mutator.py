@@ -191,9 +191,8 @@ class ITMutator:
         D.write_partitioned(self._args.outbedpe, [0] if rank == 0 else [], [bed] if rank == 0 else [], 1)
 
     def _mutate_partitioned(self):
-        """One process per GPU: contigs are partitioned; a pair that straddles two GPUs swaps the intervals each
-        member takes from the other over NCCL P2P, straight into the staging region behind the receiver's genome
-        (SURVEY.md §8e)."""
+        """One process per GPU: contigs are partitioned; for a pair that straddles two GPUs each member reads the
+        intervals it takes from the other out of the peer's HBM (see setup_partitioned)."""
         if D.shard_of(self._fasta, self._world) == "tiles":
             return self._mutate_tiles()
         self.setup_partitioned()
